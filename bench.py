@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path (BASELINE.json metric: batched env-steps/sec incl. NetMon
+forward; % of HBM roofline for the env-step kernel).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+
+One "step" = one batched rollout step over B environment instances per GPU
+(src/main.py:673-737): DQN epsilon-greedy action selection -> Routing env step with agent and
+node observations -> NetMon forward -> replay insert.  1 env-step = one env instance advanced
+one tick.  Environment instances shard across GPUs with no collective on the path (weak
+scaling: B per GPU is fixed).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same step
+driven through the public classes with the step's random draws supplied from pinned HOST memory
+and the reward read back to the host every step; `roofline` = dominant kernel of the step;
+`roofline_env_step` = the HBM-bound env-step kernel named by the metric; `cpu_baseline` = the
+oracle (CPU port of the reference path) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched_env_steps_per_sec_incl_netmon_fwd"
+UNIT = "env-steps/s"
+
+
+def peaks():
+    p = dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            j = json.load(open(f))
+            p.update(hbm_gbs=float(j["hbm_gbs"]), bf16_tflops=float(j["bf16_tflops"]),
+                     bf16_tflops_sustained=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), source="measured")
+        except Exception:
+            pass
+    return p
+
+
+def env_step_bytes(N, A):
+    """algorithmic bytes of one env-step with dense outputs materialised."""
+    E = 3 * N // 2
+    state = A * (40 + 4 * ((N + 31) // 32)) + 8 * E
+    return (2 * state + 4 * A + 4 * A * (6 * N + 10) + 4 * N * (4 * N + 8) + A * A + N * A + 4 * A + A + 32 + 4 * A)
+
+
+def gemm_flops(N, A, H, K, enc, dqn, n_act=4):
+    """dense GEMM FLOPs per env-step (NetMon + DQN)."""
+    Dn, Dj = 4 * N + 8, 6 * N + 10 + 4 * H
+    nm, prev = 0, Dn
+    for u in list(enc) + [H]:
+        nm += 2 * prev * u
+        prev = u
+    nm += (1 + K) * 16 * H * H
+    dq, prev = 0, Dj
+    for u in dqn:
+        dq += 2 * prev * u
+        prev = u
+    dq += 2 * prev * n_act
+    return N * nm + A * dq
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_arm(cfg_name, steps, warmup, envs=None, budget_s=20.0):
+    """The oracle's rollout step on the host cores, bounded sample of the same workload."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+
+    from graph_marl_b200.model import DQN, NetMon
+    from graph_marl_b200.rollout import CONFIGS
+    from oracle.cpu_rollout import CpuRollout
+
+    c = CONFIGS[cfg_name]
+    cores = len(os.sched_getaffinity(0))
+    torch.manual_seed(0)
+    N, A = c["n_nodes"], c["n_data"]
+    nm = NetMon(4 * N + 8, c["H"], c["enc"], c["K"], F.leaky_relu, rnn_type=c["rnn"], output_neighbor_hidden=True)
+    dq = DQN(6 * N + 10 + 4 * c["H"], c["dqn"], 4, F.leaky_relu)
+    B = envs or (64 * cores if N <= 50 else 2 * cores)
+    ro = CpuRollout(N, A, c["topo_seed"], c["congestion"], c["K"], c["rnn"], c["H"], c["enc"], c["dqn"], B, cores,
+                    {k: v.numpy() for k, v in nm.state_dict().items()}, {k: v.numpy() for k, v in dq.state_dict().items()},
+                    replay_capacity=4 * B)
+    ro.reset()
+    for _ in range(max(1, min(warmup, 2))):
+        ro.step()
+    t0 = time.perf_counter()
+    n = 0
+    while n < steps and (time.perf_counter() - t0 < budget_s or n < 1):
+        ro.step()
+        n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=B * n / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{B} envs x {n} rollout steps of {cfg_name} (C env oracle on {cores} threads + numpy/BLAS NetMon+DQN, "
+                       f"replay insert incl.), {dt:.1f} s"), dt / max(n, 1), B
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--envs", type=int, default=0, help="env instances per GPU (default: BASELINE config size)")
+    ap.add_argument("--math", default=os.environ.get("GM_BENCH_MATH", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-replay", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-kernel", action="store_true", help="also print a per-stage CUDA-event breakdown to stderr")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from graph_marl_b200.rollout import CONFIGS
+
+    c = CONFIGS[a.workload]
+    N, A = c["n_nodes"], c["n_data"]
+    B = a.envs or (4096 if a.workload == "cfg2" else 1024)
+    config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
+                           f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
+                           f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,
+                  replay_insert=not a.no_replay, sharding=f"env instances, {world} rank(s), no collective",
+                  l2="per-step working set (obs + node_obs + NetMon activations + replay slots) exceeds the 126 MB L2")
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb, sec_per_step, Bc = cpu_arm(a.workload, a.steps, a.warmup)
+        line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=sec_per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (numpy)"),
+                    cpu_baseline=cb, gpu_launches=0,
+                    e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from graph_marl_b200 import _lib
+    from graph_marl_b200.rollout import Rollout
+
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    _lib.require_device()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(ro, steps, warmup, host):
+        for _ in range(warmup):
+            if host:
+                ro.refresh_host_draws()
+            ro.step()
+        n0 = _lib.lib().gm_kernel_launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            if host:
+                ro.refresh_host_draws()
+            ro.step()
+        e1.record()
+        barrier()
+        w1 = time.time()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), _lib.lib().gm_kernel_launch_count() - n0, w0, w1
+
+    # ---- device-resident arm ---------------------------------------------------------------
+    ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank)
+    ro.reset()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, w0, w1 = timed(ro, a.steps, max(a.warmup, 3), host=False)
+    clocks = sampler.stop(w0, w1) if sampler else None
+    value = B * world * a.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing for the roofline (CUDA events on the launching stream) -------------
+    stage = ro.profile_stages(iters=max(5, min(a.steps, 20)))
+    del ro
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: host-supplied draws in, reward out, every step --------------------------
+    ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank,
+                 host_draws=True)
+    ro.reset()
+    ms_e, _, _, _ = timed(ro, a.steps, max(a.warmup, 3), host=True)
+    e2e = dict(value=B * world * a.steps / (ms_e * 1e-3), unit=UNIT, h2d_bytes_per_step=ro.h2d_bytes_per_step() * world,
+               d2h_bytes_per_step=ro.d2h_bytes_per_step() * world, ms_per_step=ms_e / a.steps)
+    del ro
+    torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    H, K = c["H"], c["K"]
+    flops_step = gemm_flops(N, A, H, K, c["enc"], c["dqn"]) * B
+    gemm_ms = stage["gemm_ms"]
+    env_ms = stage["env_step_ms"]
+    env_bytes = env_step_bytes(N, A) * B
+    roof_env = dict(bound="hbm", kernel="routing_kernel<STEP>", achieved=env_bytes / (env_ms * 1e-3) / 1e9,
+                    peak=pk["hbm_gbs"], unit="GB/s", frac=env_bytes / (env_ms * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None,
+                    peak_source=pk["source"], bytes_per_env_step=env_step_bytes(N, A), ms_per_launch=env_ms)
+    tf = flops_step / (gemm_ms * 1e-3) / 1e12
+    roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                     frac=tf / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
+                     flops_per_env_step=flops_step // B, ms_per_step_in_gemms=gemm_ms)
+    dominant = roof_gemm if gemm_ms >= env_ms else roof_env
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+                ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype={"fp32": "f32", "bf16x3": "bf16x3 (fp32-accurate split, fp32 accumulate)", "bf16": "bf16"}[a.math],
+                data="synthetic", config=config, agent_steps_per_sec=value * A, gpu_launches=int(launches), clocks=clocks, e2e=e2e,
+                roofline=dominant, roofline_env_step=roof_env, roofline_gemm=roof_gemm, stage_ms=stage)
+    if not a.no_cpu_baseline and world == 1:
+        try:
+            cb, _, _ = cpu_arm(a.workload, steps=10**6, warmup=1, budget_s=15.0)
+            line["cpu_baseline"] = cb
+        except Exception as ex:  # the baseline must never hide the GPU number
+            line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=len(os.sched_getaffinity(0)), kind="port", sample=f"failed: {ex}")
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+// dqn.cu -- DQN forward + epsilon-greedy action selection, device resident.
+//
+// Reference: src/model.py:199-203 (DQN.forward = MLP encoder with activation on every
+// layer, then Linear q_net.fc), src/policy.py:20-51 (EpsilonGreedy.__call__):
+//   q[mask] = -inf; random_actions = randint(n_act, size=A); random_filter = rand(A) < eps;
+//   actions = argmax(q) * ~filter + filter * random_actions       (argmax = first maximum)
+// The joint observation row [agent obs | graph obs] (wrapper.py:50) is consumed as two
+// segments so the concatenation is never materialised.
+#include "common.cuh"
+#include "linear_simt.cuh"
+
+namespace gm {
+
+int linear_dispatch(const LinearArgs& a, int math, void* ws, int64_t ws_bytes, cudaStream_t s);
+
+constexpr int MAX_ACT = 8;
+
+// one warp per agent row: q = h Wq^T + bq, mask, argmax, epsilon mix
+__global__ void dqn_head_kernel(const float* __restrict__ h, int64_t ldh, int Hd, const float* __restrict__ qw,
+                                const float* __restrict__ qb, int n_act, const uint8_t* __restrict__ mask, double eps,
+                                const int* __restrict__ rand_action, const double* __restrict__ rand_u, uint64_t seed,
+                                uint64_t step, float* __restrict__ q_out, int* __restrict__ act_out, int64_t rows) {
+    int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float acc[MAX_ACT];
+#pragma unroll
+    for (int a = 0; a < MAX_ACT; a++) acc[a] = 0.f;
+    const float* hr = h + r * ldh;
+    for (int k = lane; k < Hd; k += 32) {
+        float x = hr[k];
+#pragma unroll
+        for (int a = 0; a < MAX_ACT; a++)
+            if (a < n_act) acc[a] = fmaf(x, qw[(size_t)a * Hd + k], acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < MAX_ACT; a++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(FULL, acc[a], o);
+    if (lane == 0) {
+        int best = 0;
+        float bestv = 0.f;
+        for (int a = 0; a < n_act; a++) {
+            float q = acc[a] + qb[a];
+            if (q_out) q_out[r * n_act + a] = q;  // Q-values before masking (what the model returns)
+            if (mask && mask[r * n_act + a]) q = -INFINITY;
+            if (a == 0 || q > bestv) { best = a; bestv = q; }
+        }
+        int ra; double u;
+        if (rand_action) { ra = rand_action[r]; u = rand_u[r]; }
+        else {
+            Philox p((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x5bd1e995u, seed ^ 0xA5A5A5A5DEADBEEFull);
+            ra = (int)__umulhi(p.r[0], (uint32_t)n_act);
+            u = u53(p.r[1], p.r[2]);
+        }
+        act_out[r] = (u < eps) ? ra : best;
+    }
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" {
+
+int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows) {
+    if (!p) return 0;
+    int maxw = 0;
+    for (int i = 0; i < p->n_layers; i++) maxw = max(maxw, p->units[i]);
+    return 2 * round_up(rows * maxw * 4, 256) + (32 << 20) + gm_linear_workspace_bytes(rows, maxw, p->in_features, p->math);
+}
+
+int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda, const float* obs_g,
+               int32_t Dg, int64_t ldg, const uint8_t* action_mask, double epsilon, const int32_t* rand_action,
+               const double* rand_u, uint64_t philox_seed, uint64_t philox_step, float* q_out, int32_t* act_out,
+               void* workspace, int64_t workspace_bytes, void* stream) {
+    GM_CHECK_ARG(p && obs_a && act_out && workspace, "null pointer");
+    GM_CHECK_ARG(p->n_layers >= 1 && p->n_layers <= GM_MAX_LAYERS, "n_layers");
+    GM_CHECK_ARG(p->n_actions >= 1 && p->n_actions <= MAX_ACT, "n_actions %d > %d", p->n_actions, MAX_ACT);
+    GM_CHECK_ARG(Da + Dg == p->in_features, "Da+Dg=%d != in_features %d", Da + Dg, p->in_features);
+    GM_CHECK_ARG((rand_action == nullptr) == (rand_u == nullptr), "rand_action and rand_u must both be set or NULL");
+    GM_CHECK_ARG(workspace_bytes >= gm_dqn_workspace_bytes(p, rows), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    int maxw = 0;
+    for (int i = 0; i < p->n_layers; i++) maxw = max(maxw, p->units[i]);
+    float* buf0 = (float*)workspace;
+    float* buf1 = (float*)((char*)workspace + round_up(rows * maxw * 4, 256));
+    void* lin_ws = (char*)workspace + 2 * round_up(rows * maxw * 4, 256);
+    int64_t lin_ws_bytes = workspace_bytes - 2 * round_up(rows * maxw * 4, 256);
+    int rc;
+    // layer 0 over the two input segments: y = act(obs_a W[:, :Da]^T + obs_g W[:, Da:]^T + b)
+    {
+        int U = p->units[0];
+        int D = p->in_features;
+        if (Dg > 0) {
+            LinearArgs a{obs_a, lda, p->w[0], D, p->b[0], nullptr, buf0, U, rows, U, Da, -1, 0};
+            if ((rc = linear_dispatch(a, p->math, lin_ws, lin_ws_bytes, s))) return rc;
+            LinearArgs b{obs_g, ldg, p->w[0] + Da, D, nullptr, nullptr, buf0, U, rows, U, Dg, p->activation, 1};
+            if ((rc = linear_dispatch(b, p->math, lin_ws, lin_ws_bytes, s))) return rc;
+        } else {
+            LinearArgs a{obs_a, lda, p->w[0], D, p->b[0], nullptr, buf0, U, rows, U, Da, p->activation, 0};
+            if ((rc = linear_dispatch(a, p->math, lin_ws, lin_ws_bytes, s))) return rc;
+        }
+    }
+    float* x = buf0;
+    for (int l = 1; l < p->n_layers; l++) {
+        float* y = (x == buf0) ? buf1 : buf0;
+        LinearArgs a{x, p->units[l - 1], p->w[l], p->units[l - 1], p->b[l], nullptr, y, p->units[l], rows, p->units[l],
+                     p->units[l - 1], p->activation, 0};
+        if ((rc = linear_dispatch(a, p->math, lin_ws, lin_ws_bytes, s))) return rc;
+        x = y;
+    }
+    int Hd = p->units[p->n_layers - 1];
+    dqn_head_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(x, Hd, Hd, p->q_w, p->q_b, p->n_actions, action_mask, epsilon,
+                                                              rand_action, rand_u, philox_seed, philox_step, q_out, act_out,
+                                                              rows);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,485 @@
+// netmon.cu -- NetMon forward (graph-observation module) for B graphs of N nodes.
+//
+// Reference: src/model.py:451-631 (NetMon.forward, _update_node_states, _get_neighbor_h,
+// _get_global_h, output_to_network_obs), :213-229 (SimpleAggregation), :32-42 (MLP),
+// src/layernormlstm.py:24-42.  SURVEY.md Appendix B is the distilled math.
+//
+// Data layout (HBM, fp32): rows r = b*N + v; state [R, ns*H] with h in the first H floats
+// of a node's row and c in the next H (model.py:417-449); adjacency as padded ascending
+// neighbour lists (self included when the mask has it) instead of the reference's dense
+// [B,N,N] float mask, so aggregation is a coalesced row gather + register sum and the
+// readout is a pure gather.
+#include "common.cuh"
+#include "linear_simt.cuh"
+
+namespace gm {
+
+int linear_dispatch(const LinearArgs& a, int math, void* ws, int64_t ws_bytes, cudaStream_t s);  // gemm_dispatch.cu
+
+// ---------------------------------------------------------------------------------------
+// adjacency mask -> ascending neighbour lists (one warp per (graph, node) row)
+// ---------------------------------------------------------------------------------------
+__global__ void adj_to_lists_kernel(const float* __restrict__ mask, int B, int N, int DM, int* __restrict__ nbr,
+                                    int* __restrict__ deg, int* __restrict__ overflow) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= B * N) return;
+    const float* m = mask + (size_t)row * N;
+    int cnt = 0;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        int c = c0 + lane;
+        bool on = (c < N) && (m[c] != 0.f);
+        unsigned bal = __ballot_sync(FULL, on);
+        int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+        if (on && pos < DM) nbr[(size_t)row * DM + pos] = c;
+        cnt += __popc(bal);
+    }
+    for (int q = cnt + lane; q < DM; q += 32) nbr[(size_t)row * DM + q] = -1;
+    if (lane == 0) {
+        deg[row] = min(cnt, DM);
+        if (cnt > DM) atomicExch(overflow, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// aggregation: M[r] = sum (or mean) of h over the node's list (model.py:213-229)
+// one warp per row, lanes stride the H floats as float4
+// ---------------------------------------------------------------------------------------
+__global__ void aggregate_kernel(const float* __restrict__ h, int64_t ldh, float* __restrict__ M, int B, int N, int H,
+                                 const int* __restrict__ nbr, const int* __restrict__ deg, int DM,
+                                 const int* __restrict__ list_index, int mean) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= (int64_t)B * N) return;
+    int b = (int)(row / N), v = (int)(row - (int64_t)b * N);
+    int li = list_index ? list_index[b] : b;
+    const int* lst = nbr + ((size_t)li * N + v) * DM;
+    int dg = deg[(size_t)li * N + v];
+    const float* hb = h + (size_t)b * N * ldh;
+    for (int c = lane * 4; c < H; c += 128) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < dg; q++) {
+            int u = lst[q];
+            float4 x = *(const float4*)(hb + (size_t)u * ldh + c);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        if (mean) { acc.x /= (float)max(dg, 1); acc.y /= (float)max(dg, 1); acc.z /= (float)max(dg, 1); acc.w /= (float)max(dg, 1); }
+        *(float4*)(M + row * H + c) = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// LSTM pointwise (torch.nn.LSTMCell gate math; gate order i,f,g,o)
+// ---------------------------------------------------------------------------------------
+__global__ void lstm_pointwise_kernel(const float* __restrict__ gates, const float* __restrict__ c_in, int64_t ldc_in,
+                                      float* __restrict__ h_out, int64_t ldh_out, float* __restrict__ c_out,
+                                      int64_t ldc_out, float* __restrict__ h_out2, int64_t ldh_out2,
+                                      float* __restrict__ c_out2, int64_t ldc_out2, int64_t R, int H) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * H) return;
+    int64_t r = idx / H;
+    int j = (int)(idx - r * H);
+    const float* g = gates + r * 4 * H;
+    float i_ = sigmoidf_(g[j]), f_ = sigmoidf_(g[H + j]), g_ = tanhf(g[2 * H + j]), o_ = sigmoidf_(g[3 * H + j]);
+    float c = f_ * c_in[r * ldc_in + j] + i_ * g_;
+    float hh = o_ * tanhf(c);
+    h_out[r * ldh_out + j] = hh;
+    c_out[r * ldc_out + j] = c;
+    if (h_out2) h_out2[r * ldh_out2 + j] = hh;
+    if (c_out2) c_out2[r * ldc_out2 + j] = c;
+}
+
+// ---------------------------------------------------------------------------------------
+// LayerNormLSTM pointwise (layernormlstm.py:28-42): one warp per row.
+//   gates = LN(gi) + LN(gh) + b_ih ; c' = LN(sig(f)*c + sig(i)*tanh(g)) ; h' = sig(o)*tanh(c')
+// ---------------------------------------------------------------------------------------
+__device__ inline float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+__global__ void lnlstm_pointwise_kernel(const float* __restrict__ gi, const float* __restrict__ gh, gm_cell_params cp,
+                                        const float* __restrict__ c_in, int64_t ldc_in, float* __restrict__ h_out,
+                                        int64_t ldh_out, float* __restrict__ c_out, int64_t ldc_out,
+                                        float* __restrict__ h_out2, int64_t ldh_out2, float* __restrict__ c_out2,
+                                        int64_t ldc_out2, int64_t R, int H) {
+    int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const int G = 4 * H;
+    const float* a = gi + r * G;
+    const float* b = gh + r * G;
+    // two-pass mean / biased variance over the 4H gate pre-activations (eps 1e-5)
+    float sa = 0.f, sb = 0.f;
+    for (int c = lane; c < G; c += 32) { sa += a[c]; sb += b[c]; }
+    float ma = warp_sum(sa) / (float)G, mb = warp_sum(sb) / (float)G;
+    float va = 0.f, vb = 0.f;
+    for (int c = lane; c < G; c += 32) {
+        float da = a[c] - ma, db = b[c] - mb;
+        va += da * da; vb += db * db;
+    }
+    float ra = (1.f / sqrtf(warp_sum(va) / (float)G + 1e-5f)), rb = (1.f / sqrtf(warp_sum(vb) / (float)G + 1e-5f));
+    auto gate = [&](int c) {
+        return (a[c] - ma) * ra * cp.ln_in_w[c] + cp.ln_in_b[c] + ((b[c] - mb) * rb * cp.ln_hid_w[c] + cp.ln_hid_b[c]) +
+               cp.b_ih[c];
+    };
+    // pre-LN cell state for this lane's hidden units (H <= 32*8 handled by a strided loop, kept in registers)
+    float cpre[8];
+    float og[8];
+    float sc = 0.f;
+    int nj = 0;
+    for (int j = lane; j < H; j += 32, nj++) {
+        float i_ = sigmoidf_(gate(j)), f_ = sigmoidf_(gate(H + j)), g_ = tanhf(gate(2 * H + j));
+        og[nj] = sigmoidf_(gate(3 * H + j));
+        cpre[nj] = f_ * c_in[r * ldc_in + j] + i_ * g_;
+        sc += cpre[nj];
+    }
+    float mc = warp_sum(sc) / (float)H;
+    float vc = 0.f;
+    for (int q = 0; q < nj; q++) { float dlt = cpre[q] - mc; vc += dlt * dlt; }
+    float rc = (1.f / sqrtf(warp_sum(vc) / (float)H + 1e-5f));
+    nj = 0;
+    for (int j = lane; j < H; j += 32, nj++) {
+        float c = (cpre[nj] - mc) * rc * cp.ln_cell_w[j] + cp.ln_cell_b[j];
+        float hh = og[nj] * tanhf(c);
+        h_out[r * ldh_out + j] = hh;
+        c_out[r * ldc_out + j] = c;
+        if (h_out2) h_out2[r * ldh_out2 + j] = hh;
+        if (c_out2) c_out2[r * ldc_out2 + j] = c;
+    }
+}
+
+// GRU pointwise (torch.nn.GRUCell; gate order r,z,n)
+__global__ void gru_pointwise_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
+                                     const float* __restrict__ h_in, int64_t ldh_in, float* __restrict__ h_out,
+                                     int64_t ldh_out, float* __restrict__ h_out2, int64_t ldh_out2, int64_t R, int H) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * H) return;
+    int64_t r = idx / H;
+    int j = (int)(idx - r * H);
+    const float* a = gi + r * 3 * H;
+    const float* b = gh + r * 3 * H;
+    float rg = sigmoidf_(a[j] + b[j]);
+    float z = sigmoidf_(a[H + j] + b[H + j]);
+    float n = tanhf(a[2 * H + j] + rg * b[2 * H + j]);
+    float hh = (1.f - z) * n + z * h_in[r * ldh_in + j];
+    h_out[r * ldh_out + j] = hh;
+    if (h_out2) h_out2[r * ldh_out2 + j] = hh;
+}
+
+__global__ void copy_rows_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
+                                 int64_t R, int W) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * W) return;
+    int64_t r = idx / W;
+    int j = (int)(idx - r * W);
+    dst[r * ldd + j] = src[r * lds + j];
+}
+
+// per-graph mean of h over nodes (model.py:624-627) -> gmean [B,H]
+__global__ void global_mean_kernel(const float* __restrict__ h, int64_t ldh, float* __restrict__ gmean, int B, int N,
+                                   int H) {
+    int b = blockIdx.x;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        float s = 0.f;
+        for (int v = 0; v < N; v++) s += h[((size_t)b * N + v) * ldh + j];
+        gmean[(size_t)b * H + j] = s / (float)N;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// readout (model.py:458-469, 582-631): out row = [h_v | gmean_b | last[n_1] .. last[n_maxdeg]]
+// neighbours in ascending id order without self, zero padded.  Rows are either all nodes
+// (node_out) or the node under each agent (agent_out = node_out[agent_node], the gather form
+// of bmm with a one-hot node-agent matrix).  One warp per output row.
+// ---------------------------------------------------------------------------------------
+__global__ void readout_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ last,
+                               int64_t ldl, const float* __restrict__ gmean, const int* __restrict__ nbr,
+                               const int* __restrict__ deg, int DM, const int* __restrict__ list_index,
+                               const int* __restrict__ agent_node, int rows_per_graph, int B, int N, int H,
+                               int use_nbr, int use_glob, int max_degree, float* __restrict__ out, int64_t ldo) {
+    int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= (int64_t)B * rows_per_graph) return;
+    int b = (int)(row / rows_per_graph);
+    int v = agent_node ? agent_node[row] : (int)(row - (int64_t)b * rows_per_graph);
+    float* o = out + row * ldo;
+    const float* hv = h + ((size_t)b * N + v) * ldh;
+    for (int c = lane; c < H; c += 32) o[c] = hv[c];
+    int off = H;
+    if (use_glob) {
+        for (int c = lane; c < H; c += 32) o[off + c] = gmean[(size_t)b * H + c];
+        off += H;
+    }
+    if (use_nbr) {
+        int li = list_index ? list_index[b] : b;
+        const int* lst = nbr + ((size_t)li * N + v) * DM;
+        int dg = deg[(size_t)li * N + v];
+        int slot = 0;
+        for (int q = 0; q < dg && slot < max_degree; q++) {
+            int u = lst[q];
+            if (u == v) continue;
+            const float* lu = last + ((size_t)b * N + u) * ldl;
+            for (int c = lane; c < H; c += 32) o[off + slot * H + c] = lu[c];
+            slot++;
+        }
+        for (; slot < max_degree; slot++)
+            for (int c = lane; c < H; c += 32) o[off + slot * H + c] = 0.f;
+    }
+}
+
+// general node->agent mapping (model.py:629-631) for a non-one-hot matrix
+__global__ void map_to_agents_kernel(const float* __restrict__ node_out, const float* __restrict__ nam, int B, int N,
+                                     int A, int O, float* __restrict__ agent_out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * A * O) return;
+    int o = (int)(idx % O);
+    int a = (int)((idx / O) % A);
+    int b = (int)(idx / ((int64_t)O * A));
+    float s = 0.f;
+    for (int n = 0; n < N; n++) s += node_out[((size_t)b * N + n) * O + o] * nam[((size_t)b * N + n) * A + a];
+    agent_out[idx] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+struct NetmonWs {
+    float *act0, *act1, *g0, *g1, *hA, *hB, *cA, *cB, *M, *gmean;
+    int64_t bytes;
+};
+
+static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
+    NetmonWs w;
+    int H = p->hidden;
+    int maxw = H;
+    for (int i = 0; i < p->n_enc_layers; i++) maxw = max(maxw, p->enc_units[i]);
+    int G = p->rnn_type == GM_RNN_GRU ? 3 * H : 4 * H;
+    char* c = (char*)base;
+    int64_t off = 0;
+    auto take = [&](int64_t floats) {
+        float* ptr = (float*)(c + off);
+        off += round_up(floats * 4, 256);
+        return ptr;
+    };
+    w.act0 = take(R * maxw); w.act1 = take(R * maxw);
+    w.g0 = take(R * G); w.g1 = take(R * G);
+    w.hA = take(R * H); w.hB = take(R * H); w.cA = take(R * H); w.cB = take(R * H);
+    w.M = take(R * H);
+    w.gmean = take((int64_t)max(B, 1) * H);
+    w.bytes = off + (32 << 20);  // + room for the tensor-core path's packed operands
+    return w;
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" {
+
+int64_t gm_netmon_workspace_bytes(const gm_netmon_params* p, int64_t rows) {
+    if (!p) return 0;
+    NetmonWs w = carve(p, rows, (int)rows, nullptr);
+    return w.bytes + gm_linear_workspace_bytes(rows, 4 * p->hidden, 2 * p->hidden, p->math);
+}
+
+int gm_adj_to_lists(const float* mask, int32_t B, int32_t N, int32_t DM, int32_t* nbr_all, int32_t* deg,
+                    int32_t* overflow, void* stream) {
+    GM_CHECK_ARG(mask && nbr_all && deg && overflow && B > 0 && N > 0 && DM > 0, "bad adj_to_lists args");
+    int rows = B * N;
+    adj_to_lists_kernel<<<ceil_div(rows, 4), 128, 0, (cudaStream_t)stream>>>(mask, B, N, DM, nbr_all, deg, overflow);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+int gm_netmon_map_to_agents(const float* node_out, const float* node_agent, int32_t B, int32_t N, int32_t A,
+                            int32_t O, float* agent_out, void* stream) {
+    GM_CHECK_ARG(node_out && node_agent && agent_out, "null pointer");
+    int64_t tot = (int64_t)B * A * O;
+    map_to_agents_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(node_out, node_agent, B, N, A,
+                                                                                         O, agent_out);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs, const int32_t* nbr_all,
+                      const int32_t* deg, int32_t DM, const int32_t* list_index, const float* state_in,
+                      float* state_out, int32_t max_degree, float* node_out, const int32_t* agent_node, int32_t A,
+                      float* agent_out, int64_t agent_out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
+    GM_CHECK_ARG(p && node_obs && nbr_all && deg && state_out && workspace, "null pointer");
+    GM_CHECK_ARG(B > 0 && N > 0 && DM > 0, "bad sizes");
+    const int H = p->hidden, K = p->iterations, L = p->n_enc_layers;
+    GM_CHECK_ARG(H > 0 && (H % 4) == 0 && H <= 256, "hidden size %d: need a multiple of 4, <= 256", H);
+    GM_CHECK_ARG(L >= 1 && L <= GM_MAX_LAYERS && p->enc_units[L - 1] == H, "encoder must end in %d units", H);
+    GM_CHECK_ARG(p->rnn_type >= GM_RNN_LSTM && p->rnn_type <= GM_RNN_NONE, "rnn_type %d", p->rnn_type);
+    GM_CHECK_ARG(!(p->rnn_type == GM_RNN_GRU && !p->rnn_carryover),
+                 "gru without carryover is not built (the reference scrambles its state rows, model.py:571)");
+    GM_CHECK_ARG(K >= 1 || p->rnn_type == GM_RNN_NONE, "iterations must be >= 1 (model.py:564 fails for 0)");
+    GM_CHECK_ARG(max_degree <= DM, "max_degree %d > DM %d", max_degree, DM);
+    const bool lstm_like = p->rnn_type == GM_RNN_LSTM || p->rnn_type == GM_RNN_LNLSTM;
+    const int ns = lstm_like ? (p->rnn_carryover ? 2 : 4) : (p->rnn_type == GM_RNN_GRU ? 1 : 1);
+    const int S = ns * H;
+    const int64_t R = (int64_t)B * N;
+    GM_CHECK_ARG(workspace_bytes >= gm_netmon_workspace_bytes(p, R), "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    NetmonWs w = carve(p, R, B, workspace);
+    void* lin_ws = (char*)workspace + w.bytes - (32 << 20);
+    int64_t lin_ws_bytes = workspace_bytes - (w.bytes - (32 << 20));
+    const int math = p->rnn_type == GM_RNN_LNLSTM ? GM_MATH_FP32 : p->math;
+
+    // zero state when none is given (model.py:480-484)
+    const float* st_in = state_in;
+    if (!st_in) {
+        GM_CUDA(cudaMemsetAsync(state_out, 0, (size_t)R * S * 4, s));
+        st_in = state_out;  // read as zeros before it is overwritten (all readers finish first: same stream)
+    }
+    // NOTE: when state_in aliases state_out every read of st_in below happens in kernels
+    // enqueued before the kernels that write state_out, except the no-carryover reads of
+    // columns [2H,4H) at it==0, which are ordered the same way.  If K == 1 in no-carry mode the
+    // cell output overwrites columns it also reads -> stage through the ping-pong buffers.
+
+    // ---- encoder MLP (model.py:489): activation after every layer incl. the last ----------
+    const float* x = node_obs;
+    int64_t ldx = p->in_features;
+    int kin = p->in_features;
+    for (int l = 0; l < L; l++) {
+        float* y = (l & 1) ? w.act1 : w.act0;
+        LinearArgs a{x, ldx, p->enc_w[l], kin, p->enc_b[l], nullptr, y, p->enc_units[l], R, p->enc_units[l], kin,
+                     p->activation, 0};
+        int rc = linear_dispatch(a, p->math, lin_ws, lin_ws_bytes, s);
+        if (rc) return rc;
+        x = y; ldx = p->enc_units[l]; kin = p->enc_units[l];
+    }
+    const float* e = x;  // [R,H]
+
+    // one recurrent cell: (xin [R,H], h_prev, c_prev) -> (h_new, c_new) (+ optional second copy)
+    auto run_cell = [&](const gm_cell_params& cp, const float* xin, int64_t ldxin, const float* hp, int64_t ldhp,
+                        const float* cprev, int64_t ldcp, float* hn, int64_t ldhn, float* cn, int64_t ldcn, float* hn2,
+                        int64_t ldhn2, float* cn2, int64_t ldcn2) -> int {
+        int rc;
+        if (p->rnn_type == GM_RNN_LSTM) {
+            LinearArgs a{xin, ldxin, cp.w_ih, H, cp.b_ih, cp.b_hh, w.g0, 4 * H, R, 4 * H, H, -1, 0};
+            if ((rc = linear_dispatch(a, math, lin_ws, lin_ws_bytes, s))) return rc;
+            LinearArgs b{hp, ldhp, cp.w_hh, H, nullptr, nullptr, w.g0, 4 * H, R, 4 * H, H, -1, 1};
+            if ((rc = linear_dispatch(b, math, lin_ws, lin_ws_bytes, s))) return rc;
+            int64_t tot = R * H;
+            lstm_pointwise_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(w.g0, cprev, ldcp, hn, ldhn, cn, ldcn, hn2,
+                                                                              ldhn2, cn2, ldcn2, R, H);
+            GM_LAUNCH_CHECK();
+        } else if (p->rnn_type == GM_RNN_LNLSTM) {
+            LinearArgs a{xin, ldxin, cp.w_ih, H, nullptr, nullptr, w.g0, 4 * H, R, 4 * H, H, -1, 0};
+            if ((rc = linear_dispatch(a, math, lin_ws, lin_ws_bytes, s))) return rc;
+            LinearArgs b{hp, ldhp, cp.w_hh, H, nullptr, nullptr, w.g1, 4 * H, R, 4 * H, H, -1, 0};
+            if ((rc = linear_dispatch(b, math, lin_ws, lin_ws_bytes, s))) return rc;
+            lnlstm_pointwise_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(w.g0, w.g1, cp, cprev, ldcp, hn, ldhn, cn, ldcn,
+                                                                           hn2, ldhn2, cn2, ldcn2, R, H);
+            GM_LAUNCH_CHECK();
+        } else {  // GRU
+            LinearArgs a{xin, ldxin, cp.w_ih, H, cp.b_ih, nullptr, w.g0, 3 * H, R, 3 * H, H, -1, 0};
+            if ((rc = linear_dispatch(a, math, lin_ws, lin_ws_bytes, s))) return rc;
+            LinearArgs b{hp, ldhp, cp.w_hh, H, cp.b_hh, nullptr, w.g1, 3 * H, R, 3 * H, H, -1, 0};
+            if ((rc = linear_dispatch(b, math, lin_ws, lin_ws_bytes, s))) return rc;
+            int64_t tot = R * H;
+            gru_pointwise_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(w.g0, w.g1, hp, ldhp, hn, ldhn, hn2, ldhn2, R,
+                                                                             H);
+            GM_LAUNCH_CHECK();
+        }
+        return GM_OK;
+    };
+
+    // ---- rnn_obs (model.py:490-495) -------------------------------------------------------
+    const float* h = e;
+    const float* c = nullptr;
+    float* hbuf[2] = {w.hA, w.hB};
+    float* cbuf[2] = {w.cA, w.cB};
+    int cur = 0;
+    if (p->rnn_type != GM_RNN_NONE) {
+        // no-carryover keeps (h0,c0) in state columns [0,2H) (model.py:566); those columns of
+        // state_out are written at the very end from the ping-pong copy to stay alias-safe.
+        int rc = run_cell(p->rnn_obs, e, H, st_in, S, lstm_like ? st_in + H : nullptr, S, hbuf[0], H, cbuf[0], H, nullptr, 0,
+                          nullptr, 0);
+        if (rc) return rc;
+        h = hbuf[0]; c = cbuf[0]; cur = 0;
+    }
+    // h0/c0 for the no-carry state live in hbuf[0]/cbuf[0]; keep them untouched in that mode
+    const bool nocarry = lstm_like && !p->rnn_carryover;
+    float* h0_keep = nullptr; float* c0_keep = nullptr;
+    if (nocarry) {
+        h0_keep = w.act0; c0_keep = w.act1;  // encoder buffers are free now (e was consumed)
+        int64_t tot = R * H;
+        copy_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(hbuf[0], H, h0_keep, H, R, H);
+        GM_LAUNCH_CHECK();
+        copy_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(cbuf[0], H, c0_keep, H, R, H);
+        GM_LAUNCH_CHECK();
+    }
+
+    // ---- K x (aggregate, rnn_update) (model.py:509-554) ----------------------------------
+    const float* last = nullptr;  // value of h before the final iteration's aggregation (:510-519)
+    float* none_buf[2] = {w.hA, w.hB};
+    for (int it = 0; it < K; it++) {
+        if (it == K - 1) last = h;
+        aggregate_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(h, H, w.M, B, N, H, nbr_all, deg, DM, list_index,
+                                                                p->agg_type == GM_AGG_MEAN);
+        GM_LAUNCH_CHECK();
+        if (p->rnn_type == GM_RNN_NONE) {
+            // h = M; `last` may alias the previous h buffer, so ping-pong
+            float* dst = none_buf[it & 1];
+            int64_t tot = R * H;
+            copy_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(w.M, H, dst, H, R, H);
+            GM_LAUNCH_CHECK();
+            h = dst;
+            continue;
+        }
+        const float* hp = h; int64_t ldhp = H;
+        const float* cpv = c; int64_t ldcp = H;
+        if (nocarry && it == 0) { hp = st_in + 2 * H; ldhp = S; cpv = st_in + 3 * H; ldcp = S; }  // :538-539
+        int nxt = cur ^ 1;
+        int rc = run_cell(p->rnn_update, w.M, H, hp, ldhp, cpv, ldcp, hbuf[nxt], H, cbuf[nxt], H, nullptr, 0, nullptr, 0);
+        if (rc) return rc;
+        h = hbuf[nxt]; c = cbuf[nxt]; cur = nxt;
+    }
+
+    // ---- new state (model.py:562-578) ------------------------------------------------------
+    {
+        int64_t tot = R * H;
+        unsigned g = (unsigned)((tot + 255) / 256);
+        if (lstm_like) {
+            int o = nocarry ? 2 * H : 0;
+            if (nocarry) {
+                copy_rows_kernel<<<g, 256, 0, s>>>(h0_keep, H, state_out, S, R, H); GM_LAUNCH_CHECK();
+                copy_rows_kernel<<<g, 256, 0, s>>>(c0_keep, H, state_out + H, S, R, H); GM_LAUNCH_CHECK();
+            }
+            copy_rows_kernel<<<g, 256, 0, s>>>(h, H, state_out + o, S, R, H); GM_LAUNCH_CHECK();
+            copy_rows_kernel<<<g, 256, 0, s>>>(c, H, state_out + o + H, S, R, H); GM_LAUNCH_CHECK();
+        } else {
+            copy_rows_kernel<<<g, 256, 0, s>>>(h, H, state_out, S, R, H); GM_LAUNCH_CHECK();
+        }
+    }
+
+    // ---- readout (model.py:458-474) ---------------------------------------------------------
+    const int use_nbr = p->output_neighbor_hidden, use_glob = p->output_global_hidden;
+    if (use_glob) {
+        global_mean_kernel<<<B, 128, 0, s>>>(h, H, w.gmean, B, N, H);
+        GM_LAUNCH_CHECK();
+    }
+    if (use_nbr && last == nullptr) {  // K <= 0 with rnn none: zeros (:498-499)
+        GM_CUDA(cudaMemsetAsync(w.M, 0, (size_t)R * H * 4, s));
+        last = w.M;
+    }
+    const int O = H + (use_glob ? H : 0) + (use_nbr ? max_degree * H : 0);
+    if (node_out) {
+        readout_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(h, H, last, H, w.gmean, nbr_all, deg, DM, list_index, nullptr, N,
+                                                              B, N, H, use_nbr, use_glob, max_degree, node_out, O);
+        GM_LAUNCH_CHECK();
+    }
+    if (agent_out) {
+        GM_CHECK_ARG(agent_node && A > 0 && agent_out_ld >= O, "agent readout needs agent_node, A, ld >= %d", O);
+        int64_t rows = (int64_t)B * A;
+        readout_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(h, H, last, H, w.gmean, nbr_all, deg, DM, list_index,
+                                                                 agent_node, A, B, N, H, use_nbr, use_glob, max_degree,
+                                                                 agent_out, agent_out_ld);
+        GM_LAUNCH_CHECK();
+    }
+    return GM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// replay.cu -- device-resident replay ring: batched insert and index gather.
+//
+// Reference: src/replaybuffer.py:243-287 (add: 17 per-field copies into ring slot `index`,
+// then index = (index+1) % size), :132-187 (_get_transition_batch: fancy-index gather plus
+// dtype conversion to float32 / int64 / bool).  Here B transitions (one per env) are
+// inserted per call into consecutive slots and the ring never leaves HBM.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace gm {
+
+struct ReplayFields {
+    gm_replay_field f[GM_REPLAY_MAX_FIELDS];
+    int n;
+};
+
+// grid.y = field, grid.x strides over (transition, 16-byte / 4-byte / 1-byte unit)
+__global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t index, int64_t n) {
+    const gm_replay_field fd = F.f[blockIdx.y];
+    const int64_t eb = fd.elem_bytes;
+    const bool v16 = (eb % 16 == 0) && (((uintptr_t)fd.ring | (uintptr_t)fd.src) % 16 == 0);
+    const bool v4 = (eb % 4 == 0) && (((uintptr_t)fd.ring | (uintptr_t)fd.src) % 4 == 0);
+    const int unit = v16 ? 16 : (v4 ? 4 : 1);
+    const int64_t upe = eb / unit;  // units per element
+    const int64_t total = n * upe;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = t / upe, u = t - i * upe;
+        int64_t slot = (index + i) % capacity;
+        const char* s = (const char*)fd.src + i * eb + u * unit;
+        char* d = (char*)fd.ring + slot * eb + u * unit;
+        if (unit == 16) *(uint4*)d = *(const uint4*)s;
+        else if (unit == 4) *(uint32_t*)d = *(const uint32_t*)s;
+        else *d = *s;
+    }
+}
+
+// gather with conversion: one thread per output element
+__global__ void replay_sample_kernel(ReplayFields F, const int64_t* __restrict__ indices, int64_t n) {
+    const gm_replay_field fd = F.f[blockIdx.y];
+    const int in_size = (fd.convert == 0) ? 1 : (fd.convert == 3 ? 2 : 1);
+    const int64_t elems = fd.elem_bytes / in_size;  // for convert==0 this is bytes
+    const int64_t total = n * elems;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = t / elems, e = t - i * elems;
+        int64_t slot = indices[i];
+        const char* s = (const char*)fd.ring + slot * fd.elem_bytes;
+        switch (fd.convert) {
+            case 0: ((char*)fd.dst)[t] = s[e]; break;
+            case 1: ((float*)fd.dst)[t] = (float)(((const uint8_t*)s)[e] != 0); break;
+            case 2: ((int64_t*)fd.dst)[t] = (int64_t)((const int8_t*)s)[e]; break;
+            case 3: ((float*)fd.dst)[t] = __half2float(((const __half*)s)[e]); break;
+        }
+    }
+}
+
+}  // namespace gm
+
+using namespace gm;
+
+extern "C" {
+
+int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t capacity, int64_t index, int64_t n,
+                     void* stream) {
+    GM_CHECK_ARG(fields && n_fields > 0 && n_fields <= GM_REPLAY_MAX_FIELDS, "bad field count %d", n_fields);
+    GM_CHECK_ARG(capacity > 0 && n >= 0 && n <= capacity && index >= 0 && index < capacity, "bad ring arguments");
+    if (n == 0) return GM_OK;
+    ReplayFields F;
+    F.n = n_fields;
+    int64_t maxb = 0;
+    for (int i = 0; i < n_fields; i++) {
+        GM_CHECK_ARG(fields[i].ring && fields[i].src && fields[i].elem_bytes > 0, "field %d: null ring/src", i);
+        F.f[i] = fields[i];
+        maxb = max(maxb, fields[i].elem_bytes * n);
+    }
+    int64_t blocks = std::min<int64_t>((maxb / 16 + 255) / 256 + 1, 148 * 8);
+    dim3 grid((unsigned)blocks, n_fields);
+    replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, n);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+int gm_replay_sample(const gm_replay_field* fields, int32_t n_fields, const int64_t* indices, int64_t n, void* stream) {
+    GM_CHECK_ARG(fields && n_fields > 0 && n_fields <= GM_REPLAY_MAX_FIELDS && indices, "bad sample arguments");
+    if (n == 0) return GM_OK;
+    ReplayFields F;
+    F.n = n_fields;
+    int64_t maxe = 0;
+    for (int i = 0; i < n_fields; i++) {
+        GM_CHECK_ARG(fields[i].ring && fields[i].dst && fields[i].elem_bytes > 0, "field %d: null ring/dst", i);
+        GM_CHECK_ARG(fields[i].convert >= 0 && fields[i].convert <= 3, "field %d: convert %d", i, fields[i].convert);
+        F.f[i] = fields[i];
+        maxe = max(maxe, fields[i].elem_bytes * n);
+    }
+    int64_t blocks = std::min<int64_t>((maxe + 255) / 256, 148 * 8);
+    dim3 grid((unsigned)blocks, n_fields);
+    replay_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, indices, n);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+}  // extern "C"

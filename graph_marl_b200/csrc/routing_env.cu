@@ -1,0 +1,533 @@
+// routing_env.cu -- batched Routing environment for sm_100a.
+//
+// One warp owns one environment instance: it pulls the packed env record from HBM into
+// shared memory, replays the reference's two order-dependent packet loops with
+// warp-level "ordered by key" rounds (lanes = packets; per-edge / per-node fp64 running
+// sums are accumulated in packet-id order so every load, congestion decision and
+// observation field is bit-identical to the Python reference), writes the record back,
+// and then builds the dense agent / node observations in a shared-memory staging tile
+// that is zero-filled, scattered with the few non-zero fields per row and pushed to HBM
+// either with 16-byte vector stores or with one cp.async.bulk (TMA bulk) store per tile.
+//
+// Reference semantics: src/env/routing.py:119-144 (reset_packet), :160-178 (reset),
+// :187-235 (node obs), :256-267 (node-agent matrix), :269-358 (agent obs), :360-520 (step),
+// :522-539 (agent adjacency).  SURVEY.md Appendix A is the distilled spec.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace gm {
+
+struct RoutingLayout {
+    int off_load, off_i32, off_vis, off_mask, stride, VW;
+    // per-warp shared memory carve-up
+    int sm_scratch, sm_stage, sm_per_warp, stage_floats;
+};
+
+static RoutingLayout make_layout(int N, int A, int E, int stage_bytes) {
+    RoutingLayout L;
+    L.VW = (N + 31) / 32;
+    L.off_load = 8 * A;
+    L.off_i32 = L.off_load + 8 * E;
+    L.off_vis = L.off_i32 + 4 * 8 * A;
+    L.off_mask = L.off_vis + 4 * A * L.VW;
+    L.stride = (int)round_up(L.off_mask + 4 * A, 16);
+    // scratch: tl f64[N] | cnt i32[N] | rew f32[A] | looped u8[A]
+    L.sm_scratch = L.stride;
+    int scratch = 8 * N + 4 * N + 4 * A + A;
+    L.sm_stage = (int)round_up(L.sm_scratch + scratch, 16);
+    L.stage_floats = stage_bytes / 4;
+    L.sm_per_warp = (int)round_up(L.sm_stage + stage_bytes + 32, 16);
+    return L;
+}
+
+enum { MODE_RESET = 0, MODE_STEP = 1, MODE_OBSERVE = 2 };
+constexpr int WARPS_PER_CTA = 4;
+
+// Lanes with `valid` run fn() in ascending lane order among lanes that share `key`
+// (different keys proceed in the same round).  This reproduces the sequential
+// "for i in range(n_data)" update order of routing.py for state that is keyed by edge
+// or node id, without serialising independent keys.
+template <class F>
+__device__ __forceinline__ void ordered_by_key(bool valid, int key, int lane, F fn) {
+    unsigned any = __ballot_sync(FULL, valid);
+    if (any == 0) return;
+    unsigned grp = __match_any_sync(FULL, valid ? key : (-1 - lane));
+    int rank = __popc(grp & ((1u << lane) - 1u));
+    int maxrank = __reduce_max_sync(FULL, valid ? rank : 0);
+    for (int r = 0; r <= maxrank; r++) {
+        if (valid && rank == r) fn();
+        __syncwarp();
+    }
+}
+
+struct EnvView {
+    double* size;
+    double* load;
+    int *now, *target, *edge, *time, *ttl, *spw, *start, *steps;
+    uint32_t* vis;
+    uint8_t* mask;
+    double* tl;
+    int* cnt;
+    float* rew;
+    uint8_t* looped;
+};
+
+__device__ __forceinline__ EnvView make_view(uint8_t* sm, const RoutingLayout& L, int A, int N) {
+    EnvView v;
+    v.size = (double*)sm;
+    v.load = (double*)(sm + L.off_load);
+    v.now = (int*)(sm + L.off_i32);
+    v.target = v.now + A; v.edge = v.now + 2 * A; v.time = v.now + 3 * A; v.ttl = v.now + 4 * A;
+    v.spw = v.now + 5 * A; v.start = v.now + 6 * A; v.steps = v.now + 7 * A;
+    v.vis = (uint32_t*)(sm + L.off_vis);
+    v.mask = sm + L.off_mask;
+    v.tl = (double*)(sm + L.sm_scratch);
+    v.cnt = (int*)(sm + L.sm_scratch + 8 * N);
+    v.rew = (float*)(sm + L.sm_scratch + 12 * N);
+    v.looped = sm + L.sm_scratch + 12 * N + 4 * A;
+    return v;
+}
+
+// routing.py:119-144 (the load release of :126-127 is done by the caller in id order)
+__device__ __forceinline__ void spawn_packet(const EnvView& v, const RoutingLayout& L, int i, int start,
+                                             int target, double size, const gm_routing_desc& d,
+                                             const int* apsp) {
+    v.now[i] = start; v.target[i] = target; v.size[i] = size; v.start[i] = start;
+    v.time[i] = 0; v.edge[i] = -1; v.ttl[i] = d.ttl;
+    v.spw[i] = apsp[start * d.N + target];
+    for (int w = 0; w < L.VW; w++) v.vis[i * L.VW + w] = (w == (start >> 5)) ? (1u << (start & 31)) : 0u;
+    if (d.action_mask) {
+        *(uint32_t*)(v.mask + 4 * i) = (start != target) ? 1u : 0u;  // [idle forbidden?,0,0,0]
+    }
+}
+
+// ---- staged dense-row emitter ------------------------------------------------------
+// The env's block of `total` floats starting at g (4-byte aligned) is produced tile by
+// tile in `stage` (16-byte aligned shared memory, congruent to the global address mod 16
+// so that the interior of every tile moves as 16-byte units).
+template <class ScatterRows>
+__device__ __forceinline__ void emit_f32_block(float* g, int total, int W, float* stage, int stage_floats,
+                                               int lane, int store_mode, ScatterRows scatter_rows) {
+    int tile_cap = stage_floats - 4;
+    for (int f0 = 0; f0 < total; f0 += tile_cap) {
+        int nfl = min(tile_cap, total - f0);
+        float* gt = g + f0;
+        int shift = (int)(((uintptr_t)gt & 15u) >> 2);  // floats
+        int span4 = (shift + nfl + 3) >> 2;             // float4 units touched
+        float4* st4 = (float4*)stage;
+        for (int q = lane; q < span4; q += 32) st4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        float* s = stage + shift;
+        int r0 = f0 / W, r1 = (f0 + nfl - 1) / W;
+        // put(): write one value of row r / column c if it falls into this tile
+        scatter_rows(r0, r1, [&](int r, int c, float val) {
+            int idx = r * W + c - f0;
+            if (idx >= 0 && idx < nfl) s[idx] = val;
+        });
+        // copy out: head (unaligned floats), 16-byte interior, tail
+        int head = (4 - shift) & 3;
+        if (head > nfl) head = nfl;
+        int body4 = (nfl - head) >> 2;
+        int tail = nfl - head - 4 * body4;
+        if (store_mode == 2) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane < head) gt[lane] = s[lane];
+        if (lane < tail) gt[head + 4 * body4 + lane] = s[head + 4 * body4 + lane];
+        if (body4 > 0) {
+            if (store_mode == 2) {
+                if (lane == 0) {
+                    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s + head);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gt + head),
+                                 "r"(saddr), "r"(body4 * 16)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+            } else {
+                const float4* s4 = (const float4*)(s + head);
+                float4* g4 = (float4*)(gt + head);
+                for (int q = lane; q < body4; q += 32) __stcs(g4 + q, s4[q]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// byte block [total] at g, value(idx) computed per byte; 4 bytes per store where aligned
+template <class ByteFn>
+__device__ __forceinline__ void emit_i8_block(int8_t* g, int total, int lane, ByteFn fn) {
+    int head = (int)((4 - ((uintptr_t)g & 3u)) & 3u);
+    if (head > total) head = total;
+    if (lane < head) g[lane] = fn(lane);
+    int body = (total - head) >> 2;
+    uint32_t* g4 = (uint32_t*)(g + head);
+    for (int q = lane; q < body; q += 32) {
+        int i0 = head + 4 * q;
+        uint32_t w = (uint32_t)(uint8_t)fn(i0) | ((uint32_t)(uint8_t)fn(i0 + 1) << 8) |
+                     ((uint32_t)(uint8_t)fn(i0 + 2) << 16) | ((uint32_t)(uint8_t)fn(i0 + 3) << 24);
+        g4[q] = w;
+    }
+    int tail0 = head + 4 * body;
+    if (lane < total - tail0) g[tail0 + lane] = fn(tail0 + lane);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLayout L) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * WARPS_PER_CTA + warp;
+    if (b >= d.B) return;  // whole warp exits together; no block-wide barrier is used below
+    if (MODE == MODE_RESET && io.env_mask != nullptr && io.env_mask[b] == 0) return;
+
+    const int N = d.N, A = d.A, E = d.E;
+    const int topo = d.topo_index ? d.topo_index[b] : 0;
+    const int* __restrict__ ne = d.node_edges + (size_t)topo * N * 3;
+    const int* __restrict__ nb = d.node_nbrs + (size_t)topo * N * 3;
+    const int4* __restrict__ ed = (const int4*)d.edges + (size_t)topo * E;
+    const int* __restrict__ apsp = d.apsp + (size_t)topo * N * N;
+
+    uint8_t* sm = smem + (size_t)warp * L.sm_per_warp;
+    EnvView v = make_view(sm, L, A, N);
+    uint8_t* gstate = d.state + (size_t)b * L.stride;
+
+    // ---- load the env record ------------------------------------------------------
+    if (MODE != MODE_RESET) {
+        const uint4* src = (const uint4*)gstate;
+        uint4* dst = (uint4*)sm;
+        for (int q = lane; q < L.stride / 16; q += 32) dst[q] = src[q];
+    } else {
+        uint4* dst = (uint4*)sm;
+        for (int q = lane; q < L.stride / 16; q += 32) dst[q] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+
+    const bool host_draws = io.draw_start != nullptr;
+    auto draw = [&](int slot, int& s, int& t, double& z) {
+        if (host_draws) {
+            s = io.draw_start[(size_t)b * A + slot];
+            t = io.draw_target[(size_t)b * A + slot];
+            z = io.draw_size[(size_t)b * A + slot];
+        } else {
+            Philox p((uint32_t)slot, (uint32_t)b, (uint32_t)io.philox_step, (uint32_t)(io.philox_step >> 32),
+                     io.philox_seed);
+            s = (int)__umulhi(p.r[0], (uint32_t)N);
+            t = (int)__umulhi(p.r[1], (uint32_t)N);
+            z = u53(p.r[2], p.r[3]);
+        }
+    };
+
+    int n_resets = 0;
+    if (MODE == MODE_RESET) {
+        // routing.py:160-178: agent_steps = 0, every edge load = 0 (record already zeroed),
+        // packets 0..A-1 spawned from draw slots 0..A-1
+        for (int i = lane; i < A; i += 32) {
+            int s, t; double z;
+            draw(i, s, t, z);
+            spawn_packet(v, L, i, s, t, z, d, apsp);
+        }
+        n_resets = A;
+        __syncwarp();
+    }
+
+    if (MODE == MODE_STEP) {
+        const int* act = io.actions + (size_t)b * A;
+        int blocked = 0, n_looped = 0, n_success = 0, n_dropped = 0;
+        // ---- loop 1 (routing.py:380-412): edge admission in packet-id order -------
+        for (int c0 = 0; c0 < A; c0 += 32) {
+            int i = c0 + lane;
+            bool in = i < A;
+            int a = in ? act[i] : 0;
+            float rew = 0.f;
+            uint8_t lp = 0;
+            bool want = in && v.edge[i] == -1 && a != 0;
+            int t = -1, dst = -1;
+            if (want) {
+                int nw = v.now[i];
+                t = ne[nw * 3 + a - 1];
+                dst = nb[nw * 3 + a - 1];
+            }
+            ordered_by_key(want, t, lane, [&]() {
+                double l = v.load[t], s = v.size[i];
+                if (d.congestion && (l + s > 1.0)) {
+                    rew = -0.2f;  // np.float32(0) - 0.2
+                    blocked++;
+                } else {
+                    v.edge[i] = t;
+                    v.time[i] = ed[t].z;
+                    v.load[t] = l + s;
+                    v.now[i] = dst;
+                    uint32_t* w = &v.vis[i * L.VW + (dst >> 5)];
+                    uint32_t bit = 1u << (dst & 31);
+                    if (*w & bit) lp = 1; else *w |= bit;
+                }
+            });
+            if (in) { v.rew[i] = rew; v.looped[i] = lp; v.steps[i] += 1; }  // :371 agent_steps += 1
+        }
+        __syncwarp();
+        // ---- loop 2 (routing.py:444-491): timers, arrival, drop, delivery, respawn --
+        int slot_base = 0;
+        for (int c0 = 0; c0 < A; c0 += 32) {
+            int i = c0 + lane;
+            bool in = i < A;
+            int e = -1, nw = 0;
+            bool arrive = false, drop = false, reached = false, dn = false;
+            if (in) {
+                int tt = v.ttl[i] - 1;
+                v.ttl[i] = tt;
+                e = v.edge[i];
+                nw = v.now[i];
+                if (e != -1) {
+                    int tm = v.time[i] - 1;
+                    v.time[i] = tm;
+                    arrive = tm <= 0;
+                }
+                drop = (d.ttl > 0) && (tt <= 0);
+                bool on_edge_after = (e != -1) && !arrive;
+                if (d.action_mask) {  // :456-469
+                    uint32_t m = 0;
+                    if (!on_edge_after) {
+                        m = 1u;
+                        int all = 1;
+                        for (int q = 0; q < 3; q++) {
+                            int o = nb[nw * 3 + q];
+                            uint32_t seen = (v.vis[i * L.VW + (o >> 5)] >> (o & 31)) & 1u;
+                            m |= seen << (8 * (q + 1));
+                            all += (int)seen;
+                        }
+                        if (all == 4) drop = true;
+                    }
+                    *(uint32_t*)(v.mask + 4 * i) = m;
+                }
+                reached = !on_edge_after && (nw == v.target[i]);
+                dn = reached || drop;
+            }
+            // load release: arrival (:451-453) or reset of a packet that is still in flight (:126-127)
+            bool sub = in && (e != -1) && (arrive || dn);
+            ordered_by_key(sub, e, lane, [&]() { v.load[e] -= v.size[i]; });
+            if (in && (arrive || dn)) v.edge[i] = -1;
+            unsigned dmask = __ballot_sync(FULL, dn);
+            if (in) {
+                float rew = v.rew[i];
+                int dl = 0;
+                double sp = 0.0;
+                if (dn) {
+                    rew += reached ? 10.f : -10.f;  // float32 add, :474
+                    int st = v.steps[i];
+                    dl = st;
+                    if (reached) {
+                        int opt = max(v.spw[i], 1);
+                        sp = (double)st / (double)opt;
+                        n_success++;
+                    } else {
+                        n_dropped++;
+                    }
+                    v.steps[i] = 0;
+                    int slot = slot_base + __popc(dmask & ((1u << lane) - 1u));
+                    int s, t; double z;
+                    draw(slot, s, t, z);
+                    spawn_packet(v, L, i, s, t, z, d, apsp);
+                }
+                n_looped += v.looped[i];
+                size_t o = (size_t)b * A + i;
+                if (io.reward) io.reward[o] = rew;
+                if (io.done) io.done[o] = dn ? 1 : 0;
+                if (io.delays) io.delays[o] = dl;
+                if (io.arrived) io.arrived[o] = (dn && reached) ? 1 : 0;
+                if (io.spr) io.spr[o] = sp;
+            }
+            slot_base += __popc(dmask);
+        }
+        n_resets = slot_base;
+        __syncwarp();
+        if (io.info) {
+            int v0 = __reduce_add_sync(FULL, n_looped), v1 = __reduce_add_sync(FULL, n_success);
+            int v2 = __reduce_add_sync(FULL, n_dropped), v3 = __reduce_add_sync(FULL, blocked);
+            if (lane == 0) {
+                int4 w = make_int4(v0, v1, v2, v3);
+                *((int4*)io.info + b) = w;
+            }
+        }
+    }
+
+    // ---- write the record back ------------------------------------------------------
+    if (MODE != MODE_OBSERVE) {
+        uint4* dst = (uint4*)gstate;
+        const uint4* src = (const uint4*)sm;
+        for (int q = lane; q < L.stride / 16; q += 32) dst[q] = src[q];
+        if (io.n_resets && lane == 0) io.n_resets[b] = n_resets;
+    }
+    if (MODE == MODE_RESET) {  // outputs that only step produces are cleared on reset
+        for (int i = lane; i < A; i += 32) {
+            size_t o = (size_t)b * A + i;
+            if (io.reward) io.reward[o] = 0.f;
+            if (io.done) io.done[o] = 0;
+            if (io.delays) io.delays[o] = 0;
+            if (io.arrived) io.arrived[o] = 0;
+            if (io.spr) io.spr[o] = 0.0;
+        }
+        if (io.info && lane == 0) *((int4*)io.info + b) = make_int4(0, 0, 0, 0);
+    }
+
+    // ---- small per-agent outputs --------------------------------------------------------
+    if (io.agent_node)
+        for (int i = lane; i < A; i += 32) io.agent_node[(size_t)b * A + i] = v.now[i];
+    if (io.action_mask_out)
+        for (int i = lane; i < A; i += 32)
+            *((uint32_t*)io.action_mask_out + (size_t)b * A + i) = *(uint32_t*)(v.mask + 4 * i);
+
+    float* stage = (float*)(sm + L.sm_stage);
+    const int store_mode = d.store_mode;
+
+    // ---- agent observations (routing.py:277-305), row width 6N+10 ----------------------
+    if (io.obs) {
+        const int W = 6 * N + 10;
+        emit_f32_block(io.obs + (size_t)b * A * W, A * W, W, stage, L.stage_floats, lane, store_mode,
+                       [&](int r0, int r1, auto put) {
+                           for (int i = r0 + lane; i <= r1; i += 32) {
+                               int nw = v.now[i], e = v.edge[i];
+                               put(i, nw, 1.f);
+                               put(i, N + v.target[i], 1.f);
+                               if (e != -1) {
+                                   put(i, 2 * N, 1.f);
+                                   int4 ee = ed[e];
+                                   int prev = (ee.x == nw) ? ee.y : ee.x;
+                                   put(i, 2 * N + 1 + prev, 1.f);
+                               }
+                               put(i, 3 * N + 1, (float)v.time[i]);
+                               put(i, 3 * N + 2, (float)v.size[i]);
+                               put(i, 3 * N + 3, (float)i);
+                               for (int q = 0; q < 3; q++) {
+                                   int k = ne[nw * 3 + q], o = nb[nw * 3 + q];
+                                   int base = 3 * N + 4 + q * (N + 2);
+                                   put(i, base + o, 1.f);
+                                   put(i, base + N, (float)ed[k].z);
+                                   put(i, base + N + 1, (float)v.load[k]);
+                               }
+                           }
+                       });
+    }
+
+    // ---- node observations (routing.py:193-234), row width 4N+8 ------------------------
+    if (io.node_obs) {
+        // waiting packets per node: count and fp64 size sum in packet-id order (:200-205)
+        for (int j = lane; j < N; j += 32) { v.tl[j] = 0.0; v.cnt[j] = 0; }
+        __syncwarp();
+        for (int c0 = 0; c0 < A; c0 += 32) {
+            int i = c0 + lane;
+            bool waiting = (i < A) && v.edge[i] == -1;
+            int nw = waiting ? v.now[i] : -1;
+            ordered_by_key(waiting, nw, lane, [&]() {
+                v.cnt[nw] += 1;
+                v.tl[nw] += v.size[i];
+            });
+        }
+        __syncwarp();
+        const int W = 4 * N + 8;
+        emit_f32_block(io.node_obs + (size_t)b * N * W, N * W, W, stage, L.stage_floats, lane, store_mode,
+                       [&](int r0, int r1, auto put) {
+                           for (int j = r0 + lane; j <= r1; j += 32) {
+                               put(j, j, 1.f);
+                               put(j, N, (float)v.cnt[j]);
+                               put(j, N + 1, (float)v.tl[j]);
+                               for (int q = 0; q < 3; q++) {
+                                   int k = ne[j * 3 + q], o = nb[j * 3 + q];
+                                   int base = N + 2 + q * (N + 2);
+                                   put(j, base + o, 1.f);
+                                   put(j, base + N, (float)ed[k].z);
+                                   put(j, base + N + 1, (float)v.load[k]);
+                               }
+                           }
+                       });
+    }
+
+    // ---- agent adjacency (routing.py:522-539): adj[i,j] = node_adj[now_i, now_j] ----------
+    if (io.adj) {
+        emit_i8_block(io.adj + (size_t)b * A * A, A * A, lane, [&](int idx) -> int8_t {
+            int i = idx / A, j = idx - i * A;
+            int ni = v.now[i], nj = v.now[j];
+            return (int8_t)((ni == nj) || nb[ni * 3] == nj || nb[ni * 3 + 1] == nj || nb[ni * 3 + 2] == nj);
+        });
+    }
+    // ---- node-agent matrix (routing.py:256-267) ----------------------------------------------
+    if (io.node_agent) {
+        emit_i8_block(io.node_agent + (size_t)b * N * A, N * A, lane, [&](int idx) -> int8_t {
+            int n = idx / A, a = idx - n * A;
+            return (int8_t)(v.now[a] == n);
+        });
+    }
+}
+
+static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_io* io, void* stream) {
+    GM_CHECK_ARG(d && io, "null descriptor");
+    GM_CHECK_ARG(d->B > 0 && d->N > 0 && d->A > 0, "bad sizes B=%d N=%d A=%d", d->B, d->N, d->A);
+    GM_CHECK_ARG(d->E * 2 == d->N * 3, "E must be 3N/2 (3-regular graph), got N=%d E=%d", d->N, d->E);
+    GM_CHECK_ARG(d->env_var == 1, "env_var %d: only EnvironmentVariant.INDEPENDENT is built in CUDA", d->env_var);
+    GM_CHECK_ARG(d->state && d->node_edges && d->node_nbrs && d->edges && d->apsp, "null device table");
+    GM_CHECK_ARG(((uintptr_t)d->state & 15) == 0 && ((uintptr_t)d->edges & 15) == 0, "state/edges must be 16-byte aligned");
+    GM_CHECK_ARG((io->draw_start == nullptr) == (io->draw_target == nullptr) &&
+                     (io->draw_start == nullptr) == (io->draw_size == nullptr),
+                 "draw tables must be all set or all NULL");
+    GM_CHECK_ARG(mode != MODE_STEP || io->actions, "step needs actions");
+    GM_CHECK_ARG(io->info == nullptr || ((uintptr_t)io->info & 15) == 0, "info must be 16-byte aligned");
+
+    // staging tile: big enough for the larger of the two dense blocks, capped at 16 KiB per warp
+    int64_t need = 4ll * (int64_t)std::max((int64_t)d->A * (6 * d->N + 10), (int64_t)d->N * (4 * d->N + 8)) + 32;
+    int stage_bytes = (int)std::min<int64_t>(16384, round_up(need, 256));
+    RoutingLayout L = make_layout(d->N, d->A, d->E, stage_bytes);
+    GM_CHECK_ARG(d->state_stride == L.stride, "state_stride %d != %d", d->state_stride, L.stride);
+    while (L.sm_per_warp * WARPS_PER_CTA > 200 * 1024 && stage_bytes > 2048) {
+        stage_bytes /= 2;
+        L = make_layout(d->N, d->A, d->E, stage_bytes);
+    }
+    size_t smem = (size_t)L.sm_per_warp * WARPS_PER_CTA;
+    GM_CHECK_ARG(smem <= 227 * 1024, "env too large for shared memory (%zu bytes)", smem);
+
+    gm_routing_desc dd = *d;
+    if (dd.store_mode == 0) dd.store_mode = 2;
+    dim3 grid(ceil_div(d->B, WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (mode) {
+        case MODE_RESET:
+            GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            routing_kernel<MODE_RESET><<<grid, block, smem, s>>>(dd, *io, L);
+            break;
+        case MODE_STEP:
+            GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            routing_kernel<MODE_STEP><<<grid, block, smem, s>>>(dd, *io, L);
+            break;
+        default:
+            GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            routing_kernel<MODE_OBSERVE><<<grid, block, smem, s>>>(dd, *io, L);
+            break;
+    }
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+}  // namespace gm
+
+extern "C" {
+
+int gm_routing_state_layout(int32_t N, int32_t A, int32_t E, int32_t* out) {
+    GM_CHECK_ARG(out && N > 0 && A > 0 && E > 0, "bad layout query");
+    gm::RoutingLayout L = gm::make_layout(N, A, E, 16384);
+    out[0] = 0; out[1] = L.off_load; out[2] = L.off_i32; out[3] = L.off_vis; out[4] = L.off_mask;
+    out[5] = L.stride; out[6] = L.VW; out[7] = 0;
+    return GM_OK;
+}
+
+int gm_routing_reset(const gm_routing_desc* d, const gm_routing_io* io, void* stream) {
+    return gm::launch_routing(gm::MODE_RESET, d, io, stream);
+}
+int gm_routing_step(const gm_routing_desc* d, const gm_routing_io* io, void* stream) {
+    return gm::launch_routing(gm::MODE_STEP, d, io, stream);
+}
+int gm_routing_observe(const gm_routing_desc* d, const gm_routing_io* io, void* stream) {
+    return gm::launch_routing(gm::MODE_OBSERVE, d, io, stream);
+}
+
+}  // extern "C"

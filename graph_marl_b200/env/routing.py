@@ -1,0 +1,366 @@
+"""Routing environment, mirrors src/env/routing.py of the reference over the batched CUDA
+kernel in csrc/routing_env.cu.
+
+    Routing(network, n_data, env_var, k=3, enable_congestion=True,
+            enable_action_mask=False, ttl=0)                      # reference signature
+    ... , num_envs=B, device="cuda", seed=0)                       # batched extension
+
+* num_envs == 1 (default, "compat"): `reset()` / `step()` return numpy arrays of the
+  reference's shapes and dtypes and consume the global legacy `np.random` stream exactly
+  like routing.py:130-135 (three draws per respawned packet, in packet-id order), so the
+  class drops into src/main.py / src/eval.py unchanged.
+* num_envs  > 1 ("batched"): every returned object is a CUDA tensor with a leading num_envs
+  dimension; nothing leaves the device.  Packet draws come from a device Philox stream unless
+  `set_draws()` supplies tables.
+
+All state lives in one packed record per env in HBM and is advanced in place.
+"""
+import ctypes as C
+import textwrap
+from collections import defaultdict
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .environment import EnvironmentVariant, NetworkEnv
+from .network import Network, generate_tables, lists_from_tables
+
+
+class Discrete:
+    """Minimal stand-in for gymnasium.spaces.Discrete (only `.n`/`.start`/`.sample()` are used,
+    routing.py:108, policy.py:150)."""
+
+    def __init__(self, n, start=0):
+        self.n = int(n)
+        self.start = int(start)
+
+    def sample(self):
+        return self.start + int(np.random.randint(self.n))
+
+
+class TopologyPool:
+    """Device-resident tables of T topologies."""
+
+    def __init__(self, tables, device):
+        self.T = len(tables)
+        st = lambda k: torch.from_numpy(np.ascontiguousarray(np.stack([t[k] for t in tables]))).to(device)
+        self.node_edges = st("node_edges")
+        self.node_nbrs = st("node_nbrs")
+        self.edges = st("edges")
+        self.apsp = st("apsp")
+        lists = [lists_from_tables(t) for t in tables]
+        self.nbr_all = torch.from_numpy(np.stack([l[0] for l in lists])).to(device)
+        self.deg = torch.from_numpy(np.stack([l[1] for l in lists])).to(device)
+        self.seeds = [t.get("seed") for t in tables]
+
+
+class Routing(NetworkEnv):
+    """Packet routing on a random 3-regular graph (routing.py:43-552)."""
+
+    def __init__(self, network: Network, n_data, env_var, k=3, enable_congestion=True,
+                 enable_action_mask=False, ttl=0, num_envs=1, device=None, seed=0, store_mode=0,
+                 batched=None):
+        super().__init__()
+        assert isinstance(network, Network)
+        self.network = network
+        self.n_data = n_data
+        self.env_var = EnvironmentVariant(env_var)
+        self.k = k
+        self.num_random_targets = self.network.n_nodes
+        self.distance_map = defaultdict(list)
+        self.enable_ttl = ttl > 0
+        self.enable_congestion = enable_congestion
+        self.ttl = ttl
+        self.sum_packets_per_node = None
+        self.sum_packets_per_edge = None
+        self.enable_action_mask = enable_action_mask
+        self.action_space = Discrete(4, start=0)
+        self.eval_info_enabled = False
+
+        self.num_envs = int(num_envs)
+        self.batched = (self.num_envs > 1) if batched is None else bool(batched)
+        self.device = torch.device(device if device is not None else "cuda")
+        self._seed = int(seed)
+        self._calls = 0
+        self._store_mode = store_mode
+        N, A = network.n_nodes, n_data
+        self._N, self._A, self._E = N, A, 3 * N // 2
+        lay = np.zeros(8, np.int32)
+        _lib.check(_lib.lib().gm_routing_state_layout(N, A, self._E, _lib.ptr(lay)))
+        self._layout = dict(size=int(lay[0]), load=int(lay[1]), i32=int(lay[2]), vis=int(lay[3]),
+                            mask=int(lay[4]), stride=int(lay[5]), VW=int(lay[6]))
+        self._state = None
+        self._pool = None
+        self._topo_index = None
+        self._draws = None
+        self._out = {}
+        self.action_mask = np.zeros((n_data, 4), dtype=bool)
+        self.agent_steps = np.zeros(n_data)
+
+    # ------------------------------------------------------------------------------------------
+    def set_eval_info(self, val):
+        if val:
+            raise NotImplementedError(
+                "eval-info extras (routing.py:414-441) are a scheduled row (SURVEY 8f-4), not built yet")
+        self.eval_info_enabled = val
+
+    def __str__(self) -> str:
+        return textwrap.dedent(
+            f"""\
+            Routing environment with parameters
+            > Network: {self.network.n_nodes} nodes
+            > Number of packets: {self.n_data}
+            > Environment variant: {self.env_var.name}
+            > Number of considered neighbors (k): {self.k if self.env_var == EnvironmentVariant.WITH_K_NEIGHBORS else "disabled"}
+            > Congestion: {self.enable_congestion}
+            > Action mask: {self.enable_action_mask}
+            > TTL: {self.ttl if self.enable_ttl else "disabled"}
+            > Instances: {self.num_envs} on {self.device} (libgraphmarl_b200)\
+            """
+        )
+
+    # ---- device plumbing -----------------------------------------------------------------------
+    def set_topology_pool(self, pool: TopologyPool, topo_index=None):
+        self._pool = pool
+        self._topo_index = topo_index
+
+    def set_draws(self, start, target, size):
+        """Host-supplied packet draws for the NEXT reset/step: arrays [B,A] (or [A]); slot s
+        feeds the s-th respawn in packet-id order."""
+        B, A = self.num_envs, self._A
+
+        def mk(a, dt, tdt):
+            if torch.is_tensor(a):
+                return a.to(device=self.device, dtype=tdt).reshape(B, A).contiguous()
+            return torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dt), (B, A)))).to(self.device)
+
+        self._draws = (mk(start, np.int32, torch.int32), mk(target, np.int32, torch.int32),
+                       mk(size, np.float64, torch.float64))
+
+    def _desc(self):
+        p = self._pool
+        d = _lib.RoutingDesc()
+        d.B, d.N, d.A, d.E, d.T = self.num_envs, self._N, self._A, self._E, p.T
+        d.env_var, d.k = self.env_var.value, self.k
+        d.congestion, d.action_mask, d.ttl = int(self.enable_congestion), int(self.enable_action_mask), int(self.ttl)
+        d.state_stride, d.store_mode = self._layout["stride"], self._store_mode
+        d.node_edges, d.node_nbrs, d.edges, d.apsp = (p.node_edges.data_ptr(), p.node_nbrs.data_ptr(),
+                                                      p.edges.data_ptr(), p.apsp.data_ptr())
+        d.topo_index = None if self._topo_index is None else self._topo_index.data_ptr()
+        d.state = self._state.data_ptr()
+        return d
+
+    def _alloc_outputs(self, step):
+        B, N, A, dev = self.num_envs, self._N, self._A, self.device
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        o = dict(obs=e((B, A, 6 * N + 10), torch.float32), adj=e((B, A, A), torch.int8),
+                 node_obs=e((B, N, 4 * N + 8), torch.float32), node_agent=e((B, N, A), torch.int8),
+                 agent_node=e((B, A), torch.int32), n_resets=e((B,), torch.int32))
+        if step:
+            o.update(reward=e((B, A), torch.float32), done=e((B, A), torch.uint8), delays=e((B, A), torch.int32),
+                     arrived=e((B, A), torch.uint8), spr=e((B, A), torch.float64), info=e((B, 4), torch.int32))
+        if self.enable_action_mask:
+            o["action_mask_out"] = e((B, A, 4), torch.uint8)
+        return o
+
+    def _io(self, out, actions=None, env_mask=None):
+        io = _lib.RoutingIO()
+        io.actions = None if actions is None else actions.data_ptr()
+        io.env_mask = None if env_mask is None else env_mask.data_ptr()
+        if self._draws is not None:
+            io.draw_start, io.draw_target, io.draw_size = (t.data_ptr() for t in self._draws)
+        io.philox_seed, io.philox_step = self._seed, self._calls
+        for k, v in out.items():
+            setattr(io, k, v.data_ptr())
+        return io
+
+    def _launch(self, fn, out, actions=None, env_mask=None):
+        _lib.require_device()
+        d, io = self._desc(), self._io(out, actions, env_mask)
+        with torch.cuda.device(self.device):
+            _lib.check(fn(C.byref(d), C.byref(io), _lib.current_stream()))
+        self._keep = (d, io, actions, env_mask, self._draws)  # keep inputs alive until the next launch
+        self._draws = None
+        self._calls += 1
+        self._out = out
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def _new_topologies(self):
+        """network.reset() semantics (routing.py:162) for 1 or B instances."""
+        net = self.network
+        if not self.batched or not net.random_topology:
+            net.reset()
+            self._pool = TopologyPool([net.tables], self.device)
+            self._topo_index = None
+            return
+        B = self.num_envs
+        if len(net.seeds) > 0:  # finite pool (--num-topologies-train): upload once, draw an index per env
+            if self._pool is None or self._pool.seeds != list(net.seeds):
+                self._pool = TopologyPool([generate_tables(net.n_nodes, s) for s in net.seeds], self.device)
+            idx = np.random.randint(len(net.seeds), size=B).astype(np.int32)
+            net.reset()
+        else:  # a fresh random topology per env and episode
+            tabs = []
+            for _ in range(B):
+                net.reset()
+                tabs.append(net.tables)
+            self._pool = TopologyPool(tabs, self.device)
+            idx = np.arange(B, dtype=np.int32)
+        self._topo_index = torch.from_numpy(idx).to(self.device)
+
+    def reset(self):
+        _lib.require_device()
+        self._new_topologies()
+        B = self.num_envs
+        if self._state is None:
+            self._state = torch.zeros((B, self._layout["stride"]), dtype=torch.uint8, device=self.device)
+        if not self.batched and self._draws is None:
+            # routing.py:130-135: start, target, size per packet from the global stream, id order
+            A, N = self._A, self._N
+            ds, dt, dz = np.zeros(A, np.int32), np.zeros(A, np.int32), np.zeros(A, np.float64)
+            for i in range(A):
+                ds[i] = np.random.randint(N)
+                dt[i] = np.random.randint(self.num_random_targets)
+                dz[i] = np.random.random()
+            self.set_draws(ds, dt, dz)
+        out = self._alloc_outputs(step=False)
+        self._launch(_lib.lib().gm_routing_reset, out)
+        self.agent_steps = np.zeros(self.n_data)
+        return self._ret(out["obs"]), self._ret(out["adj"])
+
+    def step(self, act):
+        B, A = self.num_envs, self._A
+        if not torch.is_tensor(act):
+            act = torch.as_tensor(np.ascontiguousarray(np.asarray(act, dtype=np.int32)))
+        act = act.to(device=self.device, dtype=torch.int32).reshape(B, A).contiguous()
+        rng_state = None
+        if not self.batched and self._draws is None:
+            # Speculatively draw A respawn triples from a COPY of the global stream; after the
+            # step the real stream is advanced by exactly the triples the env consumed.
+            rng_state = np.random.get_state()
+            ds, dt, dz, _ = self._native_draws(rng_state, A)
+            self.set_draws(ds, dt, dz)
+        out = self._alloc_outputs(step=True)
+        self._launch(_lib.lib().gm_routing_step, out, actions=act)
+        if self.batched:
+            info = dict(looped=out["info"][:, 0], throughput=out["info"][:, 1], dropped=out["info"][:, 2],
+                        blocked=out["info"][:, 3], delays=out["delays"], arrived=out["arrived"], spr=out["spr"])
+            return out["obs"], out["adj"], out["reward"], out["done"].bool(), info
+        n = int(out["n_resets"][0].item())
+        if rng_state is not None and n > 0:
+            _, _, _, new_state = self._native_draws(rng_state, n)
+            np.random.set_state(new_state)
+        done = out["done"][0].cpu().numpy().astype(bool)
+        delays = out["delays"][0].cpu().numpy()
+        arrived = out["arrived"][0].cpu().numpy().astype(bool)
+        spr = out["spr"][0].cpu().numpy()
+        inf = out["info"][0].cpu().numpy()
+        info = {
+            "delays": [float(x) for x in delays[done]],
+            "delays_arrived": [float(x) for x in delays[arrived]],
+            "spr": [float(x) for x in spr[arrived]],
+            "looped": np.float32(inf[0]),
+            "throughput": np.int64(inf[1]),
+            "dropped": np.int64(inf[2]),
+            "blocked": int(inf[3]),
+        }
+        self.agent_steps = np.where(done, 0, self.agent_steps + 1)
+        if self.enable_action_mask:
+            self.action_mask = out["action_mask_out"][0].cpu().numpy().astype(bool)
+        return (self._ret(out["obs"]), self._ret(out["adj"]), out["reward"][0].cpu().numpy(), done, info)
+
+    def _native_draws(self, np_state, n):
+        st = np.zeros(_lib.GM_MT_STATE_WORDS, np.uint32)
+        st[:624] = np_state[1]
+        st[624] = np_state[2]
+        ds, dt, dz = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+        _lib.lib().gm_mt_packet_draws(_lib.ptr(st), self._N, n, _lib.ptr(ds), _lib.ptr(dt), _lib.ptr(dz))
+        new_state = (np_state[0], st[:624].copy(), int(st[624]), np_state[3], np_state[4])
+        return ds[:n], dt[:n], dz[:n], new_state
+
+    def observe(self):
+        """Rebuild every observation from the current state without advancing it."""
+        out = self._alloc_outputs(step=False)
+        out.pop("n_resets")
+        self._launch(_lib.lib().gm_routing_observe, out)
+        self._calls -= 1
+        return out
+
+    def _ret(self, t):
+        return t if self.batched else t[0].cpu().numpy()
+
+    def render(self):
+        self.network.render()
+
+    def get_nodes_adjacency(self):
+        if not self.batched:
+            return self.network.adj_matrix
+        p = self._pool
+        N = self._N
+        if getattr(p, "node_adj", None) is None:
+            eye = torch.zeros((p.T, N, N), dtype=torch.int8, device=self.device)
+            eye.scatter_(2, p.nbr_all.long(), 1)
+            p.node_adj = eye
+        if self._topo_index is not None:
+            return p.node_adj[self._topo_index.long()]
+        return p.node_adj.expand(self.num_envs, N, N)
+
+    def get_node_observation(self):
+        return self._ret(self._out["node_obs"])
+
+    def get_node_agent_matrix(self):
+        return self._ret(self._out["node_agent"])
+
+    def get_agent_nodes(self):
+        """[B,A] int32 node index of every agent (batched readout gather)."""
+        return self._out["agent_node"]
+
+    def get_adjacency_lists(self):
+        """(nbr_all i32[T,N,4], deg i32[T,N], list_index i32[B] or None) for NetMon."""
+        return self._pool.nbr_all, self._pool.deg, self._topo_index
+
+    def get_node_aux(self):
+        """Shortest-path weights as float32 (routing.py:237-254)."""
+        if not self.batched:
+            return np.asarray(self.network.shortest_paths_weights, dtype=np.float32)
+        a = self._pool.apsp.float()
+        return a[self._topo_index.long()] if self._topo_index is not None else a.expand(self.num_envs, -1, -1)
+
+    def get_state(self):
+        """Read back the packed env records as named host arrays (parity tests, heuristics)."""
+        raw = self._state.cpu().numpy()
+        L, A, E, B = self._layout, self._A, self._E, self.num_envs
+        i32 = raw[:, L["i32"]:L["i32"] + 32 * A].copy().view(np.int32).reshape(B, 8, A)
+        names = ["now", "target", "edge", "time", "ttl", "spw", "start", "agent_steps"]
+        s = {n: i32[:, j] for j, n in enumerate(names)}
+        s["size"] = raw[:, L["size"]:L["size"] + 8 * A].copy().view(np.float64).reshape(B, A)
+        s["load"] = raw[:, L["load"]:L["load"] + 8 * E].copy().view(np.float64).reshape(B, E)
+        s["visited"] = raw[:, L["vis"]:L["vis"] + 4 * A * L["VW"]].copy().view(np.uint32).reshape(B, A, L["VW"])
+        s["mask"] = raw[:, L["mask"]:L["mask"] + 4 * A].copy().reshape(B, A, 4)
+        return s
+
+    @property
+    def data(self):
+        """Packets of env 0 as objects with the reference's attribute names (routing.py:12-40)."""
+        s = self.get_state()
+        return [SimpleNamespace(id=i, now=int(s["now"][0, i]), target=int(s["target"][0, i]),
+                                size=float(s["size"][0, i]), start=int(s["start"][0, i]),
+                                time=int(s["time"][0, i]), edge=int(s["edge"][0, i]), ttl=int(s["ttl"][0, i]),
+                                shortest_path_weight=int(s["spw"][0, i]))
+                for i in range(self._A)]
+
+    def get_final_info(self, info: dict):
+        """routing.py:541-546 (single env)."""
+        steps = self.get_state()["agent_steps"][0] if self._state is not None else []
+        for agent_step in steps:
+            if agent_step != 0:
+                info["delays"].append(float(agent_step))
+        return info
+
+    def get_num_agents(self):
+        return self.n_data
+
+    def get_num_nodes(self):
+        return self.network.n_nodes

@@ -1,0 +1,99 @@
+"""NetMonWrapper, mirrors src/env/wrapper.py:7-109 of the reference.
+
+The reference pulls node observations / adjacency / node-agent matrix out of the env as
+numpy, uploads them, runs NetMon, maps node outputs to agents with a bmm and downloads the
+result (3 H2D + 1 D2H per step).  Here the env's outputs are already on the device, the
+adjacency is a list table of the topology pool, and the node->agent mapping is a gather by
+the agents' node index, so the whole step stays in HBM.
+"""
+import os
+
+import numpy as np
+import torch
+
+
+class NetMonWrapper:
+    def __init__(self, env, netmon, startup_iterations, split_obs=False) -> None:
+        self.env = env
+        self.netmon = netmon
+        self.device = next(netmon.parameters()).device
+        self.node_obs = None
+        self.node_adj = None
+        self.node_agent_matrix = None
+        self.last_netmon_state = None
+        self.current_netmon_state = None
+        assert startup_iterations >= 1, "Number of startup iterations must be >= 1"
+        self.startup_iterations = startup_iterations
+        self.frozen = False
+        self.split_obs = split_obs  # batched mode: return (agent_obs, graph_obs) instead of the concat
+        self.netmon_out = None
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def __str__(self) -> str:
+        return self.env.__str__() + os.linesep + "▲ environment is wrapped with NetMon (graph obs)"
+
+    @property
+    def _batched(self):
+        return getattr(self.env, "batched", False)
+
+    def _join(self, obs, network_obs):
+        if self._batched:
+            return (obs, network_obs) if self.split_obs else torch.cat((obs, network_obs), dim=-1)
+        return np.concatenate((obs, network_obs), axis=-1)
+
+    def reset(self):
+        self.frozen = False
+        self.current_netmon_state = None
+        self.last_netmon_state = None
+        obs, adj = self.env.reset()
+        for _ in range(self.startup_iterations):
+            network_obs = self._netmon_step()
+        return self._join(obs, network_obs), adj
+
+    def step(self, actions):
+        next_obs, next_adj, reward, done, info = self.env.step(actions)
+        next_network_obs = self._netmon_step()
+        return self._join(next_obs, next_network_obs), next_adj, reward, done, info
+
+    def freeze(self):
+        """Disable message passing for the rest of the episode (wrapper.py:53-58)."""
+        self.frozen = True
+
+    def get_netmon_info(self):
+        if self._batched:
+            return (self.env._out["node_obs"], self.env.get_nodes_adjacency(), self.env._out["node_agent"])
+        return (self.node_obs, self.node_adj, self.node_agent_matrix)
+
+    def get(self):
+        return self.env
+
+    def _ret(self, t):
+        return t if self._batched else t[0].cpu().numpy()
+
+    def _netmon_step(self):
+        env = self.env
+        if hasattr(env, "get_adjacency_lists"):
+            nbr_all, deg, list_index = env.get_adjacency_lists()
+            agent_node = env.get_agent_nodes()
+            node_obs = env._out["node_obs"]
+            max_degree = nbr_all.shape[-1] - 1
+        else:
+            raise TypeError("NetMonWrapper needs a graph_marl_b200 environment")
+        if not self._batched:
+            self.node_agent_matrix = env.get_node_agent_matrix()
+        if self.frozen:
+            # wrapper.py:67-75: agents keep reading the frozen node outputs at their new position
+            idx = agent_node.long().unsqueeze(-1).expand(-1, -1, self.netmon_out.shape[-1])
+            return self._ret(torch.gather(self.netmon_out, 1, idx))
+        if not self._batched:
+            self.node_obs = env.get_node_observation()
+            self.node_adj = env.get_nodes_adjacency()
+        with torch.no_grad():
+            self.last_netmon_state = self.current_netmon_state
+            self.netmon.state = self.current_netmon_state
+            self.netmon_out, agent_out = self.netmon.forward_lists(
+                node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=True)
+            self.current_netmon_state = self.netmon.state
+        return self._ret(agent_out)

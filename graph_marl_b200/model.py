@@ -1,0 +1,417 @@
+"""NetMon graph-observation module and the DQN agent model, mirroring src/model.py of the
+reference (MLP :13-42, Q_Net :119-125, DQN :187-203, NetMon :256-650) and
+src/layernormlstm.py, with the forward passes executed by libgraphmarl_b200.
+
+The modules stay `nn.Module`s with the reference's parameter names (`encode.linear_layers.i`,
+`rnn_obs.weight_ih`, `q_net.fc.weight`, ...) so reference checkpoints load and the learner can
+optimise them.  Inference (no grad) always runs the CUDA kernels and fails loudly without
+them; when autograd is recording (the learner, src/main.py:830-1006, a scheduled row of
+SURVEY 8f) the same math is composed from torch ops so gradients exist.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn import LayerNorm, RNNCellBase
+
+from . import _lib
+
+
+def _act_name(fn):
+    name = getattr(fn, "__name__", str(fn))
+    if name not in _lib.ACTIVATIONS:
+        raise ValueError(f"activation {name} is not built into libgraphmarl_b200 ({list(_lib.ACTIVATIONS)})")
+    return name
+
+
+class _Workspace:
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+class MLP(nn.Module):
+    """model.py:13-42."""
+
+    def __init__(self, in_features, mlp_units, activation_fn, activation_on_output=True):
+        super().__init__()
+        self.activation_fn = activation_fn
+        self.linear_layers = nn.ModuleList()
+        previous_units = in_features
+        if isinstance(mlp_units, int):
+            mlp_units = [mlp_units]
+        for units in mlp_units:
+            self.linear_layers.append(nn.Linear(previous_units, units))
+            previous_units = units
+        self.out_features = previous_units
+        self.activation_on_output = activation_on_output
+
+    def forward(self, x):
+        for module in self.linear_layers[:-1]:
+            x = self.activation_fn(module(x))
+        x = self.linear_layers[-1](x)
+        if self.activation_on_output:
+            x = self.activation_fn(x)
+        return x
+
+
+class Q_Net(nn.Module):
+    """model.py:119-125."""
+
+    def __init__(self, in_features, actions):
+        super().__init__()
+        self.fc = nn.Linear(in_features, actions)
+
+    def forward(self, x):
+        return self.fc(x)
+
+
+class LayerNormLSTMCell(RNNCellBase):
+    """layernormlstm.py:8-42 (parameter container + autograd math)."""
+
+    def __init__(self, input_size, hidden_size, bias=True):
+        super().__init__(input_size, hidden_size, bias, num_chunks=4)
+        del self.bias_hh
+        self.ln_input = LayerNorm(4 * hidden_size)
+        self.ln_hidden = LayerNorm(4 * hidden_size)
+        self.ln_cell = LayerNorm(hidden_size)
+
+    def forward(self, input, state):
+        hx, cx = state
+        gates = self.ln_input(torch.mm(input, self.weight_ih.t())) + self.ln_hidden(
+            torch.mm(hx, self.weight_hh.t())) + self.bias_ih
+        i, f, g, o = gates.chunk(4, 1)
+        cy = self.ln_cell(torch.sigmoid(f) * cx + torch.sigmoid(i) * torch.tanh(g))
+        return torch.sigmoid(o) * torch.tanh(cy), cy
+
+
+class DQN(nn.Module):
+    """model.py:187-203: MLP encoder (activation on every layer) + linear Q head."""
+
+    def __init__(self, in_features, mlp_units, num_actions, activation_fn, math="fp32"):
+        super().__init__()
+        self.encoder = MLP(in_features, mlp_units, activation_fn)
+        self.q_net = Q_Net(self.encoder.out_features, num_actions)
+        self.activation_fn = activation_fn
+        self.in_features = in_features
+        self.num_actions = num_actions
+        self.math = math
+        self._ws = _Workspace()
+
+    def _params(self):
+        p = _lib.DqnParams()
+        layers = list(self.encoder.linear_layers)
+        p.in_features, p.n_layers = self.in_features, len(layers)
+        for i, l in enumerate(layers):
+            p.units[i] = l.out_features
+            p.w[i], p.b[i] = l.weight.data_ptr(), l.bias.data_ptr()
+        p.n_actions = self.num_actions
+        p.activation = _lib.ACTIVATIONS[_act_name(self.activation_fn)]
+        p.math = _lib.MATH_MODES[self.math]
+        p.q_w, p.q_b = self.q_net.fc.weight.data_ptr(), self.q_net.fc.bias.data_ptr()
+        return p
+
+    def act(self, obs_a, obs_g=None, action_mask=None, epsilon=0.0, rand_action=None, rand_u=None,
+            seed=0, step=0, want_q=True):
+        """Q-values and epsilon-greedy actions for rows [..., Da] (+ [..., Dg]) on the device.
+        Returns (q [..., n_act] or None, actions int32 [...])."""
+        _lib.require_device()
+        if not obs_a.is_cuda:
+            raise _lib.GraphMarlError("DQN.act needs CUDA tensors (no CPU fallback)")
+        lead = obs_a.shape[:-1]
+        Da = obs_a.shape[-1]
+        a2 = obs_a.reshape(-1, Da)
+        a2 = a2 if a2.is_contiguous() else a2.contiguous()
+        rows = a2.shape[0]
+        g2, Dg = None, 0
+        if obs_g is not None:
+            Dg = obs_g.shape[-1]
+            g2 = obs_g.reshape(-1, Dg)
+            g2 = g2 if g2.is_contiguous() else g2.contiguous()
+        dev = obs_a.device
+        p = self._params()
+        nbytes = _lib.lib().gm_dqn_workspace_bytes(C.byref(p), rows)
+        ws = self._ws.get(nbytes, dev)
+        q = torch.empty((rows, self.num_actions), dtype=torch.float32, device=dev) if want_q else None
+        act = torch.empty((rows,), dtype=torch.int32, device=dev)
+        if action_mask is not None:
+            action_mask = action_mask.reshape(rows, self.num_actions).to(torch.uint8).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gm_dqn_act(
+                C.byref(p), rows, a2.data_ptr(), Da, a2.stride(0), _lib.ptr(g2), Dg, 0 if g2 is None else g2.stride(0),
+                _lib.ptr(action_mask), float(epsilon), _lib.ptr(rand_action), _lib.ptr(rand_u), int(seed), int(step),
+                _lib.ptr(q), act.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream()))
+        return (None if q is None else q.reshape(*lead, self.num_actions)), act.reshape(lead)
+
+    def forward(self, x, mask):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self.q_net(self.encoder(x))  # learner path (autograd)
+        q, _ = self.act(x.float())
+        return q
+
+
+class SimpleAggregation(nn.Module):
+    """model.py:206-229 (autograd path only; inference aggregates over neighbour lists)."""
+
+    def __init__(self, agg: str, mask_eye: bool) -> None:
+        super().__init__()
+        assert agg in ("mean", "sum")
+        self.agg = agg
+        self.mask_eye = mask_eye
+
+    def forward(self, node_features, node_adjacency):
+        feature_sum = torch.bmm(node_adjacency, node_features)
+        if self.agg == "sum":
+            return feature_sum
+        return feature_sum / torch.clamp(node_adjacency.sum(dim=-1), min=1).unsqueeze(-1)
+
+
+class NetMon(nn.Module):
+    """model.py:256-650 for agg_type in {sum, mean} and rnn_type in {lstm, lnlstm, gru, none}."""
+
+    def __init__(self, in_features, hidden_features: int, encoder_units, iterations, activation_fn,
+                 rnn_type="lstm", rnn_carryover=True, agg_type="sum", output_neighbor_hidden=False,
+                 output_global_hidden=False, math="fp32"):
+        super().__init__()
+        assert isinstance(hidden_features, int)
+        self.encode = MLP(in_features, (*encoder_units, hidden_features), activation_fn)
+        self.state = None
+        self.iterations = iterations
+        self.output_neighbor_hidden = output_neighbor_hidden
+        self.output_global_hidden = output_global_hidden
+        self.rnn_carryover = rnn_carryover
+        self.agg_type_str = agg_type
+        if agg_type not in ("sum", "mean"):
+            raise ValueError(
+                f"aggregation type {agg_type}: only 'sum' and 'mean' are built (the torch_geometric "
+                "variants of model.py:326-375 are out of scope, SURVEY.md 2 #9)")
+        self.aggregate = SimpleAggregation(agg=agg_type, mask_eye=False)
+        self.aggregation_def_type = 0
+        self.rnn_type = rnn_type
+        if rnn_type == "lstm":
+            self.rnn_obs = nn.LSTMCell(hidden_features, hidden_features)
+            self.rnn_update = nn.LSTMCell(hidden_features, hidden_features)
+            self.num_states = 2 if rnn_carryover else 4
+        elif rnn_type == "lnlstm":
+            self.rnn_obs = LayerNormLSTMCell(hidden_features, hidden_features)
+            self.rnn_update = LayerNormLSTMCell(hidden_features, hidden_features)
+            self.num_states = 2 if rnn_carryover else 4
+        elif rnn_type == "gru":
+            self.rnn_obs = nn.GRUCell(hidden_features, hidden_features)
+            self.rnn_update = nn.GRUCell(hidden_features, hidden_features)
+            self.num_states = 1 if rnn_carryover else 2
+        elif rnn_type == "none":
+            self.num_states = 1
+        else:
+            raise ValueError(f"Unknown rnn type {rnn_type}")
+        self.in_features = in_features
+        self.hidden_features = hidden_features
+        self.state_size = hidden_features * self.num_states
+        self.activation_fn = activation_fn
+        self.math = math
+        self._ws = _Workspace()
+
+    def get_out_features(self):
+        out = self.hidden_features
+        if self.output_neighbor_hidden:
+            out += self.hidden_features * 3
+        if self.output_global_hidden:
+            out += self.hidden_features
+        return out
+
+    def get_state_size(self):
+        return self.state_size
+
+    # ---- kernel path ---------------------------------------------------------------------------
+    def _cell(self, mod):
+        c = _lib.CellParams()
+        if mod is None:
+            return c
+        c.w_ih, c.w_hh, c.b_ih = mod.weight_ih.data_ptr(), mod.weight_hh.data_ptr(), mod.bias_ih.data_ptr()
+        if self.rnn_type == "lnlstm":
+            c.ln_in_w, c.ln_in_b = mod.ln_input.weight.data_ptr(), mod.ln_input.bias.data_ptr()
+            c.ln_hid_w, c.ln_hid_b = mod.ln_hidden.weight.data_ptr(), mod.ln_hidden.bias.data_ptr()
+            c.ln_cell_w, c.ln_cell_b = mod.ln_cell.weight.data_ptr(), mod.ln_cell.bias.data_ptr()
+        else:
+            c.b_hh = mod.bias_hh.data_ptr()
+        return c
+
+    def _params(self):
+        p = _lib.NetmonParams()
+        layers = list(self.encode.linear_layers)
+        p.in_features, p.hidden, p.n_enc_layers = self.in_features, self.hidden_features, len(layers)
+        for i, l in enumerate(layers):
+            p.enc_units[i] = l.out_features
+            p.enc_w[i], p.enc_b[i] = l.weight.data_ptr(), l.bias.data_ptr()
+        p.iterations = self.iterations
+        p.rnn_type, p.agg_type = _lib.RNN_TYPES[self.rnn_type], _lib.AGG_TYPES[self.agg_type_str]
+        p.activation = _lib.ACTIVATIONS[_act_name(self.activation_fn)]
+        p.rnn_carryover = int(self.rnn_carryover)
+        p.output_neighbor_hidden = int(self.output_neighbor_hidden)
+        p.output_global_hidden = int(self.output_global_hidden)
+        p.math = _lib.MATH_MODES[self.math]
+        p.rnn_obs = self._cell(getattr(self, "rnn_obs", None))
+        p.rnn_update = self._cell(getattr(self, "rnn_update", None))
+        return p
+
+    def out_width(self, max_degree):
+        H = self.hidden_features
+        return H + (H if self.output_global_hidden else 0) + (max_degree * H if self.output_neighbor_hidden else 0)
+
+    def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
+                      want_node_out=False, agent_out=None):
+        """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
+        nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
+        Updates self.state; returns (node_out | None, agent_out | None)."""
+        _lib.require_device()
+        if not x.is_cuda:
+            raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
+        B, N, _ = x.shape
+        dev = x.device
+        x = x.float().contiguous()
+        S = self.state_size
+        p = self._params()
+        ws = self._ws.get(_lib.lib().gm_netmon_workspace_bytes(C.byref(p), B * N), dev)
+        st_in = None
+        if self.state is not None and self.state.numel() > 0:
+            st_in = self.state.to(dev).float().reshape(B, N, S).contiguous()
+        st_out = torch.empty((B, N, S), dtype=torch.float32, device=dev)
+        O = self.out_width(max_degree)
+        node_out = torch.empty((B, N, O), dtype=torch.float32, device=dev) if want_node_out else None
+        A = 0
+        ld = O
+        if agent_node is not None:
+            A = agent_node.shape[-1]
+            if agent_out is None:
+                agent_out = torch.empty((B, A, O), dtype=torch.float32, device=dev)
+            ld = agent_out.stride(-2)
+        DM = nbr_all.shape[-1]
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gm_netmon_forward(
+                C.byref(p), B, N, x.data_ptr(), nbr_all.data_ptr(), deg.data_ptr(), DM, _lib.ptr(list_index),
+                _lib.ptr(st_in), st_out.data_ptr(), max_degree, _lib.ptr(node_out), _lib.ptr(agent_node), A,
+                _lib.ptr(agent_out) if agent_node is not None else None, ld, ws.data_ptr(), ws.numel(),
+                _lib.current_stream()))
+        self.state = st_out
+        return node_out, (agent_out if agent_node is not None else None)
+
+    @staticmethod
+    def lists_from_mask(mask, max_entries=None):
+        """Dense [B,N,N] mask -> (nbr_all, deg, max rowsum).  One host sync for the row-sum
+        maximum, like the reference's `.item()` at model.py:589."""
+        B, N, _ = mask.shape
+        m = mask.float().contiguous()
+        dm = int((m != 0).sum(dim=-1).max().item()) if max_entries is None else int(max_entries)
+        dm = max(dm, 1)
+        nbr = torch.empty((B, N, dm), dtype=torch.int32, device=m.device)
+        deg = torch.empty((B, N), dtype=torch.int32, device=m.device)
+        ovf = torch.zeros((1,), dtype=torch.int32, device=m.device)
+        with torch.cuda.device(m.device):
+            _lib.check(_lib.lib().gm_adj_to_lists(m.data_ptr(), B, N, dm, nbr.data_ptr(), deg.data_ptr(),
+                                                  ovf.data_ptr(), _lib.current_stream()))
+        return nbr, deg, dm
+
+    def forward(self, x, mask, node_agent_matrix, max_degree=None, no_agent_mapping=False):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_autograd(x, mask, node_agent_matrix, max_degree, no_agent_mapping)
+        _lib.require_device()
+        if not x.is_cuda:
+            raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
+        nbr, deg, dm = self.lists_from_mask(mask)
+        if max_degree is None:
+            max_degree = int(mask.sum(dim=-1).max().long().item()) - 1  # model.py:588-589
+        node_out, _ = self.forward_lists(x, nbr, deg, None, max(min(max_degree, dm), 0), want_node_out=True)
+        if no_agent_mapping:
+            return node_out
+        return NetMon.output_to_network_obs(node_out, node_agent_matrix)
+
+    @staticmethod
+    def output_to_network_obs(netmon_out, node_agent_matrix):
+        """model.py:629-631."""
+        if netmon_out.is_cuda and not (torch.is_grad_enabled() and netmon_out.requires_grad):
+            B, N, O = netmon_out.shape
+            A = node_agent_matrix.shape[-1]
+            out = torch.empty((B, A, O), dtype=torch.float32, device=netmon_out.device)
+            nam = node_agent_matrix.to(netmon_out.device).float().contiguous()
+            with torch.cuda.device(netmon_out.device):
+                _lib.check(_lib.lib().gm_netmon_map_to_agents(netmon_out.contiguous().data_ptr(), nam.data_ptr(), B, N,
+                                                              A, O, out.data_ptr(), _lib.current_stream()))
+            return out
+        return torch.bmm(netmon_out.transpose(1, 2), node_agent_matrix).transpose(1, 2)
+
+    # ---- autograd path (learner; same math from torch ops, model.py:476-631) ---------------------
+    def _forward_autograd(self, x, mask, node_agent_matrix, max_degree, no_agent_mapping):
+        B, N, _ = x.shape
+        H = self.hidden_features
+        xs = x.reshape(B * N, -1)
+        if self.state is None:
+            self.state = torch.zeros((B, N, self.state_size), device=x.device)
+        st = self.state.reshape(B * N, self.num_states, -1).transpose(0, 1)
+        h = self.encode(xs)
+        lstm_like = self.rnn_type in ("lstm", "lnlstm")
+        if lstm_like:
+            h0, c0 = self.rnn_obs(h, (st[0], st[1]))
+            h, c = h0, c0
+        elif self.rnn_type == "gru":
+            h0 = self.rnn_obs(h, st[0])
+            h = h0
+        last = torch.zeros_like(h) if (self.iterations <= 0 and self.output_neighbor_hidden) else None
+        for it in range(self.iterations):
+            if self.output_neighbor_hidden and it == self.iterations - 1:
+                last = h
+            M = self.aggregate(h.view(B, N, -1), mask).view(B * N, -1)
+            if lstm_like:
+                inp = (st[2], st[3]) if (not self.rnn_carryover and it == 0) else (h, c)
+                h1, c1 = self.rnn_update(M, inp)
+                h, c = h1, c1
+            elif self.rnn_type == "gru":
+                inp = st[1] if (not self.rnn_carryover and it == 0) else h
+                h1 = self.rnn_update(M, inp)
+                h = h1
+            else:
+                h = M
+        if lstm_like:
+            new = torch.stack((h1, c1)) if self.rnn_carryover else torch.stack((h0, c0, h1, c1))
+        elif self.rnn_type == "gru":
+            if not self.rnn_carryover:
+                raise NotImplementedError("gru without carryover (reference state layout is scrambled, model.py:571)")
+            new = h1.unsqueeze(0)
+        else:
+            new = h.unsqueeze(0)
+        self.state = new.transpose(0, 1).reshape(B, N, -1)
+        hb = h.reshape(B, N, -1)
+        parts = [hb]
+        if self.output_global_hidden:
+            parts.append(hb.mean(dim=1, keepdim=True).expand(B, N, H))
+        if self.output_neighbor_hidden:
+            lb = last.reshape(B, N, -1)
+            if max_degree is None:
+                max_degree = int(mask.sum(dim=-1).max().long().item()) - 1
+            eye = torch.eye(N, device=mask.device, dtype=torch.bool).unsqueeze(0)
+            nm = (mask != 0) & ~eye
+            slot = nm.cumsum(dim=-1) - 1
+            hn = torch.zeros((B, N, max(max_degree, 0), H), device=x.device, dtype=hb.dtype)
+            idx = nm.nonzero()
+            hn[idx[:, 0], idx[:, 1], slot[idx[:, 0], idx[:, 1], idx[:, 2]]] = lb[idx[:, 0], idx[:, 2]]
+            parts.append(hn.reshape(B, N, -1))
+        out = torch.cat(parts, dim=-1)
+        if no_agent_mapping:
+            return out
+        return torch.bmm(out.transpose(1, 2), node_agent_matrix).transpose(1, 2)
+
+    def summarize(self, *args):
+        import os
+
+        n = sum(p.numel() for p in self.parameters())
+        self.state = None
+        readout = "> Readout: local" + (" + last neighbors" if self.output_neighbor_hidden else "") + (
+            " + global agg" if self.output_global_hidden else "")
+        return os.linesep.join([
+            "NetMon Module (libgraphmarl_b200)", f"> Parameters: {n}", f"> Aggregation Type: {self.agg_type_str}",
+            f"> RNN Type: {self.rnn_type}", f"> Carryover: {self.rnn_carryover}",
+            f"> Iterations: {self.iterations}", readout])

@@ -1,0 +1,156 @@
+"""Device-resident replay ring, mirrors src/replaybuffer.py:9-287 of the reference.
+
+Same 17 fields, dtypes and ring arithmetic (`index = (index+1) % size`, `count` saturates),
+same `get_batch` index streams (`np.random.default_rng(seed).choice`, contiguous sequences
+anchored at the oldest element), but the arrays live in HBM: `add()` takes one transition
+(numpy or tensors, reference call shape) or a batch of B transitions (tensors with a leading
+env dimension) and lands them with one fused copy kernel; `get_batch()` gathers with one
+kernel that also performs the reference's dtype conversions.
+"""
+import ctypes as C
+from collections import namedtuple
+from typing import Iterator
+
+import numpy as np
+import torch
+
+from . import _lib
+
+TransitionBatch = namedtuple(
+    "TransitionBatch",
+    ["idx", "obs", "action", "reward", "next_obs", "adj", "next_adj", "done", "episode_done", "agent_state",
+     "node_obs", "node_adj", "node_state", "node_aux", "node_agent_matrix", "next_node_obs", "next_node_adj",
+     "next_node_agent_matrix"],
+)
+
+# add() argument order of the reference (replaybuffer.py:243-262)
+ADD_ORDER = ["obs", "action", "reward", "next_obs", "adj", "next_adj", "done", "episode_done", "agent_state",
+             "node_state", "node_aux", "node_obs", "node_adj", "node_agent_matrix", "next_node_obs",
+             "next_node_adj", "next_node_agent_matrix"]
+
+
+class ReplayBuffer(object):
+    def __init__(self, seed, buffer_size, n_agents, observation_size, agent_state_size, n_nodes=0,
+                 node_observation_size=0, node_state_size=0, node_aux_size=0, half_precision=False,
+                 device="cuda"):
+        self.buffer_size = int(buffer_size)
+        self.count = 0
+        self.index = 0
+        self.device = torch.device(device)
+        ft = torch.float16 if half_precision else torch.float32
+        A, N = n_agents, n_nodes
+        shapes = dict(
+            obs=((A, observation_size), ft), action=((A,), torch.int8), reward=((A,), ft),
+            next_obs=((A, observation_size), ft), adj=((A, A), torch.bool), next_adj=((A, A), torch.bool),
+            done=((A,), torch.bool), episode_done=((), torch.bool), agent_state=((A, agent_state_size), ft),
+            node_state=((N, node_state_size), ft), node_aux=((N, node_aux_size), ft),
+            node_obs=((N, node_observation_size), ft), next_node_obs=((N, node_observation_size), ft),
+            node_adj=((N, N), torch.bool), next_node_adj=((N, N), torch.bool),
+            node_agent_matrix=((N, A), torch.bool), next_node_agent_matrix=((N, A), torch.bool))
+        self._shapes = shapes
+        for name, (shape, dt) in shapes.items():
+            setattr(self, name, torch.zeros((self.buffer_size, *shape), dtype=dt, device=self.device))
+        self._random_generator = np.random.default_rng(seed)
+        # dtype conversion of _get_transition_batch (replaybuffer.py:132-187)
+        self._out_dtype = {n: torch.float32 for n in shapes}
+        self._out_dtype.update(action=torch.int64, done=torch.bool, episode_done=torch.bool)
+
+    # ---- insert ------------------------------------------------------------------------------
+    def _as_ring_dtype(self, name, value, n):
+        shape, dt = self._shapes[name]
+        ring = getattr(self, name)
+        if isinstance(value, (int, float)) and not isinstance(value, bool) and ring[0].numel() != 1:
+            # the reference passes the scalar 0 for absent states (main.py:659,695): broadcast
+            return torch.full((n, *shape), value, dtype=dt, device=self.device)
+        t = torch.as_tensor(value)
+        if name == "agent_state" and t.dim() == len(shape) + 1 and n == 1 and t.shape[0] == 1:
+            t = t.squeeze(0)  # replaybuffer.py:272-273
+        t = t.to(self.device)
+        if t.dtype != dt:
+            t = (t != 0) if dt == torch.bool else t.to(dt)
+        if t.numel() != n * int(np.prod(shape, dtype=np.int64)):
+            t = torch.broadcast_to(t, (n, *shape))
+        return t.reshape(n, *shape).contiguous()
+
+    def add(self, obs, action, reward, next_obs, adj, next_adj, done, episode_done, agent_state, node_state,
+            node_aux, node_obs, node_adj, node_agent_matrix, next_node_obs, next_node_adj,
+            next_node_agent_matrix, num=1):
+        """One transition (reference call, replaybuffer.py:243-287) or `num` transitions whose
+        arguments carry a leading dimension of size num (batched rollout)."""
+        _lib.require_device()
+        vals = dict(zip(ADD_ORDER, (obs, action, reward, next_obs, adj, next_adj, done, episode_done, agent_state,
+                                    node_state, node_aux, node_obs, node_adj, node_agent_matrix, next_node_obs,
+                                    next_node_adj, next_node_agent_matrix)))
+        n = int(num)
+        assert n <= self.buffer_size
+        fields = (_lib.ReplayField * len(ADD_ORDER))()
+        keep = []
+        k = 0
+        for name in ADD_ORDER:
+            ring = getattr(self, name)
+            eb = ring[0].numel() * ring.element_size()
+            if eb == 0:
+                continue
+            src = self._as_ring_dtype(name, vals[name], n)
+            keep.append(src)
+            fields[k].ring, fields[k].src, fields[k].elem_bytes = ring.data_ptr(), src.data_ptr(), eb
+            k += 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gm_replay_insert(fields, k, self.buffer_size, self.index, n, _lib.current_stream()))
+        self._keep = keep
+        self.count = min(self.buffer_size, self.count + n)
+        self.index = (self.index + n) % self.buffer_size
+
+    # ---- sample ------------------------------------------------------------------------------
+    def get_batch(self, batch_size, device, sequence_length=0) -> Iterator[TransitionBatch]:
+        if sequence_length <= 1:
+            indices = self._random_generator.choice(self.count, batch_size, replace=True, p=None)
+            yield self._get_transition_batch(indices, device)
+            return
+        buffer_start = self.index % self.count
+        batch_sequence_start = self._random_generator.choice(self.count - sequence_length, batch_size,
+                                                             replace=True, p=None)
+        batch_sequence_start = (buffer_start + batch_sequence_start) % self.count
+        for offset in range(sequence_length):
+            indices = (batch_sequence_start + offset) % self.count
+            yield self._get_transition_batch(indices, device)
+
+    def _get_transition_batch(self, indices, device) -> TransitionBatch:
+        _lib.require_device()
+        n = len(indices)
+        idx = torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)).to(self.device)
+        names = [f for f in TransitionBatch._fields if f != "idx"]
+        fields = (_lib.ReplayField * len(names))()
+        outs = {}
+        k = 0
+        for name in names:
+            ring = getattr(self, name)
+            shape, dt = self._shapes[name]
+            od = self._out_dtype[name]
+            out = torch.empty((n, *shape), dtype=od, device=self.device)
+            outs[name] = out
+            eb = ring[0].numel() * ring.element_size()
+            if eb == 0:
+                continue
+            if od == torch.float32 and dt == torch.bool:
+                conv = 1
+            elif od == torch.int64:
+                conv = 2
+            elif od == torch.float32 and dt == torch.float16:
+                conv = 3
+            else:
+                conv = 0
+            fields[k].ring, fields[k].dst, fields[k].elem_bytes, fields[k].convert = (
+                ring.data_ptr(), out.data_ptr(), eb, conv)
+            k += 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gm_replay_sample(fields, k, idx.data_ptr(), n, _lib.current_stream()))
+        dev = torch.device(device)
+        return TransitionBatch(indices, *[outs[f].to(dev, non_blocking=True) for f in names])
+
+    def get_recent_indices(self, last_n):
+        if last_n is None:
+            return np.arange(self.count), np.arange(self.count)
+        m = min(self.count, last_n)
+        x = self.index - m + np.arange(m)
+        return x, x % self.count

@@ -1,0 +1,188 @@
+"""Device-resident rollout loop: the reference's rollout section (src/main.py:673-737) for B
+environment instances at once, built only from the public classes of this package.
+
+    policy(obs, adj) -> env.step(actions) [Routing step + NetMon step] -> buff.add(...)
+
+Nothing crosses the host per step unless `host_draws=True`, in which case the step's random
+draws (policy.py:46-47 and routing.py:130-135) are supplied from pinned host memory, the
+mode used for bit-exact replays and for the end-to-end measurement.
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .env.network import Network
+from .env.routing import Routing
+from .env.wrapper import NetMonWrapper
+from .model import DQN, NetMon
+from .policy import EpsilonGreedy
+from .replaybuffer import ReplayBuffer
+
+CONFIGS = {
+    # BASELINE.json configs[1]: routing single graph, seed 923430603, DQN + NetMon, 4096 envs
+    "cfg2": dict(n_nodes=20, n_data=20, topo_seed=923430603, congestion=True, K=3, rnn="lstm", H=128,
+                 enc=(512, 256), dqn=(512, 256), episode_steps=300),
+    # BASELINE.json configs[3]: synthetic large graph 200 nodes / 100 agents, lnlstm, K=4
+    "cfg4": dict(n_nodes=200, n_data=100, topo_seed=476, congestion=True, K=4, rnn="lnlstm", H=128,
+                 enc=(512, 256), dqn=(512, 256), episode_steps=300),
+}
+
+
+class Rollout:
+    def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
+                 epsilon=1.0, seed=0, with_replay=True, host_draws=False):
+        c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
+        self.cfg, self.B, self.device = c, num_envs, torch.device(device)
+        N, A = c["n_nodes"], c["n_data"]
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        net = Network(N, random_topology=False, topology_init_seed=c["topo_seed"])
+        self.base_env = Routing(net, A, 1, enable_congestion=c["congestion"], num_envs=num_envs, device=device,
+                                seed=seed, batched=True)
+        Dn, Da = 4 * N + 8, 6 * N + 10
+        self.netmon = NetMon(Dn, c["H"], c["enc"], c["K"], F.leaky_relu, rnn_type=c["rnn"], agg_type="sum",
+                             output_neighbor_hidden=True, math=math).to(device).eval()
+        self.env = NetMonWrapper(self.base_env, self.netmon, 1)
+        Dj = Da + self.netmon.get_out_features()
+        self.model = DQN(Dj, c["dqn"], 4, F.leaky_relu, math=math).to(device).eval()
+        args = SimpleNamespace(epsilon=epsilon, step_before_train=10**9, epsilon_update_freq=100, epsilon_decay=0.996)
+        self.policy = EpsilonGreedy(self.env, self.model, 4, args, seed=seed)
+        self.buff = None
+        if with_replay:
+            cap = replay_capacity or 8 * num_envs
+            self.buff = ReplayBuffer(seed, cap, A, Dj, 0, N, Dn, self.netmon.get_state_size(), N, device=device)
+        self.sizes = dict(N=N, A=A, Dn=Dn, Da=Da, Dj=Dj, H=c["H"], K=c["K"])
+        self.host_draws = host_draws
+        if host_draws:
+            B = num_envs
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self._h = dict(ra=pin((B, A), torch.int32), ru=pin((B, A), torch.float64), ds=pin((B, A), torch.int32),
+                           dt=pin((B, A), torch.int32), dz=pin((B, A), torch.float64))
+            self._rng = np.random.default_rng(seed)
+            self._h_reward = pin((B, A), torch.float32)
+        self.episode_step = None
+        self._marks = None
+        self.obs = self.adj = None
+        self.node_aux = None
+        self.total_reward = torch.zeros((), dtype=torch.float64, device=device)
+
+    def h2d_bytes_per_step(self):
+        return sum(t.numel() * t.element_size() for t in self._h.values()) if self.host_draws else 0
+
+    def d2h_bytes_per_step(self):
+        return self._h_reward.numel() * 4 if self.host_draws else 0
+
+    def refresh_host_draws(self):
+        """New host-side random draws for the next step (outside any timed region if desired)."""
+        B, A, N = self.B, self.sizes["A"], self.sizes["N"]
+        r = self._rng
+        self._h["ra"].numpy()[...] = r.integers(0, 4, (B, A), dtype=np.int32)
+        self._h["ru"].numpy()[...] = r.random((B, A))
+        self._h["ds"].numpy()[...] = r.integers(0, N, (B, A), dtype=np.int32)
+        self._h["dt"].numpy()[...] = r.integers(0, N, (B, A), dtype=np.int32)
+        self._h["dz"].numpy()[...] = r.random((B, A))
+
+    def reset(self):
+        self.obs, self.adj = self.env.reset()
+        self.node_aux = self.env.get_node_aux()
+        self.episode_step = 0
+
+    def _mark(self, name):
+        if self._marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def step(self):
+        """One batched rollout step (main.py:673-737)."""
+        env, c = self.env, self.cfg
+        if self.episode_step is None or self.episode_step >= c["episode_steps"]:
+            self.reset()
+        last_state = env.last_netmon_state
+        netmon_info = env.get_netmon_info()
+        obs, adj = self.obs, self.adj
+        self._mark("start")
+        if self.host_draws:
+            d = {k: v.to(self.device, non_blocking=True) for k, v in self._h.items()}
+            with torch.no_grad():
+                _, actions = self.model.act(obs, None, epsilon=self.policy._epsilon, rand_action=d["ra"].reshape(-1),
+                                            rand_u=d["ru"].reshape(-1), want_q=False)
+            self.base_env.set_draws(d["ds"], d["dt"], d["dz"])
+        else:
+            actions = self.policy(obs, adj)
+        self._mark("dqn_act")
+        next_obs_a, next_adj, reward, done, info = self.base_env.step(actions)
+        self._mark("env_step")
+        next_obs = env._join(next_obs_a, env._netmon_step())
+        self._mark("netmon")
+        next_info = env.get_netmon_info()
+        self.episode_step += 1
+        episode_done = self.episode_step >= c["episode_steps"]
+        if self.buff is not None:
+            node_state = last_state if last_state is not None else 0
+            self.buff.add(obs, actions, reward, next_obs, adj, next_adj, done, episode_done, 0, node_state,
+                          self.node_aux, *netmon_info, *next_info, num=self.B)
+        self._mark("replay_insert")
+        self.obs, self.adj = next_obs, next_adj
+        if self.host_draws:
+            self._h_reward.copy_(reward, non_blocking=True)
+        return reward, done, info
+
+    def profile_stages(self, iters=10):
+        """Per-stage device time of one step (CUDA events on the launching stream), plus the time of
+        the step's GEMM launches replayed alone through gm_linear on the step's own shapes."""
+        import ctypes as C
+
+        from . import _lib
+
+        if self.episode_step is None or self.episode_step + iters + 1 >= self.cfg["episode_steps"]:
+            self.reset()
+        self.step()
+        acc = {}
+        for _ in range(iters):
+            self._marks = []
+            self.step()
+            torch.cuda.synchronize()
+            for (n0, e0), (n1, e1) in zip(self._marks[:-1], self._marks[1:]):
+                acc[n1 + "_ms"] = acc.get(n1 + "_ms", 0.0) + e0.elapsed_time(e1) / iters
+            self._marks = None
+        # the step's GEMMs: encoder (3) + 2 per cell x (1+K) on B*N rows, DQN (2 + head) on B*A rows
+        s, c = self.sizes, self.cfg
+        RN, RA, H = self.B * s["N"], self.B * s["A"], s["H"]
+        shapes = []
+        prev = s["Dn"]
+        for u in list(c["enc"]) + [H]:
+            shapes.append((RN, u, prev))
+            prev = u
+        shapes += [(RN, 4 * H, H)] * (2 * (1 + s["K"]))
+        prev = s["Dj"]
+        for u in c["dqn"]:
+            shapes.append((RA, u, prev))
+            prev = u
+        math = _lib.MATH_MODES[self.netmon.math]
+        kmax = max(k for _, _, k in shapes)
+        nmax = max(n for _, n, _ in shapes)
+        Rmax = max(RN, RA)
+        Abuf = torch.randn((Rmax, kmax), device=self.device)
+        Wbuf = torch.randn((nmax, kmax), device=self.device) * 0.05
+        Cbuf = torch.empty((Rmax, nmax), device=self.device)
+        wsb = max(_lib.lib().gm_linear_workspace_bytes(m, n, k, math) for m, n, k in shapes)
+        ws = torch.empty(max(int(wsb), 16), dtype=torch.uint8, device=self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for it in range(3):
+            e0.record()
+            for (m, n, k) in shapes:
+                _lib.check(_lib.lib().gm_linear(Abuf.data_ptr(), kmax, Wbuf.data_ptr(), None, Cbuf.data_ptr(), nmax, m, n, k,
+                                                0, math, ws.data_ptr(), ws.numel(), _lib.current_stream()))
+            e1.record()
+            torch.cuda.synchronize()
+            if it > 0:
+                tot += e0.elapsed_time(e1) / 2
+        acc["gemm_ms"] = tot
+        acc["gemm_launches_per_step"] = len(shapes)
+        acc["gemm_kernel"] = {0: "linear_simt_kernel (fp32 FFMA)", 1: "linear_tc_kernel (tcgen05 bf16x3)",
+                              2: "linear_tc_kernel (tcgen05 bf16)"}[math]
+        return acc

@@ -1,0 +1,281 @@
+/*
+ * graphmarl_b200.h -- C ABI of libgraphmarl_b200.so, the B200 (sm_100a) implementation
+ * of graph-marl's data-parallel rollout hot path.
+ *
+ * The reference (jw3il/graph-marl) is pure Python and has no FFI: its boundary is the
+ * Python class surface called by src/main.py, src/sl.py and src/eval.py.
+ * Each entry point below names the reference interface it replaces (file:line under
+ * /root/reference).  The thin Python classes in graph_marl_b200/ bind these with ctypes
+ * and keep the reference's names / signatures.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative gm_status on failure;
+ *     gm_last_error() returns a thread-local message. No C++ exception crosses.
+ *   - "device" pointers are caller-owned device memory (torch tensors' data_ptr());
+ *     the library allocates nothing persistent. "host" pointers are plain host memory.
+ *   - `stream` is a cudaStream_t passed as void*; all device work is asynchronous on it.
+ *   - no torch types, no C++ types in any signature.
+ */
+#ifndef GRAPHMARL_B200_H
+#define GRAPHMARL_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GM_API __attribute__((visibility("default")))
+#else
+#define GM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GM_OK = 0,
+    GM_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+    GM_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has the string) */
+    GM_ERR_NO_DEVICE = -3, /* no sm_100 device: the library has NO CPU fallback */
+    GM_ERR_SEED = -4       /* provided topology seed is invalid (network.py:251) */
+} gm_status;
+
+GM_API const char* gm_last_error(void);
+/* ABI version, bumped on any signature/struct change. */
+GM_API int gm_abi_version(void);
+/* 0 if a CUDA device with compute capability 10.x is present, else GM_ERR_NO_DEVICE. */
+GM_API int gm_device_check(void);
+
+/* ======================================================================== */
+/* Host-side topology + legacy RNG (replaces src/env/network.py:122-290 and  */
+/* numpy's legacy MT19937 stream used by network.py / routing.py / policy.py)*/
+/* ======================================================================== */
+
+/* np.random legacy stream. `state` is 625 uint32 (624 key words + position). */
+#define GM_MT_STATE_WORDS 625
+GM_API void gm_mt_seed(uint32_t* state, uint32_t seed);                  /* np.random.seed(int)        */
+GM_API uint32_t gm_mt_u32(uint32_t* state);
+GM_API double gm_mt_random(uint32_t* state);                             /* np.random.random()         */
+GM_API uint32_t gm_mt_randint(uint32_t* state, uint32_t high);           /* np.random.randint(high)    */
+/* packet draws of Routing.reset_packet (routing.py:130-135): n triples
+ * (randint(N), randint(N), random()) in that order. */
+GM_API void gm_mt_packet_draws(uint32_t* state, int32_t n_nodes, int32_t n, int32_t* start,
+                        int32_t* target, double* size);
+/* policy draws of EpsilonGreedy.__call__ (policy.py:46-47): randint(n_act,size=n) then rand(n) */
+GM_API void gm_mt_policy_draws(uint32_t* state, int32_t n_actions, int32_t n, int32_t* rand_action,
+                        double* rand_u);
+
+/* Network._create_valid_network + _update_shortest_paths + _update_nodes_adjacency
+ * (network.py:215-290, 385-389) for one topology.
+ *   global_state : caller's MT19937 stream (may be NULL when seed_mode == 1)
+ *   seed_mode    : 0 draw the seed from global_state (network.py:229-232); 1 use `seed`,
+ *                  fail if it is invalid (:251); 2 start from `seed` (drawn by the caller from
+ *                  its own stream) and reseed from the topology stream while invalid (:252-255)
+ *   exclude      : seeds that must not be used (EVAL_SEEDS), may be NULL
+ * Outputs (host): edges[E*4] = (start,end,length,0) in creation order, E = 3N/2;
+ *   node_edges[N*3] edge ids sorted by neighbour id; node_nbrs[N*3] those neighbours;
+ *   nbr_creation[N*3] neighbours in creation order; apsp[N*N] shortest-path weights;
+ *   xy[N*2] node positions; *repetitions; *seed_used.
+ * Returns GM_ERR_SEED if seed_mode==1 and the first attempt is not a valid graph. */
+GM_API int gm_topology_generate(uint32_t* global_state, int32_t n_nodes, int32_t seed_mode, int64_t seed,
+                         const int64_t* exclude, int32_t n_exclude, int32_t* edges,
+                         int32_t* node_edges, int32_t* node_nbrs, int32_t* nbr_creation,
+                         int32_t* apsp, double* xy, int32_t* repetitions, int64_t* seed_used);
+/* apsp only, after edge lengths changed (network.py:292-329 randomize_edge_weights) */
+GM_API int gm_topology_apsp(int32_t n_nodes, int32_t n_edges, const int32_t* edges, int32_t* apsp);
+
+/* ======================================================================== */
+/* Routing environment (replaces src/env/routing.py:119-178, 187-235,        */
+/* 256-358, 360-539 for B independent env instances advanced in place)       */
+/* ======================================================================== */
+
+typedef struct gm_routing_desc {
+    int32_t B, N, A, E, T;       /* envs, nodes, agents(=packets), edges=3N/2, pool size */
+    int32_t env_var;             /* EnvironmentVariant: 1 (only 1 is built in CUDA so far) */
+    int32_t k;                   /* neighbours in obs for env_var 2 */
+    int32_t congestion;          /* enable_congestion (routing.py:61) */
+    int32_t action_mask;         /* enable_action_mask (routing.py:62) */
+    int32_t ttl;                 /* ttl, 0 = disabled (routing.py:63) */
+    int32_t state_stride;        /* bytes per env in `state`, from gm_routing_state_layout */
+    int32_t store_mode;          /* 0 auto, 1 smem staging + vector stores, 2 + cp.async.bulk */
+    /* topology pool (device, int32) */
+    const int32_t* node_edges;   /* [T,N,3] edge ids of node n sorted by neighbour id */
+    const int32_t* node_nbrs;    /* [T,N,3] the neighbour reached by action 1..3 */
+    const int32_t* edges;        /* [T,E,4] start,end,length,0 */
+    const int32_t* apsp;         /* [T,N,N] shortest-path weights */
+    const int32_t* topo_index;   /* [B] env -> topology, NULL = all use topology 0 */
+    uint8_t* state;              /* [B,state_stride] packed env state, advanced in place */
+} gm_routing_desc;
+
+typedef struct gm_routing_io {
+    /* inputs */
+    const int32_t* actions;      /* [B,A] in {0..3}; step only */
+    const uint8_t* env_mask;     /* [B]; reset only; NULL = reset every env */
+    const int32_t* draw_start;   /* [B,A] host-supplied draws; slot s feeds the s-th reset */
+    const int32_t* draw_target;  /*        packet in id order (routing.py:130-135).        */
+    const double* draw_size;     /*        All three NULL => device Philox4x32-10 draws.    */
+    uint64_t philox_seed, philox_step;
+    /* outputs (device); any may be NULL and is then not produced */
+    float* obs;                  /* [B,A,6N+10]  routing.py:269-358 (env_var 1) */
+    int8_t* adj;                 /* [B,A,A]      routing.py:522-539 */
+    float* node_obs;             /* [B,N,4N+8]   routing.py:187-235 */
+    int8_t* node_agent;          /* [B,N,A]      routing.py:256-267 */
+    int32_t* agent_node;         /* [B,A] node of each agent (= argmax of node_agent column) */
+    float* reward;               /* [B,A] f32    routing.py:361,398,474 */
+    uint8_t* done;               /* [B,A]        routing.py:475 */
+    int32_t* delays;             /* [B,A] agent_steps at done else 0 (routing.py:488) */
+    uint8_t* arrived;            /* [B,A] success (routing.py:476) */
+    double* spr;                 /* [B,A] agent_steps/max(spw,1) where arrived (routing.py:484) */
+    int32_t* info;               /* [B,4] looped, throughput, dropped, blocked (routing.py:499-508) */
+    int32_t* n_resets;           /* [B] draw slots consumed by this call */
+    uint8_t* action_mask_out;    /* [B,A,4] env.action_mask after the call (routing.py:106) */
+} gm_routing_io;
+
+/* byte offsets inside one env's state record; out[8] =
+ * {size f64[A], load f64[E], i32 block [8][A] (now,target,edge,time,ttl,spw,start,agent_steps),
+ *  visited u32[A][ceil(N/32)], mask u8[A][4], stride, VW, 0} */
+GM_API int gm_routing_state_layout(int32_t N, int32_t A, int32_t E, int32_t* out);
+/* Routing.reset (routing.py:160-178) for envs selected by io->env_mask */
+GM_API int gm_routing_reset(const gm_routing_desc* d, const gm_routing_io* io, void* stream);
+/* Routing.step (routing.py:360-520) + observations */
+GM_API int gm_routing_step(const gm_routing_desc* d, const gm_routing_io* io, void* stream);
+/* observations of the current state without advancing it (get_node_observation etc.) */
+GM_API int gm_routing_observe(const gm_routing_desc* d, const gm_routing_io* io, void* stream);
+
+/* ======================================================================== */
+/* SimpleEnvironment (replaces src/env/simple_environment.py:217-315)        */
+/* ======================================================================== */
+/* B instances. Device arrays: scores i32[B,3], edges i32[B,2,2], start_node i32[B],
+ * start_edges i32[B,2]; actions i32[B] in {0,1}; env_var 1 or 3.
+ * Outputs: obs f32[B,1,W] (W = 1 or 1+9+3), node_obs f32[B,3,1], node_agent i8[B,3,1],
+ * node_adj i8[B,3,3], reward f32[B] (step only; NULL for reset). */
+GM_API int gm_simple_step(int32_t B, int32_t env_var, const int32_t* scores, const int32_t* edges,
+                   const int32_t* start_node, const int32_t* start_edges, const int32_t* actions,
+                   float* obs, float* node_obs, int8_t* node_agent, int8_t* node_adj,
+                   float* reward, void* stream);
+
+/* ======================================================================== */
+/* NetMon forward (replaces src/model.py:451-631, src/layernormlstm.py:24-42,*/
+/* src/env/wrapper.py:66-109)                                                */
+/* ======================================================================== */
+#define GM_MAX_LAYERS 8
+enum { GM_RNN_LSTM = 0, GM_RNN_LNLSTM = 1, GM_RNN_GRU = 2, GM_RNN_NONE = 3 };
+enum { GM_AGG_SUM = 0, GM_AGG_MEAN = 1 };
+enum { GM_ACT_LEAKY_RELU = 0, GM_ACT_RELU = 1, GM_ACT_TANH = 2, GM_ACT_SIGMOID = 3, GM_ACT_ELU = 4 };
+/* GEMM arithmetic: FP32 = CUDA-core FFMA; BF16X3 = tcgen05 bf16 hi/lo split, 3 products,
+ * fp32 accumulate (rel. error ~2^-17 per product); BF16 = single tcgen05 pass. */
+enum { GM_MATH_FP32 = 0, GM_MATH_BF16X3 = 1, GM_MATH_BF16 = 2 };
+
+typedef struct gm_cell_params {     /* nn.LSTMCell / nn.GRUCell / LayerNormLSTMCell */
+    const float *w_ih, *w_hh;       /* [G*H, H] */
+    const float *b_ih, *b_hh;       /* [G*H]; b_hh NULL for lnlstm (layernormlstm.py:19) */
+    const float *ln_in_w, *ln_in_b, *ln_hid_w, *ln_hid_b; /* [4H] lnlstm only */
+    const float *ln_cell_w, *ln_cell_b;                    /* [H]  lnlstm only */
+} gm_cell_params;
+
+typedef struct gm_netmon_params {
+    int32_t in_features, hidden;            /* D_n, H */
+    int32_t n_enc_layers;                   /* encoder MLP layers incl. the last (-> H) */
+    int32_t enc_units[GM_MAX_LAYERS];       /* output width of each encoder layer */
+    int32_t iterations;                     /* K (model.py:278) */
+    int32_t rnn_type, agg_type, activation; /* enums above */
+    int32_t rnn_carryover;                  /* model.py:281 */
+    int32_t output_neighbor_hidden, output_global_hidden; /* model.py:279-280 */
+    int32_t math;                           /* GM_MATH_* */
+    const float* enc_w[GM_MAX_LAYERS];      /* [out,in] row-major, nn.Linear layout */
+    const float* enc_b[GM_MAX_LAYERS];
+    gm_cell_params rnn_obs, rnn_update;
+} gm_netmon_params;
+
+/* bytes of device scratch gm_netmon_forward needs for R = B*N rows */
+GM_API int64_t gm_netmon_workspace_bytes(const gm_netmon_params* p, int64_t rows);
+
+/* Dense adjacency mask -> padded neighbour lists (model.py:213-229 sums over mask!=0
+ * columns; :597-614 orders neighbours by ascending node id).
+ *   mask f32[B,N,N]; out: nbr_all i32[B,N,DM] (ascending ids with mask!=0, incl. self if
+ *   set, -1 padded), deg i32[B,N]. Rows with more than DM entries set *overflow (device int). */
+GM_API int gm_adj_to_lists(const float* mask, int32_t B, int32_t N, int32_t DM, int32_t* nbr_all,
+                    int32_t* deg, int32_t* overflow, void* stream);
+
+/* One NetMon step for B graphs of N nodes.
+ *   node_obs f32[B,N,D_n]
+ *   nbr_all  i32[L,N,DM], deg i32[L,N]: adjacency lists (from gm_adj_to_lists or built from
+ *            the topology pool); list_index i32[B] maps env -> list (NULL: env b uses list b)
+ *   state_in f32[B,N,S] or NULL (= zeros, model.py:480-484); state_out f32[B,N,S]
+ *   max_degree: neighbour slots in the readout (model.py:588-589), <= DM
+ *   node_out f32[B,N,O] or NULL; agent_node i32[B,A] + agent_out f32[B,A,O] (row stride
+ *   agent_out_ld floats) or NULL: graph observation of each agent = node_out[agent_node]
+ *   (model.py:629-631 with a one-hot node-agent matrix).
+ *   workspace: device scratch of gm_netmon_workspace_bytes. */
+GM_API int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs,
+                      const int32_t* nbr_all, const int32_t* deg, int32_t DM,
+                      const int32_t* list_index, const float* state_in, float* state_out,
+                      int32_t max_degree, float* node_out, const int32_t* agent_node, int32_t A,
+                      float* agent_out, int64_t agent_out_ld, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+/* general node->agent mapping with an arbitrary (not one-hot) node_agent matrix f32[B,N,A]
+ * (NetMon.output_to_network_obs, model.py:629-631; frozen wrapper path wrapper.py:67-75) */
+GM_API int gm_netmon_map_to_agents(const float* node_out, const float* node_agent, int32_t B, int32_t N,
+                            int32_t A, int32_t O, float* agent_out, void* stream);
+
+/* ======================================================================== */
+/* DQN forward + epsilon-greedy (replaces src/model.py:199-203,              */
+/* src/policy.py:20-51)                                                      */
+/* ======================================================================== */
+typedef struct gm_dqn_params {
+    int32_t in_features;                    /* D_j = D_a + D_g */
+    int32_t n_layers;                       /* encoder MLP layers */
+    int32_t units[GM_MAX_LAYERS];
+    int32_t n_actions, activation, math;
+    const float* w[GM_MAX_LAYERS];
+    const float* b[GM_MAX_LAYERS];
+    const float *q_w, *q_b;                 /* [n_actions, units[last]] */
+} gm_dqn_params;
+
+GM_API int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows);
+/* rows = B*A agents. Input row r = [obs_a[r, 0:Da] | obs_g[r, 0:Dg]] (the concat of
+ * wrapper.py:50 without materialising it); obs_g may be NULL with Dg = 0.
+ *   action_mask u8[rows,n_actions] or NULL: masked actions get Q = -inf (policy.py:42-43)
+ *   rand_action i32[rows], rand_u f64[rows]: host-supplied draws (policy.py:46-47), both NULL
+ *   => device Philox(seed, step).  act[r] = rand_u<eps ? rand_action : argmax (first max).
+ *   q_out f32[rows,n_actions] or NULL; act_out i32[rows]. */
+GM_API int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda,
+               const float* obs_g, int32_t Dg, int64_t ldg, const uint8_t* action_mask,
+               double epsilon, const int32_t* rand_action, const double* rand_u,
+               uint64_t philox_seed, uint64_t philox_step, float* q_out, int32_t* act_out,
+               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ======================================================================== */
+/* Replay ring (replaces src/replaybuffer.py:243-287 add, :132-187 gather)   */
+/* ======================================================================== */
+#define GM_REPLAY_MAX_FIELDS 24
+typedef struct gm_replay_field {
+    void* ring;            /* device [capacity, elem_bytes] */
+    const void* src;       /* device [n, elem_bytes] for insert; unused for sample */
+    void* dst;             /* device [n, elems] for sample; unused for insert */
+    int64_t elem_bytes;    /* bytes of one transition of this field in the ring */
+    int32_t convert;       /* sample: 0 raw copy, 1 u8/bool->f32, 2 i8->i64, 3 f16->f32 */
+    int32_t pad;
+} gm_replay_field;
+/* copy n consecutive transitions into ring slots (index+i) % capacity */
+GM_API int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t capacity,
+                     int64_t index, int64_t n, void* stream);
+/* gather n transitions ring[indices[i]] -> dst[i] with the dtype conversions of
+ * ReplayBuffer._get_transition_batch; indices i64[n] on device */
+GM_API int gm_replay_sample(const gm_replay_field* fields, int32_t n_fields, const int64_t* indices,
+                     int64_t n, void* stream);
+
+/* ======================================================================== */
+/* building blocks exposed for tests / profiling                             */
+/* ======================================================================== */
+/* C[M,N] = act(A[M,K] * W[N,K]^T + bias) in the requested math mode */
+GM_API int gm_linear(const float* A, int64_t lda, const float* W, const float* bias, float* C,
+              int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t activation, int32_t math,
+              void* workspace, int64_t workspace_bytes, void* stream);
+GM_API int64_t gm_linear_workspace_bytes(int64_t M, int32_t N, int32_t K, int32_t math);
+/* number of kernels this library launched since load (all streams), for bench accounting */
+GM_API int64_t gm_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRAPHMARL_B200_H */
