@@ -319,7 +319,12 @@ class Routing(NetworkEnv):
 
     def get_adjacency_lists(self):
         """(nbr_all i32[T,N,4], deg i32[T,N], list_index i32[B] or None) for NetMon."""
-        return self._pool.nbr_all, self._pool.deg, self._topo_index
+        idx = self._topo_index
+        if idx is None and self.num_envs > 1:  # shared topology: every env reads list 0
+            if getattr(self, "_zero_index", None) is None:
+                self._zero_index = torch.zeros((self.num_envs,), dtype=torch.int32, device=self.device)
+            idx = self._zero_index
+        return self._pool.nbr_all, self._pool.deg, idx
 
     def get_node_aux(self):
         """Shortest-path weights as float32 (routing.py:237-254)."""

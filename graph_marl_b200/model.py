@@ -291,6 +291,10 @@ class NetMon(nn.Module):
                 agent_out = torch.empty((B, A, O), dtype=torch.float32, device=dev)
             ld = agent_out.stride(-2)
         DM = nbr_all.shape[-1]
+        if list_index is None and nbr_all.shape[0] != B:
+            if nbr_all.shape[0] != 1:
+                raise ValueError(f"{nbr_all.shape[0]} adjacency lists for {B} graphs need a list_index")
+            list_index = torch.zeros((B,), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gm_netmon_forward(
                 C.byref(p), B, N, x.data_ptr(), nbr_all.data_ptr(), deg.data_ptr(), DM, _lib.ptr(list_index),
