@@ -49,14 +49,15 @@ class NetmonParams(C.Structure):
                 ("rnn_carryover", C.c_int32), ("output_neighbor_hidden", C.c_int32),
                 ("output_global_hidden", C.c_int32), ("math", C.c_int32),
                 ("enc_w", C.c_void_p * GM_MAX_LAYERS), ("enc_b", C.c_void_p * GM_MAX_LAYERS),
-                ("rnn_obs", CellParams), ("rnn_update", CellParams)]
+                ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p)]
 
 
 class DqnParams(C.Structure):
     _fields_ = [("in_features", C.c_int32), ("n_layers", C.c_int32), ("units", C.c_int32 * GM_MAX_LAYERS),
                 ("n_actions", C.c_int32), ("activation", C.c_int32), ("math", C.c_int32),
                 ("w", C.c_void_p * GM_MAX_LAYERS), ("b", C.c_void_p * GM_MAX_LAYERS),
-                ("q_w", C.c_void_p), ("q_b", C.c_void_p)]
+                ("q_w", C.c_void_p), ("q_b", C.c_void_p), ("packed", C.c_void_p),
+                ("packed_split", C.c_int32), ("pad", C.c_int32)]
 
 
 class ReplayField(C.Structure):
@@ -96,6 +97,10 @@ _SIGS = {
     "gm_netmon_map_to_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]),
     "gm_dqn_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "gm_netmon_packed_bytes": (C.c_int64, [C.c_void_p]),
+    "gm_netmon_pack_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gm_dqn_packed_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
+    "gm_dqn_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_dqn_act": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
                              C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64,
                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -7,6 +7,7 @@
 // The joint observation row [agent obs | graph obs] (wrapper.py:50) is consumed as two
 // segments so the concatenation is never materialised.
 #include "common.cuh"
+#include "gemm_sm100.cuh"
 #include "linear_simt.cuh"
 
 namespace gm {
@@ -57,6 +58,40 @@ __global__ void dqn_head_kernel(const float* __restrict__ h, int64_t ldh, int Hd
     }
 }
 
+static bool dqn_tc_math(int math) { return math == GM_MATH_BF16X3 || math == GM_MATH_BF16; }
+
+// packed tensor-core weights: layer l at off[l]; layer 0 is packed for input rows split as
+// [split | in_features - split] so the joint observation is consumed without a concat
+struct DqnPack {
+    int64_t off[GM_MAX_LAYERS];
+    int64_t total;
+};
+
+static DqnPack dqn_pack_layout(const gm_dqn_params* p, int split) {
+    DqnPack L{};
+    int64_t off = 0;
+    int kin = p->in_features;
+    for (int l = 0; l < p->n_layers; l++) {
+        L.off[l] = off;
+        int k0 = (l == 0 && split > 0) ? split : kin, k1 = (l == 0 && split > 0) ? kin - split : 0;
+        off += round_up(tc_shape(p->units[l], k0, k1, EPI_LINEAR, 0).packed_bytes, 256);
+        kin = p->units[l];
+    }
+    L.total = off;
+    return L;
+}
+
+static int dqn_pack(const gm_dqn_params* p, int split, void* out, cudaStream_t s) {
+    DqnPack L = dqn_pack_layout(p, split);
+    int kin = p->in_features, rc;
+    for (int l = 0; l < p->n_layers; l++) {
+        int k0 = (l == 0 && split > 0) ? split : kin, k1 = (l == 0 && split > 0) ? kin - split : 0;
+        if ((rc = tc_pack_weights(p->w[l], kin, nullptr, 0, p->units[l], k0, k1, EPI_LINEAR, 0, (char*)out + L.off[l], s))) return rc;
+        kin = p->units[l];
+    }
+    return GM_OK;
+}
+
 }  // namespace gm
 
 using namespace gm;
@@ -67,7 +102,17 @@ int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows) {
     if (!p) return 0;
     int maxw = 0;
     for (int i = 0; i < p->n_layers; i++) maxw = max(maxw, p->units[i]);
-    return 2 * round_up(rows * maxw * 4, 256) + (32 << 20) + gm_linear_workspace_bytes(rows, maxw, p->in_features, p->math);
+    int64_t pack = dqn_tc_math(p->math) ? 2 * round_up(dqn_pack_layout(p, 8).total, 256) + 512 : 0;
+    return 2 * round_up(rows * maxw * 4, 256) + pack;
+}
+
+int64_t gm_dqn_packed_bytes(const gm_dqn_params* p, int32_t split) { return p ? dqn_pack_layout(p, split).total : 0; }
+
+int gm_dqn_pack_weights(const gm_dqn_params* p, int32_t split, void* packed, int64_t packed_bytes, void* stream) {
+    GM_CHECK_ARG(p && packed && ((uintptr_t)packed & 255) == 0, "packed buffer must be a 256-byte aligned device pointer");
+    GM_CHECK_ARG(split >= 0 && split < p->in_features, "split %d outside [0,%d)", split, p->in_features);
+    GM_CHECK_ARG(packed_bytes >= dqn_pack_layout(p, split).total, "packed buffer too small");
+    return dqn_pack(p, split, packed, (cudaStream_t)stream);
 }
 
 int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda, const float* obs_g,
@@ -88,6 +133,42 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
     void* lin_ws = (char*)workspace + 2 * round_up(rows * maxw * 4, 256);
     int64_t lin_ws_bytes = workspace_bytes - 2 * round_up(rows * maxw * 4, 256);
     int rc;
+    if (dqn_tc_math(p->math)) {
+        // ---- tensor-core path: every layer one tcgen05 launch, layer 0 over both input segments ----
+        const int split = Dg > 0 ? Da : 0;
+        const char* packed = (const char*)p->packed;
+        if (packed == nullptr || p->packed_split != split) {
+            char* dst = (char*)round_up((int64_t)lin_ws, 256);
+            if ((rc = dqn_pack(p, split, dst, s))) return rc;
+            packed = dst;
+        }
+        DqnPack PL = dqn_pack_layout(p, split);
+        const float* x = obs_a;
+        int64_t ldx = lda;
+        int kin = p->in_features;
+        for (int l = 0; l < p->n_layers; l++) {
+            float* y = (l & 1) ? buf1 : buf0;
+            TcArgs a{};
+            if (l == 0) {
+                a.A0 = obs_a; a.lda0 = lda; a.K0 = Da;
+                if (Dg > 0) { a.A1 = obs_g; a.lda1 = ldg; a.K1 = Dg; }
+            } else {
+                a.A0 = x; a.lda0 = ldx; a.K0 = kin;
+            }
+            a.Wp = (const uint8_t*)packed + PL.off[l];
+            a.bias = p->b[l];
+            a.C = y; a.ldc = p->units[l]; a.act = p->activation;
+            a.M = rows; a.N = p->units[l];
+            if ((rc = tc_launch(a, p->math, EPI_LINEAR, s))) return rc;
+            x = y; ldx = p->units[l]; kin = p->units[l];
+        }
+        int Hd = p->units[p->n_layers - 1];
+        dqn_head_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(x, Hd, Hd, p->q_w, p->q_b, p->n_actions, action_mask, epsilon,
+                                                                  rand_action, rand_u, philox_seed, philox_step, q_out,
+                                                                  act_out, rows);
+        GM_LAUNCH_CHECK();
+        return GM_OK;
+    }
     // layer 0 over the two input segments: y = act(obs_a W[:, :Da]^T + obs_g W[:, Da:]^T + b)
     {
         int U = p->units[0];

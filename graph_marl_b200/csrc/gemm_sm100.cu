@@ -416,8 +416,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 // Packed K space: segment 0 = [0,K0p) (K0 real columns, zero padded), segment 1 from K0p.
 // lstm != 0: packed row n of tile nt, n = gate*U + jj, comes from source row gate*H + nt*U + jj.
 // -------------------------------------------------------------------------------------------------
-__global__ void pack_w_kernel(const float* __restrict__ W, int64_t ldw, int N, int K0, int K1, int K0p, int Kp, int BN,
-                              int n_tiles, int lstm, int H, uint8_t* __restrict__ out) {
+__global__ void pack_w_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ W1, int64_t ldw1, int N,
+                              int K0, int K1, int K0p, int Kp, int BN, int n_tiles, int lstm, int H,
+                              uint8_t* __restrict__ out) {
     const int kblocks = Kp / BK;
     const int64_t total = (int64_t)n_tiles * kblocks * BN * (BK / 8);  // one thread per (row, 8-element chunk)
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -439,8 +440,16 @@ __global__ void pack_w_kernel(const float* __restrict__ W, int64_t ldw, int N, i
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             int k = kb * BK + kc * 8 + e;
-            int ks = (k < K0p) ? (k < K0 ? k : -1) : ((k - K0p) < K1 ? K0 + (k - K0p) : -1);
-            x[e] = (n_src >= 0 && n_src < N && ks >= 0) ? W[(int64_t)n_src * ldw + ks] : 0.f;
+            float v = 0.f;
+            if (n_src >= 0 && n_src < N) {
+                if (k < K0p) {
+                    if (k < K0) v = W[(int64_t)n_src * ldw + k];
+                } else if (k - K0p < K1) {
+                    // segment 1: the tail columns of W, or a second matrix (e.g. weight_hh next to weight_ih)
+                    v = W1 ? W1[(int64_t)n_src * ldw1 + (k - K0p)] : W[(int64_t)n_src * ldw + K0 + (k - K0p)];
+                }
+            }
+            x[e] = v;
         }
         uint4 hi, lo;
         split8(x, hi, lo);
@@ -469,12 +478,13 @@ TcShape tc_shape(int N, int K0, int K1, int epi, int H) {
     return s;
 }
 
-int tc_pack_weights(const float* W, int64_t ldw, int N, int K0, int K1, int epi, int H, void* out, cudaStream_t s) {
+int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, int N, int K0, int K1, int epi, int H,
+                    void* out, cudaStream_t s) {
     TcShape sh = tc_shape(N, K0, K1, epi, H);
     int64_t total = (int64_t)sh.n_tiles * (sh.Kp / tc::BK) * sh.BN * (tc::BK / 8);
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-    tc::pack_w_kernel<<<blocks, 256, 0, s>>>(W, ldw, N, K0, K1, sh.K0p, sh.Kp, sh.BN, sh.n_tiles, epi == EPI_LSTM, H,
-                                             (uint8_t*)out);
+    tc::pack_w_kernel<<<blocks, 256, 0, s>>>(W, ldw, W1, ldw1, N, K0, K1, sh.K0p, sh.Kp, sh.BN, sh.n_tiles, epi == EPI_LSTM,
+                                             H, (uint8_t*)out);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -520,7 +530,7 @@ int linear_tc(const LinearArgs& l, int math, void* ws, int64_t ws_bytes, cudaStr
     TcShape sh = tc_shape(l.N, l.K, 0, EPI_LINEAR, 0);
     GM_CHECK_ARG(ws != nullptr && ws_bytes >= sh.packed_bytes, "tensor-core linear needs %lld workspace bytes, got %lld",
                  (long long)sh.packed_bytes, (long long)ws_bytes);
-    int rc = tc_pack_weights(l.W, l.ldw, l.N, l.K, 0, EPI_LINEAR, 0, ws, s);
+    int rc = tc_pack_weights(l.W, l.ldw, nullptr, 0, l.N, l.K, 0, EPI_LINEAR, 0, ws, s);
     if (rc) return rc;
     TcArgs a{};
     a.A0 = l.A; a.lda0 = l.lda; a.K0 = l.K;

@@ -33,8 +33,10 @@ struct TcShape {
 };
 
 TcShape tc_shape(int N, int K0, int K1, int epi, int H);
-// W fp32 [N, K0+K1] (row stride ldw) -> packed bf16 hi/lo tiles (tc_shape(...).packed_bytes)
-int tc_pack_weights(const float* W, int64_t ldw, int N, int K0, int K1, int epi, int H, void* out, cudaStream_t s);
+// W fp32 [N, K0+K1] (row stride ldw), or W [N,K0] next to W1 [N,K1] -> packed bf16 hi/lo tiles
+// (tc_shape(...).packed_bytes, 256-byte aligned destination)
+int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, int N, int K0, int K1, int epi, int H,
+                    void* out, cudaStream_t s);
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
 
 }  // namespace gm

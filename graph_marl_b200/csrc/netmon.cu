@@ -10,6 +10,7 @@
 // [B,N,N] float mask, so aggregation is a coalesced row gather + register sum and the
 // readout is a pure gather.
 #include "common.cuh"
+#include "gemm_sm100.cuh"
 #include "linear_simt.cuh"
 
 namespace gm {
@@ -243,6 +244,55 @@ __global__ void map_to_agents_kernel(const float* __restrict__ node_out, const f
 }
 
 // ---------------------------------------------------------------------------------------
+// packed tensor-core weights: encoder layers, then [W_ih | W_hh] of rnn_obs and rnn_update with
+// the gate rows interleaved per 64 hidden units (fused LSTM epilogue)
+struct NetmonPack {
+    int64_t enc[GM_MAX_LAYERS];
+    int64_t obs, upd, total;
+    bool fused_cells;
+};
+
+static bool tc_math(int math) { return math == GM_MATH_BF16X3 || math == GM_MATH_BF16; }
+
+static NetmonPack pack_layout(const gm_netmon_params* p) {
+    NetmonPack L{};
+    int64_t off = 0;
+    int kin = p->in_features;
+    for (int l = 0; l < p->n_enc_layers; l++) {
+        L.enc[l] = off;
+        off += round_up(tc_shape(p->enc_units[l], kin, 0, EPI_LINEAR, 0).packed_bytes, 256);
+        kin = p->enc_units[l];
+    }
+    const int H = p->hidden;
+    L.fused_cells = p->rnn_type == GM_RNN_LSTM && p->rnn_carryover && (H % 64) == 0;
+    L.obs = L.upd = off;
+    if (L.fused_cells) {
+        int64_t cell = round_up(tc_shape(4 * H, H, H, EPI_LSTM, H).packed_bytes, 256);
+        L.obs = off;
+        L.upd = off + cell;
+        off += 2 * cell;
+    }
+    L.total = off;
+    return L;
+}
+
+static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
+    NetmonPack L = pack_layout(p);
+    int kin = p->in_features, rc;
+    for (int l = 0; l < p->n_enc_layers; l++) {
+        if ((rc = tc_pack_weights(p->enc_w[l], kin, nullptr, 0, p->enc_units[l], kin, 0, EPI_LINEAR, 0, (char*)out + L.enc[l], s)))
+            return rc;
+        kin = p->enc_units[l];
+    }
+    if (L.fused_cells) {
+        const int H = p->hidden;
+        if ((rc = tc_pack_weights(p->rnn_obs.w_ih, H, p->rnn_obs.w_hh, H, 4 * H, H, H, EPI_LSTM, H, (char*)out + L.obs, s))) return rc;
+        if ((rc = tc_pack_weights(p->rnn_update.w_ih, H, p->rnn_update.w_hh, H, 4 * H, H, H, EPI_LSTM, H, (char*)out + L.upd, s)))
+            return rc;
+    }
+    return GM_OK;
+}
+
 struct NetmonWs {
     float *act0, *act1, *g0, *g1, *hA, *hB, *cA, *cB, *M, *gmean;
     int64_t bytes;
@@ -266,7 +316,7 @@ static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
     w.hA = take(R * H); w.hB = take(R * H); w.cA = take(R * H); w.cB = take(R * H);
     w.M = take(R * H);
     w.gmean = take((int64_t)max(B, 1) * H);
-    w.bytes = off + (32 << 20);  // + room for the tensor-core path's packed operands
+    w.bytes = off + (32 << 20);  // + room for per-call packed weights of the unfused tensor-core layers
     return w;
 }
 
@@ -279,7 +329,15 @@ extern "C" {
 int64_t gm_netmon_workspace_bytes(const gm_netmon_params* p, int64_t rows) {
     if (!p) return 0;
     NetmonWs w = carve(p, rows, (int)rows, nullptr);
-    return w.bytes + gm_linear_workspace_bytes(rows, 4 * p->hidden, 2 * p->hidden, p->math);
+    return w.bytes + (tc_math(p->math) ? round_up(pack_layout(p).total, 256) + 256 : 0);
+}
+
+int64_t gm_netmon_packed_bytes(const gm_netmon_params* p) { return p ? pack_layout(p).total : 0; }
+
+int gm_netmon_pack_weights(const gm_netmon_params* p, void* packed, int64_t packed_bytes, void* stream) {
+    GM_CHECK_ARG(p && packed && ((uintptr_t)packed & 255) == 0, "packed buffer must be a 256-byte aligned device pointer");
+    GM_CHECK_ARG(packed_bytes >= pack_layout(p).total, "packed buffer too small");
+    return netmon_pack(p, packed, (cudaStream_t)stream);
 }
 
 int gm_adj_to_lists(const float* mask, int32_t B, int32_t N, int32_t DM, int32_t* nbr_all, int32_t* deg,
@@ -325,6 +383,16 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     void* lin_ws = (char*)workspace + w.bytes - (32 << 20);
     int64_t lin_ws_bytes = workspace_bytes - (w.bytes - (32 << 20));
     const int math = p->rnn_type == GM_RNN_LNLSTM ? GM_MATH_FP32 : p->math;
+    const bool tc = tc_math(math);
+    const NetmonPack PL = pack_layout(p);
+    const char* packed = (const char*)p->packed;
+    if (tc && packed == nullptr) {  // no cached pack: build it in the workspace tail
+        char* dst = (char*)round_up((int64_t)((char*)workspace + w.bytes), 256);
+        int rc = netmon_pack(p, dst, s);
+        if (rc) return rc;
+        packed = dst;
+    }
+    GM_CHECK_ARG(!tc || ((uintptr_t)packed & 255) == 0, "packed weights must be 256-byte aligned");
 
     // zero state when none is given (model.py:480-484)
     const float* st_in = state_in;
@@ -332,10 +400,6 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         GM_CUDA(cudaMemsetAsync(state_out, 0, (size_t)R * S * 4, s));
         st_in = state_out;  // read as zeros before it is overwritten (all readers finish first: same stream)
     }
-    // NOTE: when state_in aliases state_out every read of st_in below happens in kernels
-    // enqueued before the kernels that write state_out, except the no-carryover reads of
-    // columns [2H,4H) at it==0, which are ordered the same way.  If K == 1 in no-carry mode the
-    // cell output overwrites columns it also reads -> stage through the ping-pong buffers.
 
     // ---- encoder MLP (model.py:489): activation after every layer incl. the last ----------
     const float* x = node_obs;
@@ -343,14 +407,67 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     int kin = p->in_features;
     for (int l = 0; l < L; l++) {
         float* y = (l & 1) ? w.act1 : w.act0;
-        LinearArgs a{x, ldx, p->enc_w[l], kin, p->enc_b[l], nullptr, y, p->enc_units[l], R, p->enc_units[l], kin,
-                     p->activation, 0};
-        int rc = linear_dispatch(a, p->math, lin_ws, lin_ws_bytes, s);
+        int rc;
+        if (tc) {
+            TcArgs a{};
+            a.A0 = x; a.lda0 = ldx; a.K0 = kin;
+            a.Wp = (const uint8_t*)packed + PL.enc[l];
+            a.bias = p->enc_b[l];
+            a.C = y; a.ldc = p->enc_units[l]; a.act = p->activation;
+            a.M = R; a.N = p->enc_units[l];
+            rc = tc_launch(a, math, EPI_LINEAR, s);
+        } else {
+            LinearArgs a{x, ldx, p->enc_w[l], kin, p->enc_b[l], nullptr, y, p->enc_units[l], R, p->enc_units[l], kin,
+                         p->activation, 0};
+            rc = linear_dispatch(a, math, lin_ws, lin_ws_bytes, s);
+        }
         if (rc) return rc;
         x = y; ldx = p->enc_units[l]; kin = p->enc_units[l];
     }
     const float* e = x;  // [R,H]
 
+    const float* h = e;
+    int64_t ldh_cur = H;
+    const float* c = nullptr;
+    const float* last = nullptr;  // value of h before the final iteration's aggregation (:510-519)
+    float* hbuf[2] = {w.hA, w.hB};
+    float* cbuf[2] = {w.cA, w.cB};
+
+    if (tc && PL.fused_cells && DM <= 4) {
+        // ===== fused tensor-core path: one launch per cell.  The producer warps gather and sum the
+        // neighbour rows (aggregation), the gate GEMM [x | h] x [W_ih | W_hh]^T runs on tcgen05 and
+        // the LSTM pointwise is the epilogue, so M and the gates never touch HBM. =====
+        auto cell = [&](int64_t woff, const gm_cell_params& cp, const float* xin, int64_t ldxin, bool gather, const float* hp,
+                        int64_t ldhp, const float* cprev, int64_t ldcp, float* hn, int64_t ldhn, float* cn, int64_t ldcn) -> int {
+            TcArgs a{};
+            a.A0 = xin; a.lda0 = ldxin; a.K0 = H;
+            a.A1 = hp; a.lda1 = ldhp; a.K1 = H;
+            if (gather) {
+                a.nbr = nbr_all; a.deg = deg; a.DM = DM; a.list_index = list_index; a.nodes = N;
+                a.mean = p->agg_type == GM_AGG_MEAN;
+            }
+            a.Wp = (const uint8_t*)packed + woff;
+            a.bias = cp.b_ih; a.bias2 = cp.b_hh;
+            a.c_in = cprev; a.ldc_in = ldcp;
+            a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn;
+            a.H = H; a.M = R; a.N = 4 * H;
+            return tc_launch(a, math, EPI_LSTM, s);
+        };
+        int rc = cell(PL.obs, p->rnn_obs, e, H, false, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], H);  // :491
+        if (rc) return rc;
+        h = hbuf[0]; c = cbuf[0];
+        int cur = 0;
+        for (int it = 0; it < K; it++) {  // :509-554
+            const bool final_it = it == K - 1;
+            if (final_it) last = h;
+            float* hn = final_it ? state_out : hbuf[cur ^ 1];       // the last cell writes the new state in place (:562-564)
+            float* cn = final_it ? state_out + H : cbuf[cur ^ 1];
+            int64_t ldn = final_it ? S : H;
+            rc = cell(PL.upd, p->rnn_update, h, H, true, h, H, c, H, hn, ldn, cn, ldn);
+            if (rc) return rc;
+            h = hn; c = cn; ldh_cur = ldn; cur ^= 1;
+        }
+    } else {
     // one recurrent cell: (xin [R,H], h_prev, c_prev) -> (h_new, c_new) (+ optional second copy)
     auto run_cell = [&](const gm_cell_params& cp, const float* xin, int64_t ldxin, const float* hp, int64_t ldhp,
                         const float* cprev, int64_t ldcp, float* hn, int64_t ldhn, float* cn, int64_t ldcn, float* hn2,
@@ -387,10 +504,6 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     };
 
     // ---- rnn_obs (model.py:490-495) -------------------------------------------------------
-    const float* h = e;
-    const float* c = nullptr;
-    float* hbuf[2] = {w.hA, w.hB};
-    float* cbuf[2] = {w.cA, w.cB};
     int cur = 0;
     if (p->rnn_type != GM_RNN_NONE) {
         // no-carryover keeps (h0,c0) in state columns [0,2H) (model.py:566); those columns of
@@ -413,7 +526,6 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     }
 
     // ---- K x (aggregate, rnn_update) (model.py:509-554) ----------------------------------
-    const float* last = nullptr;  // value of h before the final iteration's aggregation (:510-519)
     float* none_buf[2] = {w.hA, w.hB};
     for (int it = 0; it < K; it++) {
         if (it == K - 1) last = h;
@@ -454,11 +566,12 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             copy_rows_kernel<<<g, 256, 0, s>>>(h, H, state_out, S, R, H); GM_LAUNCH_CHECK();
         }
     }
+    }  // unfused path
 
     // ---- readout (model.py:458-474) ---------------------------------------------------------
     const int use_nbr = p->output_neighbor_hidden, use_glob = p->output_global_hidden;
     if (use_glob) {
-        global_mean_kernel<<<B, 128, 0, s>>>(h, H, w.gmean, B, N, H);
+        global_mean_kernel<<<B, 128, 0, s>>>(h, ldh_cur, w.gmean, B, N, H);
         GM_LAUNCH_CHECK();
     }
     if (use_nbr && last == nullptr) {  // K <= 0 with rnn none: zeros (:498-499)
@@ -467,14 +580,15 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     }
     const int O = H + (use_glob ? H : 0) + (use_nbr ? max_degree * H : 0);
     if (node_out) {
-        readout_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(h, H, last, H, w.gmean, nbr_all, deg, DM, list_index, nullptr, N,
-                                                              B, N, H, use_nbr, use_glob, max_degree, node_out, O);
+        readout_kernel<<<(unsigned)((R + 3) / 4), 128, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index,
+                                                              nullptr, N, B, N, H, use_nbr, use_glob, max_degree, node_out,
+                                                              O);
         GM_LAUNCH_CHECK();
     }
     if (agent_out) {
         GM_CHECK_ARG(agent_node && A > 0 && agent_out_ld >= O, "agent readout needs agent_node, A, ld >= %d", O);
         int64_t rows = (int64_t)B * A;
-        readout_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(h, H, last, H, w.gmean, nbr_all, deg, DM, list_index,
+        readout_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index,
                                                                  agent_node, A, B, N, H, use_nbr, use_glob, max_degree,
                                                                  agent_out, agent_out_ld);
         GM_LAUNCH_CHECK();

@@ -35,6 +35,43 @@ class _Workspace:
         return self.buf
 
 
+def _rows2d(t):
+    """[..., D] tensor -> 2-D row view [rows, D] with unit column stride, without copying when the
+    leading dimensions collapse to one uniform row stride (e.g. a column slice of a joint tensor)."""
+    D = t.shape[-1]
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.stride(-1) == 1 or D == 1:
+        ok = all(t.stride(i) == t.stride(i + 1) * t.shape[i + 1] for i in range(t.dim() - 2))
+        if ok and t.dtype == torch.float32:
+            rows = 1
+            for n in t.shape[:-1]:
+                rows *= n
+            return t.as_strided((rows, D), (t.stride(-2), 1))
+    return t.reshape(-1, D).float().contiguous()
+
+
+class _PackedWeights:
+    """Cache of the tensor-core weight pack (bf16 hi/lo tiles) of a module; rebuilt whenever a
+    parameter's storage or version counter changes (optimizer step, load_state_dict, .to())."""
+
+    def __init__(self):
+        self.buf, self.key = None, None
+
+    def get(self, module, extra, nbytes_fn, pack_fn):
+        params = list(module.parameters())
+        key = (extra,) + tuple((q.data_ptr(), q._version) for q in params)
+        if key != self.key:
+            dev = params[0].device
+            n = int(nbytes_fn())
+            if self.buf is None or self.buf.numel() < n or self.buf.device != dev:
+                self.buf = torch.empty(max(n, 256), dtype=torch.uint8, device=dev)
+            assert self.buf.data_ptr() % 256 == 0
+            pack_fn(self.buf)
+            self.key = key
+        return self.buf
+
+
 class MLP(nn.Module):
     """model.py:13-42."""
 
@@ -102,8 +139,9 @@ class DQN(nn.Module):
         self.num_actions = num_actions
         self.math = math
         self._ws = _Workspace()
+        self._pack = _PackedWeights()
 
-    def _params(self):
+    def _params(self, split=0):
         p = _lib.DqnParams()
         layers = list(self.encoder.linear_layers)
         p.in_features, p.n_layers = self.in_features, len(layers)
@@ -114,6 +152,16 @@ class DQN(nn.Module):
         p.activation = _lib.ACTIVATIONS[_act_name(self.activation_fn)]
         p.math = _lib.MATH_MODES[self.math]
         p.q_w, p.q_b = self.q_net.fc.weight.data_ptr(), self.q_net.fc.bias.data_ptr()
+        if self.math != "fp32" and layers[0].weight.is_cuda:
+            dev = layers[0].weight.device
+
+            def pack(buf):
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().gm_dqn_pack_weights(C.byref(p), split, buf.data_ptr(), buf.numel(),
+                                                              _lib.current_stream()))
+
+            buf = self._pack.get(self, split, lambda: _lib.lib().gm_dqn_packed_bytes(C.byref(p), split), pack)
+            p.packed, p.packed_split = buf.data_ptr(), split
         return p
 
     def act(self, obs_a, obs_g=None, action_mask=None, epsilon=0.0, rand_action=None, rand_u=None,
@@ -125,16 +173,14 @@ class DQN(nn.Module):
             raise _lib.GraphMarlError("DQN.act needs CUDA tensors (no CPU fallback)")
         lead = obs_a.shape[:-1]
         Da = obs_a.shape[-1]
-        a2 = obs_a.reshape(-1, Da)
-        a2 = a2 if a2.is_contiguous() else a2.contiguous()
+        a2 = _rows2d(obs_a)
         rows = a2.shape[0]
         g2, Dg = None, 0
         if obs_g is not None:
             Dg = obs_g.shape[-1]
-            g2 = obs_g.reshape(-1, Dg)
-            g2 = g2 if g2.is_contiguous() else g2.contiguous()
+            g2 = _rows2d(obs_g)
         dev = obs_a.device
-        p = self._params()
+        p = self._params(split=Da if g2 is not None else 0)
         nbytes = _lib.lib().gm_dqn_workspace_bytes(C.byref(p), rows)
         ws = self._ws.get(nbytes, dev)
         q = torch.empty((rows, self.num_actions), dtype=torch.float32, device=dev) if want_q else None
@@ -215,6 +261,7 @@ class NetMon(nn.Module):
         self.activation_fn = activation_fn
         self.math = math
         self._ws = _Workspace()
+        self._pack = _PackedWeights()
 
     def get_out_features(self):
         out = self.hidden_features
@@ -257,6 +304,15 @@ class NetMon(nn.Module):
         p.math = _lib.MATH_MODES[self.math]
         p.rnn_obs = self._cell(getattr(self, "rnn_obs", None))
         p.rnn_update = self._cell(getattr(self, "rnn_update", None))
+        if self.math != "fp32" and layers[0].weight.is_cuda:
+            dev = layers[0].weight.device
+
+            def pack(buf):
+                with torch.cuda.device(dev):
+                    _lib.check(_lib.lib().gm_netmon_pack_weights(C.byref(p), buf.data_ptr(), buf.numel(),
+                                                                 _lib.current_stream()))
+
+            p.packed = self._pack.get(self, 0, lambda: _lib.lib().gm_netmon_packed_bytes(C.byref(p)), pack).data_ptr()
         return p
 
     def out_width(self, max_degree):

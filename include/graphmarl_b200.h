@@ -41,7 +41,7 @@ typedef enum {
 
 GM_API const char* gm_last_error(void);
 /* ABI version, bumped on any signature/struct change. */
-GM_API int gm_abi_version(void);
+GM_API int gm_abi_version(void);   /* currently 2 */
 /* 0 if a CUDA device with compute capability 10.x is present, else GM_ERR_NO_DEVICE. */
 GM_API int gm_device_check(void);
 
@@ -184,7 +184,16 @@ typedef struct gm_netmon_params {
     const float* enc_w[GM_MAX_LAYERS];      /* [out,in] row-major, nn.Linear layout */
     const float* enc_b[GM_MAX_LAYERS];
     gm_cell_params rnn_obs, rnn_update;
+    /* tensor-core modes only: weights packed by gm_netmon_pack_weights (device, 256-byte aligned),
+     * or NULL = pack into the workspace on every forward call */
+    const void* packed;
 } gm_netmon_params;
+
+/* Packed tensor-core weights (GM_MATH_BF16X3 / GM_MATH_BF16): the fp32 parameters split into bf16
+ * hi/lo tiles in the shared-memory layout the tcgen05 kernels stream with bulk copies.  Pack once
+ * per parameter update and pass the buffer in params.packed. */
+GM_API int64_t gm_netmon_packed_bytes(const gm_netmon_params* p);
+GM_API int gm_netmon_pack_weights(const gm_netmon_params* p, void* packed, int64_t packed_bytes, void* stream);
 
 /* bytes of device scratch gm_netmon_forward needs for R = B*N rows */
 GM_API int64_t gm_netmon_workspace_bytes(const gm_netmon_params* p, int64_t rows);
@@ -229,7 +238,14 @@ typedef struct gm_dqn_params {
     const float* w[GM_MAX_LAYERS];
     const float* b[GM_MAX_LAYERS];
     const float *q_w, *q_b;                 /* [n_actions, units[last]] */
+    /* tensor-core modes only: weights packed by gm_dqn_pack_weights for input rows split as
+     * [packed_split | in_features - packed_split] (0 = one segment); NULL = pack every call */
+    const void* packed;
+    int32_t packed_split, pad;
 } gm_dqn_params;
+
+GM_API int64_t gm_dqn_packed_bytes(const gm_dqn_params* p, int32_t split);
+GM_API int gm_dqn_pack_weights(const gm_dqn_params* p, int32_t split, void* packed, int64_t packed_bytes, void* stream);
 
 GM_API int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows);
 /* rows = B*A agents. Input row r = [obs_a[r, 0:Da] | obs_g[r, 0:Dg]] (the concat of

@@ -1,0 +1,131 @@
+"""GPU parity of the tcgen05 paths of NetMon / DQN (fused aggregate + gate GEMM + LSTM-cell kernel,
+packed-weight cache, two-segment DQN input) against the reference's recorded outputs and the fp64
+numpy oracle.
+
+Stated tolerances (max abs error on outputs of magnitude O(1), identical weights + inputs):
+  bf16x3 (fp32-accurate split): 1e-4 single step, 3e-4 over the recorded recurrent rollouts
+  bf16   (single pass)        : 3e-2 -- reported as a speed/accuracy option, not the parity mode
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from helpers import det_weights, dqn_shapes, netmon_case, netmon_shapes
+
+pytestmark = pytest.mark.gpu
+
+G = load_golden("netmon")
+LSTM_CASES = [str(x) for x in G["case_names"] if str(x).split("|")[1] in ("lstm", "gru", "none")
+              and str(x).split("|")[0] != "gru_nocarry_k2"]
+
+
+def _netmon(cfg, in_features, math):
+    from graph_marl_b200.model import NetMon
+
+    nm = NetMon(in_features, cfg["hidden"], cfg["enc"], cfg["iterations"], F.leaky_relu, rnn_type=cfg["rnn_type"],
+                rnn_carryover=cfg["rnn_carryover"], agg_type=cfg["agg_type"],
+                output_neighbor_hidden=cfg["output_neighbor_hidden"],
+                output_global_hidden=cfg["output_global_hidden"], math=math)
+    w = det_weights(netmon_shapes(in_features, cfg["hidden"], cfg["enc"], cfg["rnn_type"]), cfg["wseed"])
+    nm.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    return nm.cuda().eval(), w
+
+
+@pytest.mark.parametrize("entry", LSTM_CASES)
+def test_netmon_golden_rollout_bf16x3(entry):
+    name, cfg = netmon_case(G, entry)
+    X, ADJ, NAM = G["node_obs"], G["node_adj"], G["node_agent"]
+    nm, _ = _netmon(cfg, X.shape[-1], "bf16x3")
+    with torch.no_grad():
+        nm.state = None
+        for t in range(X.shape[0]):
+            out = nm(torch.from_numpy(X[t]).cuda(), torch.from_numpy(ADJ[t]).float().cuda(),
+                     torch.from_numpy(NAM[t]).float().cuda())
+            err = np.abs(out.cpu().numpy() - G[name + "_agent_out"][t]).max()
+            serr = np.abs(nm.state.cpu().numpy() - G[name + "_state"][t]).max()
+            assert err < 3e-4 and serr < 3e-4, (t, err, serr)
+
+
+@pytest.mark.parametrize("math,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
+@pytest.mark.parametrize("K,agg,B,N", [(3, "sum", 96, 20), (1, "mean", 7, 20), (2, "sum", 5, 200)])
+def test_netmon_fused_cells_against_fp64_oracle(K, agg, B, N, math, tol):
+    from oracle import netmon_oracle as NO
+    from oracle import oracle as O
+
+    Dn, H = 4 * N + 8, 128
+    cfg = dict(hidden=H, iterations=K, rnn_type="lstm", rnn_carryover=True, agg_type=agg, output_neighbor_hidden=True,
+               output_global_hidden=False, enc=[512, 256], wseed=31)
+    nm, w = _netmon(cfg, Dn, math)
+    topo = O.generate_topology(N, seed=923430603 if N == 20 else 476)
+    rng = np.random.default_rng(2)
+    x = ((rng.random((B, N, Dn)) < 0.05).astype(np.float32) + rng.random((B, N, Dn)).astype(np.float32) * (rng.random((B, N, Dn)) < 0.02))
+    mask = np.broadcast_to(topo["adj"], (B, N, N)).astype(np.float32)
+    st = (rng.standard_normal((B, N, 2 * H)) * 0.3).astype(np.float32)
+    agent_node = rng.integers(0, N, (B, 11)).astype(np.int32)
+    ref_out, ref_state, ref_agent = NO.netmon_forward(w, cfg, x, mask, st, agent_node=agent_node, dtype=np.float64)
+    from graph_marl_b200.model import NetMon
+
+    with torch.no_grad():
+        # dense-mask API
+        nm.state = torch.from_numpy(st).cuda()
+        out = nm(torch.from_numpy(x).cuda(), torch.from_numpy(mask.copy()).cuda(), None, no_agent_mapping=True)
+        assert np.abs(out.cpu().numpy() - ref_out).max() < tol
+        assert np.abs(nm.state.cpu().numpy() - ref_state).max() < tol
+        # list API with a shared list table + agent gather, state None on a second module call chain
+        nbr, deg, dm = NetMon.lists_from_mask(torch.from_numpy(mask[:1].copy()).cuda())
+        nm.state = torch.from_numpy(st).cuda()
+        _, ao = nm.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, agent_node=torch.from_numpy(agent_node).cuda())
+        assert np.abs(ao.cpu().numpy() - ref_agent).max() < tol
+        # zero initial state
+        ref0, ref_state0, _ = NO.netmon_forward(w, cfg, x, mask, None, dtype=np.float64)
+        nm.state = None
+        out0 = nm(torch.from_numpy(x).cuda(), torch.from_numpy(mask.copy()).cuda(), None, no_agent_mapping=True)
+        assert np.abs(out0.cpu().numpy() - ref0).max() < tol
+        assert np.abs(nm.state.cpu().numpy() - ref_state0).max() < tol
+
+
+def test_packed_weight_cache_follows_parameter_updates():
+    cfg = dict(hidden=64, iterations=1, rnn_type="lstm", rnn_carryover=True, agg_type="sum", output_neighbor_hidden=True,
+               output_global_hidden=False, enc=[32], wseed=3)
+    from oracle import netmon_oracle as NO
+    from oracle import oracle as O
+
+    N = 20
+    nm, w = _netmon(cfg, 4 * N + 8, "bf16x3")
+    topo = O.generate_topology(N, seed=923430603)
+    rng = np.random.default_rng(0)
+    x = rng.random((3, N, 4 * N + 8)).astype(np.float32)
+    mask = np.broadcast_to(topo["adj"], (3, N, N)).astype(np.float32)
+    with torch.no_grad():
+        for scale in (1.0, 0.5):
+            for q in nm.parameters():
+                q.mul_(scale)  # in-place update bumps the version counter -> repack
+            w2 = {k: v.detach().cpu().numpy() for k, v in nm.state_dict().items()}
+            ref, _, _ = NO.netmon_forward(w2, cfg, x, mask, None, dtype=np.float64)
+            nm.state = None
+            out = nm(torch.from_numpy(x).cuda(), torch.from_numpy(mask.copy()).cuda(), None, no_agent_mapping=True)
+            assert np.abs(out.cpu().numpy() - ref).max() < 1e-4, scale
+
+
+@pytest.mark.parametrize("math,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
+def test_dqn_tensorcore_q_values(math, tol):
+    from graph_marl_b200.model import DQN
+
+    g = load_golden("dqn_policy")
+    D, h1, h2, n_act, wseed = [int(x) for x in g["cfg"]]
+    dqn = DQN(D, (h1, h2), n_act, F.leaky_relu, math=math)
+    w = det_weights(dqn_shapes(D, [h1, h2], n_act), wseed)
+    dqn.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+    dqn = dqn.cuda().eval()
+    obs = torch.from_numpy(g["obs"]).cuda()
+    with torch.no_grad():
+        q, a = dqn.act(obs)
+        q2, a2 = dqn.act(obs[..., :130].contiguous(), obs[..., 130:].contiguous())
+        q3, a3 = dqn.act(obs[..., :130], obs[..., 130:])  # strided views of the joint tensor
+    for qq in (q, q2, q3):
+        assert np.abs(qq.cpu().numpy() - g["q"]).max() < tol
+    if math == "bf16x3":
+        assert np.array_equal(a.cpu().numpy(), g["q"].argmax(-1))
+        assert np.array_equal(a2.cpu().numpy(), g["q"].argmax(-1))
