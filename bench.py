@@ -262,9 +262,12 @@ def main():
                     peak=pk["hbm_gbs"], unit="GB/s", frac=env_bytes / (env_ms * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None,
                     peak_source=pk["source"], bytes_per_env_step=env_step_bytes(N, A), ms_per_launch=env_ms)
     tf = flops_step / (gemm_ms * 1e-3) / 1e12
+    passes = {"fp32": 1, "bf16x3": 3, "bf16": 1}[a.math]
     roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                      frac=tf / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
-                     flops_per_env_step=flops_step // B, ms_per_step_in_gemms=gemm_ms)
+                     flops_per_env_step=flops_step // B, ms_per_step_in_gemms=gemm_ms,
+                     note=f"achieved = algorithmic dense-GEMM flops (2mnk, fp32 semantics) / (NetMon + DQN stage time); the "
+                          f"tensor pipe executes {passes}x that in bf16 MMAs", tensor_pipe_tflops_executed=tf * passes)
     dominant = roof_gemm if gemm_ms >= env_ms else roof_env
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,

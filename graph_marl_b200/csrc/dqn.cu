@@ -74,7 +74,7 @@ static DqnPack dqn_pack_layout(const gm_dqn_params* p, int split) {
     for (int l = 0; l < p->n_layers; l++) {
         L.off[l] = off;
         int k0 = (l == 0 && split > 0) ? split : kin, k1 = (l == 0 && split > 0) ? kin - split : 0;
-        off += round_up(tc_shape(p->units[l], k0, k1, EPI_LINEAR, 0).packed_bytes, 256);
+        off += tc_shape(p->units[l], k0, k1, EPI_LINEAR, 0).packed_bytes;
         kin = p->units[l];
     }
     L.total = off;
@@ -86,7 +86,8 @@ static int dqn_pack(const gm_dqn_params* p, int split, void* out, cudaStream_t s
     int kin = p->in_features, rc;
     for (int l = 0; l < p->n_layers; l++) {
         int k0 = (l == 0 && split > 0) ? split : kin, k1 = (l == 0 && split > 0) ? kin - split : 0;
-        if ((rc = tc_pack_weights(p->w[l], kin, nullptr, 0, p->units[l], k0, k1, EPI_LINEAR, 0, (char*)out + L.off[l], s))) return rc;
+        if ((rc = tc_pack_weights(p->w[l], kin, nullptr, 0, p->b[l], nullptr, p->units[l], k0, k1, EPI_LINEAR, 0, (char*)out + L.off[l], s)))
+            return rc;
         kin = p->units[l];
     }
     return GM_OK;
@@ -156,7 +157,6 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
                 a.A0 = x; a.lda0 = ldx; a.K0 = kin;
             }
             a.Wp = (const uint8_t*)packed + PL.off[l];
-            a.bias = p->b[l];
             a.C = y; a.ldc = p->units[l]; a.act = p->activation;
             a.M = rows; a.N = p->units[l];
             if ((rc = tc_launch(a, p->math, EPI_LINEAR, s))) return rc;

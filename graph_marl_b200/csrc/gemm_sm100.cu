@@ -7,17 +7,18 @@
 // accumulated in fp32 in TMEM ("bf16x3", relative error per product ~2^-16, i.e. the results sit
 // inside the fp32 tolerance the parity tests state).  GM_MATH_BF16 runs the hi*hi pass only.
 //
-// Structure (one persistent CTA per SM, 10 warps, warp specialised):
-//   warps 0-3  epilogue : tcgen05.ld accumulator rows TMEM -> registers, bias / activation or
-//                         the whole LSTM cell pointwise (gates never leave the SM), fp32 stores
-//   warps 4-7  producer : thread = one tile row; reads fp32 activations (optionally the sum over
-//                         the node's adjacency list = NetMon aggregation, model.py:213-229, and
-//                         optionally two concatenated sources), splits to bf16 hi/lo and writes
-//                         the UMMA canonical K-major (no swizzle) core-matrix layout in smem
-//   warp  8    MMA      : one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM,
-//                         tcgen05.commit releases smem stages / publishes accumulators
-//   warp  9    weights  : one thread streams pre-packed bf16 hi/lo weight tiles with
-//                         cp.async.bulk (TMA bulk copy) signalling the stage mbarrier
+// Structure (one persistent CTA per SM, 18 warps, warp specialised):
+//   warps 0-7   epilogue : tcgen05.ld accumulator rows TMEM -> registers (warp e: TMEM quadrant e%4,
+//                          column half e/4), bias + activation or the whole LSTM cell pointwise (gates
+//                          never leave the SM), 32-byte fp32 stores
+//   warps 8-15  producer : read fp32 activations with 32-byte loads (optionally the sum over the node's
+//                          adjacency list = NetMon aggregation, model.py:213-229, and optionally two
+//                          concatenated sources), split to bf16 hi/lo and write the UMMA canonical
+//                          K-major (no swizzle) core-matrix layout in smem
+//   warp  16    MMA      : one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM,
+//                          tcgen05.commit releases smem stages / publishes accumulators
+//   warp  17    weights  : one thread streams pre-packed bf16 hi/lo weight tiles with
+//                          cp.async.bulk (TMA bulk copy) signalling the stage mbarrier
 // smem ring of 2 stages x (A hi/lo 32 KiB + W hi/lo BN*256 B); 2 accumulator stages in TMEM.
 #include <cuda_bf16.h>
 
@@ -32,9 +33,9 @@ namespace gm {
 namespace tc {
 
 constexpr int BM = 128, BK = 64, STAGES = 2, ACC_STAGES = 2;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
-constexpr int MMA_WARP = 8, W_WARP = 9;
-constexpr int THREADS = 32 * 10;
+constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
+constexpr int MMA_WARP = 16, W_WARP = 17;
+constexpr int THREADS = 32 * 18;
 constexpr int A_PART_BYTES = BM * BK * 2;  // one bf16 part (hi or lo) of an A stage
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +107,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                    "=r"(v[15])                                                                                      \
                  : "r"(addr)                                                                                        \
                  : "memory")
+#define TMEM_LD8(addr, v)                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+                 : "r"(addr)                                                                              \
+                 : "memory")
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -145,6 +151,40 @@ __device__ __forceinline__ void load8(const float* __restrict__ row, int k, int 
     }
 }
 
+// one 8-float chunk of a row; widest vector the alignment allows, zero beyond kvalid
+__device__ __forceinline__ void load_chunk(const float* __restrict__ row, int k, int kvalid, int align, float (&x)[8]) {
+    if (k + 8 <= kvalid && align >= 8) {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7])
+                     : "l"(row + k));
+    } else {
+        load8(row, k, kvalid, align, x);
+    }
+}
+
+__device__ __forceinline__ void st_global_v8(float* ptr, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* ptr, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(ptr));
+}
+
+// fast transcendental forms for the fused LSTM epilogue (abs. error ~1e-7, inside the stated tolerance)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+__device__ __forceinline__ int ptr_align_floats(const float* p, int64_t ld) {
+    if (p == nullptr) return 1;
+    if (((uintptr_t)p & 31) == 0 && (ld & 7) == 0) return 8;
+    if (((uintptr_t)p & 15) == 0 && (ld & 3) == 0) return 4;
+    if (((uintptr_t)p & 7) == 0 && (ld & 1) == 0) return 2;
+    return 1;
+}
+
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     constexpr int W_PART_BYTES = BN * BK * 2;
@@ -161,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(bar_full + 8 * s, PROD_WARPS * 32 + 1);  // 128 producer threads + the weight copy's expect_tx
+            mbar_init(bar_full + 8 * s, PROD_WARPS * 32 + 1);  // 256 producer threads + the weight copy's expect_tx
             mbar_init(bar_empty + 8 * s, 1);                   // tcgen05.commit
         }
         for (int a = 0; a < ACC_STAGES; a++) {
@@ -187,70 +227,95 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ================= producer: activations -> bf16 hi/lo core matrices ===================
-        const int r = threadIdx.x - EPI_WARPS * 32;  // tile row 0..127
-        const uint32_t row_off = (uint32_t)((r >> 3) * (BK * 16) + (r & 7) * 16);
-        const int al0 = (((uintptr_t)p.A0 & 15) == 0 && (p.lda0 & 3) == 0) ? 4 : ((((uintptr_t)p.A0 & 7) == 0 && (p.lda0 & 1) == 0) ? 2 : 1);
-        const int al1 = (p.A1 && ((uintptr_t)p.A1 & 15) == 0 && (p.lda1 & 3) == 0) ? 4 : ((p.A1 && ((uintptr_t)p.A1 & 7) == 0 && (p.lda1 & 1) == 0) ? 2 : 1);
+        // Warp pw owns tile rows [16pw, 16pw+16).  Lane = (r8 = lane/4, part = lane%4): one 32-byte load
+        // per lane covers 8 rows x one 128-byte line each per warp instruction (8 L1 line requests instead
+        // of 32 for a row-per-lane mapping), and the four lanes of a row write the four adjacent 16-byte
+        // rows... i.e. lanes (r8, part) fill core matrices (kc0+part) of row group g: conflict-free stores.
+        const int pw = warp - EPI_WARPS;
+        const int r8 = lane >> 2, part = lane & 3;
+        const int al0 = ptr_align_floats(p.A0, p.lda0), al1 = ptr_align_floats(p.A1, p.lda1);
+        const bool gather = p.nbr != nullptr;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int64_t m = (int64_t)(tile / n_tiles) * BM + r;
-            const bool live = m < p.M;
-            const float* a0 = p.A0 + (live ? m : 0) * p.lda0;
-            const float* a1 = p.A1 ? p.A1 + (live ? m : 0) * p.lda1 : nullptr;
-            // aggregation: rows of A0 summed over the node's adjacency list (model.py:213-229)
-            int nb[4] = {0, 0, 0, 0};
-            int dg = 0;
-            const float* g0 = nullptr;
-            if (p.nbr != nullptr && live) {
-                int b = (int)(m / p.nodes), v = (int)(m - (int64_t)b * p.nodes);
-                int li = p.list_index ? p.list_index[b] : b;
-                const int* lst = p.nbr + ((size_t)li * p.nodes + v) * p.DM;
-                dg = min(p.deg[(size_t)li * p.nodes + v], 4);
-                for (int q = 0; q < dg; q++) nb[q] = lst[q];
-                g0 = p.A0 + (int64_t)b * p.nodes * p.lda0;
+            const int64_t m0 = (int64_t)(tile / n_tiles) * BM + pw * 16 + r8;
+            const float* a0[2];
+            const float* a1[2];
+            const float* gp[2][4];
+            int dg[2];
+            bool live[2];
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                const int64_t m = m0 + 8 * g;
+                live[g] = m < p.M;
+                a0[g] = p.A0 + (live[g] ? m : 0) * p.lda0;
+                a1[g] = p.A1 ? p.A1 + (live[g] ? m : 0) * p.lda1 : nullptr;
+                dg[g] = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) gp[g][q] = a0[g];
+                if (gather && live[g]) {  // aggregation over the node's adjacency list (model.py:213-229)
+                    int b = (int)(m / p.nodes), v = (int)(m - (int64_t)b * p.nodes);
+                    int li = p.list_index ? p.list_index[b] : b;
+                    const int* lst = p.nbr + ((size_t)li * p.nodes + v) * p.DM;
+                    dg[g] = min(p.deg[(size_t)li * p.nodes + v], 4);
+                    const float* g0 = p.A0 + (int64_t)b * p.nodes * p.lda0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (q < dg[g]) gp[g][q] = g0 + (int64_t)lst[q] * p.lda0;
+                }
             }
             for (int kb = 0; kb < kblocks; kb++, it++) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint32_t st_hi = smem_base + s * STAGE_BYTES + row_off;
-                const uint32_t st_lo = st_hi + A_PART_BYTES;
+                uint8_t* st_base = smem + s * STAGE_BYTES + (2 * pw) * (BK * 16) + r8 * 16 + part * 128;
+                bool waited = false;
 #pragma unroll
-                for (int kc = 0; kc < BK / 8; kc++) {
-                    const int k = kb * BK + kc * 8;  // packed K coordinate
-                    float x[8];
-                    if (!live) {
+                for (int g = 0; g < 2; g++) {
+                    float x[2][8];
 #pragma unroll
-                        for (int i = 0; i < 8; i++) x[i] = 0.f;
-                    } else if (k < p.K0p) {
-                        if (g0 != nullptr) {
+                    for (int kh = 0; kh < 2; kh++) {
+                        const int k = kb * BK + kh * 32 + part * 8;  // packed K coordinate of this chunk
 #pragma unroll
-                            for (int i = 0; i < 8; i++) x[i] = 0.f;
-                            for (int q = 0; q < dg; q++) {
-                                float y[8];
-                                load8(g0 + (int64_t)nb[q] * p.lda0, k, p.K0, al0, y);
+                        for (int i = 0; i < 8; i++) x[kh][i] = 0.f;
+                        if (live[g]) {
+                            if (k < p.K0p) {
+                                if (gather) {
+                                    float y[4][8];
 #pragma unroll
-                                for (int i = 0; i < 8; i++) x[i] += y[i];
+                                    for (int q = 0; q < 4; q++) {
+                                        if (q < dg[g]) load_chunk(gp[g][q], k, p.K0, al0, y[q]);
+                                        else {
+#pragma unroll
+                                            for (int i = 0; i < 8; i++) y[q][i] = 0.f;
+                                        }
+                                    }
+                                    // ascending list order = the summation order of the reference's bmm row
+#pragma unroll
+                                    for (int i = 0; i < 8; i++) x[kh][i] = ((y[0][i] + y[1][i]) + y[2][i]) + y[3][i];
+                                    if (p.mean) {
+                                        const float d = (float)max(dg[g], 1);
+#pragma unroll
+                                        for (int i = 0; i < 8; i++) x[kh][i] = x[kh][i] / d;
+                                    }
+                                } else {
+                                    load_chunk(a0[g], k, p.K0, al0, x[kh]);
+                                }
+                            } else if (a1[g] != nullptr) {
+                                load_chunk(a1[g], k - p.K0p, p.K1, al1, x[kh]);
                             }
-                            if (p.mean) {
-#pragma unroll
-                                for (int i = 0; i < 8; i++) x[i] = x[i] / (float)max(dg, 1);
-                            }
-                        } else {
-                            load8(a0, k, p.K0, al0, x);
-                        }
-                    } else {
-                        if (a1 != nullptr) load8(a1, k - p.K0p, p.K1, al1, x);
-                        else {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) x[i] = 0.f;
                         }
                     }
-                    uint4 hi, lo;
-                    split8(x, hi, lo);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st_hi + kc * 128), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-                    if (PASSES == 3)
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(st_lo + kc * 128), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+                    if (!waited) {
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int kh = 0; kh < 2; kh++) {
+                        uint4 hi, lo;
+                        split8(x[kh], hi, lo);
+                        uint8_t* dst = st_base + g * (BK * 16) + kh * 4 * 128;
+                        *(uint4*)dst = hi;
+                        if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
+                    }
                 }
                 fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 mbar_arrive(bar_full + 8 * s);
@@ -308,7 +373,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         }
     } else {
         // ================= epilogue: TMEM -> registers -> global ==========================================
-        const int r = warp * 32 + lane;  // accumulator lane == tile row; warp w owns TMEM lanes 32w..32w+31
+        // 8 warps: warp e reads TMEM lanes 32*(e%4).. (its hardware quadrant) and the column half e/4.
+        const int quad = warp & 3, chalf = warp >> 2;
+        const int r = quad * 32 + lane;  // accumulator lane == tile row
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
             const int as = tcount % ACC_STAGES;
@@ -316,33 +383,45 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
             const int mt = tile / n_tiles, nt = tile % n_tiles;
             const int64_t m = (int64_t)mt * BM + r;
             const bool live = m < p.M;
+            const float* bias_t = p.bias_tile + (size_t)nt * BN;  // tile-ordered, zero padded, biases pre-summed
             mbar_wait(bar_tfull + 8 * as, aph);
             tc_fence_after();
-            const uint32_t t = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
+            const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
             if (EPI == EPI_LINEAR) {
                 const int n0 = nt * BN;
-                const bool vec = ((p.ldc & 3) == 0) && (((uintptr_t)p.C & 15) == 0);
+                const int al = ptr_align_floats(p.C, p.ldc);
+                const bool fast = p.accumulate == 0 && (p.act == GM_ACT_LEAKY_RELU || p.act < 0);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 16) {
+                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 16) {
                     uint32_t v[16];
                     TMEM_LD16(t + c, v);
+                    float bb[16];
+                    ld_global_v8(bias_t + c, bb);
+                    ld_global_v8(bias_t + c + 8, bb + 8);
                     tmem_ld_wait();
                     if (!live || n0 + c >= p.N) continue;
                     float* crow = p.C + m * p.ldc + n0 + c;
                     float o[16];
+                    if (fast) {
+                        const float slope = p.act < 0 ? 1.f : 0.01f;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        int n = n0 + c + i;
-                        float x = __uint_as_float(v[i]);
-                        if (n < p.N) {
-                            if (p.bias) x += __ldg(p.bias + n);
-                            if (p.bias2) x += __ldg(p.bias2 + n);
-                            if (p.accumulate) x += crow[i];
-                            if (p.act >= 0) x = apply_act(x, p.act);
+                        for (int i = 0; i < 16; i++) {
+                            float x = __uint_as_float(v[i]) + bb[i];
+                            o[i] = fmaxf(x, slope * x);  // leaky_relu(x) = max(x, 0.01x); identity for slope 1
                         }
-                        o[i] = x;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            float x = __uint_as_float(v[i]) + bb[i];
+                            if (p.accumulate && n0 + c + i < p.N) x += crow[i];
+                            if (p.act >= 0) x = apply_act(x, p.act);
+                            o[i] = x;
+                        }
                     }
-                    if (vec && n0 + c + 16 <= p.N) {
+                    if (n0 + c + 16 <= p.N && al >= 8) {
+                        st_global_v8(crow, o);
+                        st_global_v8(crow + 8, o + 8);
+                    } else if (n0 + c + 16 <= p.N && al >= 4) {
 #pragma unroll
                         for (int i = 0; i < 4; i++) *(float4*)(crow + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     } else {
@@ -357,42 +436,34 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 constexpr int U = BN / 4;
                 const int j0 = nt * U;
 #pragma unroll 1
-                for (int c = 0; c < U; c += 16) {
-                    uint32_t vi[16], vf[16], vg[16], vo[16];
-                    TMEM_LD16(t + c, vi);
-                    TMEM_LD16(t + U + c, vf);
-                    TMEM_LD16(t + 2 * U + c, vg);
-                    TMEM_LD16(t + 3 * U + c, vo);
+                for (int c = chalf * (U / 2); c < (chalf + 1) * (U / 2); c += 8) {
+                    float cin[8], bi[8], bf[8], bg[8], bo[8];
+                    if (live) ld_global_v8(p.c_in + m * p.ldc_in + j0 + c, cin);
+                    ld_global_v8(bias_t + c, bi);
+                    ld_global_v8(bias_t + U + c, bf);
+                    ld_global_v8(bias_t + 2 * U + c, bg);
+                    ld_global_v8(bias_t + 3 * U + c, bo);
+                    uint32_t vi[8], vf[8], vg[8], vo[8];
+                    TMEM_LD8(t + c, vi);
+                    TMEM_LD8(t + U + c, vf);
+                    TMEM_LD8(t + 2 * U + c, vg);
+                    TMEM_LD8(t + 3 * U + c, vo);
                     tmem_ld_wait();
                     if (!live) continue;
-                    const float* cin = p.c_in + m * p.ldc_in + j0 + c;
-                    float* hout = p.h_out + m * p.ldh + j0 + c;
-                    float* cout = p.c_out + m * p.ldco + j0 + c;
-                    float hh[16], cc[16];
+                    float hh[8], cc[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        int j = j0 + c + i;
-                        float bi = __ldg(p.bias + j), bf = __ldg(p.bias + p.H + j), bg = __ldg(p.bias + 2 * p.H + j), bo = __ldg(p.bias + 3 * p.H + j);
-                        if (p.bias2) { bi += __ldg(p.bias2 + j); bf += __ldg(p.bias2 + p.H + j); bg += __ldg(p.bias2 + 2 * p.H + j); bo += __ldg(p.bias2 + 3 * p.H + j); }
-                        float i_ = sigmoidf_(__uint_as_float(vi[i]) + bi), f_ = sigmoidf_(__uint_as_float(vf[i]) + bf);
-                        float g_ = tanhf(__uint_as_float(vg[i]) + bg), o_ = sigmoidf_(__uint_as_float(vo[i]) + bo);
+                    for (int i = 0; i < 8; i++) {
+                        float i_ = fast_sigmoid(__uint_as_float(vi[i]) + bi[i]), f_ = fast_sigmoid(__uint_as_float(vf[i]) + bf[i]);
+                        float g_ = fast_tanh(__uint_as_float(vg[i]) + bg[i]), o_ = fast_sigmoid(__uint_as_float(vo[i]) + bo[i]);
                         float cv = f_ * cin[i] + i_ * g_;
                         cc[i] = cv;
-                        hh[i] = o_ * tanhf(cv);
+                        hh[i] = o_ * fast_tanh(cv);
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        *(float4*)(hout + 4 * i) = make_float4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
-                        *(float4*)(cout + 4 * i) = make_float4(cc[4 * i], cc[4 * i + 1], cc[4 * i + 2], cc[4 * i + 3]);
-                    }
+                    st_global_v8(p.h_out + m * p.ldh + j0 + c, hh);
+                    st_global_v8(p.c_out + m * p.ldco + j0 + c, cc);
                     if (p.h_out2) {
-                        float* h2 = p.h_out2 + m * p.ldh2 + j0 + c;
-                        float* c2 = p.c_out2 + m * p.ldh2 + j0 + c;
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            *(float4*)(h2 + 4 * i) = make_float4(hh[4 * i], hh[4 * i + 1], hh[4 * i + 2], hh[4 * i + 3]);
-                            *(float4*)(c2 + 4 * i) = make_float4(cc[4 * i], cc[4 * i + 1], cc[4 * i + 2], cc[4 * i + 3]);
-                        }
+                        st_global_v8(p.h_out2 + m * p.ldh2 + j0 + c, hh);
+                        st_global_v8(p.c_out2 + m * p.ldh2 + j0 + c, cc);
                     }
                 }
             }
@@ -460,6 +531,23 @@ __global__ void pack_w_kernel(const float* __restrict__ W, int64_t ldw, const fl
     }
 }
 
+// tile-ordered bias (b + b2, zero padded to n_tiles*BN) stored behind the weight tiles
+__global__ void pack_bias_kernel(const float* __restrict__ b, const float* __restrict__ b2, int N, int BN, int n_tiles,
+                                 int lstm, int H, float* __restrict__ out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_tiles * BN) return;
+    int nt = idx / BN, row = idx % BN, n_src;
+    if (lstm) {
+        int U = BN / 4, gate = row / U, jj = row % U;
+        n_src = (nt * U + jj < H) ? gate * H + nt * U + jj : -1;
+    } else {
+        n_src = nt * BN + row;
+    }
+    float v = 0.f;
+    if (n_src >= 0 && n_src < N) v = (b ? b[n_src] : 0.f) + (b2 ? b2[n_src] : 0.f);
+    out[idx] = v;
+}
+
 }  // namespace tc
 
 // -------------------------------------------------------------------------------------------------
@@ -474,17 +562,21 @@ TcShape tc_shape(int N, int K0, int K1, int epi, int H) {
     s.K0p = (K1 > 0) ? (int)round_up(K0, 8) : K0;
     s.Kp = (int)round_up(s.K0p + K1, tc::BK);
     s.n_tiles = (epi == EPI_LSTM) ? ceil_div(H, s.BN / 4) : ceil_div(N, s.BN);
-    s.packed_bytes = (int64_t)s.n_tiles * (s.Kp / tc::BK) * 2 * s.BN * tc::BK * 2;
+    s.w_bytes = (int64_t)s.n_tiles * (s.Kp / tc::BK) * 2 * s.BN * tc::BK * 2;
+    s.packed_bytes = round_up(s.w_bytes + (int64_t)s.n_tiles * s.BN * 4, 256);
     return s;
 }
 
-int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, int N, int K0, int K1, int epi, int H,
-                    void* out, cudaStream_t s) {
+int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, const float* bias, const float* bias2, int N,
+                    int K0, int K1, int epi, int H, void* out, cudaStream_t s) {
     TcShape sh = tc_shape(N, K0, K1, epi, H);
     int64_t total = (int64_t)sh.n_tiles * (sh.Kp / tc::BK) * sh.BN * (tc::BK / 8);
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
     tc::pack_w_kernel<<<blocks, 256, 0, s>>>(W, ldw, W1, ldw1, N, K0, K1, sh.K0p, sh.Kp, sh.BN, sh.n_tiles, epi == EPI_LSTM,
                                              H, (uint8_t*)out);
+    GM_LAUNCH_CHECK();
+    tc::pack_bias_kernel<<<ceil_div(sh.n_tiles * sh.BN, 256), 256, 0, s>>>(bias, bias2, N, sh.BN, sh.n_tiles, epi == EPI_LSTM, H,
+                                                                          (float*)((char*)out + sh.w_bytes));
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -510,12 +602,13 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     a.Kp = sh.Kp;
     a.n_tiles = sh.n_tiles;
     a.m_tiles = (int)((a.M + tc::BM - 1) / tc::BM);
-    GM_CHECK_ARG(((uintptr_t)a.Wp & 15) == 0, "packed weights must be 16-byte aligned");
+    GM_CHECK_ARG(((uintptr_t)a.Wp & 255) == 0, "packed weights must be 256-byte aligned");
+    a.bias_tile = (const float*)(a.Wp + sh.w_bytes);
     if (epi == EPI_LSTM) {
         GM_CHECK_ARG(a.H % 64 == 0, "fused LSTM epilogue needs hidden %% 64 == 0, got %d", a.H);
-        GM_CHECK_ARG((a.ldc_in & 3) == 0 && (a.ldh & 3) == 0 && (a.ldco & 3) == 0 && (a.ldh2 & 3) == 0 &&
-                         (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out | (uintptr_t)a.h_out2 | (uintptr_t)a.c_out2) & 15) == 0,
-                     "fused LSTM epilogue needs 16-byte aligned state rows");
+        GM_CHECK_ARG((a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 && (a.ldh2 & 7) == 0 &&
+                         (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out | (uintptr_t)a.h_out2 | (uintptr_t)a.c_out2) & 31) == 0,
+                     "fused LSTM epilogue needs 32-byte aligned state rows");
     }
     const int passes = math == GM_MATH_BF16 ? 1 : 3;
     if (epi == EPI_LSTM) return passes == 3 ? launch_tc<256, 3, EPI_LSTM>(a, s) : launch_tc<256, 1, EPI_LSTM>(a, s);
@@ -524,18 +617,18 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
 }
 
 // ---- generic entry used by gm_linear and the unfused layers: packs W into `ws`, then runs -------------
-int64_t linear_tc_workspace_bytes(int64_t, int N, int K, int) { return round_up(tc_shape(N, K, 0, EPI_LINEAR, 0).packed_bytes, 256); }
+int64_t linear_tc_workspace_bytes(int64_t, int N, int K, int) { return tc_shape(N, K, 0, EPI_LINEAR, 0).packed_bytes + 256; }
 
 int linear_tc(const LinearArgs& l, int math, void* ws, int64_t ws_bytes, cudaStream_t s) {
     TcShape sh = tc_shape(l.N, l.K, 0, EPI_LINEAR, 0);
-    GM_CHECK_ARG(ws != nullptr && ws_bytes >= sh.packed_bytes, "tensor-core linear needs %lld workspace bytes, got %lld",
-                 (long long)sh.packed_bytes, (long long)ws_bytes);
-    int rc = tc_pack_weights(l.W, l.ldw, nullptr, 0, l.N, l.K, 0, EPI_LINEAR, 0, ws, s);
+    char* wsa = (char*)round_up((int64_t)ws, 256);
+    GM_CHECK_ARG(ws != nullptr && ws_bytes - (wsa - (char*)ws) >= sh.packed_bytes,
+                 "tensor-core linear needs %lld workspace bytes, got %lld", (long long)sh.packed_bytes + 256, (long long)ws_bytes);
+    int rc = tc_pack_weights(l.W, l.ldw, nullptr, 0, l.bias, l.bias2, l.N, l.K, 0, EPI_LINEAR, 0, wsa, s);
     if (rc) return rc;
     TcArgs a{};
     a.A0 = l.A; a.lda0 = l.lda; a.K0 = l.K;
-    a.Wp = (const uint8_t*)ws;
-    a.bias = l.bias; a.bias2 = l.bias2;
+    a.Wp = (const uint8_t*)wsa;
     a.C = l.C; a.ldc = l.ldc; a.act = l.act; a.accumulate = l.accumulate;
     a.M = l.M; a.N = l.N;
     return tc_launch(a, math, EPI_LINEAR, s);

@@ -14,8 +14,8 @@ struct TcArgs {
     // optional aggregation of segment 0 over adjacency lists: row m = (graph b, node v) reads
     // sum_q A0[b*nodes + nbr[list(b)][v][q]] for q < deg (model.py:213-229)
     const int* nbr; const int* deg; int DM; const int* list_index; int nodes; int mean;
-    const uint8_t* Wp;  // weights packed by tc_pack_weights
-    const float* bias; const float* bias2;
+    const uint8_t* Wp;        // weights (+ tile-ordered bias behind them) packed by tc_pack_weights
+    const float* bias_tile;   // filled by tc_launch
     // EPI_LINEAR
     float* C; int64_t ldc; int act; int accumulate;
     int64_t M; int N;
@@ -29,14 +29,15 @@ struct TcArgs {
 
 struct TcShape {
     int BN, K0p, Kp, n_tiles;
-    int64_t packed_bytes;
+    int64_t w_bytes, packed_bytes;  // weight tiles; weights + bias, rounded to 256
 };
 
 TcShape tc_shape(int N, int K0, int K1, int epi, int H);
 // W fp32 [N, K0+K1] (row stride ldw), or W [N,K0] next to W1 [N,K1] -> packed bf16 hi/lo tiles
 // (tc_shape(...).packed_bytes, 256-byte aligned destination)
-int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, int N, int K0, int K1, int epi, int H,
-                    void* out, cudaStream_t s);
+// bias (+ bias2) are summed and stored tile-ordered behind the weights (either may be NULL)
+int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, const float* bias, const float* bias2, int N,
+                    int K0, int K1, int epi, int H, void* out, cudaStream_t s);
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
 
 }  // namespace gm

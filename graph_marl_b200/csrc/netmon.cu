@@ -260,14 +260,14 @@ static NetmonPack pack_layout(const gm_netmon_params* p) {
     int kin = p->in_features;
     for (int l = 0; l < p->n_enc_layers; l++) {
         L.enc[l] = off;
-        off += round_up(tc_shape(p->enc_units[l], kin, 0, EPI_LINEAR, 0).packed_bytes, 256);
+        off += tc_shape(p->enc_units[l], kin, 0, EPI_LINEAR, 0).packed_bytes;
         kin = p->enc_units[l];
     }
     const int H = p->hidden;
     L.fused_cells = p->rnn_type == GM_RNN_LSTM && p->rnn_carryover && (H % 64) == 0;
     L.obs = L.upd = off;
     if (L.fused_cells) {
-        int64_t cell = round_up(tc_shape(4 * H, H, H, EPI_LSTM, H).packed_bytes, 256);
+        int64_t cell = tc_shape(4 * H, H, H, EPI_LSTM, H).packed_bytes;
         L.obs = off;
         L.upd = off + cell;
         off += 2 * cell;
@@ -280,14 +280,18 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
     NetmonPack L = pack_layout(p);
     int kin = p->in_features, rc;
     for (int l = 0; l < p->n_enc_layers; l++) {
-        if ((rc = tc_pack_weights(p->enc_w[l], kin, nullptr, 0, p->enc_units[l], kin, 0, EPI_LINEAR, 0, (char*)out + L.enc[l], s)))
+        if ((rc = tc_pack_weights(p->enc_w[l], kin, nullptr, 0, p->enc_b[l], nullptr, p->enc_units[l], kin, 0, EPI_LINEAR, 0,
+                                  (char*)out + L.enc[l], s)))
             return rc;
         kin = p->enc_units[l];
     }
     if (L.fused_cells) {
         const int H = p->hidden;
-        if ((rc = tc_pack_weights(p->rnn_obs.w_ih, H, p->rnn_obs.w_hh, H, 4 * H, H, H, EPI_LSTM, H, (char*)out + L.obs, s))) return rc;
-        if ((rc = tc_pack_weights(p->rnn_update.w_ih, H, p->rnn_update.w_hh, H, 4 * H, H, H, EPI_LSTM, H, (char*)out + L.upd, s)))
+        if ((rc = tc_pack_weights(p->rnn_obs.w_ih, H, p->rnn_obs.w_hh, H, p->rnn_obs.b_ih, p->rnn_obs.b_hh, 4 * H, H, H, EPI_LSTM, H,
+                                  (char*)out + L.obs, s)))
+            return rc;
+        if ((rc = tc_pack_weights(p->rnn_update.w_ih, H, p->rnn_update.w_hh, H, p->rnn_update.b_ih, p->rnn_update.b_hh, 4 * H, H, H,
+                                  EPI_LSTM, H, (char*)out + L.upd, s)))
             return rc;
     }
     return GM_OK;
@@ -412,7 +416,6 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             TcArgs a{};
             a.A0 = x; a.lda0 = ldx; a.K0 = kin;
             a.Wp = (const uint8_t*)packed + PL.enc[l];
-            a.bias = p->enc_b[l];
             a.C = y; a.ldc = p->enc_units[l]; a.act = p->activation;
             a.M = R; a.N = p->enc_units[l];
             rc = tc_launch(a, math, EPI_LINEAR, s);
@@ -447,7 +450,6 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                 a.mean = p->agg_type == GM_AGG_MEAN;
             }
             a.Wp = (const uint8_t*)packed + woff;
-            a.bias = cp.b_ih; a.bias2 = cp.b_hh;
             a.c_in = cprev; a.ldc_in = ldcp;
             a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn;
             a.H = H; a.M = R; a.N = 4 * H;
