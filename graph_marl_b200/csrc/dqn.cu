@@ -6,6 +6,8 @@
 //   actions = argmax(q) * ~filter + filter * random_actions       (argmax = first maximum)
 // The joint observation row [agent obs | graph obs] (wrapper.py:50) is consumed as two
 // segments so the concatenation is never materialised.
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "linear_simt.cuh"
@@ -60,6 +62,11 @@ __global__ void dqn_head_kernel(const float* __restrict__ h, int64_t ldh, int Hd
 
 static bool dqn_tc_math(int math) { return math == GM_MATH_BF16X3 || math == GM_MATH_BF16; }
 
+// one activation buffer: fp32 [rows, maxw] or the same matrix tile-packed (rows rounded up to 128)
+static int64_t dqn_buf_bytes(int64_t rows, int maxw) {
+    return round_up(std::max<int64_t>(rows * maxw * 4, tc_pk_bytes(rows, (int)round_up(maxw, TC_BK))), 256);
+}
+
 // packed tensor-core weights: layer l at off[l]; layer 0 is packed for input rows split as
 // [split | in_features - split] so the joint observation is consumed without a concat
 struct DqnPack {
@@ -104,7 +111,7 @@ int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows) {
     int maxw = 0;
     for (int i = 0; i < p->n_layers; i++) maxw = max(maxw, p->units[i]);
     int64_t pack = dqn_tc_math(p->math) ? 2 * round_up(dqn_pack_layout(p, 8).total, 256) + 512 : 0;
-    return 2 * round_up(rows * maxw * 4, 256) + pack;
+    return 2 * dqn_buf_bytes(rows, maxw) + pack;
 }
 
 int64_t gm_dqn_packed_bytes(const gm_dqn_params* p, int32_t split) { return p ? dqn_pack_layout(p, split).total : 0; }
@@ -129,10 +136,11 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
     cudaStream_t s = (cudaStream_t)stream;
     int maxw = 0;
     for (int i = 0; i < p->n_layers; i++) maxw = max(maxw, p->units[i]);
+    GM_CHECK_ARG(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     float* buf0 = (float*)workspace;
-    float* buf1 = (float*)((char*)workspace + round_up(rows * maxw * 4, 256));
-    void* lin_ws = (char*)workspace + 2 * round_up(rows * maxw * 4, 256);
-    int64_t lin_ws_bytes = workspace_bytes - 2 * round_up(rows * maxw * 4, 256);
+    float* buf1 = (float*)((char*)workspace + dqn_buf_bytes(rows, maxw));
+    void* lin_ws = (char*)workspace + 2 * dqn_buf_bytes(rows, maxw);
+    int64_t lin_ws_bytes = workspace_bytes - 2 * dqn_buf_bytes(rows, maxw);
     int rc;
     if (dqn_tc_math(p->math)) {
         // ---- tensor-core path: every layer one tcgen05 launch, layer 0 over both input segments ----
@@ -144,22 +152,29 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
             packed = dst;
         }
         DqnPack PL = dqn_pack_layout(p, split);
+        // hidden activations stay tile-packed between layers (bulk-copied by the next layer); the last
+        // hidden layer is written as fp32 rows for the Q head
         const float* x = obs_a;
+        const uint8_t* xpk = nullptr;
         int64_t ldx = lda;
         int kin = p->in_features;
         for (int l = 0; l < p->n_layers; l++) {
             float* y = (l & 1) ? buf1 : buf0;
+            const bool out_pk = l + 1 < p->n_layers && (p->units[l] % TC_BK) == 0;
             TcArgs a{};
             if (l == 0) {
                 a.A0 = obs_a; a.lda0 = lda; a.K0 = Da;
                 if (Dg > 0) { a.A1 = obs_g; a.lda1 = ldg; a.K1 = Dg; }
             } else {
-                a.A0 = x; a.lda0 = ldx; a.K0 = kin;
+                if (xpk) a.A0pk = xpk; else { a.A0 = x; a.lda0 = ldx; }
+                a.K0 = kin;
             }
             a.Wp = (const uint8_t*)packed + PL.off[l];
-            a.C = y; a.ldc = p->units[l]; a.act = p->activation;
+            if (out_pk) a.Cpk = (uint8_t*)y; else { a.C = y; a.ldc = p->units[l]; }
+            a.act = p->activation;
             a.M = rows; a.N = p->units[l];
             if ((rc = tc_launch(a, p->math, EPI_LINEAR, s))) return rc;
+            xpk = out_pk ? (const uint8_t*)y : nullptr;
             x = y; ldx = p->units[l]; kin = p->units[l];
         }
         int Hd = p->units[p->n_layers - 1];

@@ -1,42 +1,49 @@
 // gemm_sm100.cu -- tcgen05 / TMEM fused linear layer for sm_100a (GM_MATH_BF16X3, GM_MATH_BF16).
 //
-//   C[M,N] = epilogue( [A0 | A1][M,K] * W[N,K]^T )           (torch.nn.Linear layout, fp32 in/out)
+//   C[M,N] = epilogue( [seg0 | seg1][M,K] * W[N,K]^T )        (torch.nn.Linear layout)
 //
-// Arithmetic.  fp32 operands are split on the fly into bf16 hi + bf16 lo (x = hi + lo up to
-// 2^-17 relative) and the product is formed from three tensor-core passes hi*hi + hi*lo + lo*hi
-// accumulated in fp32 in TMEM ("bf16x3", relative error per product ~2^-16, i.e. the results sit
-// inside the fp32 tolerance the parity tests state).  GM_MATH_BF16 runs the hi*hi pass only.
+// Arithmetic.  fp32 operands are split into bf16 hi + bf16 lo (x = hi + lo up to 2^-17 relative)
+// and the product is formed from three tensor-core passes hi*hi + hi*lo + lo*hi accumulated in
+// fp32 in TMEM ("bf16x3", relative error per product ~2^-16, inside the fp32 tolerance the parity
+// tests state).  GM_MATH_BF16 runs the hi*hi pass only.
+//
+// Data flow.  Activations travel between layers "tile-packed" (gemm_sm100.cuh): already split to
+// bf16 hi/lo and already in the shared-memory core-matrix layout of the tensor core, written by
+// the producing layer's epilogue and pulled by the consuming layer with ONE bulk copy (TMA) per
+// 32-wide k-block.  Only raw fp32 inputs (node observations, carried state, agent observations)
+// go through the producer warps, which split them on the fly.
 //
 // Structure (one persistent CTA per SM, 18 warps, warp specialised):
 //   warps 0-7   epilogue : tcgen05.ld accumulator rows TMEM -> registers (warp e: TMEM quadrant e%4,
 //                          column half e/4), bias + activation or the whole LSTM cell pointwise (gates
-//                          never leave the SM), 32-byte fp32 stores
-//   warps 8-15  producer : read fp32 activations with 32-byte loads (optionally the sum over the node's
-//                          adjacency list = NetMon aggregation, model.py:213-229, and optionally two
-//                          concatenated sources), split to bf16 hi/lo and write the UMMA canonical
-//                          K-major (no swizzle) core-matrix layout in smem
+//                          never leave the SM); stores fp32 rows and/or tile-packed bf16 hi/lo
+//   warps 8-15  producer : fp32 segments only: 32-byte loads (8 rows x 128-byte lines per warp
+//                          instruction), split to bf16 hi/lo, conflict-free 16-byte smem stores in the
+//                          UMMA canonical K-major (no swizzle) layout; loads of k-block i+1 are in
+//                          flight while k-block i is converted
 //   warp  16    MMA      : one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM,
 //                          tcgen05.commit releases smem stages / publishes accumulators
-//   warp  17    weights  : one thread streams pre-packed bf16 hi/lo weight tiles with
+//   warp  17    copies   : one thread streams weight tiles and tile-packed activation blocks with
 //                          cp.async.bulk (TMA bulk copy) signalling the stage mbarrier
-// smem ring of 2 stages x (A hi/lo 32 KiB + W hi/lo BN*256 B); 2 accumulator stages in TMEM.
+// smem ring of 4 stages x (A hi/lo 16 KiB + W hi/lo BN*128 B); 2 accumulator stages in TMEM.
 #include <cuda_bf16.h>
 
 #include <algorithm>
 
 #include "common.cuh"
-#include "linear_simt.cuh"
 #include "gemm_sm100.cuh"
+#include "linear_simt.cuh"
 
 namespace gm {
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, STAGES = 2, ACC_STAGES = 2;
+constexpr int BM = TC_BM, BK = TC_BK, STAGES = 4, ACC_STAGES = 2;
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
 constexpr int MMA_WARP = 16, W_WARP = 17;
 constexpr int THREADS = 32 * 18;
-constexpr int A_PART_BYTES = BM * BK * 2;  // one bf16 part (hi or lo) of an A stage
+constexpr int A_PART_BYTES = BM * BK * 2;  // one bf16 part (hi or lo) of an A stage: 8 KiB
+constexpr int SBO_BYTES = BK * 16;         // distance between 8-row groups: 512 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -79,9 +86,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: core matrix = 8 rows x 16 bytes stored
 // as 128 contiguous bytes; LBO = distance between the two K core matrices of one MMA (128 B),
-// SBO = distance between consecutive 8-row groups (BK/8 core matrices = 1024 B).
+// SBO = distance between consecutive 8-row groups (BK/8 core matrices = 512 B).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    constexpr uint64_t LBO = 128 >> 4, SBO = (BK * 16) >> 4;
+    constexpr uint64_t LBO = 128 >> 4, SBO = SBO_BYTES >> 4;
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (LBO << 16) | (SBO << 32) | (1ull << 46);
 }
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=BN
@@ -134,9 +141,22 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// 8 consecutive floats of a row (zero beyond kvalid); vector width chosen from the alignment
-__device__ __forceinline__ void load8(const float* __restrict__ row, int k, int kvalid, int align, float (&x)[8]) {
-    if (k + 8 <= kvalid && align >= 4) {
+__device__ __forceinline__ void ld_global_v8(const float* ptr, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(ptr));
+}
+__device__ __forceinline__ void st_global_v8(float* ptr, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+// one 8-float chunk of a row; widest vector the alignment allows, zero beyond kvalid
+__device__ __forceinline__ void load_chunk(const float* __restrict__ row, int k, int kvalid, int align, float (&x)[8]) {
+    if (k + 8 <= kvalid && align >= 8) {
+        ld_global_v8(row + k, x);
+    } else if (k + 8 <= kvalid && align >= 4) {
         float4 a = __ldg((const float4*)(row + k)), b = __ldg((const float4*)(row + k + 4));
         x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
     } else if (k + 8 <= kvalid && align >= 2) {
@@ -151,28 +171,6 @@ __device__ __forceinline__ void load8(const float* __restrict__ row, int k, int 
     }
 }
 
-// one 8-float chunk of a row; widest vector the alignment allows, zero beyond kvalid
-__device__ __forceinline__ void load_chunk(const float* __restrict__ row, int k, int kvalid, int align, float (&x)[8]) {
-    if (k + 8 <= kvalid && align >= 8) {
-        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]), "=f"(x[4]), "=f"(x[5]), "=f"(x[6]), "=f"(x[7])
-                     : "l"(row + k));
-    } else {
-        load8(row, k, kvalid, align, x);
-    }
-}
-
-__device__ __forceinline__ void st_global_v8(float* ptr, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void ld_global_v8(const float* ptr, float* v) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(ptr));
-}
-
 // fast transcendental forms for the fused LSTM epilogue (abs. error ~1e-7, inside the stated tolerance)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
@@ -184,6 +182,9 @@ __device__ __forceinline__ int ptr_align_floats(const float* p, int64_t ld) {
     if (((uintptr_t)p & 7) == 0 && (ld & 1) == 0) return 2;
     return 1;
 }
+
+// byte offset of the 16-byte chunk (row r, k-chunk kc) inside one bf16 part of a [128 x 32] block
+__device__ __forceinline__ uint32_t core_off(int r, int kc) { return (uint32_t)((r >> 3) * SBO_BYTES + kc * 128 + (r & 7) * 16); }
 
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
@@ -201,8 +202,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
-            mbar_init(bar_full + 8 * s, PROD_WARPS * 32 + 1);  // 256 producer threads + the weight copy's expect_tx
-            mbar_init(bar_empty + 8 * s, 1);                   // tcgen05.commit
+            // the copy thread's expect_tx arrive, plus the 256 producer threads when a segment is fp32
+            mbar_init(bar_full + 8 * s, 1 + (p.has_prod ? PROD_WARPS * 32 : 0));
+            mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
         }
         for (int a = 0; a < ACC_STAGES; a++) {
             mbar_init(bar_tfull + 8 * a, 1);                // tcgen05.commit
@@ -224,117 +226,98 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     const int n_tiles = p.n_tiles;
     const int total_tiles = p.m_tiles * n_tiles;
     const int kblocks = p.Kp / BK;
+    const int kb_seg1 = p.K0p / BK;  // first k-block of segment 1
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-        // ================= producer: activations -> bf16 hi/lo core matrices ===================
-        // Warp pw owns tile rows [16pw, 16pw+16).  Lane = (r8 = lane/4, part = lane%4): one 32-byte load
-        // per lane covers 8 rows x one 128-byte line each per warp instruction (8 L1 line requests instead
-        // of 32 for a row-per-lane mapping), and the four lanes of a row write the four adjacent 16-byte
-        // rows... i.e. lanes (r8, part) fill core matrices (kc0+part) of row group g: conflict-free stores.
-        const int pw = warp - EPI_WARPS;
-        const int r8 = lane >> 2, part = lane & 3;
-        const int al0 = ptr_align_floats(p.A0, p.lda0), al1 = ptr_align_floats(p.A1, p.lda1);
-        const bool gather = p.nbr != nullptr;
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int64_t m0 = (int64_t)(tile / n_tiles) * BM + pw * 16 + r8;
-            const float* a0[2];
-            const float* a1[2];
-            const float* gp[2][4];
-            int dg[2];
-            bool live[2];
+        // ================= producer: fp32 activations -> bf16 hi/lo core matrices ================
+        // Warp pw owns tile rows [16pw, 16pw+16) as two 8-row groups.  Lane = (r8 = lane/4, part = lane%4):
+        // one 32-byte load per lane = 8 rows x one 128-byte line per warp instruction, and lanes
+        // (r8, part) fill the 16-byte rows of core matrix `part` of their group: conflict-free stores.
+        if (p.has_prod) {
+            const int pw = warp - EPI_WARPS;
+            const int r8 = lane >> 2, part = lane & 3;
+            const int al0 = ptr_align_floats(p.A0, p.lda0), al1 = ptr_align_floats(p.A1, p.lda1);
+            const bool prod0 = p.A0pk == nullptr, prod1 = p.K1 > 0 && p.A1pk == nullptr;
+            const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)kblocks;
+            uint8_t* const st_base = smem + (2 * pw) * SBO_BYTES + r8 * 16 + part * 128;
+
+            // fetch the two chunks (row groups g = 0,1) of iteration `it` into registers
+            auto fetch = [&](uint32_t it, float (&x)[2][8]) {
 #pragma unroll
-            for (int g = 0; g < 2; g++) {
-                const int64_t m = m0 + 8 * g;
-                live[g] = m < p.M;
-                a0[g] = p.A0 + (live[g] ? m : 0) * p.lda0;
-                a1[g] = p.A1 ? p.A1 + (live[g] ? m : 0) * p.lda1 : nullptr;
-                dg[g] = 0;
+                for (int g = 0; g < 2; g++)
 #pragma unroll
-                for (int q = 0; q < 4; q++) gp[g][q] = a0[g];
-                if (gather && live[g]) {  // aggregation over the node's adjacency list (model.py:213-229)
-                    int b = (int)(m / p.nodes), v = (int)(m - (int64_t)b * p.nodes);
-                    int li = p.list_index ? p.list_index[b] : b;
-                    const int* lst = p.nbr + ((size_t)li * p.nodes + v) * p.DM;
-                    dg[g] = min(p.deg[(size_t)li * p.nodes + v], 4);
-                    const float* g0 = p.A0 + (int64_t)b * p.nodes * p.lda0;
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-                        if (q < dg[g]) gp[g][q] = g0 + (int64_t)lst[q] * p.lda0;
-                }
-            }
-            for (int kb = 0; kb < kblocks; kb++, it++) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                uint8_t* st_base = smem + s * STAGE_BYTES + (2 * pw) * (BK * 16) + r8 * 16 + part * 128;
-                bool waited = false;
+                    for (int i = 0; i < 8; i++) x[g][i] = 0.f;
+                if (it >= total_it) return;
+                const int tile = blockIdx.x + (int)(it / kblocks) * gridDim.x;
+                const int kb = (int)(it % kblocks);
+                const bool seg1 = kb >= kb_seg1;
+                if (seg1 ? !prod1 : !prod0) return;  // this k-block arrives by bulk copy
+                const int k = (seg1 ? kb - kb_seg1 : kb) * BK + part * 8;
+                const int64_t m0 = (int64_t)(tile / n_tiles) * BM + pw * 16 + r8;
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
-                    float x[2][8];
-#pragma unroll
-                    for (int kh = 0; kh < 2; kh++) {
-                        const int k = kb * BK + kh * 32 + part * 8;  // packed K coordinate of this chunk
-#pragma unroll
-                        for (int i = 0; i < 8; i++) x[kh][i] = 0.f;
-                        if (live[g]) {
-                            if (k < p.K0p) {
-                                if (gather) {
-                                    float y[4][8];
-#pragma unroll
-                                    for (int q = 0; q < 4; q++) {
-                                        if (q < dg[g]) load_chunk(gp[g][q], k, p.K0, al0, y[q]);
-                                        else {
-#pragma unroll
-                                            for (int i = 0; i < 8; i++) y[q][i] = 0.f;
-                                        }
-                                    }
-                                    // ascending list order = the summation order of the reference's bmm row
-#pragma unroll
-                                    for (int i = 0; i < 8; i++) x[kh][i] = ((y[0][i] + y[1][i]) + y[2][i]) + y[3][i];
-                                    if (p.mean) {
-                                        const float d = (float)max(dg[g], 1);
-#pragma unroll
-                                        for (int i = 0; i < 8; i++) x[kh][i] = x[kh][i] / d;
-                                    }
-                                } else {
-                                    load_chunk(a0[g], k, p.K0, al0, x[kh]);
-                                }
-                            } else if (a1[g] != nullptr) {
-                                load_chunk(a1[g], k - p.K0p, p.K1, al1, x[kh]);
-                            }
-                        }
-                    }
-                    if (!waited) {
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                        waited = true;
-                    }
-#pragma unroll
-                    for (int kh = 0; kh < 2; kh++) {
-                        uint4 hi, lo;
-                        split8(x[kh], hi, lo);
-                        uint8_t* dst = st_base + g * (BK * 16) + kh * 4 * 128;
-                        *(uint4*)dst = hi;
-                        if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
+                    const int64_t m = m0 + 8 * g;
+                    if (m < p.M) {
+                        if (seg1) load_chunk(p.A1 + m * p.lda1, k, p.K1, al1, x[g]);
+                        else load_chunk(p.A0 + m * p.lda0, k, p.K0, al0, x[g]);
                     }
                 }
-                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                mbar_arrive(bar_full + 8 * s);
+            };
+            // register ring of 3 k-blocks: the loads of k-blocks it+1 and it+2 are in flight while k-block
+            // `it` is converted (2 x 32-byte loads per thread and k-block -> ~32 KB in flight per SM)
+            float buf[3][2][8];
+            fetch(0, buf[0]);
+            fetch(1, buf[1]);
+            for (uint32_t base = 0; base < total_it; base += 3) {
+#pragma unroll
+                for (int u = 0; u < 3; u++) {
+                    const uint32_t it = base + u;
+                    if (it >= total_it) break;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    fetch(it + 2, buf[(u + 2) % 3]);
+                    const int kb = (int)(it % kblocks);
+                    const bool mine = (kb >= kb_seg1) ? prod1 : prod0;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    if (mine) {
+#pragma unroll
+                        for (int g = 0; g < 2; g++) {
+                            uint4 hi, lo;
+                            split8(buf[u][g], hi, lo);
+                            uint8_t* dst = st_base + s * STAGE_BYTES + g * SBO_BYTES;
+                            *(uint4*)dst = hi;
+                            if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
+                        }
+                        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    }
+                    mbar_arrive(bar_full + 8 * s);
+                }
             }
         }
     } else if (warp == W_WARP) {
-        // ================= weights: one bulk copy per stage ==========================================
+        // ================= bulk copies: weight tile (+ tile-packed activations) per stage ==============
         if (lane == 0) {
-            constexpr uint32_t bytes = (PASSES == 3 ? 2 : 1) * W_PART_BYTES;
+            constexpr uint32_t w_bytes = (PASSES == 3 ? 2 : 1) * W_PART_BYTES;
+            constexpr uint32_t a_bytes = (PASSES == 3 ? 2 : 1) * A_PART_BYTES;
+            const int kb0_blocks = kb_seg1, kb1_blocks = kblocks - kb_seg1;
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % n_tiles;
+                const int mt = tile / n_tiles, nt = tile % n_tiles;
                 for (int kb = 0; kb < kblocks; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const bool seg1 = kb >= kb_seg1;
+                    const uint8_t* apk = seg1 ? p.A1pk : p.A0pk;
+                    if (seg1 && p.K1 == 0) apk = nullptr;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                    mbar_arrive_expect_tx(bar_full + 8 * s, bytes);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, w_bytes + (apk ? a_bytes : 0u));
                     const uint8_t* src = p.Wp + ((size_t)nt * kblocks + kb) * (2 * W_PART_BYTES);
-                    bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_PART_BYTES, src, bytes, bar_full + 8 * s);
+                    bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_PART_BYTES, src, w_bytes, bar_full + 8 * s);
+                    if (apk) {
+                        const size_t blk = seg1 ? ((size_t)mt * kb1_blocks + (kb - kb_seg1)) : ((size_t)mt * kb0_blocks + kb);
+                        bulk_g2s(smem_base + s * STAGE_BYTES, apk + blk * TC_PK_BLOCK, a_bytes, bar_full + 8 * s);
+                    }
                 }
             }
         }
@@ -391,6 +374,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 const int n0 = nt * BN;
                 const int al = ptr_align_floats(p.C, p.ldc);
                 const bool fast = p.accumulate == 0 && (p.act == GM_ACT_LEAKY_RELU || p.act < 0);
+                uint8_t* const pk_row = p.Cpk ? p.Cpk + (size_t)mt * (size_t)(p.N / BK) * TC_PK_BLOCK + core_off(r, 0) : nullptr;
 #pragma unroll 1
                 for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 16) {
                     uint32_t v[16];
@@ -400,7 +384,6 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     ld_global_v8(bias_t + c + 8, bb + 8);
                     tmem_ld_wait();
                     if (!live || n0 + c >= p.N) continue;
-                    float* crow = p.C + m * p.ldc + n0 + c;
                     float o[16];
                     if (fast) {
                         const float slope = p.act < 0 ? 1.f : 0.01f;
@@ -413,21 +396,38 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             float x = __uint_as_float(v[i]) + bb[i];
-                            if (p.accumulate && n0 + c + i < p.N) x += crow[i];
+                            if (p.accumulate && n0 + c + i < p.N) x += p.C[m * p.ldc + n0 + c + i];
                             if (p.act >= 0) x = apply_act(x, p.act);
                             o[i] = x;
                         }
                     }
-                    if (n0 + c + 16 <= p.N && al >= 8) {
-                        st_global_v8(crow, o);
-                        st_global_v8(crow + 8, o + 8);
-                    } else if (n0 + c + 16 <= p.N && al >= 4) {
+                    if (p.C) {
+                        float* crow = p.C + m * p.ldc + n0 + c;
+                        if (n0 + c + 16 <= p.N && al >= 8) {
+                            st_global_v8(crow, o);
+                            st_global_v8(crow + 8, o + 8);
+                        } else if (n0 + c + 16 <= p.N && al >= 4) {
 #pragma unroll
-                        for (int i = 0; i < 4; i++) *(float4*)(crow + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                    } else {
+                            for (int i = 0; i < 4; i++) *(float4*)(crow + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if (n0 + c + i < p.N) crow[i] = o[i];
+                            for (int i = 0; i < 16; i++)
+                                if (n0 + c + i < p.N) crow[i] = o[i];
+                        }
+                    }
+                    if (pk_row) {  // tile-packed split copy for the next layer (N % 32 == 0 checked on the host)
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            const int n = n0 + c + 8 * q;
+                            float xx[8];
+#pragma unroll
+                            for (int i = 0; i < 8; i++) xx[i] = o[8 * q + i];
+                            uint4 hi, lo;
+                            split8(xx, hi, lo);
+                            uint8_t* dst = pk_row + (size_t)(n / BK) * TC_PK_BLOCK + ((n % BK) >> 3) * 128;
+                            *(uint4*)dst = hi;
+                            if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
+                        }
                     }
                 }
             } else {
@@ -435,6 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 // tile: [i | f | g | o] for hidden units nt*U .. nt*U+U-1 (U = BN/4).
                 constexpr int U = BN / 4;
                 const int j0 = nt * U;
+                uint8_t* const pk_row = p.Hpk ? p.Hpk + (size_t)mt * (size_t)(p.H / BK) * TC_PK_BLOCK + core_off(r, 0) : nullptr;
 #pragma unroll 1
                 for (int c = chalf * (U / 2); c < (chalf + 1) * (U / 2); c += 8) {
                     float cin[8], bi[8], bf[8], bg[8], bo[8];
@@ -461,9 +462,13 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     }
                     st_global_v8(p.h_out + m * p.ldh + j0 + c, hh);
                     st_global_v8(p.c_out + m * p.ldco + j0 + c, cc);
-                    if (p.h_out2) {
-                        st_global_v8(p.h_out2 + m * p.ldh2 + j0 + c, hh);
-                        st_global_v8(p.c_out2 + m * p.ldh2 + j0 + c, cc);
+                    if (pk_row) {
+                        const int n = j0 + c;
+                        uint4 hi, lo;
+                        split8(hh, hi, lo);
+                        uint8_t* dst = pk_row + (size_t)(n / BK) * TC_PK_BLOCK + ((n % BK) >> 3) * 128;
+                        *(uint4*)dst = hi;
+                        if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
                     }
                 }
             }
@@ -525,7 +530,7 @@ __global__ void pack_w_kernel(const float* __restrict__ W, int64_t ldw, const fl
         uint4 hi, lo;
         split8(x, hi, lo);
         size_t base = ((size_t)nt * kblocks + kb) * (size_t)(2 * BN * BK * 2);
-        size_t off = (size_t)(row >> 3) * (BK * 16) + (size_t)kc * 128 + (size_t)(row & 7) * 16;
+        size_t off = (size_t)(row >> 3) * SBO_BYTES + (size_t)kc * 128 + (size_t)(row & 7) * 16;
         *(uint4*)(out + base + off) = hi;
         *(uint4*)(out + base + (size_t)BN * BK * 2 + off) = lo;
     }
@@ -559,8 +564,8 @@ int tc_pick_bn(int N, int epi) {
 TcShape tc_shape(int N, int K0, int K1, int epi, int H) {
     TcShape s;
     s.BN = tc_pick_bn(N, epi);
-    s.K0p = (K1 > 0) ? (int)round_up(K0, 8) : K0;
-    s.Kp = (int)round_up(s.K0p + K1, tc::BK);
+    s.K0p = (int)round_up(K0, tc::BK);  // segment 1 starts on a k-block boundary
+    s.Kp = s.K0p + (int)round_up(K1, tc::BK);
     s.n_tiles = (epi == EPI_LSTM) ? ceil_div(H, s.BN / 4) : ceil_div(N, s.BN);
     s.w_bytes = (int64_t)s.n_tiles * (s.Kp / tc::BK) * 2 * s.BN * tc::BK * 2;
     s.packed_bytes = round_up(s.w_bytes + (int64_t)s.n_tiles * s.BN * 4, 256);
@@ -604,11 +609,23 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     a.m_tiles = (int)((a.M + tc::BM - 1) / tc::BM);
     GM_CHECK_ARG(((uintptr_t)a.Wp & 255) == 0, "packed weights must be 256-byte aligned");
     a.bias_tile = (const float*)(a.Wp + sh.w_bytes);
+    GM_CHECK_ARG((a.A0 != nullptr) != (a.A0pk != nullptr), "segment 0 needs exactly one of fp32 / tile-packed source");
+    GM_CHECK_ARG(a.K1 == 0 || ((a.A1 != nullptr) != (a.A1pk != nullptr)), "segment 1 needs exactly one of fp32 / tile-packed source");
+    GM_CHECK_ARG(a.A0pk == nullptr || ((a.K0 % tc::BK) == 0 && ((uintptr_t)a.A0pk & 127) == 0),
+                 "tile-packed segment 0: K %% 32 and 128-byte alignment");
+    GM_CHECK_ARG(a.K1 == 0 || a.A1pk == nullptr || ((a.K1 % tc::BK) == 0 && ((uintptr_t)a.A1pk & 127) == 0),
+                 "tile-packed segment 1: K %% 32 and 128-byte alignment");
+    a.has_prod = (a.A0 != nullptr) || (a.K1 > 0 && a.A1 != nullptr);
     if (epi == EPI_LSTM) {
         GM_CHECK_ARG(a.H % 64 == 0, "fused LSTM epilogue needs hidden %% 64 == 0, got %d", a.H);
-        GM_CHECK_ARG((a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 && (a.ldh2 & 7) == 0 &&
-                         (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out | (uintptr_t)a.h_out2 | (uintptr_t)a.c_out2) & 31) == 0,
+        GM_CHECK_ARG((a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 &&
+                         (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out) & 31) == 0 && ((uintptr_t)a.Hpk & 127) == 0,
                      "fused LSTM epilogue needs 32-byte aligned state rows");
+    } else {
+        GM_CHECK_ARG(a.C != nullptr || a.Cpk != nullptr, "no output");
+        GM_CHECK_ARG(a.Cpk == nullptr || ((a.N % tc::BK) == 0 && ((uintptr_t)a.Cpk & 127) == 0 && !a.accumulate),
+                     "tile-packed output needs N %% 32 == 0 and 128-byte alignment");
+        GM_CHECK_ARG(!a.accumulate || a.C != nullptr, "accumulate needs an fp32 output");
     }
     const int passes = math == GM_MATH_BF16 ? 1 : 3;
     if (epi == EPI_LSTM) return passes == 3 ? launch_tc<256, 3, EPI_LSTM>(a, s) : launch_tc<256, 1, EPI_LSTM>(a, s);

@@ -6,25 +6,32 @@ namespace gm {
 
 enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
 
+// "pk" = tile-packed split activations: an fp32 matrix [R, Kact] (Kact % 32 == 0) stored as bf16
+// hi/lo core matrices exactly as the tensor core reads them from shared memory, one 16 KiB block
+// per (128-row tile mt, 32-column k-block kb) at ((mt * Kact/32) + kb) * 16 KiB:
+//   hi part at +0, lo part at +8 KiB; element (r, k) at (r>>3)*512 + ((k&31)>>3)*128 + (r&7)*16 + (k&7)*2
+// Producing layers write it from their epilogue, consuming layers pull it with one bulk copy per
+// k-block, so no thread touches the activations between layers.
+constexpr int TC_BM = 128, TC_BK = 32;
+constexpr int64_t TC_PK_BLOCK = 2 * TC_BM * TC_BK * 2;  // 16 KiB
+inline int64_t tc_pk_bytes(int64_t rows, int kact) { return ((rows + TC_BM - 1) / TC_BM) * (int64_t)(kact / TC_BK) * TC_PK_BLOCK; }
+
 struct TcArgs {
-    // activations: logical row = [A0[m, 0:K0] | A1[m, 0:K1]] (A1 optional)
-    const float* A0; int64_t lda0; int K0;
-    const float* A1; int64_t lda1; int K1;
-    int K0p, Kp;  // filled by tc_launch: start of segment 1 / total K in the packed K space
-    // optional aggregation of segment 0 over adjacency lists: row m = (graph b, node v) reads
-    // sum_q A0[b*nodes + nbr[list(b)][v][q]] for q < deg (model.py:213-229)
-    const int* nbr; const int* deg; int DM; const int* list_index; int nodes; int mean;
+    // activations: logical row = [seg0 | seg1]; each segment is either fp32 row-major (A*, lda*) read by
+    // the producer warps, or tile-packed (A*pk) pulled by bulk copies.  seg1 optional (K1 = 0).
+    const float* A0; int64_t lda0; const uint8_t* A0pk; int K0;
+    const float* A1; int64_t lda1; const uint8_t* A1pk; int K1;
+    int K0p, Kp;              // filled by tc_launch: start of segment 1 / total K in the packed K space
     const uint8_t* Wp;        // weights (+ tile-ordered bias behind them) packed by tc_pack_weights
     const float* bias_tile;   // filled by tc_launch
-    // EPI_LINEAR
-    float* C; int64_t ldc; int act; int accumulate;
+    // EPI_LINEAR: C fp32 row-major (may be NULL) and/or Cpk tile-packed (may be NULL)
+    float* C; int64_t ldc; uint8_t* Cpk; int act; int accumulate;
     int64_t M; int N;
-    // EPI_LSTM: c' = sig(f)*c_in + sig(i)*tanh(g), h' = sig(o)*tanh(c'); optional second copy
+    // EPI_LSTM: c' = sig(f)*c_in + sig(i)*tanh(g), h' = sig(o)*tanh(c'); h also tile-packed if Hpk
     const float* c_in; int64_t ldc_in;
-    float* h_out; int64_t ldh; float* c_out; int64_t ldco;
-    float* h_out2; float* c_out2; int64_t ldh2;
+    float* h_out; int64_t ldh; float* c_out; int64_t ldco; uint8_t* Hpk;
     int H;
-    int m_tiles, n_tiles;  // filled by tc_launch
+    int m_tiles, n_tiles, has_prod;  // filled by tc_launch
 };
 
 struct TcShape {

@@ -9,6 +9,8 @@
 // neighbour lists (self included when the mask has it) instead of the reference's dense
 // [B,N,N] float mask, so aggregation is a coalesced row gather + register sum and the
 // readout is a pure gather.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "linear_simt.cuh"
@@ -67,6 +69,60 @@ __global__ void aggregate_kernel(const float* __restrict__ h, int64_t ldh, float
         if (mean) { acc.x /= (float)max(dg, 1); acc.y /= (float)max(dg, 1); acc.z /= (float)max(dg, 1); acc.w /= (float)max(dg, 1); }
         *(float4*)(M + row * H + c) = acc;
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// aggregation for the tensor-core cell: same sum (ascending list order) but written tile-packed
+// (bf16 hi/lo core matrices, gemm_sm100.cuh) so the update cell pulls M with bulk copies.
+// warp = 8 rows x one 32-column k-block; lane = (r8 = lane/4, part = lane%4) owns 8 floats: every
+// warp load touches 8 rows x one 128-byte line, every warp store fills 4 complete 128-byte lines.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t agg_pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
+                                                           int B, int N, int H, const int* __restrict__ nbr,
+                                                           const int* __restrict__ deg, int DM,
+                                                           const int* __restrict__ list_index, int mean, int write_lo) {
+    const int lane = threadIdx.x & 31;
+    const int kbs = H / TC_BK;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t R = (int64_t)B * N;
+    const int64_t row = (gw / kbs) * 8 + (lane >> 2);
+    const int kb = (int)(gw % kbs), part = lane & 3;
+    if (row >= R) return;
+    const int b = (int)(row / N), v = (int)(row - (int64_t)b * N);
+    const int li = list_index ? list_index[b] : b;
+    const int* lst = nbr + ((size_t)li * N + v) * DM;
+    const int dg = deg[(size_t)li * N + v];
+    const float* hb = h + (size_t)b * N * ldh + kb * TC_BK + part * 8;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = 0.f;
+    for (int q = 0; q < dg; q++) {
+        const float4* src = (const float4*)(hb + (size_t)lst[q] * ldh);
+        float4 a = __ldg(src), c = __ldg(src + 1);
+        x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += c.x; x[5] += c.y; x[6] += c.z; x[7] += c.w;
+    }
+    if (mean) {
+        const float d = (float)max(dg, 1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = x[i] / d;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        __nv_bfloat16 a = __float2bfloat16_rn(x[2 * i]), c = __float2bfloat16_rn(x[2 * i + 1]);
+        hi[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(c) << 16);
+        lo[i] = agg_pack2(x[2 * i] - __bfloat162float(a), x[2 * i + 1] - __bfloat162float(c));
+    }
+    const int64_t mt = row / TC_BM;
+    const int r = (int)(row - mt * TC_BM);
+    uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16;
+    *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -252,7 +308,6 @@ struct NetmonPack {
     bool fused_cells;
 };
 
-static bool tc_math(int math) { return math == GM_MATH_BF16X3 || math == GM_MATH_BF16; }
 
 static NetmonPack pack_layout(const gm_netmon_params* p) {
     NetmonPack L{};
@@ -299,8 +354,11 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
 
 struct NetmonWs {
     float *act0, *act1, *g0, *g1, *hA, *hB, *cA, *cB, *M, *gmean;
+    uint8_t *pk0, *pk1, *e_pk, *m_pk, *h_pk0, *h_pk1;  // tile-packed activations of the tensor-core path
     int64_t bytes;
 };
+
+static bool tc_math(int math) { return math == GM_MATH_BF16X3 || math == GM_MATH_BF16; }
 
 static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
     NetmonWs w;
@@ -320,6 +378,12 @@ static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
     w.hA = take(R * H); w.hB = take(R * H); w.cA = take(R * H); w.cB = take(R * H);
     w.M = take(R * H);
     w.gmean = take((int64_t)max(B, 1) * H);
+    w.pk0 = w.pk1 = w.e_pk = w.m_pk = w.h_pk0 = w.h_pk1 = nullptr;
+    if (tc_math(p->math)) {
+        auto take_pk = [&](int width) { return (uint8_t*)take(tc_pk_bytes(R, (int)round_up(width, TC_BK)) / 4 + 64); };
+        w.pk0 = take_pk(maxw); w.pk1 = take_pk(maxw);
+        w.e_pk = take_pk(H); w.m_pk = take_pk(H); w.h_pk0 = take_pk(H); w.h_pk1 = take_pk(H);
+    }
     w.bytes = off + (32 << 20);  // + room for per-call packed weights of the unfused tensor-core layers
     return w;
 }
@@ -406,19 +470,29 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     }
 
     // ---- encoder MLP (model.py:489): activation after every layer incl. the last ----------
+    // Tensor-core path with fused cells: layer outputs stay tile-packed (bf16 hi/lo) and are pulled
+    // by the next layer with bulk copies; the last layer feeds the rnn_obs cell the same way.
+    const bool fused = tc && PL.fused_cells;
     const float* x = node_obs;
+    const uint8_t* xpk = nullptr;
     int64_t ldx = p->in_features;
     int kin = p->in_features;
     for (int l = 0; l < L; l++) {
         float* y = (l & 1) ? w.act1 : w.act0;
         int rc;
         if (tc) {
+            const int U = p->enc_units[l];
+            const bool out_pk = fused && (U % TC_BK) == 0;
+            uint8_t* ypk = (l == L - 1) ? w.e_pk : ((l & 1) ? w.pk1 : w.pk0);
             TcArgs a{};
-            a.A0 = x; a.lda0 = ldx; a.K0 = kin;
+            if (xpk) a.A0pk = xpk; else { a.A0 = x; a.lda0 = ldx; }
+            a.K0 = kin;
             a.Wp = (const uint8_t*)packed + PL.enc[l];
-            a.C = y; a.ldc = p->enc_units[l]; a.act = p->activation;
-            a.M = R; a.N = p->enc_units[l];
+            if (out_pk) a.Cpk = ypk; else { a.C = y; a.ldc = U; }
+            a.act = p->activation;
+            a.M = R; a.N = U;
             rc = tc_launch(a, math, EPI_LINEAR, s);
+            xpk = out_pk ? ypk : nullptr;
         } else {
             LinearArgs a{x, ldx, p->enc_w[l], kin, p->enc_b[l], nullptr, y, p->enc_units[l], R, p->enc_units[l], kin,
                          p->activation, 0};
@@ -427,7 +501,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         if (rc) return rc;
         x = y; ldx = p->enc_units[l]; kin = p->enc_units[l];
     }
-    const float* e = x;  // [R,H]
+    const float* e = x;  // [R,H] (fp32 path) / xpk (tile-packed path)
 
     const float* h = e;
     int64_t ldh_cur = H;
@@ -436,36 +510,42 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     float* hbuf[2] = {w.hA, w.hB};
     float* cbuf[2] = {w.cA, w.cB};
 
-    if (tc && PL.fused_cells && DM <= 4) {
-        // ===== fused tensor-core path: one launch per cell.  The producer warps gather and sum the
-        // neighbour rows (aggregation), the gate GEMM [x | h] x [W_ih | W_hh]^T runs on tcgen05 and
-        // the LSTM pointwise is the epilogue, so M and the gates never touch HBM. =====
-        auto cell = [&](int64_t woff, const gm_cell_params& cp, const float* xin, int64_t ldxin, bool gather, const float* hp,
-                        int64_t ldhp, const float* cprev, int64_t ldcp, float* hn, int64_t ldhn, float* cn, int64_t ldcn) -> int {
+    if (fused) {
+        // ===== fused tensor-core path: one launch per cell.  Gate GEMM [x | h] x [W_ih | W_hh]^T on
+        // tcgen05 with the LSTM pointwise as epilogue (gates never touch HBM); x and h arrive
+        // tile-packed by bulk copy, the new h leaves both as fp32 (state, readout, aggregation) and
+        // tile-packed (next cell). =====
+        uint8_t* hpk[2] = {w.h_pk0, w.h_pk1};
+        auto cell = [&](int64_t woff, const uint8_t* xin_pk, const float* xin, const uint8_t* hp_pk, const float* hp, int64_t ldhp,
+                        const float* cprev, int64_t ldcp, float* hn, int64_t ldhn, float* cn, int64_t ldcn, uint8_t* hn_pk) -> int {
             TcArgs a{};
-            a.A0 = xin; a.lda0 = ldxin; a.K0 = H;
-            a.A1 = hp; a.lda1 = ldhp; a.K1 = H;
-            if (gather) {
-                a.nbr = nbr_all; a.deg = deg; a.DM = DM; a.list_index = list_index; a.nodes = N;
-                a.mean = p->agg_type == GM_AGG_MEAN;
-            }
+            if (xin_pk) a.A0pk = xin_pk; else { a.A0 = xin; a.lda0 = H; }
+            a.K0 = H;
+            if (hp_pk) a.A1pk = hp_pk; else { a.A1 = hp; a.lda1 = ldhp; }
+            a.K1 = H;
             a.Wp = (const uint8_t*)packed + woff;
             a.c_in = cprev; a.ldc_in = ldcp;
-            a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn;
+            a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn; a.Hpk = hn_pk;
             a.H = H; a.M = R; a.N = 4 * H;
             return tc_launch(a, math, EPI_LSTM, s);
         };
-        int rc = cell(PL.obs, p->rnn_obs, e, H, false, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], H);  // :491
+        // rnn_obs (:491): x = encoder output, (h, c) = carried state (fp32, split by the producer warps)
+        int rc = cell(PL.obs, xpk, e, nullptr, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], H, hpk[0]);
         if (rc) return rc;
         h = hbuf[0]; c = cbuf[0];
         int cur = 0;
+        const int kbs = H / TC_BK;
+        const unsigned agg_blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
         for (int it = 0; it < K; it++) {  // :509-554
             const bool final_it = it == K - 1;
             if (final_it) last = h;
-            float* hn = final_it ? state_out : hbuf[cur ^ 1];       // the last cell writes the new state in place (:562-564)
+            aggregate_pk_kernel<<<agg_blocks, 256, 0, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
+                                                           p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16);
+            GM_LAUNCH_CHECK();
+            float* hn = final_it ? state_out : hbuf[cur ^ 1];  // the last cell writes the new state in place (:562-564)
             float* cn = final_it ? state_out + H : cbuf[cur ^ 1];
             int64_t ldn = final_it ? S : H;
-            rc = cell(PL.upd, p->rnn_update, h, H, true, h, H, c, H, hn, ldn, cn, ldn);
+            rc = cell(PL.upd, w.m_pk, nullptr, hpk[cur], nullptr, 0, c, H, hn, ldn, cn, ldn, final_it ? nullptr : hpk[cur ^ 1]);
             if (rc) return rc;
             h = hn; c = cn; ldh_cur = ldn; cur ^= 1;
         }
