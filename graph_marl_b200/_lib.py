@@ -62,7 +62,9 @@ class DqnParams(C.Structure):
 
 class ReplayField(C.Structure):
     _fields_ = [("ring", C.c_void_p), ("src", C.c_void_p), ("dst", C.c_void_p),
-                ("elem_bytes", C.c_int64), ("convert", C.c_int32), ("pad", C.c_int32)]
+                ("elem_bytes", C.c_int64), ("convert", C.c_int32), ("broadcast", C.c_int32),
+                ("rows", C.c_int32), ("pad", C.c_int32), ("row_bytes", C.c_int64), ("ring_pitch", C.c_int64),
+                ("ring_offset", C.c_int64)]
 
 
 _lib = None
@@ -92,8 +94,9 @@ _SIGS = {
                                   C.c_void_p, C.c_void_p]),
     "gm_netmon_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p]),
+    "gm_packed_activation_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "gm_netmon_map_to_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]),
     "gm_dqn_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
@@ -102,7 +105,7 @@ _SIGS = {
     "gm_dqn_packed_bytes": (C.c_int64, [C.c_void_p, C.c_int32]),
     "gm_dqn_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_dqn_act": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
-                             C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64,
+                             C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64,
                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_replay_insert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "gm_replay_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

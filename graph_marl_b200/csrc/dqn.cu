@@ -124,10 +124,11 @@ int gm_dqn_pack_weights(const gm_dqn_params* p, int32_t split, void* packed, int
 }
 
 int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda, const float* obs_g,
-               int32_t Dg, int64_t ldg, const uint8_t* action_mask, double epsilon, const int32_t* rand_action,
+               int32_t Dg, int64_t ldg, const void* obs_g_pk, const uint8_t* action_mask, double epsilon, const int32_t* rand_action,
                const double* rand_u, uint64_t philox_seed, uint64_t philox_step, float* q_out, int32_t* act_out,
                void* workspace, int64_t workspace_bytes, void* stream) {
     GM_CHECK_ARG(p && obs_a && act_out && workspace, "null pointer");
+    GM_CHECK_ARG(Dg == 0 || obs_g || obs_g_pk, "obs_g missing");
     GM_CHECK_ARG(p->n_layers >= 1 && p->n_layers <= GM_MAX_LAYERS, "n_layers");
     GM_CHECK_ARG(p->n_actions >= 1 && p->n_actions <= MAX_ACT, "n_actions %d > %d", p->n_actions, MAX_ACT);
     GM_CHECK_ARG(Da + Dg == p->in_features, "Da+Dg=%d != in_features %d", Da + Dg, p->in_features);
@@ -164,7 +165,11 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
             TcArgs a{};
             if (l == 0) {
                 a.A0 = obs_a; a.lda0 = lda; a.K0 = Da;
-                if (Dg > 0) { a.A1 = obs_g; a.lda1 = ldg; a.K1 = Dg; }
+                if (Dg > 0) {
+                    if (obs_g_pk && (Dg % TC_BK) == 0) a.A1pk = (const uint8_t*)obs_g_pk;  // bulk-copied, no producer work
+                    else { a.A1 = obs_g; a.lda1 = ldg; }
+                    a.K1 = Dg;
+                }
             } else {
                 if (xpk) a.A0pk = xpk; else { a.A0 = x; a.lda0 = ldx; }
                 a.K0 = kin;

@@ -16,7 +16,13 @@ int linear_dispatch(const LinearArgs& a, int math, void* ws, int64_t ws_bytes, c
 
 }  // namespace gm
 
+#include "gemm_sm100.cuh"
+
 extern "C" {
+
+int64_t gm_packed_activation_bytes(int64_t rows, int32_t width) {
+    return gm::tc_pk_bytes(rows, (int)gm::round_up(width, gm::TC_BK));
+}
 
 int64_t gm_linear_workspace_bytes(int64_t M, int32_t N, int32_t K, int32_t math) {
     if (math == GM_MATH_FP32) return 0;

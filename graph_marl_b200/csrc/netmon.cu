@@ -286,6 +286,73 @@ __global__ void readout_kernel(const float* __restrict__ h, int64_t ldh, const f
     }
 }
 
+// Agent readout for the tensor-core DQN: the same rows as readout_kernel(agent_node != NULL) but one
+// warp = 8 agent rows x one 32-column k-block (lane = (r8, part) owns 8 floats), written as fp32
+// rows (32-byte stores, 8 rows x one 128-byte line per warp instruction) and/or tile-packed bf16
+// hi/lo (gemm_sm100.cuh) so the DQN's first layer pulls the graph observation with bulk copies.
+__global__ void __launch_bounds__(256) readout_agents_pk_kernel(
+    const float* __restrict__ h, int64_t ldh, const float* __restrict__ last, int64_t ldl, const float* __restrict__ gmean,
+    const int* __restrict__ nbr, const int* __restrict__ deg, int DM, const int* __restrict__ list_index,
+    const int* __restrict__ agent_node, int A, int B, int N, int H, int use_nbr, int use_glob, int max_degree,
+    float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_pk, int write_lo) {
+    const int lane = threadIdx.x & 31;
+    const int O = H + (use_glob ? H : 0) + (use_nbr ? max_degree * H : 0);
+    const int kbs = O / TC_BK;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t rows = (int64_t)B * A;
+    const int64_t row = (gw / kbs) * 8 + (lane >> 2);
+    const int kb = (int)(gw % kbs), part = lane & 3;
+    if (row >= rows) return;
+    const int b = (int)(row / A);
+    const int v = agent_node[row];
+    const int col = kb * TC_BK + part * 8;
+    int seg = col / H;
+    const int within = col - seg * H;
+    const float* src = nullptr;
+    if (seg == 0) {
+        src = h + ((size_t)b * N + v) * ldh + within;
+    } else if (use_glob && seg == 1) {
+        src = gmean + (size_t)b * H + within;
+    } else {
+        int slot = seg - 1 - (use_glob ? 1 : 0);
+        const int li = list_index ? list_index[b] : b;
+        const int* lst = nbr + ((size_t)li * N + v) * DM;
+        const int dg = deg[(size_t)li * N + v];
+        for (int q = 0; q < dg; q++) {
+            int u = lst[q];
+            if (u == v) continue;
+            if (slot-- == 0) { src = last + ((size_t)b * N + u) * ldl + within; break; }
+        }
+    }
+    float x[8];
+    if (src) {
+        float4 a = __ldg((const float4*)src), c = __ldg((const float4*)src + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = 0.f;
+    }
+    if (out) {
+        float4* o = (float4*)(out + row * ldo + col);
+        o[0] = make_float4(x[0], x[1], x[2], x[3]);
+        o[1] = make_float4(x[4], x[5], x[6], x[7]);
+    }
+    if (out_pk) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            __nv_bfloat16 a = __float2bfloat16_rn(x[2 * i]), c = __float2bfloat16_rn(x[2 * i + 1]);
+            hi[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(c) << 16);
+            lo[i] = agg_pack2(x[2 * i] - __bfloat162float(a), x[2 * i + 1] - __bfloat162float(c));
+        }
+        const int64_t mt = row / TC_BM;
+        const int r = (int)(row - mt * TC_BM);
+        uint8_t* dst = out_pk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16;
+        *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
 // general node->agent mapping (model.py:629-631) for a non-one-hot matrix
 __global__ void map_to_agents_kernel(const float* __restrict__ node_out, const float* __restrict__ nam, int B, int N,
                                      int A, int O, float* __restrict__ agent_out) {
@@ -430,7 +497,8 @@ int gm_netmon_map_to_agents(const float* node_out, const float* node_agent, int3
 int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs, const int32_t* nbr_all,
                       const int32_t* deg, int32_t DM, const int32_t* list_index, const float* state_in,
                       float* state_out, int32_t max_degree, float* node_out, const int32_t* agent_node, int32_t A,
-                      float* agent_out, int64_t agent_out_ld, void* workspace, int64_t workspace_bytes, void* stream) {
+                      float* agent_out, int64_t agent_out_ld, void* agent_out_pk, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
     GM_CHECK_ARG(p && node_obs && nbr_all && deg && state_out && workspace, "null pointer");
     GM_CHECK_ARG(B > 0 && N > 0 && DM > 0, "bad sizes");
     const int H = p->hidden, K = p->iterations, L = p->n_enc_layers;
@@ -667,7 +735,19 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                                                               O);
         GM_LAUNCH_CHECK();
     }
-    if (agent_out) {
+    if (agent_out_pk) {
+        GM_CHECK_ARG(agent_node && A > 0 && (H % TC_BK) == 0 && ((uintptr_t)agent_out_pk & 127) == 0 &&
+                         (agent_out == nullptr || (agent_out_ld >= O && (agent_out_ld & 3) == 0 && ((uintptr_t)agent_out & 15) == 0)) &&
+                         (ldh_cur & 3) == 0,
+                     "tile-packed agent readout needs agent_node, hidden %% 32 == 0 and 16-byte aligned rows");
+        int64_t rows = (int64_t)B * A;
+        const int kbs = O / TC_BK;
+        const unsigned blocks = (unsigned)((((rows + 7) / 8) * kbs + 7) / 8);
+        readout_agents_pk_kernel<<<blocks, 256, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index, agent_node, A, B,
+                                                        N, H, use_nbr, use_glob, max_degree, agent_out, agent_out_ld,
+                                                        (uint8_t*)agent_out_pk, math != GM_MATH_BF16);
+        GM_LAUNCH_CHECK();
+    } else if (agent_out) {
         GM_CHECK_ARG(agent_node && A > 0 && agent_out_ld >= O, "agent readout needs agent_node, A, ld >= %d", O);
         int64_t rows = (int64_t)B * A;
         readout_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index,

@@ -17,21 +17,36 @@ struct ReplayFields {
     int n;
 };
 
-// grid.y = field, grid.x strides over (transition, 16-byte / 4-byte / 1-byte unit)
+// grid.y = field, grid.x strides over (transition, 16 / 8 / 4 / 1-byte unit)
 __global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t index, int64_t n) {
     const gm_replay_field fd = F.f[blockIdx.y];
     const int64_t eb = fd.elem_bytes;
-    const bool v16 = (eb % 16 == 0) && (((uintptr_t)fd.ring | (uintptr_t)fd.src) % 16 == 0);
-    const bool v4 = (eb % 4 == 0) && (((uintptr_t)fd.ring | (uintptr_t)fd.src) % 4 == 0);
-    const int unit = v16 ? 16 : (v4 ? 4 : 1);
-    const int64_t upe = eb / unit;  // units per element
-    const int64_t total = n * upe;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        int64_t i = t / upe, u = t - i * upe;
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (fd.convert == 4) {  // int32 source elements -> int8 ring elements (actions)
+        const int64_t total = n * eb;
+        for (int64_t t = tid0; t < total; t += nthreads) {
+            int64_t i = t / eb, e = t - i * eb;
+            int64_t slot = (index + i) % capacity;
+            ((int8_t*)fd.ring)[slot * eb + e] = (int8_t)((const int32_t*)fd.src)[(fd.broadcast ? 0 : i) * eb + e];
+        }
+        return;
+    }
+    const bool two_d = fd.rows > 0;
+    const int64_t rb = two_d ? fd.row_bytes : eb;           // contiguous run
+    const int64_t runs = two_d ? fd.rows : 1;               // runs per transition
+    const uintptr_t align_bits = (uintptr_t)fd.ring | (uintptr_t)fd.src | (uintptr_t)rb | (uintptr_t)eb |
+                                 (two_d ? ((uintptr_t)fd.ring_pitch | (uintptr_t)fd.ring_offset) : 0);
+    const int unit = (align_bits % 16 == 0) ? 16 : (align_bits % 8 == 0) ? 8 : (align_bits % 4 == 0) ? 4 : 1;
+    const int64_t upr = rb / unit;  // units per run
+    const int64_t total = n * runs * upr;
+    for (int64_t t = tid0; t < total; t += nthreads) {
+        int64_t u = t % upr, q = t / upr;
+        int64_t row = q % runs, i = q / runs;
         int64_t slot = (index + i) % capacity;
-        const char* s = (const char*)fd.src + i * eb + u * unit;
-        char* d = (char*)fd.ring + slot * eb + u * unit;
+        const char* s = (const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * unit;
+        char* d = (char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * unit;
         if (unit == 16) *(uint4*)d = *(const uint4*)s;
+        else if (unit == 8) *(uint2*)d = *(const uint2*)s;
         else if (unit == 4) *(uint32_t*)d = *(const uint32_t*)s;
         else *d = *s;
     }
@@ -72,6 +87,11 @@ int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t ca
     int64_t maxb = 0;
     for (int i = 0; i < n_fields; i++) {
         GM_CHECK_ARG(fields[i].ring && fields[i].src && fields[i].elem_bytes > 0, "field %d: null ring/src", i);
+        GM_CHECK_ARG(fields[i].convert == 0 || fields[i].convert == 4, "field %d: insert convert %d", i, fields[i].convert);
+        GM_CHECK_ARG(fields[i].rows == 0 ||
+                         (fields[i].row_bytes > 0 && fields[i].ring_offset >= 0 &&
+                          fields[i].ring_offset + (fields[i].rows - 1) * fields[i].ring_pitch + fields[i].row_bytes <= fields[i].elem_bytes),
+                     "field %d: 2-D block does not fit the ring element", i);
         F.f[i] = fields[i];
         maxb = max(maxb, fields[i].elem_bytes * n);
     }

@@ -247,7 +247,7 @@ class Routing(NetworkEnv):
         if self.batched:
             info = dict(looped=out["info"][:, 0], throughput=out["info"][:, 1], dropped=out["info"][:, 2],
                         blocked=out["info"][:, 3], delays=out["delays"], arrived=out["arrived"], spr=out["spr"])
-            return out["obs"], out["adj"], out["reward"], out["done"].bool(), info
+            return out["obs"], out["adj"], out["reward"], out["done"].view(torch.bool), info
         n = int(out["n_resets"][0].item())
         if rng_state is not None and n > 0:
             _, _, _, new_state = self._native_draws(rng_state, n)

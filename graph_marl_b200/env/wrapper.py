@@ -85,6 +85,8 @@ class NetMonWrapper:
             self.node_agent_matrix = env.get_node_agent_matrix()
         if self.frozen:
             # wrapper.py:67-75: agents keep reading the frozen node outputs at their new position
+            if self.netmon_out is None:
+                raise RuntimeError("freeze() needs the node readout: construct NetMonWrapper with split_obs=False")
             idx = agent_node.long().unsqueeze(-1).expand(-1, -1, self.netmon_out.shape[-1])
             return self._ret(torch.gather(self.netmon_out, 1, idx))
         if not self._batched:
@@ -93,7 +95,11 @@ class NetMonWrapper:
         with torch.no_grad():
             self.last_netmon_state = self.current_netmon_state
             self.netmon.state = self.current_netmon_state
+            # batched split mode: only the agents' rows are read out (plus their tile-packed copy for
+            # the tensor-core DQN); the full node readout is kept for compat / freeze()
+            lean = self._batched and self.split_obs
             self.netmon_out, agent_out = self.netmon.forward_lists(
-                node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=True)
+                node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=not lean,
+                want_agent_pk=lean)
             self.current_netmon_state = self.netmon.state
         return self._ret(agent_out)

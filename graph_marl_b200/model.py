@@ -176,9 +176,13 @@ class DQN(nn.Module):
         a2 = _rows2d(obs_a)
         rows = a2.shape[0]
         g2, Dg = None, 0
+        g_pk = None
         if obs_g is not None:
             Dg = obs_g.shape[-1]
             g2 = _rows2d(obs_g)
+            pk = getattr(obs_g, "_gm_pk", None)  # tile-packed copy written by NetMon's readout (same math mode)
+            if pk is not None and pk[1] == self.math and self.math != "fp32":
+                g_pk = pk[0]
         dev = obs_a.device
         p = self._params(split=Da if g2 is not None else 0)
         nbytes = _lib.lib().gm_dqn_workspace_bytes(C.byref(p), rows)
@@ -190,7 +194,7 @@ class DQN(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gm_dqn_act(
                 C.byref(p), rows, a2.data_ptr(), Da, a2.stride(0), _lib.ptr(g2), Dg, 0 if g2 is None else g2.stride(0),
-                _lib.ptr(action_mask), float(epsilon), _lib.ptr(rand_action), _lib.ptr(rand_u), int(seed), int(step),
+                _lib.ptr(g_pk), _lib.ptr(action_mask), float(epsilon), _lib.ptr(rand_action), _lib.ptr(rand_u), int(seed), int(step),
                 _lib.ptr(q), act.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream()))
         return (None if q is None else q.reshape(*lead, self.num_actions)), act.reshape(lead)
 
@@ -320,7 +324,7 @@ class NetMon(nn.Module):
         return H + (H if self.output_global_hidden else 0) + (max_degree * H if self.output_neighbor_hidden else 0)
 
     def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
-                      want_node_out=False, agent_out=None):
+                      want_node_out=False, agent_out=None, want_agent_pk=False):
         """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
         nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
         Updates self.state; returns (node_out | None, agent_out | None)."""
@@ -346,6 +350,9 @@ class NetMon(nn.Module):
             if agent_out is None:
                 agent_out = torch.empty((B, A, O), dtype=torch.float32, device=dev)
             ld = agent_out.stride(-2)
+        agent_pk = None
+        if want_agent_pk and agent_node is not None and self.math != "fp32" and self.hidden_features % 32 == 0:
+            agent_pk = torch.empty(int(_lib.lib().gm_packed_activation_bytes(B * A, O)), dtype=torch.uint8, device=dev)
         DM = nbr_all.shape[-1]
         if list_index is None and nbr_all.shape[0] != B:
             if nbr_all.shape[0] != 1:
@@ -355,9 +362,11 @@ class NetMon(nn.Module):
             _lib.check(_lib.lib().gm_netmon_forward(
                 C.byref(p), B, N, x.data_ptr(), nbr_all.data_ptr(), deg.data_ptr(), DM, _lib.ptr(list_index),
                 _lib.ptr(st_in), st_out.data_ptr(), max_degree, _lib.ptr(node_out), _lib.ptr(agent_node), A,
-                _lib.ptr(agent_out) if agent_node is not None else None, ld, ws.data_ptr(), ws.numel(),
+                _lib.ptr(agent_out) if agent_node is not None else None, ld, _lib.ptr(agent_pk), ws.data_ptr(), ws.numel(),
                 _lib.current_stream()))
         self.state = st_out
+        if agent_pk is not None:
+            agent_out._gm_pk = (agent_pk, self.math)  # consumed by DQN.act of the same math mode
         return node_out, (agent_out if agent_node is not None else None)
 
     @staticmethod

@@ -50,40 +50,58 @@ class ReplayBuffer(object):
         self._shapes = shapes
         for name, (shape, dt) in shapes.items():
             setattr(self, name, torch.zeros((self.buffer_size, *shape), dtype=dt, device=self.device))
+        self._consts = {}
         self._random_generator = np.random.default_rng(seed)
         # dtype conversion of _get_transition_batch (replaybuffer.py:132-187)
         self._out_dtype = {n: torch.float32 for n in shapes}
         self._out_dtype.update(action=torch.int64, done=torch.bool, episode_done=torch.bool)
 
     # ---- insert ------------------------------------------------------------------------------
-    def _as_ring_dtype(self, name, value, n):
+    def _source(self, name, value, n):
+        """(tensor, convert, broadcast) for one ring field without staging copies where possible:
+        0/1 int8/uint8 tensors are reinterpreted as bool, int32 actions are narrowed by the insert
+        kernel, python scalars / expanded (stride-0) tensors are written as one broadcast transition."""
         shape, dt = self._shapes[name]
-        ring = getattr(self, name)
-        if isinstance(value, (int, float)) and not isinstance(value, bool) and ring[0].numel() != 1:
-            # the reference passes the scalar 0 for absent states (main.py:659,695): broadcast
-            return torch.full((n, *shape), value, dtype=dt, device=self.device)
+        numel = int(np.prod(shape, dtype=np.int64))
+        if isinstance(value, (bool, int, float)):
+            key = (name, value)
+            if key not in self._consts:  # e.g. the scalar 0 for absent states (main.py:659,695), episode_done
+                self._consts[key] = torch.full((1, *shape), value, dtype=dt, device=self.device)
+            return self._consts[key], 0, 1
         t = torch.as_tensor(value)
         if name == "agent_state" and t.dim() == len(shape) + 1 and n == 1 and t.shape[0] == 1:
             t = t.squeeze(0)  # replaybuffer.py:272-273
-        t = t.to(self.device)
+        if t.device != self.device:
+            t = t.to(self.device)
+        bcast = 0
+        if t.dim() == len(shape) + 1 and t.shape[0] == n and n > 1 and t.stride(0) == 0:
+            t, bcast = t[:1], 1  # expanded per-topology tensor (node_adj, node_aux): one copy for all envs
+        rows = 1 if bcast else n
+        convert = 0
         if t.dtype != dt:
-            t = (t != 0) if dt == torch.bool else t.to(dt)
-        if t.numel() != n * int(np.prod(shape, dtype=np.int64)):
-            t = torch.broadcast_to(t, (n, *shape))
-        return t.reshape(n, *shape).contiguous()
+            if dt == torch.bool and t.dtype in (torch.int8, torch.uint8):
+                t = t.contiguous().view(torch.bool)  # env outputs are exactly 0/1
+            elif dt == torch.int8 and t.dtype == torch.int32 and name == "action":
+                convert = 4
+            else:
+                t = (t != 0) if dt == torch.bool else t.to(dt)
+        if t.numel() != rows * numel:
+            t = torch.broadcast_to(t, (rows, *shape))
+        return t.reshape(rows, *shape).contiguous(), convert, bcast
 
     def add(self, obs, action, reward, next_obs, adj, next_adj, done, episode_done, agent_state, node_state,
             node_aux, node_obs, node_adj, node_agent_matrix, next_node_obs, next_node_adj,
             next_node_agent_matrix, num=1):
         """One transition (reference call, replaybuffer.py:243-287) or `num` transitions whose
-        arguments carry a leading dimension of size num (batched rollout)."""
+        arguments carry a leading dimension of size num (batched rollout).  `obs` / `next_obs` may be
+        (agent_obs, graph_obs) pairs: both parts land in the joint ring row without a concat."""
         _lib.require_device()
         vals = dict(zip(ADD_ORDER, (obs, action, reward, next_obs, adj, next_adj, done, episode_done, agent_state,
                                     node_state, node_aux, node_obs, node_adj, node_agent_matrix, next_node_obs,
                                     next_node_adj, next_node_agent_matrix)))
         n = int(num)
         assert n <= self.buffer_size
-        fields = (_lib.ReplayField * len(ADD_ORDER))()
+        fields = (_lib.ReplayField * _lib.GM_REPLAY_MAX_FIELDS)()
         keep = []
         k = 0
         for name in ADD_ORDER:
@@ -91,9 +109,28 @@ class ReplayBuffer(object):
             eb = ring[0].numel() * ring.element_size()
             if eb == 0:
                 continue
-            src = self._as_ring_dtype(name, vals[name], n)
+            v = vals[name]
+            if name in ("obs", "next_obs") and isinstance(v, (tuple, list)):
+                # split joint observation: column blocks of the [A, D] ring element
+                (A, D), dt = self._shapes[name]
+                col = 0
+                for part in v:
+                    w = part.shape[-1]
+                    t = part if part.dtype == dt else part.to(dt)
+                    t = t.reshape(n * A, w).contiguous()
+                    keep.append(t)
+                    f = fields[k]
+                    f.ring, f.src, f.elem_bytes = ring.data_ptr(), t.data_ptr(), eb
+                    f.rows, f.row_bytes = A, w * ring.element_size()
+                    f.ring_pitch, f.ring_offset = D * ring.element_size(), col * ring.element_size()
+                    col += w
+                    k += 1
+                assert col == D, f"{name}: parts cover {col} of {D} columns"
+                continue
+            src, convert, bcast = self._source(name, v, n)
             keep.append(src)
-            fields[k].ring, fields[k].src, fields[k].elem_bytes = ring.data_ptr(), src.data_ptr(), eb
+            f = fields[k]
+            f.ring, f.src, f.elem_bytes, f.convert, f.broadcast = ring.data_ptr(), src.data_ptr(), eb, convert, bcast
             k += 1
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().gm_replay_insert(fields, k, self.buffer_size, self.index, n, _lib.current_stream()))

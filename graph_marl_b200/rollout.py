@@ -44,7 +44,7 @@ class Rollout:
         Dn, Da = 4 * N + 8, 6 * N + 10
         self.netmon = NetMon(Dn, c["H"], c["enc"], c["K"], F.leaky_relu, rnn_type=c["rnn"], agg_type="sum",
                              output_neighbor_hidden=True, math=math).to(device).eval()
-        self.env = NetMonWrapper(self.base_env, self.netmon, 1)
+        self.env = NetMonWrapper(self.base_env, self.netmon, 1, split_obs=True)
         Dj = Da + self.netmon.get_out_features()
         self.model = DQN(Dj, c["dqn"], 4, F.leaky_relu, math=math).to(device).eval()
         args = SimpleNamespace(epsilon=epsilon, step_before_train=10**9, epsilon_update_freq=100, epsilon_decay=0.996)
@@ -107,7 +107,7 @@ class Rollout:
         if self.host_draws:
             d = {k: v.to(self.device, non_blocking=True) for k, v in self._h.items()}
             with torch.no_grad():
-                _, actions = self.model.act(obs, None, epsilon=self.policy._epsilon, rand_action=d["ra"].reshape(-1),
+                _, actions = self.model.act(obs[0], obs[1], epsilon=self.policy._epsilon, rand_action=d["ra"].reshape(-1),
                                             rand_u=d["ru"].reshape(-1), want_q=False)
             self.base_env.set_draws(d["ds"], d["dt"], d["dz"])
         else:

@@ -41,7 +41,7 @@ typedef enum {
 
 GM_API const char* gm_last_error(void);
 /* ABI version, bumped on any signature/struct change. */
-GM_API int gm_abi_version(void);   /* currently 2 */
+GM_API int gm_abi_version(void);   /* currently 3 */
 /* 0 if a CUDA device with compute capability 10.x is present, else GM_ERR_NO_DEVICE. */
 GM_API int gm_device_check(void);
 
@@ -214,12 +214,16 @@ GM_API int gm_adj_to_lists(const float* mask, int32_t B, int32_t N, int32_t DM, 
  *   node_out f32[B,N,O] or NULL; agent_node i32[B,A] + agent_out f32[B,A,O] (row stride
  *   agent_out_ld floats) or NULL: graph observation of each agent = node_out[agent_node]
  *   (model.py:629-631 with a one-hot node-agent matrix).
- *   workspace: device scratch of gm_netmon_workspace_bytes. */
+ *   agent_out_pk: optional (tensor-core modes) copy of agent_out as tile-packed bf16 hi/lo blocks
+ *   (gm_packed_activation_bytes(B*A, O) bytes, 128-byte aligned) that gm_dqn_act can consume as
+ *   obs_g_pk instead of re-reading the fp32 rows.
+ *   workspace: device scratch of gm_netmon_workspace_bytes (256-byte aligned). */
+GM_API int64_t gm_packed_activation_bytes(int64_t rows, int32_t width);
 GM_API int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs,
                       const int32_t* nbr_all, const int32_t* deg, int32_t DM,
                       const int32_t* list_index, const float* state_in, float* state_out,
                       int32_t max_degree, float* node_out, const int32_t* agent_node, int32_t A,
-                      float* agent_out, int64_t agent_out_ld, void* workspace,
+                      float* agent_out, int64_t agent_out_ld, void* agent_out_pk, void* workspace,
                       int64_t workspace_bytes, void* stream);
 /* general node->agent mapping with an arbitrary (not one-hot) node_agent matrix f32[B,N,A]
  * (NetMon.output_to_network_obs, model.py:629-631; frozen wrapper path wrapper.py:67-75) */
@@ -250,12 +254,13 @@ GM_API int gm_dqn_pack_weights(const gm_dqn_params* p, int32_t split, void* pack
 GM_API int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows);
 /* rows = B*A agents. Input row r = [obs_a[r, 0:Da] | obs_g[r, 0:Dg]] (the concat of
  * wrapper.py:50 without materialising it); obs_g may be NULL with Dg = 0.
+ *   obs_g_pk: optional tile-packed copy of obs_g written by gm_netmon_forward (same math mode).
  *   action_mask u8[rows,n_actions] or NULL: masked actions get Q = -inf (policy.py:42-43)
  *   rand_action i32[rows], rand_u f64[rows]: host-supplied draws (policy.py:46-47), both NULL
  *   => device Philox(seed, step).  act[r] = rand_u<eps ? rand_action : argmax (first max).
  *   q_out f32[rows,n_actions] or NULL; act_out i32[rows]. */
 GM_API int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda,
-               const float* obs_g, int32_t Dg, int64_t ldg, const uint8_t* action_mask,
+               const float* obs_g, int32_t Dg, int64_t ldg, const void* obs_g_pk, const uint8_t* action_mask,
                double epsilon, const int32_t* rand_action, const double* rand_u,
                uint64_t philox_seed, uint64_t philox_step, float* q_out, int32_t* act_out,
                void* workspace, int64_t workspace_bytes, void* stream);
@@ -266,11 +271,18 @@ GM_API int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, 
 #define GM_REPLAY_MAX_FIELDS 24
 typedef struct gm_replay_field {
     void* ring;            /* device [capacity, elem_bytes] */
-    const void* src;       /* device [n, elem_bytes] for insert; unused for sample */
+    const void* src;       /* device source for insert; unused for sample */
     void* dst;             /* device [n, elems] for sample; unused for insert */
     int64_t elem_bytes;    /* bytes of one transition of this field in the ring */
-    int32_t convert;       /* sample: 0 raw copy, 1 u8/bool->f32, 2 i8->i64, 3 f16->f32 */
-    int32_t pad;
+    int32_t convert;       /* sample: 0 raw copy, 1 u8/bool->f32, 2 i8->i64, 3 f16->f32;
+                              insert: 0 raw copy, 4 i32 source elements -> i8 ring elements */
+    int32_t broadcast;     /* insert: src holds ONE transition that is written to all n slots */
+    /* insert, optional 2-D sub-block: per transition the source holds `rows` contiguous rows of
+     * `row_bytes`, written at byte offset ring_offset + row * ring_pitch inside the transition
+     * (e.g. the agent part and the graph part of the joint observation, wrapper.py:50, land in
+     * one ring row without a concat).  rows = 0: plain contiguous copy of elem_bytes. */
+    int32_t rows, pad;
+    int64_t row_bytes, ring_pitch, ring_offset;
 } gm_replay_field;
 /* copy n consecutive transitions into ring slots (index+i) % capacity */
 GM_API int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t capacity,
