@@ -67,6 +67,12 @@ static int64_t dqn_buf_bytes(int64_t rows, int maxw) {
     return round_up(std::max<int64_t>(rows * maxw * 4, tc_pk_bytes(rows, (int)round_up(maxw, TC_BK))), 256);
 }
 
+// the last hidden layer carries the Q head in its epilogue when it fits one 256-column tile
+static int dqn_layer_epi(const gm_dqn_params* p, int l) {
+    const int U = p->units[p->n_layers - 1];
+    return (l == p->n_layers - 1 && U <= 256 && (U & 3) == 0 && p->n_actions <= TC_MAX_ACT) ? EPI_QHEAD : EPI_LINEAR;
+}
+
 // packed tensor-core weights: layer l at off[l]; layer 0 is packed for input rows split as
 // [split | in_features - split] so the joint observation is consumed without a concat
 struct DqnPack {
@@ -81,7 +87,7 @@ static DqnPack dqn_pack_layout(const gm_dqn_params* p, int split) {
     for (int l = 0; l < p->n_layers; l++) {
         L.off[l] = off;
         int k0 = (l == 0 && split > 0) ? split : kin, k1 = (l == 0 && split > 0) ? kin - split : 0;
-        off += tc_shape(p->units[l], k0, k1, EPI_LINEAR, 0).packed_bytes;
+        off += tc_shape(p->units[l], k0, k1, dqn_layer_epi(p, l), 0).packed_bytes;
         kin = p->units[l];
     }
     L.total = off;
@@ -93,7 +99,8 @@ static int dqn_pack(const gm_dqn_params* p, int split, void* out, cudaStream_t s
     int kin = p->in_features, rc;
     for (int l = 0; l < p->n_layers; l++) {
         int k0 = (l == 0 && split > 0) ? split : kin, k1 = (l == 0 && split > 0) ? kin - split : 0;
-        if ((rc = tc_pack_weights(p->w[l], kin, nullptr, 0, p->b[l], nullptr, p->units[l], k0, k1, EPI_LINEAR, 0, (char*)out + L.off[l], s)))
+        if ((rc = tc_pack_weights(p->w[l], kin, nullptr, 0, p->b[l], nullptr, p->units[l], k0, k1, dqn_layer_epi(p, l), 0,
+                                  (char*)out + L.off[l], s)))
             return rc;
         kin = p->units[l];
     }
@@ -175,10 +182,17 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
                 a.K0 = kin;
             }
             a.Wp = (const uint8_t*)packed + PL.off[l];
-            if (out_pk) a.Cpk = (uint8_t*)y; else { a.C = y; a.ldc = p->units[l]; }
+            const int epi = dqn_layer_epi(p, l);
+            if (epi == EPI_QHEAD) {
+                a.q_w = p->q_w; a.q_b = p->q_b; a.n_act = p->n_actions;
+                a.action_mask = action_mask; a.epsilon = epsilon; a.rand_action = rand_action; a.rand_u = rand_u;
+                a.philox_seed = philox_seed; a.philox_step = philox_step;
+                a.q_out = q_out; a.act_out = act_out;
+            } else if (out_pk) a.Cpk = (uint8_t*)y; else { a.C = y; a.ldc = p->units[l]; }
             a.act = p->activation;
             a.M = rows; a.N = p->units[l];
-            if ((rc = tc_launch(a, p->math, EPI_LINEAR, s))) return rc;
+            if ((rc = tc_launch(a, p->math, epi, s))) return rc;
+            if (epi == EPI_QHEAD) return GM_OK;  // Q head, mask, argmax and epsilon mix ran in the epilogue
             xpk = out_pk ? (const uint8_t*)y : nullptr;
             x = y; ldx = p->units[l]; kin = p->units[l];
         }

@@ -28,11 +28,20 @@
 // smem ring of 4 stages x (A hi/lo 16 KiB + W hi/lo BN*128 B); 2 accumulator stages in TMEM.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 #include "linear_simt.cuh"
+
+#ifndef GM_LSTM_SHARED_RCP
+#define GM_LSTM_SHARED_RCP 1
+#endif
+#ifndef GM_LSTM_UNROLL
+#define GM_LSTM_UNROLL 1
+#endif
 
 namespace gm {
 
@@ -44,6 +53,7 @@ constexpr int MMA_WARP = 16, W_WARP = 17;
 constexpr int THREADS = 32 * 18;
 constexpr int A_PART_BYTES = BM * BK * 2;  // one bf16 part (hi or lo) of an A stage: 8 KiB
 constexpr int SBO_BYTES = BK * 16;         // distance between 8-row groups: 512 B
+constexpr int kLstmUnroll = GM_LSTM_UNROLL;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -77,6 +87,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// multicast form: the bytes land at the same CTA-relative smem offset of every CTA in `mask` and
+// complete_tx on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -194,6 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
@@ -204,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         for (int s = 0; s < STAGES; s++) {
             // the copy thread's expect_tx arrive, plus the 256 producer threads when a segment is fp32
             mbar_init(bar_full + 8 * s, 1 + (p.has_prod ? PROD_WARPS * 32 : 0));
-            mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
+            mbar_init(bar_empty + 8 * s, p.csz);  // one tcgen05.commit per CTA of the cluster (weights are multicast)
         }
         for (int a = 0; a < ACC_STAGES; a++) {
             mbar_init(bar_tfull + 8 * a, 1);                // tcgen05.commit
@@ -220,13 +254,23 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (p.csz > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
+    // Work units: (group of csz consecutive M tiles, one N tile).  The CTAs of a cluster walk the same
+    // unit list in lockstep; CTA `rank` owns M tile mg*csz + rank and 1/csz of every weight stage copy.
+    const int csz = p.csz;
+    const int rank = csz > 1 ? (int)cluster_ctarank() : 0;
+    const uint16_t mc_mask = (uint16_t)((1u << csz) - 1u);
     const int n_tiles = p.n_tiles;
-    const int total_tiles = p.m_tiles * n_tiles;
+    const int n_clusters = (int)gridDim.x / csz, cluster_id = (int)blockIdx.x / csz;
+    const int total_units = ((p.m_tiles + csz - 1) / csz) * n_tiles;
+    const int my_units = (total_units - cluster_id + n_clusters - 1) / n_clusters;
     const int kblocks = p.Kp / BK;
     const int kb_seg1 = p.K0p / BK;  // first k-block of segment 1
+    auto unit_mt = [&](int i) { return ((cluster_id + i * n_clusters) / n_tiles) * csz + rank; };
+    auto unit_nt = [&](int i) { return (cluster_id + i * n_clusters) % n_tiles; };
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ================= producer: fp32 activations -> bf16 hi/lo core matrices ================
@@ -238,8 +282,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
             const int r8 = lane >> 2, part = lane & 3;
             const int al0 = ptr_align_floats(p.A0, p.lda0), al1 = ptr_align_floats(p.A1, p.lda1);
             const bool prod0 = p.A0pk == nullptr, prod1 = p.K1 > 0 && p.A1pk == nullptr;
-            const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)kblocks;
+            const uint32_t total_it = (uint32_t)my_units * (uint32_t)kblocks;
             uint8_t* const st_base = smem + (2 * pw) * SBO_BYTES + r8 * 16 + part * 128;
 
             // fetch the two chunks (row groups g = 0,1) of iteration `it` into registers
@@ -249,12 +292,11 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) x[g][i] = 0.f;
                 if (it >= total_it) return;
-                const int tile = blockIdx.x + (int)(it / kblocks) * gridDim.x;
                 const int kb = (int)(it % kblocks);
                 const bool seg1 = kb >= kb_seg1;
                 if (seg1 ? !prod1 : !prod0) return;  // this k-block arrives by bulk copy
                 const int k = (seg1 ? kb - kb_seg1 : kb) * BK + part * 8;
-                const int64_t m0 = (int64_t)(tile / n_tiles) * BM + pw * 16 + r8;
+                const int64_t m0 = (int64_t)unit_mt((int)(it / kblocks)) * BM + pw * 16 + r8;
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     const int64_t m = m0 + 8 * g;
@@ -301,19 +343,29 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
             constexpr uint32_t w_bytes = (PASSES == 3 ? 2 : 1) * W_PART_BYTES;
             constexpr uint32_t a_bytes = (PASSES == 3 ? 2 : 1) * A_PART_BYTES;
             const int kb0_blocks = kb_seg1, kb1_blocks = kblocks - kb_seg1;
+            const uint32_t w_slice = W_PART_BYTES / csz;  // this CTA's share of each weight part
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile / n_tiles, nt = tile % n_tiles;
+            for (int u = 0; u < my_units; u++) {
+                const int mt = unit_mt(u), nt = unit_nt(u);
+                const bool tile_live = mt < p.m_tiles;  // a dead tile of the last group copies no activations
                 for (int kb = 0; kb < kblocks; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     const bool seg1 = kb >= kb_seg1;
                     const uint8_t* apk = seg1 ? p.A1pk : p.A0pk;
-                    if (seg1 && p.K1 == 0) apk = nullptr;
-                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    if (!tile_live) apk = nullptr;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);  // every CTA of the cluster has retired its MMAs on this stage
                     mbar_arrive_expect_tx(bar_full + 8 * s, w_bytes + (apk ? a_bytes : 0u));
                     const uint8_t* src = p.Wp + ((size_t)nt * kblocks + kb) * (2 * W_PART_BYTES);
-                    bulk_g2s(smem_base + s * STAGE_BYTES + 2 * A_PART_BYTES, src, w_bytes, bar_full + 8 * s);
+                    const uint32_t w_dst = smem_base + s * STAGE_BYTES + 2 * A_PART_BYTES;
+                    if (csz == 1) {
+                        bulk_g2s(w_dst, src, w_bytes, bar_full + 8 * s);
+                    } else {
+#pragma unroll
+                        for (int part = 0; part < (PASSES == 3 ? 2 : 1); part++)
+                            bulk_g2s_mc(w_dst + part * W_PART_BYTES + rank * w_slice, src + part * W_PART_BYTES + rank * w_slice, w_slice,
+                                        bar_full + 8 * s, mc_mask);
+                    }
                     if (apk) {
                         const size_t blk = seg1 ? ((size_t)mt * kb1_blocks + (kb - kb_seg1)) : ((size_t)mt * kb0_blocks + kb);
                         bulk_g2s(smem_base + s * STAGE_BYTES, apk + blk * TC_PK_BLOCK, a_bytes, bar_full + 8 * s);
@@ -324,8 +376,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer ==================================================================
         if (lane == 0) {
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+            uint32_t it = 0;
+            for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
                 const int as = tcount % ACC_STAGES;
                 const uint32_t aph = (tcount / ACC_STAGES) & 1;
                 mbar_wait(bar_tempty + 8 * as, aph ^ 1);  // epilogue drained this accumulator
@@ -349,7 +401,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                             umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
                         }
                     }
-                    umma_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs retire
+                    // smem stage reusable once these MMAs retire; with multicast weights every CTA of the
+                    // cluster must know, because peers write into this CTA's stage
+                    if (csz == 1) umma_commit(bar_empty + 8 * s);
+                    else umma_commit_mc(bar_empty + 8 * s, mc_mask);
                 }
                 umma_commit(bar_tfull + 8 * as);  // accumulator complete
             }
@@ -359,19 +414,28 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         // 8 warps: warp e reads TMEM lanes 32*(e%4).. (its hardware quadrant) and the column half e/4.
         const int quad = warp & 3, chalf = warp >> 2;
         const int r = quad * 32 + lane;  // accumulator lane == tile row
-        uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+        for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
             const int as = tcount % ACC_STAGES;
             const uint32_t aph = (tcount / ACC_STAGES) & 1;
-            const int mt = tile / n_tiles, nt = tile % n_tiles;
+            const int mt = unit_mt((int)tcount), nt = unit_nt((int)tcount);
             const int64_t m = (int64_t)mt * BM + r;
             const bool live = m < p.M;
             const float* bias_t = p.bias_tile + (size_t)nt * BN;  // tile-ordered, zero padded, biases pre-summed
+            // LSTM: the previous cell state of this row's hidden units is fetched while the MMAs still run
+            float cin[EPI == EPI_LSTM ? BN / 4 / 2 / 8 : 1][8];
+            if (EPI == EPI_LSTM && live) {
+#pragma unroll
+                for (int itr = 0; itr < BN / 4 / 2 / 8; itr++)
+                    ld_global_v8(p.c_in + m * p.ldc_in + nt * (BN / 4) + chalf * (BN / 8) + itr * 8, cin[itr]);
+            }
             mbar_wait(bar_tfull + 8 * as, aph);
             tc_fence_after();
             const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
-            if (EPI == EPI_LINEAR) {
+            if (EPI == EPI_LINEAR || EPI == EPI_QHEAD) {
                 const int n0 = nt * BN;
+                float qacc[TC_MAX_ACT];
+#pragma unroll
+                for (int a = 0; a < TC_MAX_ACT; a++) qacc[a] = 0.f;
                 const int al = ptr_align_floats(p.C, p.ldc);
                 const bool fast = p.accumulate == 0 && (p.act == GM_ACT_LEAKY_RELU || p.act < 0);
                 uint8_t* const pk_row = p.Cpk ? p.Cpk + (size_t)mt * (size_t)(p.N / BK) * TC_PK_BLOCK + core_off(r, 0) : nullptr;
@@ -399,6 +463,21 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                             if (p.accumulate && n0 + c + i < p.N) x += p.C[m * p.ldc + n0 + c + i];
                             if (p.act >= 0) x = apply_act(x, p.act);
                             o[i] = x;
+                        }
+                    }
+                    if (EPI == EPI_QHEAD) {  // partial Q-values over this thread's columns (padding columns hold 0)
+#pragma unroll
+                        for (int a = 0; a < TC_MAX_ACT; a++) {
+                            if (a < p.n_act) {
+                                const float4* wq = (const float4*)(p.q_w + (size_t)a * p.N + n0 + c);
+#pragma unroll
+                                for (int i = 0; i < 4; i++) {
+                                    if (n0 + c + 4 * i >= p.N) break;
+                                    float4 w4 = __ldg(wq + i);
+                                    qacc[a] = fmaf(o[4 * i], w4.x, qacc[a]); qacc[a] = fmaf(o[4 * i + 1], w4.y, qacc[a]);
+                                    qacc[a] = fmaf(o[4 * i + 2], w4.z, qacc[a]); qacc[a] = fmaf(o[4 * i + 3], w4.w, qacc[a]);
+                                }
+                            }
                         }
                     }
                     if (p.C) {
@@ -430,16 +509,45 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                         }
                     }
                 }
+                if (EPI == EPI_QHEAD) {
+                    // combine the two column halves through shared memory, then finish the policy step
+                    const int pb = tcount & 1;
+                    if (chalf == 1) {
+#pragma unroll
+                        for (int a = 0; a < TC_MAX_ACT; a++) qpart[pb][r][a] = qacc[a];
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // epilogue warps only
+                    if (chalf == 0 && live) {
+                        int best = 0;
+                        float bestv = 0.f;
+                        for (int a = 0; a < p.n_act; a++) {
+                            float q = qacc[a] + qpart[pb][r][a] + __ldg(p.q_b + a);
+                            if (p.q_out) p.q_out[m * p.n_act + a] = q;  // Q-values before masking (what the model returns)
+                            if (p.action_mask && p.action_mask[m * p.n_act + a]) q = -INFINITY;
+                            if (a == 0 || q > bestv) { best = a; bestv = q; }
+                        }
+                        int ra; double u;
+                        if (p.rand_action) { ra = p.rand_action[m]; u = p.rand_u[m]; }
+                        else {
+                            Philox ph((uint32_t)m, (uint32_t)((uint64_t)m >> 32), (uint32_t)p.philox_step,
+                                      (uint32_t)(p.philox_step >> 32) ^ 0x5bd1e995u, p.philox_seed ^ 0xA5A5A5A5DEADBEEFull);
+                            ra = (int)__umulhi(ph.r[0], (uint32_t)p.n_act);
+                            u = u53(ph.r[1], ph.r[2]);
+                        }
+                        p.act_out[m] = (u < p.epsilon) ? ra : best;
+                    }
+                }
             } else {
                 // LSTM cell pointwise (torch.nn.LSTMCell; gate order i,f,g,o).  Packed columns of this
                 // tile: [i | f | g | o] for hidden units nt*U .. nt*U+U-1 (U = BN/4).
                 constexpr int U = BN / 4;
+                constexpr int NIT = U / 2 / 8;  // 8 hidden units per iteration, U/2 units per warp
                 const int j0 = nt * U;
                 uint8_t* const pk_row = p.Hpk ? p.Hpk + (size_t)mt * (size_t)(p.H / BK) * TC_PK_BLOCK + core_off(r, 0) : nullptr;
-#pragma unroll 1
-                for (int c = chalf * (U / 2); c < (chalf + 1) * (U / 2); c += 8) {
-                    float cin[8], bi[8], bf[8], bg[8], bo[8];
-                    if (live) ld_global_v8(p.c_in + m * p.ldc_in + j0 + c, cin);
+#pragma unroll kLstmUnroll
+                for (int itr = 0; itr < NIT; itr++) {
+                    const int c = chalf * (U / 2) + itr * 8;
+                    float bi[8], bf[8], bg[8], bo[8];
                     ld_global_v8(bias_t + c, bi);
                     ld_global_v8(bias_t + U + c, bf);
                     ld_global_v8(bias_t + 2 * U + c, bg);
@@ -454,9 +562,25 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     float hh[8], cc[8];
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
-                        float i_ = fast_sigmoid(__uint_as_float(vi[i]) + bi[i]), f_ = fast_sigmoid(__uint_as_float(vf[i]) + bf[i]);
-                        float g_ = fast_tanh(__uint_as_float(vg[i]) + bg[i]), o_ = fast_sigmoid(__uint_as_float(vo[i]) + bo[i]);
-                        float cv = f_ * cin[i] + i_ * g_;
+#if GM_LSTM_SHARED_RCP
+                        // sigmoid(i), sigmoid(f), sigmoid(o), tanh(g) from four exponentials and ONE reciprocal:
+                        // with A=1+e^-i, F=1+e^-f, O=1+e^-o, G=1+e^2g and R=1/(A*F*O*G):
+                        //   sig(i)=R*F*O*G, sig(f)=R*A*O*G, sig(o)=R*A*F*G, tanh(g)=1-2*R*A*F*O.
+                        // Arguments are clamped to +-20 (saturation error < 3e-9) so the product stays finite.
+                        const float xi = fminf(fmaxf(__uint_as_float(vi[i]) + bi[i], -20.f), 20.f);
+                        const float xf = fminf(fmaxf(__uint_as_float(vf[i]) + bf[i], -20.f), 20.f);
+                        const float xo = fminf(fmaxf(__uint_as_float(vo[i]) + bo[i], -20.f), 20.f);
+                        const float xg = fminf(fmaxf(__uint_as_float(vg[i]) + bg[i], -10.f), 10.f);
+                        const float Ai = 1.f + __expf(-xi), Af = 1.f + __expf(-xf), Ao = 1.f + __expf(-xo), Ag = 1.f + __expf(2.f * xg);
+                        const float AiAf = Ai * Af, AoAg = Ao * Ag;
+                        const float R = __fdividef(1.f, AiAf * AoAg);
+                        const float i_ = R * Af * AoAg, f_ = R * Ai * AoAg, o_ = R * AiAf * Ag;
+                        const float g_ = 1.f - 2.f * (R * AiAf * Ao);
+#else
+                        const float i_ = fast_sigmoid(__uint_as_float(vi[i]) + bi[i]), f_ = fast_sigmoid(__uint_as_float(vf[i]) + bf[i]);
+                        const float g_ = fast_tanh(__uint_as_float(vg[i]) + bg[i]), o_ = fast_sigmoid(__uint_as_float(vo[i]) + bo[i]);
+#endif
+                        const float cv = f_ * cin[itr][i] + i_ * g_;
                         cc[i] = cv;
                         hh[i] = o_ * fast_tanh(cv);
                     }
@@ -479,6 +603,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 
     tc_fence_before();
     __syncthreads();
+    if (p.csz > 1) cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
     if (warp == MMA_WARP) {
         tc_fence_after();
         uint32_t cols = ACC_STAGES * BN;
@@ -557,7 +682,7 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, const float* __res
 
 // -------------------------------------------------------------------------------------------------
 int tc_pick_bn(int N, int epi) {
-    if (epi == EPI_LSTM) return 256;
+    if (epi == EPI_LSTM || epi == EPI_QHEAD) return 256;
     return N <= 128 ? 128 : 256;
 }
 
@@ -586,17 +711,53 @@ int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, 
     return GM_OK;
 }
 
+static int tc_cluster_size() {
+    static int csz = -1;
+    if (csz < 0) {
+        const char* e = getenv("GM_TC_CLUSTER");
+        csz = e ? atoi(e) : 1;  // measured on B200: multicast of the weight stages (2, 4) brings no gain at these shapes
+        if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+    }
+    return csz;
+}
+
 template <int BN, int PASSES, int EPI>
-static int launch_tc(const TcArgs& a, cudaStream_t s) {
+static int launch_tc(TcArgs a, cudaStream_t s) {
     constexpr int smem = tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2);
     static bool configured = false;
+    static int max_clusters[5] = {0, 0, 0, 0, 0};
+    auto kern = tc::linear_tc_kernel<BN, PASSES, EPI>;
     if (!configured) {
-        GM_CUDA(cudaFuncSetAttribute(tc::linear_tc_kernel<BN, PASSES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    int grid = std::min(a.m_tiles * a.n_tiles, kNumSMs);
-    tc::linear_tc_kernel<BN, PASSES, EPI><<<grid, tc::THREADS, smem, s>>>(a);
-    GM_LAUNCH_CHECK();
+    // weight stages are multicast to the CTAs of a cluster (each CTA fetches 1/csz of every weight tile)
+    int csz = std::min(tc_cluster_size(), std::max(1, a.m_tiles));
+    while (csz > 1 && csz > a.m_tiles) csz >>= 1;
+    if (csz == 3) csz = 2;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (csz > 1 && max_clusters[csz] == 0) {
+        cfg.gridDim = dim3((kNumSMs / csz) * csz);
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+        max_clusters[csz] = n;
+    }
+    if (csz > 1 && max_clusters[csz] < 0) csz = 1;  // clusters of this size cannot be scheduled: plain launch
+    attr[0].val.clusterDim.x = csz;
+    a.csz = csz;
+    const int units = ((a.m_tiles + csz - 1) / csz) * a.n_tiles;
+    const int n_clusters = std::min(units, csz > 1 ? max_clusters[csz] : kNumSMs);
+    cfg.gridDim = dim3(n_clusters * csz);
+    GM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    count_launch();
     return GM_OK;
 }
 
@@ -621,6 +782,10 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
         GM_CHECK_ARG((a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 &&
                          (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out) & 31) == 0 && ((uintptr_t)a.Hpk & 127) == 0,
                      "fused LSTM epilogue needs 32-byte aligned state rows");
+    } else if (epi == EPI_QHEAD) {
+        GM_CHECK_ARG(a.N <= 256 && (a.N & 3) == 0 && a.q_w && a.q_b && a.act_out && a.n_act >= 1 && a.n_act <= TC_MAX_ACT &&
+                         ((uintptr_t)a.q_w & 15) == 0 && !a.accumulate,
+                     "fused Q head needs a last hidden layer of <= 256 units (multiple of 4) and <= %d actions", TC_MAX_ACT);
     } else {
         GM_CHECK_ARG(a.C != nullptr || a.Cpk != nullptr, "no output");
         GM_CHECK_ARG(a.Cpk == nullptr || ((a.N % tc::BK) == 0 && ((uintptr_t)a.Cpk & 127) == 0 && !a.accumulate),
@@ -629,6 +794,7 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     }
     const int passes = math == GM_MATH_BF16 ? 1 : 3;
     if (epi == EPI_LSTM) return passes == 3 ? launch_tc<256, 3, EPI_LSTM>(a, s) : launch_tc<256, 1, EPI_LSTM>(a, s);
+    if (epi == EPI_QHEAD) return passes == 3 ? launch_tc<256, 3, EPI_QHEAD>(a, s) : launch_tc<256, 1, EPI_QHEAD>(a, s);
     if (sh.BN == 128) return passes == 3 ? launch_tc<128, 3, EPI_LINEAR>(a, s) : launch_tc<128, 1, EPI_LINEAR>(a, s);
     return passes == 3 ? launch_tc<256, 3, EPI_LINEAR>(a, s) : launch_tc<256, 1, EPI_LINEAR>(a, s);
 }

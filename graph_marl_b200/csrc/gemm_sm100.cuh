@@ -4,7 +4,8 @@
 
 namespace gm {
 
-enum { EPI_LINEAR = 0, EPI_LSTM = 1 };
+enum { EPI_LINEAR = 0, EPI_LSTM = 1, EPI_QHEAD = 2 };
+constexpr int TC_MAX_ACT = 8;
 
 // "pk" = tile-packed split activations: an fp32 matrix [R, Kact] (Kact % 32 == 0) stored as bf16
 // hi/lo core matrices exactly as the tensor core reads them from shared memory, one 16 KiB block
@@ -31,7 +32,13 @@ struct TcArgs {
     const float* c_in; int64_t ldc_in;
     float* h_out; int64_t ldh; float* c_out; int64_t ldco; uint8_t* Hpk;
     int H;
-    int m_tiles, n_tiles, has_prod;  // filled by tc_launch
+    // EPI_QHEAD (N <= 256): the layer's activated output never leaves the SM; the epilogue applies the
+    // Q head q = y Wq^T + bq, the action mask, argmax and the epsilon mix (model.py:199-203, policy.py:42-51)
+    const float* q_w; const float* q_b; int n_act;
+    const uint8_t* action_mask; double epsilon; const int* rand_action; const double* rand_u;
+    uint64_t philox_seed, philox_step;
+    float* q_out; int* act_out;
+    int m_tiles, n_tiles, has_prod, csz;  // filled by tc_launch (csz = cluster size, weights multicast)
 };
 
 struct TcShape {
