@@ -152,7 +152,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
     ap.add_argument("--envs", type=int, default=0, help="env instances per GPU (default: BASELINE config size)")
-    ap.add_argument("--math", default=os.environ.get("GM_BENCH_MATH", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--math", default=os.environ.get("GM_BENCH_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
+                    help="GEMM arithmetic: bf16x3 = tcgen05 with the fp32-accurate hi/lo split (default, parity mode), "
+                         "bf16 = single tensor-core pass (reduced precision, reported only on request), fp32 = CUDA-core FFMA")
     ap.add_argument("--no-replay", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-kernel", action="store_true", help="also print a per-stage CUDA-event breakdown to stderr")
@@ -266,12 +268,15 @@ def main():
     roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                      frac=tf / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
                      flops_per_env_step=flops_step // B, ms_per_step_in_gemms=gemm_ms,
-                     note=f"achieved = algorithmic dense-GEMM flops (2mnk, fp32 semantics) / (NetMon + DQN stage time); the "
-                          f"tensor pipe executes {passes}x that in bf16 MMAs", tensor_pipe_tflops_executed=tf * passes)
+                     launches_per_step=stage.get("gemm_launches_per_step"),
+                     note=f"achieved = algorithmic dense-GEMM flops of one step (2mnk, fp32 semantics) / summed CUDA-event time of the "
+                          f"step's GEMM launches; the tensor pipe executes {passes}x that in bf16 MMAs",
+                     tensor_pipe_tflops_executed=tf * passes)
     dominant = roof_gemm if gemm_ms >= env_ms else roof_env
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype={"fp32": "f32", "bf16x3": "bf16x3 (fp32-accurate split, fp32 accumulate)", "bf16": "bf16"}[a.math],
+                dtype={"fp32": "f32", "bf16x3": "f32 (tcgen05 bf16 hi/lo split x3, fp32 accumulate; env state int32/f64)",
+                       "bf16": "bf16 (single pass, fp32 accumulate) -- reduced precision"}[a.math],
                 data="synthetic", config=config, agent_steps_per_sec=value * A, gpu_launches=int(launches), clocks=clocks, e2e=e2e,
                 roofline=dominant, roofline_env_step=roof_env, roofline_gemm=roof_gemm, stage_ms=stage)
     if not a.no_cpu_baseline and world == 1:
