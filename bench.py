@@ -190,7 +190,7 @@ def main():
     import torch.distributed as dist
 
     from graph_marl_b200 import _lib
-    from graph_marl_b200.rollout import Rollout
+    from graph_marl_b200.rollout import Rollout, aggregate_throughput
 
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
@@ -221,18 +221,16 @@ def main():
         barrier()
         w1 = time.time()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _lib.lib().gm_kernel_launch_count() - n0, w0, w1
+        # whole-job units / MAX device time over ranks
+        value, ms_max = aggregate_throughput(B * steps, ms, world)
+        return value, ms_max, _lib.lib().gm_kernel_launch_count() - n0, w0, w1
 
     # ---- device-resident arm ---------------------------------------------------------------
     ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank)
     ro.reset()
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches, w0, w1 = timed(ro, a.steps, max(a.warmup, 3), host=False)
+    value, ms, launches, w0, w1 = timed(ro, a.steps, max(a.warmup, 3), host=False)
     clocks = sampler.stop(w0, w1) if sampler else None
-    value = B * world * a.steps / (ms * 1e-3)
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) -------------
     stage = ro.profile_stages(iters=max(5, min(a.steps, 20)))
@@ -243,8 +241,8 @@ def main():
     ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank,
                  host_draws=True)
     ro.reset()
-    ms_e, _, _, _ = timed(ro, a.steps, max(a.warmup, 3), host=True)
-    e2e = dict(value=B * world * a.steps / (ms_e * 1e-3), unit=UNIT, h2d_bytes_per_step=ro.h2d_bytes_per_step() * world,
+    value_e, ms_e, _, _, _ = timed(ro, a.steps, max(a.warmup, 3), host=True)
+    e2e = dict(value=value_e, unit=UNIT, h2d_bytes_per_step=ro.h2d_bytes_per_step() * world,
                d2h_bytes_per_step=ro.d2h_bytes_per_step() * world, ms_per_step=ms_e / a.steps)
     del ro
     torch.cuda.empty_cache()

@@ -30,6 +30,28 @@ CONFIGS = {
 }
 
 
+def shard_envs(total_envs, world_size, rank):
+    """Contiguous block of env instances owned by `rank`: [lo, hi).  Independent
+    environments shard across the GPUs of one box with no collective on the rollout path."""
+    base, rem = divmod(int(total_envs), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def aggregate_throughput(units_per_rank, ms_local, world_size):
+    """Whole-job throughput from per-rank device times: all ranks' units / the MAX time over ranks
+    (all-reduced over the default process group when world_size > 1)."""
+    import torch.distributed as dist
+
+    t = torch.tensor([float(ms_local)], dtype=torch.float64,
+                     device="cuda" if (dist.is_initialized() and dist.get_backend() == "nccl") else "cpu")
+    n = torch.tensor([float(units_per_rank)], dtype=torch.float64, device=t.device)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    return float(n.item()) / (float(t.item()) * 1e-3), float(t.item())
+
+
 class Rollout:
     def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
                  epsilon=1.0, seed=0, with_replay=True, host_draws=False):

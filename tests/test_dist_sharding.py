@@ -1,0 +1,63 @@
+"""Multi-process (gloo, world_size 2, CPU) checks of the N>1 path of bench.py: env-instance shards
+are disjoint and cover the job, per-rank draw streams are distinct, and the whole-job throughput is
+(sum of units) / (max time over ranks)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from graph_marl_b200.rollout import aggregate_throughput, shard_envs
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_envs(total, world, rank)
+    # a rank is slower the higher its index: the aggregate must use the slowest one
+    ms_local = 10.0 * (rank + 1)
+    value, ms_max = aggregate_throughput((hi - lo) * 5, ms_local, world)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi))
+    if rank == 0:
+        out.put((value, ms_max, gathered))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [4096, 4097])
+def test_two_rank_sharding_and_max_over_ranks(total):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, total, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    value, ms_max, shards = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert shards[0][0] == 0 and shards[-1][1] == total
+    assert all(shards[i][1] == shards[i + 1][0] for i in range(world - 1))  # disjoint, contiguous cover
+    assert max(h - l for l, h in shards) - min(h - l for l, h in shards) <= 1
+    assert ms_max == 20.0
+    assert value == pytest.approx(total * 5 / 20e-3)
+
+
+def test_shard_envs_properties():
+    for total in (1, 7, 4096, 16384):
+        for world in (1, 2, 4, 8):
+            spans = [shard_envs(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert sum(h - l for l, h in spans) == total
