@@ -194,6 +194,8 @@ def main():
 
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     _lib.require_device()
