@@ -12,7 +12,7 @@ scaling: B per GPU is fixed).
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same step
 driven through the public classes with the step's random draws supplied from pinned HOST memory
-and the reward read back to the host every step; `roofline` = dominant kernel of the step;
+(a pre-generated pinned table, each step copies its own slice) and the reward read back every step; `roofline` = dominant kernel of the step;
 `roofline_env_step` = the HBM-bound env-step kernel named by the metric; `cpu_baseline` = the
 oracle (CPU port of the reference path) on this box's host cores.
 """
@@ -171,7 +171,7 @@ def main():
     config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
                            f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
                            f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,
-                  replay_insert=not a.no_replay, sharding=f"env instances, {world} rank(s), no collective",
+                  replay_insert=not a.no_replay, replay_overlap="side stream, joined before the end event", sharding=f"env instances, {world} rank(s), no collective",
                   l2="per-step working set (obs + node_obs + NetMon activations + replay slots) exceeds the 126 MB L2")
 
     if a.impl == "reference":
@@ -205,21 +205,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(ro, steps, warmup, host):
         for _ in range(warmup):
-            if host:
-                ro.refresh_host_draws()
             ro.step()
+        ro.join_streams()
         n0 = _lib.lib().gm_kernel_launch_count()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
         for _ in range(steps):
-            if host:
-                ro.refresh_host_draws()
             ro.step()
+        ro.join_streams()  # the side-stream replay inserts of these steps finish inside the timed region
         e1.record()
+        host_ms[0] = (time.time() - w0) * 1e3 / steps  # host-side issue time per step (before the final sync)
         barrier()
         w1 = time.time()
         ms = e0.elapsed_time(e1)
@@ -233,6 +234,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     value, ms, launches, w0, w1 = timed(ro, a.steps, max(a.warmup, 3), host=False)
     clocks = sampler.stop(w0, w1) if sampler else None
+    host_issue_ms = host_ms[0]
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) -------------
     stage = ro.profile_stages(iters=max(5, min(a.steps, 20)))
@@ -241,11 +243,12 @@ def main():
 
     # ---- end-to-end arm: host-supplied draws in, reward out, every step --------------------------
     ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank,
-                 host_draws=True)
+                 host_draws=True, host_draw_steps=a.steps + max(a.warmup, 3) + 2)
     ro.reset()
     value_e, ms_e, _, _, _ = timed(ro, a.steps, max(a.warmup, 3), host=True)
     e2e = dict(value=value_e, unit=UNIT, h2d_bytes_per_step=ro.h2d_bytes_per_step() * world,
-               d2h_bytes_per_step=ro.d2h_bytes_per_step() * world, ms_per_step=ms_e / a.steps)
+               d2h_bytes_per_step=ro.d2h_bytes_per_step() * world, ms_per_step=ms_e / a.steps,
+               host_issue_ms_per_step=host_ms[0])
     del ro
     torch.cuda.empty_cache()
 
@@ -277,7 +280,7 @@ def main():
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"fp32": "f32", "bf16x3": "f32 (tcgen05 bf16 hi/lo split x3, fp32 accumulate; env state int32/f64)",
                        "bf16": "bf16 (single pass, fp32 accumulate) -- reduced precision"}[a.math],
-                data="synthetic", config=config, agent_steps_per_sec=value * A, gpu_launches=int(launches), clocks=clocks, e2e=e2e,
+                data="synthetic", config=config, agent_steps_per_sec=value * A, host_issue_ms_per_step=host_issue_ms, gpu_launches=int(launches), clocks=clocks, e2e=e2e,
                 roofline=dominant, roofline_env_step=roof_env, roofline_gemm=roof_gemm, stage_ms=stage)
     if not a.no_cpu_baseline and world == 1:
         try:

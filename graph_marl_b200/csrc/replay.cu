@@ -34,8 +34,24 @@ __global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t i
     const bool two_d = fd.rows > 0;
     const int64_t rb = two_d ? fd.row_bytes : eb;           // contiguous run
     const int64_t runs = two_d ? fd.rows : 1;               // runs per transition
-    const uintptr_t align_bits = (uintptr_t)fd.ring | (uintptr_t)fd.src | (uintptr_t)rb | (uintptr_t)eb |
-                                 (two_d ? ((uintptr_t)fd.ring_pitch | (uintptr_t)fd.ring_offset) : 0);
+    const uintptr_t src_bits = (uintptr_t)fd.src | (uintptr_t)rb;
+    const uintptr_t dst_bits = (uintptr_t)fd.ring | (uintptr_t)eb | (two_d ? ((uintptr_t)fd.ring_pitch | (uintptr_t)fd.ring_offset) : 0);
+    const uintptr_t align_bits = src_bits | dst_bits;
+    if (align_bits % 16 != 0 && src_bits % 16 == 0 && dst_bits % 8 == 0) {
+        // 16-byte aligned source, destination only 8-byte aligned (the graph part of a joint observation row
+        // starts 520 bytes into the ring row): one 16-byte load, two 8-byte stores
+        const int64_t upr = rb / 16, total = n * runs * upr;
+        for (int64_t t = tid0; t < total; t += nthreads) {
+            int64_t u = t % upr, q = t / upr;
+            int64_t row = q % runs, i = q / runs;
+            int64_t slot = (index + i) % capacity;
+            const uint4 v = *(const uint4*)((const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * 16);
+            uint2* d = (uint2*)((char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * 16);
+            d[0] = make_uint2(v.x, v.y);
+            d[1] = make_uint2(v.z, v.w);
+        }
+        return;
+    }
     const int unit = (align_bits % 16 == 0) ? 16 : (align_bits % 8 == 0) ? 8 : (align_bits % 4 == 0) ? 4 : 1;
     const int64_t upr = rb / unit;  // units per run
     const int64_t total = n * runs * upr;
@@ -95,7 +111,7 @@ int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t ca
         F.f[i] = fields[i];
         maxb = max(maxb, fields[i].elem_bytes * n);
     }
-    int64_t blocks = std::min<int64_t>((maxb / 16 + 255) / 256 + 1, 148 * 8);
+    int64_t blocks = std::min<int64_t>((maxb / 16 + 255) / 256 + 1, 148 * 4);
     dim3 grid((unsigned)blocks, n_fields);
     replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, n);
     GM_LAUNCH_CHECK();

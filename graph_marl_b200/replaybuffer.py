@@ -134,6 +134,12 @@ class ReplayBuffer(object):
             k += 1
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().gm_replay_insert(fields, k, self.buffer_size, self.index, n, _lib.current_stream()))
+            cur = torch.cuda.current_stream()
+            if cur != torch.cuda.default_stream():
+                # insert running on a side stream (overlapped with the next rollout step): keep the caching
+                # allocator from recycling the sources before the copy has run
+                for t in keep:
+                    t.record_stream(cur)
         self._keep = keep
         self.count = min(self.buffer_size, self.count + n)
         self.index = (self.index + n) % self.buffer_size

@@ -54,7 +54,7 @@ def aggregate_throughput(units_per_rank, ms_local, world_size):
 
 class Rollout:
     def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
-                 epsilon=1.0, seed=0, with_replay=True, host_draws=False):
+                 epsilon=1.0, seed=0, with_replay=True, host_draws=False, overlap_replay=True, host_draw_steps=64):
         c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
         self.cfg, self.B, self.device = c, num_envs, torch.device(device)
         N, A = c["n_nodes"], c["n_data"]
@@ -78,12 +78,18 @@ class Rollout:
         self.sizes = dict(N=N, A=A, Dn=Dn, Da=Da, Dj=Dj, H=c["H"], K=c["K"])
         self.host_draws = host_draws
         if host_draws:
-            B = num_envs
+            # a table of `host_draw_steps` steps of host-generated draws in pinned memory (policy.py:46-47 and
+            # routing.py:130-135 consume host randomness in the reference); every step copies ITS slice H2D
+            B, T = num_envs, int(host_draw_steps)
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-            self._h = dict(ra=pin((B, A), torch.int32), ru=pin((B, A), torch.float64), ds=pin((B, A), torch.int32),
-                           dt=pin((B, A), torch.int32), dz=pin((B, A), torch.float64))
+            self._h = dict(ra=pin((T, B, A), torch.int32), ru=pin((T, B, A), torch.float64), ds=pin((T, B, A), torch.int32),
+                           dt=pin((T, B, A), torch.int32), dz=pin((T, B, A), torch.float64))
             self._rng = np.random.default_rng(seed)
             self._h_reward = pin((B, A), torch.float32)
+            self._h_steps, self._h_cursor = T, 0
+            self.refresh_host_draws()
+        self.overlap_replay = overlap_replay and with_replay
+        self._replay_stream = torch.cuda.Stream(device=self.device) if self.overlap_replay else None
         self.episode_step = None
         self._marks = None
         self.obs = self.adj = None
@@ -91,20 +97,25 @@ class Rollout:
         self.total_reward = torch.zeros((), dtype=torch.float64, device=device)
 
     def h2d_bytes_per_step(self):
-        return sum(t.numel() * t.element_size() for t in self._h.values()) if self.host_draws else 0
+        return sum(t[0].numel() * t.element_size() for t in self._h.values()) if self.host_draws else 0
 
     def d2h_bytes_per_step(self):
         return self._h_reward.numel() * 4 if self.host_draws else 0
 
+    def join_streams(self):
+        """Make the current stream wait for the side-stream replay insert (end of a timed region)."""
+        if self._replay_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._replay_stream)
+
     def refresh_host_draws(self):
-        """New host-side random draws for the next step (outside any timed region if desired)."""
-        B, A, N = self.B, self.sizes["A"], self.sizes["N"]
+        """Regenerate the host draw table (call outside a timed region, with the device idle)."""
+        T, B, A, N = self._h_steps, self.B, self.sizes["A"], self.sizes["N"]
         r = self._rng
-        self._h["ra"].numpy()[...] = r.integers(0, 4, (B, A), dtype=np.int32)
-        self._h["ru"].numpy()[...] = r.random((B, A))
-        self._h["ds"].numpy()[...] = r.integers(0, N, (B, A), dtype=np.int32)
-        self._h["dt"].numpy()[...] = r.integers(0, N, (B, A), dtype=np.int32)
-        self._h["dz"].numpy()[...] = r.random((B, A))
+        self._h["ra"].numpy()[...] = r.integers(0, 4, (T, B, A), dtype=np.int32)
+        self._h["ru"].numpy()[...] = r.random((T, B, A))
+        self._h["ds"].numpy()[...] = r.integers(0, N, (T, B, A), dtype=np.int32)
+        self._h["dt"].numpy()[...] = r.integers(0, N, (T, B, A), dtype=np.int32)
+        self._h["dz"].numpy()[...] = r.random((T, B, A))
 
     def reset(self):
         self.obs, self.adj = self.env.reset()
@@ -127,7 +138,9 @@ class Rollout:
         obs, adj = self.obs, self.adj
         self._mark("start")
         if self.host_draws:
-            d = {k: v.to(self.device, non_blocking=True) for k, v in self._h.items()}
+            i = self._h_cursor % self._h_steps
+            self._h_cursor += 1
+            d = {k: v[i].to(self.device, non_blocking=True) for k, v in self._h.items()}
             with torch.no_grad():
                 _, actions = self.model.act(obs[0], obs[1], epsilon=self.policy._epsilon, rand_action=d["ra"].reshape(-1),
                                             rand_u=d["ru"].reshape(-1), want_q=False)
@@ -144,8 +157,17 @@ class Rollout:
         episode_done = self.episode_step >= c["episode_steps"]
         if self.buff is not None:
             node_state = last_state if last_state is not None else 0
-            self.buff.add(obs, actions, reward, next_obs, adj, next_adj, done, episode_done, 0, node_state,
-                          self.node_aux, *netmon_info, *next_info, num=self.B)
+            if self.overlap_replay:
+                # the insert is off the critical path (nothing in the next step reads the ring): run it on a
+                # side stream so its HBM-bound copies overlap the next step's tensor-core kernels
+                main = torch.cuda.current_stream()
+                self._replay_stream.wait_stream(main)
+                with torch.cuda.stream(self._replay_stream):
+                    self.buff.add(obs, actions, reward, next_obs, adj, next_adj, done, episode_done, 0, node_state,
+                                  self.node_aux, *netmon_info, *next_info, num=self.B)
+            else:
+                self.buff.add(obs, actions, reward, next_obs, adj, next_adj, done, episode_done, 0, node_state,
+                              self.node_aux, *netmon_info, *next_info, num=self.B)
         self._mark("replay_insert")
         self.obs, self.adj = next_obs, next_adj
         if self.host_draws:
@@ -154,13 +176,15 @@ class Rollout:
 
     def profile_stages(self, iters=10):
         """Per-stage device time of one step (CUDA events on the launching stream), plus the time of
-        the step's GEMM launches replayed alone through gm_linear on the step's own shapes."""
+        the summed event time of the step's tensor-core GEMM launches."""
         import ctypes as C
 
         from . import _lib
 
         if self.episode_step is None or self.episode_step + iters + 1 >= self.cfg["episode_steps"]:
             self.reset()
+        overlap, self.overlap_replay = self.overlap_replay, False  # stage times are taken with everything on one stream
+        self.join_streams()
         self.step()
         acc = {}
         for _ in range(iters):
@@ -184,6 +208,7 @@ class Rollout:
             _lib.check(_lib.lib().gm_profile_collect(C.byref(tc_ms), C.byref(tc_n)))
             acc["gemm_ms"] = tc_ms.value / iters
             acc["gemm_launches_per_step"] = tc_n.value / iters
+        self.overlap_replay = overlap
         acc["gemm_kernel"] = {"fp32": "linear_simt_kernel (fp32 FFMA)", "bf16x3": "linear_tc_kernel (tcgen05, bf16 hi/lo split x3)",
                               "bf16": "linear_tc_kernel (tcgen05, single bf16 pass)"}[math]
         return acc
