@@ -34,7 +34,8 @@ class RoutingIO(C.Structure):
                [("philox_seed", C.c_uint64), ("philox_step", C.c_uint64)] + \
                [(n, C.c_void_p) for n in ("obs", "adj", "node_obs", "node_agent", "agent_node", "reward",
                                           "done", "delays", "arrived", "spr", "info", "n_resets",
-                                          "action_mask_out")]
+                                          "action_mask_out", "eval_f64", "eval_i32", "packet_dist", "packet_sizes",
+                                          "sum_packets_per_node", "sum_packets_per_edge")]
 
 
 class CellParams(C.Structure):

@@ -236,6 +236,10 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     if (MODE == MODE_STEP) {
         const int* act = io.actions + (size_t)b * A;
         int blocked = 0, n_looped = 0, n_success = 0, n_dropped = 0;
+        if (io.sum_packets_per_node) {  // routing.py:384-386: waiting packets seen at the start of the step
+            for (int i = lane; i < A; i += 32)
+                if (v.edge[i] == -1) atomicAdd(io.sum_packets_per_node + (size_t)b * N + v.now[i], 1);
+        }
         // ---- loop 1 (routing.py:380-412): edge admission in packet-id order -------
         for (int c0 = 0; c0 < A; c0 += 32) {
             int i = c0 + lane;
@@ -268,6 +272,22 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             if (in) { v.rew[i] = rew; v.looped[i] = lp; v.steps[i] += 1; }  // :371 agent_steps += 1
         }
         __syncwarp();
+        if (io.eval_f64) {  // routing.py:414-441, between the two loops
+            for (int i = lane; i < A; i += 32) {
+                if (v.edge[i] != -1 && io.sum_packets_per_edge) atomicAdd(io.sum_packets_per_edge + (size_t)b * E + v.edge[i], 1);
+                if (io.packet_sizes) io.packet_sizes[(size_t)b * A + i] = v.size[i];
+                if (io.packet_dist) io.packet_dist[(size_t)b * A + i] = apsp[v.now[i] * N + v.target[i]];
+            }
+            if (lane == 0) {  // sequential fp64 sums in edge / packet id order, like the python loops
+                double tel = 0.0, tps = 0.0;
+                int occ = 0, on_edges = 0;
+                for (int e = 0; e < E; e++) { tel += v.load[e]; occ += v.load[e] > 0.0; }
+                for (int i = 0; i < A; i++) { tps += v.size[i]; on_edges += v.edge[i] != -1; }
+                io.eval_f64[2 * (size_t)b] = tel; io.eval_f64[2 * (size_t)b + 1] = tps;
+                if (io.eval_i32) { io.eval_i32[2 * (size_t)b] = occ; io.eval_i32[2 * (size_t)b + 1] = on_edges; }
+            }
+            __syncwarp();
+        }
         // ---- loop 2 (routing.py:444-491): timers, arrival, drop, delivery, respawn --
         int slot_base = 0;
         for (int c0 = 0; c0 < A; c0 += 32) {
@@ -382,9 +402,43 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     float* stage = (float*)(sm + L.sm_stage);
     const int store_mode = d.store_mode;
 
-    // ---- agent observations (routing.py:277-305), row width 6N+10 ----------------------
+    // waiting packets per node: count and fp64 size sum in packet-id order (routing.py:200-205); needed by
+    // the node observations and by the GLOBAL agent observation
+    const bool need_wait = io.node_obs != nullptr || (io.obs != nullptr && d.env_var == 3);
+    if (need_wait) {
+        for (int j = lane; j < N; j += 32) { v.tl[j] = 0.0; v.cnt[j] = 0; }
+        __syncwarp();
+        for (int c0 = 0; c0 < A; c0 += 32) {
+            int i = c0 + lane;
+            bool waiting = (i < A) && v.edge[i] == -1;
+            int nw = waiting ? v.now[i] : -1;
+            ordered_by_key(waiting, nw, lane, [&]() {
+                v.cnt[nw] += 1;
+                v.tl[nw] += v.size[i];
+            });
+        }
+        __syncwarp();
+    }
+    // non-zero fields of node row j (routing.py:193-234) placed at column offset `base` of row r
+    auto node_row = [&](int r, int base, int j, auto put) {
+        put(r, base + j, 1.f);
+        put(r, base + N, (float)v.cnt[j]);
+        put(r, base + N + 1, (float)v.tl[j]);
+        for (int q = 0; q < 3; q++) {
+            int k = ne[j * 3 + q], o = nb[j * 3 + q];
+            int b2 = base + N + 2 + q * (N + 2);
+            put(r, b2 + o, 1.f);
+            put(r, b2 + N, (float)ed[k].z);
+            put(r, b2 + N + 1, (float)v.load[k]);
+        }
+    };
+
+    // ---- agent observations (routing.py:277-358) ------------------------------------------
+    // row = 6N+10 packet/edge fields | env_var 2: 5 fields of up to k neighbouring agents (:328-348)
+    //                                | env_var 3: flattened node adjacency + node observations (:271-275,353-354)
     if (io.obs) {
-        const int W = 6 * N + 10;
+        const int W0 = 6 * N + 10;
+        const int W = W0 + (d.env_var == 2 ? 5 * d.k : 0) + (d.env_var == 3 ? N * N + N * (4 * N + 8) : 0);
         emit_f32_block(io.obs + (size_t)b * A * W, A * W, W, stage, L.stage_floats, lane, store_mode,
                        [&](int r0, int r1, auto put) {
                            for (int i = r0 + lane; i <= r1; i += 32) {
@@ -407,40 +461,40 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                                    put(i, base + N, (float)ed[k].z);
                                    put(i, base + N + 1, (float)v.load[k]);
                                }
+                               if (d.env_var == 2) {
+                                   int count = 0;
+                                   for (int j = 0; j < A && count < d.k; j++) {
+                                       if (j == i) continue;
+                                       int nj = v.now[j];
+                                       if (nj == nw || nb[nw * 3] == nj || nb[nw * 3 + 1] == nj || nb[nw * 3 + 2] == nj) {
+                                           int base = W0 + 5 * count;
+                                           put(i, base, (float)nj);
+                                           put(i, base + 1, (float)v.target[j]);
+                                           put(i, base + 2, (float)v.edge[j]);
+                                           put(i, base + 3, (float)v.size[j]);
+                                           put(i, base + 4, (float)i);
+                                           count++;
+                                       }
+                                   }
+                                   for (; count < d.k; count++)
+                                       for (int q = 0; q < 5; q++) put(i, W0 + 5 * count + q, -1.f);
+                               } else if (d.env_var == 3) {
+                                   for (int j = 0; j < N; j++) {
+                                       put(i, W0 + j * N + j, 1.f);
+                                       for (int q = 0; q < 3; q++) put(i, W0 + j * N + nb[j * 3 + q], 1.f);
+                                       node_row(i, W0 + N * N + j * (4 * N + 8), j, put);
+                                   }
+                               }
                            }
                        });
     }
 
     // ---- node observations (routing.py:193-234), row width 4N+8 ------------------------
     if (io.node_obs) {
-        // waiting packets per node: count and fp64 size sum in packet-id order (:200-205)
-        for (int j = lane; j < N; j += 32) { v.tl[j] = 0.0; v.cnt[j] = 0; }
-        __syncwarp();
-        for (int c0 = 0; c0 < A; c0 += 32) {
-            int i = c0 + lane;
-            bool waiting = (i < A) && v.edge[i] == -1;
-            int nw = waiting ? v.now[i] : -1;
-            ordered_by_key(waiting, nw, lane, [&]() {
-                v.cnt[nw] += 1;
-                v.tl[nw] += v.size[i];
-            });
-        }
-        __syncwarp();
         const int W = 4 * N + 8;
         emit_f32_block(io.node_obs + (size_t)b * N * W, N * W, W, stage, L.stage_floats, lane, store_mode,
                        [&](int r0, int r1, auto put) {
-                           for (int j = r0 + lane; j <= r1; j += 32) {
-                               put(j, j, 1.f);
-                               put(j, N, (float)v.cnt[j]);
-                               put(j, N + 1, (float)v.tl[j]);
-                               for (int q = 0; q < 3; q++) {
-                                   int k = ne[j * 3 + q], o = nb[j * 3 + q];
-                                   int base = N + 2 + q * (N + 2);
-                                   put(j, base + o, 1.f);
-                                   put(j, base + N, (float)ed[k].z);
-                                   put(j, base + N + 1, (float)v.load[k]);
-                               }
-                           }
+                           for (int j = r0 + lane; j <= r1; j += 32) node_row(j, 0, j, put);
                        });
     }
 
@@ -465,7 +519,8 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
     GM_CHECK_ARG(d && io, "null descriptor");
     GM_CHECK_ARG(d->B > 0 && d->N > 0 && d->A > 0, "bad sizes B=%d N=%d A=%d", d->B, d->N, d->A);
     GM_CHECK_ARG(d->E * 2 == d->N * 3, "E must be 3N/2 (3-regular graph), got N=%d E=%d", d->N, d->E);
-    GM_CHECK_ARG(d->env_var == 1, "env_var %d: only EnvironmentVariant.INDEPENDENT is built in CUDA", d->env_var);
+    GM_CHECK_ARG(d->env_var >= 1 && d->env_var <= 3, "env_var %d", d->env_var);
+    GM_CHECK_ARG(d->env_var != 2 || (d->k >= 0 && d->k <= d->A), "k = %d", d->k);
     GM_CHECK_ARG(d->state && d->node_edges && d->node_nbrs && d->edges && d->apsp, "null device table");
     GM_CHECK_ARG(((uintptr_t)d->state & 15) == 0 && ((uintptr_t)d->edges & 15) == 0, "state/edges must be 16-byte aligned");
     GM_CHECK_ARG((io->draw_start == nullptr) == (io->draw_target == nullptr) &&
@@ -475,7 +530,8 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
     GM_CHECK_ARG(io->info == nullptr || ((uintptr_t)io->info & 15) == 0, "info must be 16-byte aligned");
 
     // staging tile: big enough for the larger of the two dense blocks, capped at 16 KiB per warp
-    int64_t need = 4ll * (int64_t)std::max((int64_t)d->A * (6 * d->N + 10), (int64_t)d->N * (4 * d->N + 8)) + 32;
+    const int64_t W_obs = 6 * d->N + 10 + (d->env_var == 2 ? 5 * d->k : 0) + (d->env_var == 3 ? d->N * d->N + d->N * (4 * d->N + 8) : 0);
+    int64_t need = 4ll * (int64_t)std::max((int64_t)d->A * W_obs, (int64_t)d->N * (4 * d->N + 8)) + 32;
     int stage_bytes = (int)std::min<int64_t>(16384, round_up(need, 256));
     RoutingLayout L = make_layout(d->N, d->A, d->E, stage_bytes);
     GM_CHECK_ARG(d->state_stride == L.stride, "state_stride %d != %d", d->state_stride, L.stride);

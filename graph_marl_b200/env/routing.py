@@ -96,15 +96,23 @@ class Routing(NetworkEnv):
         self._topo_index = None
         self._draws = None
         self._out = {}
+        self._sum_node = self._sum_edge = None
         self.action_mask = np.zeros((n_data, 4), dtype=bool)
         self.agent_steps = np.zeros(n_data)
 
     # ------------------------------------------------------------------------------------------
     def set_eval_info(self, val):
-        if val:
-            raise NotImplementedError(
-                "eval-info extras (routing.py:414-441) are a scheduled row (SURVEY 8f-4), not built yet")
-        self.eval_info_enabled = val
+        """Whether step() returns the evaluation extras (routing.py:111-117, 384-386, 414-441)."""
+        self.eval_info_enabled = bool(val)
+
+    def obs_width(self):
+        N = self._N
+        W = 6 * N + 10
+        if self.env_var == EnvironmentVariant.WITH_K_NEIGHBORS:
+            W += 5 * self.k
+        elif self.env_var == EnvironmentVariant.GLOBAL:
+            W += N * N + N * (4 * N + 8)
+        return W
 
     def __str__(self) -> str:
         return textwrap.dedent(
@@ -134,7 +142,7 @@ class Routing(NetworkEnv):
         def mk(a, dt, tdt):
             if torch.is_tensor(a):
                 return a.to(device=self.device, dtype=tdt).reshape(B, A).contiguous()
-            return torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dt), (B, A)))).to(self.device)
+            return torch.from_numpy(np.array(np.broadcast_to(np.asarray(a, dtype=dt), (B, A)), dtype=dt, order="C", copy=True)).to(self.device)
 
         self._draws = (mk(start, np.int32, torch.int32), mk(target, np.int32, torch.int32),
                        mk(size, np.float64, torch.float64))
@@ -155,7 +163,7 @@ class Routing(NetworkEnv):
     def _alloc_outputs(self, step):
         B, N, A, dev = self.num_envs, self._N, self._A, self.device
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
-        o = dict(obs=e((B, A, 6 * N + 10), torch.float32), adj=e((B, A, A), torch.int8),
+        o = dict(obs=e((B, A, self.obs_width()), torch.float32), adj=e((B, A, A), torch.int8),
                  node_obs=e((B, N, 4 * N + 8), torch.float32), node_agent=e((B, N, A), torch.int8),
                  agent_node=e((B, A), torch.int32), n_resets=e((B,), torch.int32))
         if step:
@@ -163,6 +171,13 @@ class Routing(NetworkEnv):
                      arrived=e((B, A), torch.uint8), spr=e((B, A), torch.float64), info=e((B, 4), torch.int32))
         if self.enable_action_mask:
             o["action_mask_out"] = e((B, A, 4), torch.uint8)
+        if step and self.eval_info_enabled:
+            o.update(eval_f64=e((B, 2), torch.float64), eval_i32=e((B, 2), torch.int32),
+                     packet_dist=e((B, A), torch.int32), packet_sizes=e((B, A), torch.float64))
+            if self._sum_node is None:
+                self._sum_node = torch.zeros((B, N), dtype=torch.int32, device=dev)
+                self._sum_edge = torch.zeros((B, self._E), dtype=torch.int32, device=dev)
+            o.update(sum_packets_per_node=self._sum_node, sum_packets_per_edge=self._sum_edge)
         return o
 
     def _io(self, out, actions=None, env_mask=None):
@@ -225,6 +240,10 @@ class Routing(NetworkEnv):
                 dt[i] = np.random.randint(self.num_random_targets)
                 dz[i] = np.random.random()
             self.set_draws(ds, dt, dz)
+        if self.eval_info_enabled:  # routing.py:167-169
+            self._sum_node = self._sum_edge = None
+            self.sum_packets_per_node = np.zeros(self._N)
+            self.sum_packets_per_edge = np.zeros(self._E)
         out = self._alloc_outputs(step=False)
         self._launch(_lib.lib().gm_routing_reset, out)
         self.agent_steps = np.zeros(self.n_data)
@@ -247,6 +266,10 @@ class Routing(NetworkEnv):
         if self.batched:
             info = dict(looped=out["info"][:, 0], throughput=out["info"][:, 1], dropped=out["info"][:, 2],
                         blocked=out["info"][:, 3], delays=out["delays"], arrived=out["arrived"], spr=out["spr"])
+            if self.eval_info_enabled:
+                info.update(total_edge_load=out["eval_f64"][:, 0], total_packet_size=out["eval_f64"][:, 1],
+                            occupied_edges=out["eval_i32"][:, 0], packets_on_edges=out["eval_i32"][:, 1],
+                            packet_sizes=out["packet_sizes"], packet_distances=out["packet_dist"])
             return out["obs"], out["adj"], out["reward"], out["done"].view(torch.bool), info
         n = int(out["n_resets"][0].item())
         if rng_state is not None and n > 0:
@@ -266,6 +289,17 @@ class Routing(NetworkEnv):
             "dropped": np.int64(inf[2]),
             "blocked": int(inf[3]),
         }
+        if self.eval_info_enabled:  # routing.py:509-519, 484-486
+            ef, ei = out["eval_f64"][0].cpu().numpy(), out["eval_i32"][0].cpu().numpy()
+            info.update(total_edge_load=float(ef[0]) if ef[0] != 0 else 0, occupied_edges=int(ei[0]),
+                        packets_on_edges=int(ei[1]), total_packet_size=float(ef[1]),
+                        packet_sizes=[float(x) for x in out["packet_sizes"][0].cpu().numpy()],
+                        packet_distances=[int(x) for x in out["packet_dist"][0].cpu().numpy()])
+            self.sum_packets_per_node = self._sum_node[0].cpu().numpy().astype(np.float64)
+            self.sum_packets_per_edge = self._sum_edge[0].cpu().numpy().astype(np.float64)
+            for st, sp in zip(delays[arrived], spr[arrived]):
+                opt = int(round(st / sp)) if sp > 0 else 1
+                self.distance_map[opt].append(float(st))
         self.agent_steps = np.where(done, 0, self.agent_steps + 1)
         if self.enable_action_mask:
             self.action_mask = out["action_mask_out"][0].cpu().numpy().astype(bool)

@@ -90,7 +90,7 @@ GM_API int gm_topology_apsp(int32_t n_nodes, int32_t n_edges, const int32_t* edg
 
 typedef struct gm_routing_desc {
     int32_t B, N, A, E, T;       /* envs, nodes, agents(=packets), edges=3N/2, pool size */
-    int32_t env_var;             /* EnvironmentVariant: 1 (only 1 is built in CUDA so far) */
+    int32_t env_var;             /* EnvironmentVariant 1 (independent), 2 (with k neighbours), 3 (global) */
     int32_t k;                   /* neighbours in obs for env_var 2 */
     int32_t congestion;          /* enable_congestion (routing.py:61) */
     int32_t action_mask;         /* enable_action_mask (routing.py:62) */
@@ -115,7 +115,7 @@ typedef struct gm_routing_io {
     const double* draw_size;     /*        All three NULL => device Philox4x32-10 draws.    */
     uint64_t philox_seed, philox_step;
     /* outputs (device); any may be NULL and is then not produced */
-    float* obs;                  /* [B,A,6N+10]  routing.py:269-358 (env_var 1) */
+    float* obs;                  /* [B,A,W] routing.py:269-358; W = 6N+10 (+5k for env_var 2, +N*N+N*(4N+8) for 3) */
     int8_t* adj;                 /* [B,A,A]      routing.py:522-539 */
     float* node_obs;             /* [B,N,4N+8]   routing.py:187-235 */
     int8_t* node_agent;          /* [B,N,A]      routing.py:256-267 */
@@ -128,6 +128,13 @@ typedef struct gm_routing_io {
     int32_t* info;               /* [B,4] looped, throughput, dropped, blocked (routing.py:499-508) */
     int32_t* n_resets;           /* [B] draw slots consumed by this call */
     uint8_t* action_mask_out;    /* [B,A,4] env.action_mask after the call (routing.py:106) */
+    /* set_eval_info(True) extras (routing.py:384-386, 414-441); enabled by eval_f64 != NULL, step only */
+    double* eval_f64;            /* [B,2] total_edge_load, total_packet_size (sequential fp64 sums) */
+    int32_t* eval_i32;           /* [B,2] occupied_edges, packets_on_edges */
+    int32_t* packet_dist;        /* [B,A] shortest-path weight now->target of every packet */
+    double* packet_sizes;        /* [B,A] packet sizes before respawns */
+    int32_t* sum_packets_per_node; /* [B,N] cumulative: += 1 per waiting packet per step (routing.py:384-386) */
+    int32_t* sum_packets_per_edge; /* [B,E] cumulative: += 1 per in-flight packet per step (routing.py:428-429) */
 } gm_routing_io;
 
 /* byte offsets inside one env's state record; out[8] =

@@ -11,7 +11,7 @@ from helpers import cfg_from_golden, draws_for_step, topo_from_golden
 pytestmark = pytest.mark.gpu
 
 CASES = ["routing_A_seed923430603_cong", "routing_B_nocong", "routing_C_mask", "routing_D_ttl",
-         "routing_E_a35_nocong_mask_ttl", "routing_F_n200"]
+         "routing_E_a35_nocong_mask_ttl", "routing_F_n200", "routing_G_var2", "routing_H_var3", "routing_I_evalinfo"]
 
 
 def _make_env(g, c, num_envs=1, store_mode=0, batched=None):
@@ -37,6 +37,7 @@ def test_golden_trajectory(case, store_mode):
     c = cfg_from_golden(g)
     A = c["n_data"]
     env = _make_env(g, c, store_mode=store_mode)
+    env.set_eval_info(c["eval_info"])
     ds, dt, dz, n = draws_for_step(g, -1, A)
     env.set_draws(ds, dt, dz)
     obs, adj = env.reset()
@@ -58,6 +59,10 @@ def test_golden_trajectory(case, store_mode):
         assert info["delays"] == [float(x) for x in g["delays"][t][g["done"][t] == 1]]
         assert info["spr"] == [float(x) for x in g["spr"][t][g["arrived"][t] == 1]]
         assert int(env._out["n_resets"][0]) == n
+        if c["eval_info"]:  # routing.py:414-441
+            extra = [info["total_edge_load"], info["occupied_edges"], info["packets_on_edges"], info["total_packet_size"]]
+            assert np.array_equal(np.array(extra, dtype=np.float64), g["eval_extra"][t]), t
+            assert info["packet_sizes"] == g["s_size"][t].tolist()  # sizes before this step's respawns
         _check_state(env, g, t + 1)
         if c["mask"]:
             assert np.array_equal(env.action_mask, g["s_mask"][t + 1].astype(bool))
@@ -66,6 +71,10 @@ def test_golden_trajectory(case, store_mode):
             assert np.array_equal(adj, g["adj"][t + 1]), t
             assert np.array_equal(env.get_node_observation(), g["node_obs"][t + 1]), t
             assert np.array_equal(env.get_node_agent_matrix(), g["node_agent"][t + 1]), t
+    if c["eval_info"]:
+        assert np.array_equal(env.sum_packets_per_node, g["sum_packets_per_node"])
+        assert np.array_equal(env.sum_packets_per_edge, g["sum_packets_per_edge"])
+        assert sum(len(v) for v in env.distance_map.values()) == int(g["arrived"].sum())
     fi = env.get_final_info({"delays": []})
     assert fi["delays"] == g["final_delays"].tolist()
     assert np.array_equal(env.get_node_aux(), g["node_aux"])
@@ -195,3 +204,40 @@ def test_full_size_properties_and_philox_draws():
     nam = env._out["node_agent"].cpu().numpy()
     assert (nam.sum(1) == 1).all()
     assert np.array_equal(nam.argmax(1), s["now"])
+
+
+def test_simple_environment_golden():
+    """SimpleEnvironment (BASELINE config 1) through gm_simple_step: observations, node tables and
+    rewards of 12 recorded episodes per (env_var, random_topology), compat mode; then a batched run
+    whose rewards are the scores of the chosen neighbours."""
+    from graph_marl_b200.env.simple_environment import SimpleEnvironment
+
+    g = load_golden("simple_env")
+    for var in (1, 3):
+        for rt in (0, 1):
+            tag = f"v{var}_rt{rt}_"
+            np.random.seed(10 + var + rt)
+            env = SimpleEnvironment(env_var=var, random_topology=rt)
+            for ep in range(len(g[tag + "act"])):
+                obs, adj = env.reset()
+                assert np.array_equal(obs, g[tag + "obs"][ep]) and obs.dtype == np.float32
+                assert np.array_equal(adj, np.eye(1, dtype=np.int8))
+                assert np.array_equal(env.get_node_observation(), g[tag + "node_obs"][ep])
+                assert np.array_equal(env.get_node_agent_matrix(), g[tag + "node_agent"][ep])
+                assert np.array_equal(env.get_nodes_adjacency(), g[tag + "node_adj"][ep])
+                obs2, adj2, rew, done, info = env.step([int(g[tag + "act"][ep])])
+                assert done == [True] and np.array_equal(obs2, obs) and info == {}
+                assert np.array_equal(rew.astype(np.float64), g[tag + "reward"][ep])
+            assert np.random.random() == g[tag + "after"][0]
+    np.random.seed(5)
+    env = SimpleEnvironment(env_var=1, random_topology=1, num_envs=257)
+    obs, adj = env.reset()
+    act = torch.randint(0, 2, (257,), device="cuda", dtype=torch.int32)
+    obs2, adj2, rew, done, info = env.step(act)
+    assert obs2.shape == (257, 1, 1) and done.all() and rew.shape == (257, 1)
+    a = act.cpu().numpy()
+    for b, net in enumerate(env._host):
+        t = net["start_edges"][a[b]]
+        e = net["edges"][t]
+        dst = e[1] if e[0] == net["start_node"] else e[0]
+        assert rew[b, 0].item() == net["scores"][dst]

@@ -132,3 +132,24 @@ def test_networkx_views_and_weight_randomisation():
         for b in range(20):
             assert net.shortest_paths_weights[a][b] == d[a][b]
     assert not np.array_equal(w0, net.shortest_paths_weights)
+
+
+def test_simple_environment_topology_draws_match_reference():
+    """SimpleEnvironment._draw_network consumes the global legacy stream like the reference's
+    _build_network (simple_environment.py:106-187): scores, edges, start node / edge order and the
+    stream position after 12 episodes are those recorded from the reference."""
+    from conftest import load_golden
+    from graph_marl_b200.env.simple_environment import SimpleEnvironment
+
+    g = load_golden("simple_env")
+    for var in (1, 3):
+        for rt in (0, 1):
+            tag = f"v{var}_rt{rt}_"
+            np.random.seed(10 + var + rt)
+            env = SimpleEnvironment(env_var=var, random_topology=rt)
+            for ep in range(len(g[tag + "act"])):
+                net = env._draw_network()
+                assert np.array_equal(net["scores"], g[tag + "scores"][ep])
+                assert np.array_equal(net["edges"], g[tag + "edges"][ep])
+                assert [net["start_node"]] + net["start_edges"].tolist() == g[tag + "start_edges"][ep].tolist()
+            assert np.random.random() == g[tag + "after"][0]
