@@ -59,6 +59,15 @@ __global__ void aggregate_kernel(const float* __restrict__ h, int64_t ldh, float
     const int* lst = nbr + ((size_t)li * N + v) * DM;
     int dg = deg[(size_t)li * N + v];
     const float* hb = h + (size_t)b * N * ldh;
+    if ((H & 3) != 0 || (ldh & 3) != 0 || (((uintptr_t)h | (uintptr_t)M) & 15) != 0) {  // small / odd hidden sizes: scalar
+        for (int c = lane; c < H; c += 32) {
+            float acc = 0.f;
+            for (int q = 0; q < dg; q++) acc += hb[(size_t)lst[q] * ldh + c];
+            if (mean) acc /= (float)max(dg, 1);
+            M[row * H + c] = acc;
+        }
+        return;
+    }
     for (int c = lane * 4; c < H; c += 128) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int q = 0; q < dg; q++) {
@@ -502,7 +511,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     GM_CHECK_ARG(p && node_obs && nbr_all && deg && state_out && workspace, "null pointer");
     GM_CHECK_ARG(B > 0 && N > 0 && DM > 0, "bad sizes");
     const int H = p->hidden, K = p->iterations, L = p->n_enc_layers;
-    GM_CHECK_ARG(H > 0 && (H % 4) == 0 && H <= 256, "hidden size %d: need a multiple of 4, <= 256", H);
+    GM_CHECK_ARG(H > 0 && H <= 256, "hidden size %d: need 1..256", H);
     GM_CHECK_ARG(L >= 1 && L <= GM_MAX_LAYERS && p->enc_units[L - 1] == H, "encoder must end in %d units", H);
     GM_CHECK_ARG(p->rnn_type >= GM_RNN_LSTM && p->rnn_type <= GM_RNN_NONE, "rnn_type %d", p->rnn_type);
     GM_CHECK_ARG(!(p->rnn_type == GM_RNN_GRU && !p->rnn_carryover),

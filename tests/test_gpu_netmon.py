@@ -226,3 +226,15 @@ def test_wrapper_closed_loop_golden():
         assert np.abs(env.current_netmon_state.cpu().numpy()[0] - g["cur_state"][t][0]).max() < 1e-4
         node_obs, node_adj, nam = env.get_netmon_info()
         assert node_obs.shape == (20, 88) and node_adj.shape == (20, 20) and nam.shape == (20, 20)
+
+
+def test_ci_known_answer_simple_env_training_reaches_reward_mean_1():
+    """The reference's only known-answer test (.github/workflows/train-example.yml:26-27, BASELINE
+    config 1): DQN + NetMon on SimpleEnvironment, 5000 steps, final evaluation reward_mean == 1.0 --
+    with the classes of this package dropped into the reference's rollout/learner/eval loop."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import train_simple
+
+    metrics = train_simple.main(["--total-steps", "5000", "--step-before-train", "1000", "--eval-episodes", "100"])
+    assert metrics["reward_mean"] == 1.0
