@@ -208,7 +208,9 @@ def main():
     host_ms = [0.0]
 
     def timed(ro, steps, warmup, host):
-        for _ in range(warmup):
+        # untimed warm-up: at least the requested steps and one full wrap of the replay ring (8 x B slots), so
+        # first-touch effects of the ring are outside the timed region
+        for _ in range(max(warmup, 10)):
             ro.step()
         ro.join_streams()
         n0 = _lib.lib().gm_kernel_launch_count()

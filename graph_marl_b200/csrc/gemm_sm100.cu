@@ -26,6 +26,7 @@
 //   warp  17    copies   : one thread streams weight tiles and tile-packed activation blocks with
 //                          cp.async.bulk (TMA bulk copy) signalling the stage mbarrier
 // smem ring of 4 stages x (A hi/lo 16 KiB + W hi/lo BN*128 B); 2 accumulator stages in TMEM.
+// (Measured on B200: separate, deeper activation / weight rings with their own copy threads were slower.)
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
@@ -422,182 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
             const int mt = unit_mt((int)tcount), nt = unit_nt((int)tcount);
             const int64_t m = (int64_t)mt * BM + r;
             const bool live = m < p.M;
-            const float* bias_t = p.bias_tile + (size_t)nt * BN;  // tile-ordered, zero padded, biases pre-summed
-            // LSTM: the previous cell state of this row's hidden units is fetched while the MMAs still run
-            float cin[EPI == EPI_LSTM ? BN / 4 / 2 / 8 : 1][8];
-            if (EPI == EPI_LSTM && live) {
-#pragma unroll
-                for (int itr = 0; itr < BN / 4 / 2 / 8; itr++)
-                    ld_global_v8(p.c_in + m * p.ldc_in + nt * (BN / 4) + chalf * (BN / 8) + itr * 8, cin[itr]);
-            }
-            mbar_wait(bar_tfull + 8 * as, aph);
-            tc_fence_after();
-            const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN;
-            if (EPI == EPI_LINEAR || EPI == EPI_QHEAD) {
-                const int n0 = nt * BN;
-                float qacc[TC_MAX_ACT];
-#pragma unroll
-                for (int a = 0; a < TC_MAX_ACT; a++) qacc[a] = 0.f;
-                const int al = ptr_align_floats(p.C, p.ldc);
-                const bool fast = p.accumulate == 0 && (p.act == GM_ACT_LEAKY_RELU || p.act < 0);
-                uint8_t* const pk_row = p.Cpk ? p.Cpk + (size_t)mt * (size_t)(p.N / BK) * TC_PK_BLOCK + core_off(r, 0) : nullptr;
-#pragma unroll 1
-                for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 16) {
-                    uint32_t v[16];
-                    TMEM_LD16(t + c, v);
-                    float bb[16];
-                    ld_global_v8(bias_t + c, bb);
-                    ld_global_v8(bias_t + c + 8, bb + 8);
-                    tmem_ld_wait();
-                    if (!live || n0 + c >= p.N) continue;
-                    float o[16];
-                    if (fast) {
-                        const float slope = p.act < 0 ? 1.f : 0.01f;
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            float x = __uint_as_float(v[i]) + bb[i];
-                            o[i] = fmaxf(x, slope * x);  // leaky_relu(x) = max(x, 0.01x); identity for slope 1
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            float x = __uint_as_float(v[i]) + bb[i];
-                            if (p.accumulate && n0 + c + i < p.N) x += p.C[m * p.ldc + n0 + c + i];
-                            if (p.act >= 0) x = apply_act(x, p.act);
-                            o[i] = x;
-                        }
-                    }
-                    if (EPI == EPI_QHEAD) {  // partial Q-values over this thread's columns (padding columns hold 0)
-#pragma unroll
-                        for (int a = 0; a < TC_MAX_ACT; a++) {
-                            if (a < p.n_act) {
-                                const float4* wq = (const float4*)(p.q_w + (size_t)a * p.N + n0 + c);
-#pragma unroll
-                                for (int i = 0; i < 4; i++) {
-                                    if (n0 + c + 4 * i >= p.N) break;
-                                    float4 w4 = __ldg(wq + i);
-                                    qacc[a] = fmaf(o[4 * i], w4.x, qacc[a]); qacc[a] = fmaf(o[4 * i + 1], w4.y, qacc[a]);
-                                    qacc[a] = fmaf(o[4 * i + 2], w4.z, qacc[a]); qacc[a] = fmaf(o[4 * i + 3], w4.w, qacc[a]);
-                                }
-                            }
-                        }
-                    }
-                    if (p.C) {
-                        float* crow = p.C + m * p.ldc + n0 + c;
-                        if (n0 + c + 16 <= p.N && al >= 8) {
-                            st_global_v8(crow, o);
-                            st_global_v8(crow + 8, o + 8);
-                        } else if (n0 + c + 16 <= p.N && al >= 4) {
-#pragma unroll
-                            for (int i = 0; i < 4; i++) *(float4*)(crow + 4 * i) = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; i++)
-                                if (n0 + c + i < p.N) crow[i] = o[i];
-                        }
-                    }
-                    if (pk_row) {  // tile-packed split copy for the next layer (N % 32 == 0 checked on the host)
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            const int n = n0 + c + 8 * q;
-                            float xx[8];
-#pragma unroll
-                            for (int i = 0; i < 8; i++) xx[i] = o[8 * q + i];
-                            uint4 hi, lo;
-                            split8(xx, hi, lo);
-                            uint8_t* dst = pk_row + (size_t)(n / BK) * TC_PK_BLOCK + ((n % BK) >> 3) * 128;
-                            *(uint4*)dst = hi;
-                            if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
-                        }
-                    }
-                }
-                if (EPI == EPI_QHEAD) {
-                    // combine the two column halves through shared memory, then finish the policy step
-                    const int pb = tcount & 1;
-                    if (chalf == 1) {
-#pragma unroll
-                        for (int a = 0; a < TC_MAX_ACT; a++) qpart[pb][r][a] = qacc[a];
-                    }
-                    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");  // epilogue warps only
-                    if (chalf == 0 && live) {
-                        int best = 0;
-                        float bestv = 0.f;
-                        for (int a = 0; a < p.n_act; a++) {
-                            float q = qacc[a] + qpart[pb][r][a] + __ldg(p.q_b + a);
-                            if (p.q_out) p.q_out[m * p.n_act + a] = q;  // Q-values before masking (what the model returns)
-                            if (p.action_mask && p.action_mask[m * p.n_act + a]) q = -INFINITY;
-                            if (a == 0 || q > bestv) { best = a; bestv = q; }
-                        }
-                        int ra; double u;
-                        if (p.rand_action) { ra = p.rand_action[m]; u = p.rand_u[m]; }
-                        else {
-                            Philox ph((uint32_t)m, (uint32_t)((uint64_t)m >> 32), (uint32_t)p.philox_step,
-                                      (uint32_t)(p.philox_step >> 32) ^ 0x5bd1e995u, p.philox_seed ^ 0xA5A5A5A5DEADBEEFull);
-                            ra = (int)__umulhi(ph.r[0], (uint32_t)p.n_act);
-                            u = u53(ph.r[1], ph.r[2]);
-                        }
-                        p.act_out[m] = (u < p.epsilon) ? ra : best;
-                    }
-                }
-            } else {
-                // LSTM cell pointwise (torch.nn.LSTMCell; gate order i,f,g,o).  Packed columns of this
-                // tile: [i | f | g | o] for hidden units nt*U .. nt*U+U-1 (U = BN/4).
-                constexpr int U = BN / 4;
-                constexpr int NIT = U / 2 / 8;  // 8 hidden units per iteration, U/2 units per warp
-                const int j0 = nt * U;
-                uint8_t* const pk_row = p.Hpk ? p.Hpk + (size_t)mt * (size_t)(p.H / BK) * TC_PK_BLOCK + core_off(r, 0) : nullptr;
-#pragma unroll kLstmUnroll
-                for (int itr = 0; itr < NIT; itr++) {
-                    const int c = chalf * (U / 2) + itr * 8;
-                    float bi[8], bf[8], bg[8], bo[8];
-                    ld_global_v8(bias_t + c, bi);
-                    ld_global_v8(bias_t + U + c, bf);
-                    ld_global_v8(bias_t + 2 * U + c, bg);
-                    ld_global_v8(bias_t + 3 * U + c, bo);
-                    uint32_t vi[8], vf[8], vg[8], vo[8];
-                    TMEM_LD8(t + c, vi);
-                    TMEM_LD8(t + U + c, vf);
-                    TMEM_LD8(t + 2 * U + c, vg);
-                    TMEM_LD8(t + 3 * U + c, vo);
-                    tmem_ld_wait();
-                    if (!live) continue;
-                    float hh[8], cc[8];
-#pragma unroll
-                    for (int i = 0; i < 8; i++) {
-#if GM_LSTM_SHARED_RCP
-                        // sigmoid(i), sigmoid(f), sigmoid(o), tanh(g) from four exponentials and ONE reciprocal:
-                        // with A=1+e^-i, F=1+e^-f, O=1+e^-o, G=1+e^2g and R=1/(A*F*O*G):
-                        //   sig(i)=R*F*O*G, sig(f)=R*A*O*G, sig(o)=R*A*F*G, tanh(g)=1-2*R*A*F*O.
-                        // Arguments are clamped to +-20 (saturation error < 3e-9) so the product stays finite.
-                        const float xi = fminf(fmaxf(__uint_as_float(vi[i]) + bi[i], -20.f), 20.f);
-                        const float xf = fminf(fmaxf(__uint_as_float(vf[i]) + bf[i], -20.f), 20.f);
-                        const float xo = fminf(fmaxf(__uint_as_float(vo[i]) + bo[i], -20.f), 20.f);
-                        const float xg = fminf(fmaxf(__uint_as_float(vg[i]) + bg[i], -10.f), 10.f);
-                        const float Ai = 1.f + __expf(-xi), Af = 1.f + __expf(-xf), Ao = 1.f + __expf(-xo), Ag = 1.f + __expf(2.f * xg);
-                        const float AiAf = Ai * Af, AoAg = Ao * Ag;
-                        const float R = __fdividef(1.f, AiAf * AoAg);
-                        const float i_ = R * Af * AoAg, f_ = R * Ai * AoAg, o_ = R * AiAf * Ag;
-                        const float g_ = 1.f - 2.f * (R * AiAf * Ao);
-#else
-                        const float i_ = fast_sigmoid(__uint_as_float(vi[i]) + bi[i]), f_ = fast_sigmoid(__uint_as_float(vf[i]) + bf[i]);
-                        const float g_ = fast_tanh(__uint_as_float(vg[i]) + bg[i]), o_ = fast_sigmoid(__uint_as_float(vo[i]) + bo[i]);
-#endif
-                        const float cv = f_ * cin[itr][i] + i_ * g_;
-                        cc[i] = cv;
-                        hh[i] = o_ * fast_tanh(cv);
-                    }
-                    st_global_v8(p.h_out + m * p.ldh + j0 + c, hh);
-                    st_global_v8(p.c_out + m * p.ldco + j0 + c, cc);
-                    if (pk_row) {
-                        const int n = j0 + c;
-                        uint4 hi, lo;
-                        split8(hh, hi, lo);
-                        uint8_t* dst = pk_row + (size_t)(n / BK) * TC_PK_BLOCK + ((n % BK) >> 3) * 128;
-                        *(uint4*)dst = hi;
-                        if (PASSES == 3) *(uint4*)(dst + A_PART_BYTES) = lo;
-                    }
-                }
-            }
+#include "gemm_sm100_epilogue.inc"
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * as);
         }
@@ -607,6 +433,163 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     __syncthreads();
     if (p.csz > 1) cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
     if (warp == MMA_WARP) {
+        tc_fence_after();
+        uint32_t cols = ACC_STAGES * BN;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Weight-stationary cluster variant (all activations tile-packed).
+//
+// The layers of this workload have small weights and a huge M (rows = envs x nodes): streaming the
+// weight tile once per M tile makes linear_tc_kernel operand-bandwidth bound.  Here a cluster of csz
+// CTAs splits the N dimension: CTA `rank` keeps ITS BN-column slice of the packed weights resident in
+// shared memory for the whole kernel (<= 128 KiB), and the cluster walks the M tiles together: each
+// CTA bulk-copies 1/csz of every activation k-block and multicasts it to all CTAs of the cluster, so
+// an activation block is read from L2/HBM once per cluster and no weight byte moves after the prologue.
+// 10 warps: 8 epilogue (same code as linear_tc_kernel), 1 MMA thread, 1 copy thread.
+// -------------------------------------------------------------------------------------------------
+constexpr int WS_THREADS = 32 * 10, WS_MMA_WARP = 8, WS_COPY_WARP = 9, WS_MAX_A_STAGES = 8;
+
+template <int BN, int PASSES, int EPI>
+__global__ void __launch_bounds__(WS_THREADS, 1) linear_ws_kernel(const TcArgs p) {
+    constexpr int W_PART_BYTES = BN * BK * 2;
+    constexpr int W_KB_BYTES = 2 * W_PART_BYTES, A_STAGE_BYTES = 2 * A_PART_BYTES;
+    constexpr int ACC_STAGES = (512 / BN) > 4 ? 4 : (512 / BN);
+    constexpr uint32_t IDESC = umma_idesc(BN);
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[2 * WS_MAX_A_STAGES + 1 + 2 * 4];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float qpart[1][1][TC_MAX_ACT];  // unused here (no fused Q head), referenced by the shared epilogue text
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a_stages = p.a_stages;
+    const int kblocks = p.Kp / BK;
+    const int kb_seg1 = p.K0p / BK;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t a_ring = smem_base + (uint32_t)kblocks * W_KB_BYTES;  // activation ring sits behind the weights
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[WS_MAX_A_STAGES]);
+    const uint32_t bar_w = smem_u32(&bars[2 * WS_MAX_A_STAGES]);
+    const uint32_t bar_tfull = smem_u32(&bars[2 * WS_MAX_A_STAGES + 1]), bar_tempty = smem_u32(&bars[2 * WS_MAX_A_STAGES + 5]);
+    const int csz = p.csz;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < a_stages; s++) {
+            mbar_init(bar_afull + 8 * s, 1);     // own expect_tx arrive; the bytes come from every CTA's multicast share
+            mbar_init(bar_aempty + 8 * s, csz);  // one tcgen05.commit per CTA of the cluster
+        }
+        mbar_init(bar_w, 1);
+        for (int a = 0; a < ACC_STAGES; a++) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, EPI_WARPS * 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WS_MMA_WARP) {
+        uint32_t dst = smem_u32(&tmem_base_smem);
+        uint32_t cols = ACC_STAGES * BN;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (csz > 1) cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int rank = csz > 1 ? (int)cluster_ctarank() : 0;  // == this CTA's N tile
+    const uint16_t mc_mask = (uint16_t)((1u << csz) - 1u);
+    const int n_clusters = (int)gridDim.x / csz, cluster_id = (int)blockIdx.x / csz;
+    const int my_units = (p.m_tiles - cluster_id + n_clusters - 1) / n_clusters;  // M tiles of this cluster
+
+    if (warp == WS_COPY_WARP) {
+        if (lane == 0) {
+            // ---- the weight slice of this CTA: resident for the whole kernel --------------------
+            constexpr uint32_t w_kb = (PASSES == 3 ? 2 : 1) * W_PART_BYTES;
+            mbar_arrive_expect_tx(bar_w, (uint32_t)kblocks * w_kb);
+            for (int kb = 0; kb < kblocks; kb++)
+                bulk_g2s(smem_base + kb * W_KB_BYTES, p.Wp + ((size_t)rank * kblocks + kb) * W_KB_BYTES, w_kb, bar_w);
+            // ---- activation k-blocks: 1/csz each, multicast to the cluster -----------------------------
+            constexpr uint32_t a_bytes = (PASSES == 3 ? 2 : 1) * A_PART_BYTES;
+            const uint32_t slice = A_PART_BYTES / csz;
+            const int kb0_blocks = kb_seg1, kb1_blocks = kblocks - kb_seg1;
+            uint32_t it = 0;
+            for (int u = 0; u < my_units; u++) {
+                const int mt = cluster_id + u * n_clusters;
+                for (int kb = 0; kb < kblocks; kb++, it++) {
+                    const int sa = it % a_stages;
+                    const uint32_t pha = (it / a_stages) & 1;
+                    const bool seg1 = kb >= kb_seg1;
+                    const uint8_t* apk = seg1 ? p.A1pk : p.A0pk;
+                    const size_t blk = seg1 ? ((size_t)mt * kb1_blocks + (kb - kb_seg1)) : ((size_t)mt * kb0_blocks + kb);
+                    const uint8_t* src = apk + blk * TC_PK_BLOCK;
+                    mbar_wait(bar_aempty + 8 * sa, pha ^ 1);  // every CTA of the cluster retired its MMAs on this stage
+                    mbar_arrive_expect_tx(bar_afull + 8 * sa, a_bytes);
+                    const uint32_t dst = a_ring + sa * A_STAGE_BYTES;
+                    if (csz == 1) {
+                        bulk_g2s(dst, src, a_bytes, bar_afull + 8 * sa);
+                    } else {
+#pragma unroll
+                        for (int part = 0; part < (PASSES == 3 ? 2 : 1); part++)
+                            bulk_g2s_mc(dst + part * A_PART_BYTES + rank * slice, src + part * A_PART_BYTES + rank * slice, slice,
+                                        bar_afull + 8 * sa, mc_mask);
+                    }
+                }
+            }
+        }
+    } else if (warp == WS_MMA_WARP) {
+        if (lane == 0) {
+            mbar_wait(bar_w, 0);
+            uint32_t it = 0;
+            for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
+                const int as = tcount % ACC_STAGES;
+                const uint32_t aph = (tcount / ACC_STAGES) & 1;
+                mbar_wait(bar_tempty + 8 * as, aph ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + as * BN;
+                for (int kb = 0; kb < kblocks; kb++, it++) {
+                    const int sa = it % a_stages;
+                    mbar_wait(bar_afull + 8 * sa, (it / a_stages) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = a_ring + sa * A_STAGE_BYTES, a_lo = a_hi + A_PART_BYTES;
+                    const uint32_t w_hi = smem_base + kb * W_KB_BYTES, w_lo = w_hi + W_PART_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ks++) {
+                        const uint32_t o = ks * 256;
+                        if (PASSES == 3) {
+                            umma(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
+                            umma(d, umma_desc(a_hi + o), umma_desc(w_lo + o), IDESC, 1);
+                            umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, 1);
+                        } else {
+                            umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
+                        }
+                    }
+                    if (csz == 1) umma_commit(bar_aempty + 8 * sa);
+                    else umma_commit_mc(bar_aempty + 8 * sa, mc_mask);
+                }
+                umma_commit(bar_tfull + 8 * as);
+            }
+        }
+    } else {
+        const int quad = warp & 3, chalf = warp >> 2;
+        const int r = quad * 32 + lane;
+        for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
+            const int as = tcount % ACC_STAGES;
+            const uint32_t aph = (tcount / ACC_STAGES) & 1;
+            const int mt = cluster_id + (int)tcount * n_clusters, nt = rank;
+            const int64_t m = (int64_t)mt * BM + r;
+            const bool live = m < p.M;
+#include "gemm_sm100_epilogue.inc"
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * as);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (csz > 1) cluster_sync_all();
+    if (warp == WS_MMA_WARP) {
         tc_fence_after();
         uint32_t cols = ACC_STAGES * BN;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
@@ -688,9 +671,11 @@ int tc_pick_bn(int N, int epi) {
     return N <= 128 ? 128 : 256;
 }
 
-TcShape tc_shape(int N, int K0, int K1, int epi, int H) {
+TcShape tc_shape(int N, int K0, int K1, int epi, int H, int ws) {
     TcShape s;
     s.BN = tc_pick_bn(N, epi);
+    TcWsPlan plan;
+    if (ws && tc_ws_plan(N, K0, K1, epi, H, &plan)) s.BN = plan.BN;
     s.K0p = (int)round_up(K0, tc::BK);  // segment 1 starts on a k-block boundary
     s.Kp = s.K0p + (int)round_up(K1, tc::BK);
     s.n_tiles = (epi == EPI_LSTM) ? ceil_div(H, s.BN / 4) : ceil_div(N, s.BN);
@@ -700,8 +685,8 @@ TcShape tc_shape(int N, int K0, int K1, int epi, int H) {
 }
 
 int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, const float* bias, const float* bias2, int N,
-                    int K0, int K1, int epi, int H, void* out, cudaStream_t s) {
-    TcShape sh = tc_shape(N, K0, K1, epi, H);
+                    int K0, int K1, int epi, int H, void* out, cudaStream_t s, int ws) {
+    TcShape sh = tc_shape(N, K0, K1, epi, H, ws);
     int64_t total = (int64_t)sh.n_tiles * (sh.Kp / tc::BK) * sh.BN * (tc::BK / 8);
     int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
     tc::pack_w_kernel<<<blocks, 256, 0, s>>>(W, ldw, W1, ldw1, N, K0, K1, sh.K0p, sh.Kp, sh.BN, sh.n_tiles, epi == EPI_LSTM,
@@ -777,9 +762,86 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
     return GM_OK;
 }
 
+
+// ---- weight-stationary plan ---------------------------------------------------------------------------
+// Splits the packed N columns over a cluster so that one slice (BN columns x Kp, hi+lo) fits in shared
+// memory next to >= 3 activation stages.  Returns false when the layer does not qualify.
+bool tc_ws_plan(int N, int K0, int K1, int epi, int H, TcWsPlan* out) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("GM_TC_WS");
+        enabled = e ? atoi(e) : 0;  // measured on B200: slower than the streaming kernel (multicast replicates the bytes in flight, HBM-latency bound)
+    }
+    if (!enabled || epi == EPI_QHEAD) return false;
+    const int cols = epi == EPI_LSTM ? 4 * H : N;
+    const int Kp = (int)round_up(K0, tc::BK) + (int)round_up(K1, tc::BK);
+    const int bns[2] = {128, 64};
+    for (int bi = 0; bi < 2; bi++) {
+        const int BN = bns[bi];
+        if (epi == EPI_LSTM && BN != 128) continue;  // instantiated for 32 hidden units x 4 gates per CTA
+        if (cols % BN != 0) continue;
+        const int csz = cols / BN;
+        if (csz != 1 && csz != 2 && csz != 4) continue;
+        const int64_t w_bytes = (int64_t)(Kp / tc::BK) * 2 * BN * tc::BK * 2;
+        const int64_t room = 227 * 1024 - 1024 - w_bytes;
+        const int stages = (int)std::min<int64_t>(room / (2 * tc::A_PART_BYTES), tc::WS_MAX_A_STAGES);
+        if (stages < 3) continue;
+        out->BN = BN; out->csz = csz; out->a_stages = stages;
+        out->smem = (int)(w_bytes + (int64_t)stages * 2 * tc::A_PART_BYTES);
+        return true;
+    }
+    return false;
+}
+
+template <int BN, int PASSES, int EPI>
+static int launch_ws(TcArgs a, const TcWsPlan& plan, cudaStream_t s) {
+    static int configured_smem = 0;
+    static int max_clusters[5] = {0, 0, 0, 0, 0};
+    auto kern = tc::linear_ws_kernel<BN, PASSES, EPI>;
+    if (configured_smem < plan.smem) {
+        GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
+        if (plan.csz > 2) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), cudaGetLastError();
+        configured_smem = plan.smem;
+        for (int i = 0; i < 5; i++) max_clusters[i] = 0;
+    }
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(tc::WS_THREADS);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = s;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan.csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (max_clusters[plan.csz] == 0) {
+        cfg.gridDim = dim3((kNumSMs / plan.csz) * plan.csz);
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+        if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
+        max_clusters[plan.csz] = n;
+    }
+    if (max_clusters[plan.csz] < 0) return 1;  // clusters of this shape cannot be scheduled: caller falls back
+    a.csz = plan.csz;
+    a.a_stages = plan.a_stages;
+    const int n_clusters = std::min(a.m_tiles, max_clusters[plan.csz]);
+    cfg.gridDim = dim3(n_clusters * plan.csz);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_tc_profile) {
+        GM_CUDA(cudaEventCreate(&e0));
+        GM_CUDA(cudaEventCreate(&e1));
+        GM_CUDA(cudaEventRecord(e0, s));
+    }
+    GM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    count_launch();
+    if (g_tc_profile) {
+        GM_CUDA(cudaEventRecord(e1, s));
+        g_tc_events.emplace_back(e0, e1);
+    }
+    return GM_OK;
+}
+
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     if (a.M <= 0) return GM_OK;
-    TcShape sh = tc_shape(a.N, a.K0, a.K1, epi, a.H);
+    TcShape sh = tc_shape(a.N, a.K0, a.K1, epi, a.H, a.ws);
     a.K0p = sh.K0p;
     a.Kp = sh.Kp;
     a.n_tiles = sh.n_tiles;
@@ -809,6 +871,19 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
         GM_CHECK_ARG(!a.accumulate || a.C != nullptr, "accumulate needs an fp32 output");
     }
     const int passes = math == GM_MATH_BF16 ? 1 : 3;
+    if (a.ws) {  // weight-stationary cluster variant: weights were packed for the plan's BN
+        TcWsPlan plan;
+        GM_CHECK_ARG(!a.has_prod && tc_ws_plan(a.N, a.K0, a.K1, epi, a.H, &plan), "layer does not qualify for the weight-stationary kernel");
+        int rc = 1;
+        if (epi == EPI_LSTM) rc = passes == 3 ? launch_ws<128, 3, EPI_LSTM>(a, plan, s) : launch_ws<128, 1, EPI_LSTM>(a, plan, s);
+        else if (plan.BN == 128) rc = passes == 3 ? launch_ws<128, 3, EPI_LINEAR>(a, plan, s) : launch_ws<128, 1, EPI_LINEAR>(a, plan, s);
+        else rc = passes == 3 ? launch_ws<64, 3, EPI_LINEAR>(a, plan, s) : launch_ws<64, 1, EPI_LINEAR>(a, plan, s);
+        if (rc == 1) {
+            set_error("cluster launch of the weight-stationary kernel is not possible on this device (set GM_TC_WS=0)");
+            return GM_ERR_CUDA;
+        }
+        return rc;
+    }
     if (epi == EPI_LSTM) return passes == 3 ? launch_tc<256, 3, EPI_LSTM>(a, s) : launch_tc<256, 1, EPI_LSTM>(a, s);
     if (epi == EPI_QHEAD) return passes == 3 ? launch_tc<256, 3, EPI_QHEAD>(a, s) : launch_tc<256, 1, EPI_QHEAD>(a, s);
     if (sh.BN == 128) return passes == 3 ? launch_tc<128, 3, EPI_LINEAR>(a, s) : launch_tc<128, 1, EPI_LINEAR>(a, s);

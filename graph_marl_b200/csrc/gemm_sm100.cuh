@@ -38,7 +38,8 @@ struct TcArgs {
     const uint8_t* action_mask; double epsilon; const int* rand_action; const double* rand_u;
     uint64_t philox_seed, philox_step;
     float* q_out; int* act_out;
-    int m_tiles, n_tiles, has_prod, csz;  // filled by tc_launch (csz = cluster size, weights multicast)
+    int ws;  // use the weight-stationary cluster kernel (tc_ws_plan must hold; weights packed with ws = 1)
+    int m_tiles, n_tiles, has_prod, csz, a_stages;  // filled by tc_launch
 };
 
 struct TcShape {
@@ -46,12 +47,18 @@ struct TcShape {
     int64_t w_bytes, packed_bytes;  // weight tiles; weights + bias, rounded to 256
 };
 
-TcShape tc_shape(int N, int K0, int K1, int epi, int H);
+struct TcWsPlan {
+    int BN, csz, a_stages, smem;
+};
+// weight-stationary cluster plan for a layer whose activations are all tile-packed (false: not eligible)
+bool tc_ws_plan(int N, int K0, int K1, int epi, int H, TcWsPlan* out);
+
+TcShape tc_shape(int N, int K0, int K1, int epi, int H, int ws = 0);
 // W fp32 [N, K0+K1] (row stride ldw), or W [N,K0] next to W1 [N,K1] -> packed bf16 hi/lo tiles
 // (tc_shape(...).packed_bytes, 256-byte aligned destination)
 // bias (+ bias2) are summed and stored tile-ordered behind the weights (either may be NULL)
 int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, const float* bias, const float* bias2, int N,
-                    int K0, int K1, int epi, int H, void* out, cudaStream_t s);
+                    int K0, int K1, int epi, int H, void* out, cudaStream_t s, int ws = 0);
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
 
 }  // namespace gm

@@ -134,6 +134,33 @@ __global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restri
     if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// fp32 rows [R, H] (row stride ld) -> tile-packed bf16 hi/lo (the carried hidden state for the
+// weight-stationary rnn_obs cell).  Same thread mapping as aggregate_pk_kernel.
+__global__ void __launch_bounds__(256) split_pk_kernel(const float* __restrict__ src, int64_t ld, uint8_t* __restrict__ dst_pk,
+                                                       int64_t R, int H, int write_lo) {
+    const int lane = threadIdx.x & 31;
+    const int kbs = H / TC_BK;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row = (gw / kbs) * 8 + (lane >> 2);
+    const int kb = (int)(gw % kbs), part = lane & 3;
+    if (row >= R) return;
+    const float4* s4 = (const float4*)(src + row * ld + kb * TC_BK + part * 8);
+    const float4 a = __ldg(s4), c = __ldg(s4 + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        __nv_bfloat16 p0 = __float2bfloat16_rn(x[2 * i]), p1 = __float2bfloat16_rn(x[2 * i + 1]);
+        hi[i] = (uint32_t)__bfloat16_as_ushort(p0) | ((uint32_t)__bfloat16_as_ushort(p1) << 16);
+        lo[i] = agg_pack2(x[2 * i] - __bfloat162float(p0), x[2 * i + 1] - __bfloat162float(p1));
+    }
+    const int64_t mt = row / TC_BM;
+    const int r = (int)(row - mt * TC_BM);
+    uint8_t* dst = dst_pk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16;
+    *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 // ---------------------------------------------------------------------------------------
 // LSTM pointwise (torch.nn.LSTMCell gate math; gate order i,f,g,o)
 // ---------------------------------------------------------------------------------------
@@ -382,23 +409,29 @@ struct NetmonPack {
     int64_t enc[GM_MAX_LAYERS];
     int64_t obs, upd, total;
     bool fused_cells;
+    bool ws_enc[GM_MAX_LAYERS];  // layer runs on the weight-stationary cluster kernel (tile-packed input)
+    bool ws_cells;
 };
-
 
 static NetmonPack pack_layout(const gm_netmon_params* p) {
     NetmonPack L{};
     int64_t off = 0;
     int kin = p->in_features;
-    for (int l = 0; l < p->n_enc_layers; l++) {
-        L.enc[l] = off;
-        off += tc_shape(p->enc_units[l], kin, 0, EPI_LINEAR, 0).packed_bytes;
-        kin = p->enc_units[l];
-    }
     const int H = p->hidden;
     L.fused_cells = p->rnn_type == GM_RNN_LSTM && p->rnn_carryover && (H % 64) == 0;
+    TcWsPlan plan;
+    for (int l = 0; l < p->n_enc_layers; l++) {
+        L.enc[l] = off;
+        // layers behind the first one read the previous layer's tile-packed output (fused path only)
+        L.ws_enc[l] = L.fused_cells && l >= 1 && (kin % TC_BK) == 0 && tc_ws_plan(p->enc_units[l], kin, 0, EPI_LINEAR, 0, &plan);
+        off += tc_shape(p->enc_units[l], kin, 0, EPI_LINEAR, 0, L.ws_enc[l]).packed_bytes;
+        kin = p->enc_units[l];
+    }
     L.obs = L.upd = off;
+    L.ws_cells = false;
     if (L.fused_cells) {
-        int64_t cell = tc_shape(4 * H, H, H, EPI_LSTM, H).packed_bytes;
+        L.ws_cells = tc_ws_plan(4 * H, H, H, EPI_LSTM, H, &plan);
+        int64_t cell = tc_shape(4 * H, H, H, EPI_LSTM, H, L.ws_cells).packed_bytes;
         L.obs = off;
         L.upd = off + cell;
         off += 2 * cell;
@@ -412,17 +445,17 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
     int kin = p->in_features, rc;
     for (int l = 0; l < p->n_enc_layers; l++) {
         if ((rc = tc_pack_weights(p->enc_w[l], kin, nullptr, 0, p->enc_b[l], nullptr, p->enc_units[l], kin, 0, EPI_LINEAR, 0,
-                                  (char*)out + L.enc[l], s)))
+                                  (char*)out + L.enc[l], s, L.ws_enc[l])))
             return rc;
         kin = p->enc_units[l];
     }
     if (L.fused_cells) {
         const int H = p->hidden;
         if ((rc = tc_pack_weights(p->rnn_obs.w_ih, H, p->rnn_obs.w_hh, H, p->rnn_obs.b_ih, p->rnn_obs.b_hh, 4 * H, H, H, EPI_LSTM, H,
-                                  (char*)out + L.obs, s)))
+                                  (char*)out + L.obs, s, L.ws_cells)))
             return rc;
         if ((rc = tc_pack_weights(p->rnn_update.w_ih, H, p->rnn_update.w_hh, H, p->rnn_update.b_ih, p->rnn_update.b_hh, 4 * H, H, H,
-                                  EPI_LSTM, H, (char*)out + L.upd, s)))
+                                  EPI_LSTM, H, (char*)out + L.upd, s, L.ws_cells)))
             return rc;
     }
     return GM_OK;
@@ -568,6 +601,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             if (out_pk) a.Cpk = ypk; else { a.C = y; a.ldc = U; }
             a.act = p->activation;
             a.M = R; a.N = U;
+            a.ws = PL.ws_enc[l] && xpk != nullptr;
+            GM_CHECK_ARG(a.ws == (int)PL.ws_enc[l], "encoder layer %d: weights were packed for the weight-stationary kernel", l);
             rc = tc_launch(a, math, EPI_LINEAR, s);
             xpk = out_pk ? ypk : nullptr;
         } else {
@@ -604,14 +639,26 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             a.c_in = cprev; a.ldc_in = ldcp;
             a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn; a.Hpk = hn_pk;
             a.H = H; a.M = R; a.N = 4 * H;
+            a.ws = PL.ws_cells;
             return tc_launch(a, math, EPI_LSTM, s);
         };
-        // rnn_obs (:491): x = encoder output, (h, c) = carried state (fp32, split by the producer warps)
-        int rc = cell(PL.obs, xpk, e, nullptr, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], H, hpk[0]);
+        // rnn_obs (:491): x = encoder output, (h, c) = carried state.  The weight-stationary kernel takes
+        // tile-packed operands only, so the carried h is split once by a small kernel; otherwise the
+        // producer warps split it on the fly.
+        const int kbs = H / TC_BK;
+        int rc;
+        if (PL.ws_cells) {
+            GM_CHECK_ARG(xpk != nullptr, "weight-stationary cells need a tile-packed encoder output");
+            const unsigned blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
+            split_pk_kernel<<<blocks, 256, 0, s>>>(st_in, S, hpk[1], R, H, math != GM_MATH_BF16);
+            GM_LAUNCH_CHECK();
+            rc = cell(PL.obs, xpk, e, hpk[1], nullptr, 0, st_in + H, S, hbuf[0], H, cbuf[0], H, hpk[0]);
+        } else {
+            rc = cell(PL.obs, xpk, e, nullptr, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], H, hpk[0]);
+        }
         if (rc) return rc;
         h = hbuf[0]; c = cbuf[0];
         int cur = 0;
-        const int kbs = H / TC_BK;
         const unsigned agg_blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
         for (int it = 0; it < K; it++) {  // :509-554
             const bool final_it = it == K - 1;

@@ -129,3 +129,40 @@ def test_dqn_tensorcore_q_values(math, tol):
     if math == "bf16x3":
         assert np.array_equal(a.cpu().numpy(), g["q"].argmax(-1))
         assert np.array_equal(a2.cpu().numpy(), g["q"].argmax(-1))
+
+
+def test_weight_stationary_cluster_kernel_matches(monkeypatch):
+    """The optional weight-stationary cluster variant (GM_TC_WS=1: weights resident in smem, activations
+    multicast to a 4-CTA cluster) gives the same NetMon outputs as the streaming kernel.  Run in a
+    subprocess because the switch is read once per process."""
+    import os, subprocess, sys, textwrap
+
+    code = textwrap.dedent("""
+        import sys, numpy as np, torch, torch.nn.functional as F
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from helpers import det_weights, netmon_shapes
+        from graph_marl_b200.model import NetMon
+        from oracle import netmon_oracle as NO, oracle as O
+        N, H, K, B = 20, 128, 3, 300
+        Dn = 4 * N + 8
+        cfg = dict(hidden=H, iterations=K, rnn_type="lstm", rnn_carryover=True, agg_type="sum", output_neighbor_hidden=True,
+                   output_global_hidden=False, enc=[512, 256], wseed=5)
+        nm = NetMon(Dn, H, cfg["enc"], K, F.leaky_relu, output_neighbor_hidden=True, math="bf16x3")
+        w = det_weights(netmon_shapes(Dn, H, cfg["enc"], "lstm"), 5)
+        nm.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}); nm = nm.cuda().eval()
+        topo = O.generate_topology(N, seed=923430603)
+        rng = np.random.default_rng(0)
+        x = (rng.random((B, N, Dn)) < 0.05).astype(np.float32)
+        mask = np.broadcast_to(topo["adj"], (B, N, N)).astype(np.float32)
+        st = (rng.standard_normal((B, N, 2 * H)) * 0.3).astype(np.float32)
+        ref, ref_state, _ = NO.netmon_forward(w, cfg, x, mask, st, dtype=np.float64)
+        with torch.no_grad():
+            nm.state = torch.from_numpy(st).cuda()
+            out = nm(torch.from_numpy(x).cuda(), torch.from_numpy(mask.copy()).cuda(), None, no_agent_mapping=True)
+        e1, e2 = np.abs(out.cpu().numpy() - ref).max(), np.abs(nm.state.cpu().numpy() - ref_state).max()
+        assert e1 < 1e-4 and e2 < 1e-4, (e1, e2)
+        print("ok", e1, e2)
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, GM_TC_WS="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
