@@ -69,44 +69,65 @@ def gemm_flops(N, A, H, K, enc, dqn, n_act=4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Sampled in-process
+    through NVML every 10 ms (an external `nvidia-smi -lms` loop was seen to stall kernel launches of the
+    timed process on some boxes); falls back to one nvidia-smi query if NVML is unavailable."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.stop_flag, self.h, self.nv = [], False, None, None
+        self.index = index
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = nv
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
+        if self.nv is None:
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+                f = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": f[0], "sm_max_mhz": f[1], "reasons": [], "samples": 1, "note": "after the timed region (NVML unavailable)"}
             except Exception:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=1.0)
+        nv = self.nv
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
+        reasons = set()
+        for r in rows:
+            for bit, name in self.REASONS.items():
+                if r[2] & bit:
+                    reasons.add(name)
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = None
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
