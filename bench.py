@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--math", default=os.environ.get("GM_BENCH_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="GEMM arithmetic: bf16x3 = tcgen05 with the fp32-accurate hi/lo split (default, parity mode), "
                          "bf16 = single tensor-core pass (reduced precision, reported only on request), fp32 = CUDA-core FFMA")
+    ap.add_argument("--graph-steps", type=int, default=int(os.environ.get("GM_BENCH_GRAPH_STEPS", "10")),
+                    help="rollout steps per captured CUDA graph unit (0 = launch every kernel from Python)")
     ap.add_argument("--no-replay", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-kernel", action="store_true", help="also print a per-stage CUDA-event breakdown to stderr")
@@ -192,7 +194,8 @@ def main():
     config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
                            f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
                            f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,
-                  replay_insert=not a.no_replay, replay_overlap="side stream, joined before the end event", sharding=f"env instances, {world} rank(s), no collective",
+                  replay_insert=not a.no_replay, replay_overlap="side stream, joined before the end event",
+                  cuda_graph_steps=a.graph_steps, sharding=f"env instances, {world} rank(s), no collective",
                   l2="per-step working set (obs + node_obs + NetMon activations + replay slots) exceeds the 126 MB L2")
 
     if a.impl == "reference":
@@ -231,16 +234,15 @@ def main():
     def timed(ro, steps, warmup, host):
         # untimed warm-up: at least the requested steps and one full wrap of the replay ring (8 x B slots), so
         # first-touch effects of the ring are outside the timed region
-        for _ in range(max(warmup, 10)):
-            ro.step()
+        ro.precapture()  # CUDA-graph units are captured before anything is timed
+        ro.run(max(warmup, 10) + 2 * max(ro.graph_steps, 1))
         ro.join_streams()
-        n0 = _lib.lib().gm_kernel_launch_count()
+        n0 = _lib.lib().gm_kernel_launch_count() + ro.graph_launches
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
-        for _ in range(steps):
-            ro.step()
+        ro.run(steps)
         ro.join_streams()  # the side-stream replay inserts of these steps finish inside the timed region
         e1.record()
         host_ms[0] = (time.time() - w0) * 1e3 / steps  # host-side issue time per step (before the final sync)
@@ -249,10 +251,11 @@ def main():
         ms = e0.elapsed_time(e1)
         # whole-job units / MAX device time over ranks
         value, ms_max = aggregate_throughput(B * steps, ms, world)
-        return value, ms_max, _lib.lib().gm_kernel_launch_count() - n0, w0, w1
+        return value, ms_max, _lib.lib().gm_kernel_launch_count() + ro.graph_launches - n0, w0, w1
 
     # ---- device-resident arm ---------------------------------------------------------------
-    ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank)
+    G = a.graph_steps
+    ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank, graph_steps=G)
     ro.reset()
     sampler = ClockSampler(local) if rank == 0 else None
     value, ms, launches, w0, w1 = timed(ro, a.steps, max(a.warmup, 3), host=False)
@@ -266,7 +269,8 @@ def main():
 
     # ---- end-to-end arm: host-supplied draws in, reward out, every step --------------------------
     ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank,
-                 host_draws=True, host_draw_steps=a.steps + max(a.warmup, 3) + 2)
+                 host_draws=True, graph_steps=G,
+                 host_draw_steps=((a.steps + 2 * max(a.warmup, 10) + 4 * max(G, 1)) // max(G, 1) + 1) * max(G, 1))
     ro.reset()
     value_e, ms_e, _, _, _ = timed(ro, a.steps, max(a.warmup, 3), host=True)
     e2e = dict(value=value_e, unit=UNIT, h2d_bytes_per_step=ro.h2d_bytes_per_step() * world,

@@ -31,7 +31,7 @@ class RoutingDesc(C.Structure):
 
 class RoutingIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("actions", "env_mask", "draw_start", "draw_target", "draw_size")] + \
-               [("philox_seed", C.c_uint64), ("philox_step", C.c_uint64)] + \
+               [("philox_seed", C.c_uint64), ("philox_step", C.c_uint64), ("philox_step_dev", C.c_void_p)] + \
                [(n, C.c_void_p) for n in ("obs", "adj", "node_obs", "node_agent", "agent_node", "reward",
                                           "done", "delays", "arrived", "spr", "info", "n_resets",
                                           "action_mask_out", "eval_f64", "eval_i32", "packet_dist", "packet_sizes",
@@ -109,8 +109,8 @@ _SIGS = {
     "gm_dqn_pack_weights": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_dqn_act": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int32,
                              C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64,
-                             C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
-    "gm_replay_insert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+                             C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gm_replay_insert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_replay_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -166,3 +166,25 @@ def current_stream():
     import torch
 
     return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceCounter:
+    """A 64-bit device scalar that shadows a host counter so that a captured CUDA graph can replay calls
+    whose step / ring index advances between replays: kernels read `*ptr + offset`, where `offset` (baked
+    into the graph) is the host value at capture time minus `base`, and `set()` moves the base."""
+
+    def __init__(self, device):
+        import torch
+
+        self.t = torch.zeros((1,), dtype=torch.int64, device=device)
+        self.base = 0
+
+    def set(self, value):
+        self.base = int(value)
+        self.t.fill_(self.base)
+
+    def offset(self, value):
+        return int(value) - self.base
+
+    def ptr(self):
+        return self.t.data_ptr()

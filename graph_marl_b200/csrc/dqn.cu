@@ -22,7 +22,9 @@ constexpr int MAX_ACT = 8;
 __global__ void dqn_head_kernel(const float* __restrict__ h, int64_t ldh, int Hd, const float* __restrict__ qw,
                                 const float* __restrict__ qb, int n_act, const uint8_t* __restrict__ mask, double eps,
                                 const int* __restrict__ rand_action, const double* __restrict__ rand_u, uint64_t seed,
-                                uint64_t step, float* __restrict__ q_out, int* __restrict__ act_out, int64_t rows) {
+                                uint64_t step0, const uint64_t* __restrict__ step_dev, float* __restrict__ q_out,
+                                int* __restrict__ act_out, int64_t rows) {
+    const uint64_t step = step0 + (step_dev ? *step_dev : 0ull);
     int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -132,7 +134,8 @@ int gm_dqn_pack_weights(const gm_dqn_params* p, int32_t split, void* packed, int
 
 int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda, const float* obs_g,
                int32_t Dg, int64_t ldg, const void* obs_g_pk, const uint8_t* action_mask, double epsilon, const int32_t* rand_action,
-               const double* rand_u, uint64_t philox_seed, uint64_t philox_step, float* q_out, int32_t* act_out,
+               const double* rand_u, uint64_t philox_seed, uint64_t philox_step, const uint64_t* philox_step_dev, float* q_out,
+               int32_t* act_out,
                void* workspace, int64_t workspace_bytes, void* stream) {
     GM_CHECK_ARG(p && obs_a && act_out && workspace, "null pointer");
     GM_CHECK_ARG(Dg == 0 || obs_g || obs_g_pk, "obs_g missing");
@@ -186,7 +189,7 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
             if (epi == EPI_QHEAD) {
                 a.q_w = p->q_w; a.q_b = p->q_b; a.n_act = p->n_actions;
                 a.action_mask = action_mask; a.epsilon = epsilon; a.rand_action = rand_action; a.rand_u = rand_u;
-                a.philox_seed = philox_seed; a.philox_step = philox_step;
+                a.philox_seed = philox_seed; a.philox_step = philox_step; a.philox_step_dev = philox_step_dev;
                 a.q_out = q_out; a.act_out = act_out;
             } else if (out_pk) a.Cpk = (uint8_t*)y; else { a.C = y; a.ldc = p->units[l]; }
             a.act = p->activation;
@@ -198,8 +201,8 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
         }
         int Hd = p->units[p->n_layers - 1];
         dqn_head_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(x, Hd, Hd, p->q_w, p->q_b, p->n_actions, action_mask, epsilon,
-                                                                  rand_action, rand_u, philox_seed, philox_step, q_out,
-                                                                  act_out, rows);
+                                                                  rand_action, rand_u, philox_seed, philox_step, philox_step_dev,
+                                                                  q_out, act_out, rows);
         GM_LAUNCH_CHECK();
         return GM_OK;
     }
@@ -227,7 +230,7 @@ int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t
     }
     int Hd = p->units[p->n_layers - 1];
     dqn_head_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, s>>>(x, Hd, Hd, p->q_w, p->q_b, p->n_actions, action_mask, epsilon,
-                                                              rand_action, rand_u, philox_seed, philox_step, q_out, act_out,
+                                                              rand_action, rand_u, philox_seed, philox_step, philox_step_dev, q_out, act_out,
                                                               rows);
     GM_LAUNCH_CHECK();
     return GM_OK;

@@ -36,7 +36,7 @@ struct TcArgs {
     // Q head q = y Wq^T + bq, the action mask, argmax and the epsilon mix (model.py:199-203, policy.py:42-51)
     const float* q_w; const float* q_b; int n_act;
     const uint8_t* action_mask; double epsilon; const int* rand_action; const double* rand_u;
-    uint64_t philox_seed, philox_step;
+    uint64_t philox_seed, philox_step; const uint64_t* philox_step_dev;
     float* q_out; int* act_out;
     int ws;  // use the weight-stationary cluster kernel (tc_ws_plan must hold; weights packed with ws = 1)
     int m_tiles, n_tiles, has_prod, csz, a_stages;  // filled by tc_launch

@@ -18,7 +18,9 @@ struct ReplayFields {
 };
 
 // grid.y = field, grid.x strides over (transition, 16 / 8 / 4 / 1-byte unit)
-__global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t index, int64_t n) {
+__global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t index0, const int64_t* __restrict__ index_dev,
+                                     int64_t n) {
+    const int64_t index = index0 + (index_dev ? *index_dev : 0);
     const gm_replay_field fd = F.f[blockIdx.y];
     const int64_t eb = fd.elem_bytes;
     const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -93,10 +95,10 @@ using namespace gm;
 
 extern "C" {
 
-int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t capacity, int64_t index, int64_t n,
-                     void* stream) {
+int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t capacity, int64_t index, const int64_t* index_dev,
+                     int64_t n, void* stream) {
     GM_CHECK_ARG(fields && n_fields > 0 && n_fields <= GM_REPLAY_MAX_FIELDS, "bad field count %d", n_fields);
-    GM_CHECK_ARG(capacity > 0 && n >= 0 && n <= capacity && index >= 0 && index < capacity, "bad ring arguments");
+    GM_CHECK_ARG(capacity > 0 && n >= 0 && n <= capacity && index >= 0 && (index_dev != nullptr || index < capacity), "bad ring arguments");
     if (n == 0) return GM_OK;
     ReplayFields F;
     F.n = n_fields;
@@ -113,7 +115,7 @@ int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t ca
     }
     int64_t blocks = std::min<int64_t>((maxb / 16 + 255) / 256 + 1, 148 * 4);
     dim3 grid((unsigned)blocks, n_fields);
-    replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, n);
+    replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, index_dev, n);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

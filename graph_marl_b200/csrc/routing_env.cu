@@ -211,13 +211,14 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     __syncwarp();
 
     const bool host_draws = io.draw_start != nullptr;
+    const uint64_t pstep = io.philox_step + (io.philox_step_dev ? *io.philox_step_dev : 0ull);
     auto draw = [&](int slot, int& s, int& t, double& z) {
         if (host_draws) {
             s = io.draw_start[(size_t)b * A + slot];
             t = io.draw_target[(size_t)b * A + slot];
             z = io.draw_size[(size_t)b * A + slot];
         } else {
-            Philox p((uint32_t)slot, (uint32_t)b, (uint32_t)io.philox_step, (uint32_t)(io.philox_step >> 32),
+            Philox p((uint32_t)slot, (uint32_t)b, (uint32_t)pstep, (uint32_t)(pstep >> 32),
                      io.philox_seed);
             s = (int)__umulhi(p.r[0], (uint32_t)N);
             t = (int)__umulhi(p.r[1], (uint32_t)N);

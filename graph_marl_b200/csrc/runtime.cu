@@ -17,7 +17,7 @@ void set_error(const char* fmt, ...) {
 
 extern "C" {
 const char* gm_last_error(void) { return gm::g_err; }
-int gm_abi_version(void) { return 3; }
+int gm_abi_version(void) { return 4; }
 int64_t gm_kernel_launch_count(void) { return gm::g_launches.load(); }
 
 int gm_device_check(void) {

@@ -54,6 +54,7 @@ class TopologyPool:
         self.nbr_all = torch.from_numpy(np.stack([l[0] for l in lists])).to(device)
         self.deg = torch.from_numpy(np.stack([l[1] for l in lists])).to(device)
         self.seeds = [t.get("seed") for t in tables]
+        self.edges_host = np.array(tables[0]["edges"], copy=True) if self.T == 1 else None
 
 
 class Routing(NetworkEnv):
@@ -97,6 +98,7 @@ class Routing(NetworkEnv):
         self._draws = None
         self._out = {}
         self._sum_node = self._sum_edge = None
+        self._dev_step = None
         self.action_mask = np.zeros((n_data, 4), dtype=bool)
         self.agent_steps = np.zeros(n_data)
 
@@ -187,6 +189,8 @@ class Routing(NetworkEnv):
         if self._draws is not None:
             io.draw_start, io.draw_target, io.draw_size = (t.data_ptr() for t in self._draws)
         io.philox_seed, io.philox_step = self._seed, self._calls
+        if self._dev_step is not None:  # CUDA-graph mode: the device counter carries the base
+            io.philox_step, io.philox_step_dev = self._dev_step.offset(self._calls), self._dev_step.ptr()
         for k, v in out.items():
             setattr(io, k, v.data_ptr())
         return io
@@ -207,7 +211,12 @@ class Routing(NetworkEnv):
         net = self.network
         if not self.batched or not net.random_topology:
             net.reset()
-            self._pool = TopologyPool([net.tables], self.device)
+            # a fixed topology keeps its device tables (and their addresses: captured CUDA graphs hold them)
+            same = (self._pool is not None and not net.random_topology and self._pool.T == 1
+                    and self._pool.seeds == [net.tables.get("seed")]
+                    and np.array_equal(self._pool.edges_host, net.tables["edges"]))  # edge weights may be re-randomised
+            if not same:
+                self._pool = TopologyPool([net.tables], self.device)
             self._topo_index = None
             return
         B = self.num_envs

@@ -165,7 +165,7 @@ class DQN(nn.Module):
         return p
 
     def act(self, obs_a, obs_g=None, action_mask=None, epsilon=0.0, rand_action=None, rand_u=None,
-            seed=0, step=0, want_q=True):
+            seed=0, step=0, want_q=True, step_dev=None):
         """Q-values and epsilon-greedy actions for rows [..., Da] (+ [..., Dg]) on the device.
         Returns (q [..., n_act] or None, actions int32 [...])."""
         _lib.require_device()
@@ -195,7 +195,7 @@ class DQN(nn.Module):
             _lib.check(_lib.lib().gm_dqn_act(
                 C.byref(p), rows, a2.data_ptr(), Da, a2.stride(0), _lib.ptr(g2), Dg, 0 if g2 is None else g2.stride(0),
                 _lib.ptr(g_pk), _lib.ptr(action_mask), float(epsilon), _lib.ptr(rand_action), _lib.ptr(rand_u), int(seed), int(step),
-                _lib.ptr(q), act.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream()))
+                step_dev, _lib.ptr(q), act.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream()))
         return (None if q is None else q.reshape(*lead, self.num_actions)), act.reshape(lead)
 
     def forward(self, x, mask):

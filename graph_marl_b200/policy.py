@@ -22,6 +22,7 @@ class EpsilonGreedy:
         self._step = 0
         self._epsilon_tmp = None
         self._seed = seed
+        self._dev_step = None  # _lib.DeviceCounter in CUDA-graph mode (rollout.Rollout)
 
     def _decay(self):
         if (self._epsilon > 0 and self._step > self._args.step_before_train
@@ -41,8 +42,11 @@ class EpsilonGreedy:
                 if self._enable_action_mask:
                     mask = self._env._out.get("action_mask_out")
                 if isinstance(self._model, DQN):
+                    step, step_dev = self._step, None
+                    if self._dev_step is not None:
+                        step, step_dev = self._dev_step.offset(self._step), self._dev_step.ptr()
                     _, actions = self._model.act(obs_a, obs_g, action_mask=mask, epsilon=self._epsilon,
-                                                 seed=self._seed, step=self._step, want_q=False)
+                                                 seed=self._seed, step=step, want_q=False, step_dev=step_dev)
                 else:
                     x = obs_a if obs_g is None else torch.cat((obs_a, obs_g), -1)
                     q = self._model(x, adj.float())

@@ -51,6 +51,7 @@ class ReplayBuffer(object):
         for name, (shape, dt) in shapes.items():
             setattr(self, name, torch.zeros((self.buffer_size, *shape), dtype=dt, device=self.device))
         self._consts = {}
+        self._dev_index = None  # _lib.DeviceCounter in CUDA-graph mode (rollout.Rollout)
         self._random_generator = np.random.default_rng(seed)
         # dtype conversion of _get_transition_batch (replaybuffer.py:132-187)
         self._out_dtype = {n: torch.float32 for n in shapes}
@@ -132,10 +133,13 @@ class ReplayBuffer(object):
             f = fields[k]
             f.ring, f.src, f.elem_bytes, f.convert, f.broadcast = ring.data_ptr(), src.data_ptr(), eb, convert, bcast
             k += 1
+        index, index_dev = self.index, None
+        if self._dev_index is not None:
+            index, index_dev = self._dev_index.offset(self.index) % self.buffer_size, self._dev_index.ptr()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().gm_replay_insert(fields, k, self.buffer_size, self.index, n, _lib.current_stream()))
+            _lib.check(_lib.lib().gm_replay_insert(fields, k, self.buffer_size, index, index_dev, n, _lib.current_stream()))
             cur = torch.cuda.current_stream()
-            if cur != torch.cuda.default_stream():
+            if cur != torch.cuda.default_stream() and not torch.cuda.is_current_stream_capturing():
                 # insert running on a side stream (overlapped with the next rollout step): keep the caching
                 # allocator from recycling the sources before the copy has run
                 for t in keep:

@@ -54,7 +54,8 @@ def aggregate_throughput(units_per_rank, ms_local, world_size):
 
 class Rollout:
     def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
-                 epsilon=1.0, seed=0, with_replay=True, host_draws=False, overlap_replay=True, host_draw_steps=64):
+                 epsilon=1.0, seed=0, with_replay=True, host_draws=False, overlap_replay=True, host_draw_steps=64,
+                 graph_steps=0):
         c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
         self.cfg, self.B, self.device = c, num_envs, torch.device(device)
         N, A = c["n_nodes"], c["n_data"]
@@ -90,6 +91,11 @@ class Rollout:
             self.refresh_host_draws()
         self.overlap_replay = overlap_replay and with_replay
         self._replay_stream = torch.cuda.Stream(device=self.device) if self.overlap_replay else None
+        self.graph_steps = int(graph_steps)
+        self._graphs, self._graph_pool, self._static, self._graph_tables = {}, None, None, None
+        self.graph_launches = 0  # kernels of this library launched through graph replays
+        if host_draws and self.graph_steps > 0:
+            assert host_draw_steps % self.graph_steps == 0, "host draw table must hold whole graph units"
         self.episode_step = None
         self._marks = None
         self.obs = self.adj = None
@@ -128,7 +134,7 @@ class Rollout:
             e.record()
             self._marks.append((name, e))
 
-    def step(self):
+    def _step_eager(self):
         """One batched rollout step (main.py:673-737)."""
         env, c = self.env, self.cfg
         if self.episode_step is None or self.episode_step >= c["episode_steps"]:
@@ -173,6 +179,156 @@ class Rollout:
         if self.host_draws:
             self._h_reward.copy_(reward, non_blocking=True)
         return reward, done, info
+
+    # ---- CUDA-graph execution ----------------------------------------------------------------------
+    # A rollout step launches ~25 kernels from ~0.8 ms of Python; on a busy host that issue time, not the
+    # GPU, bounds the throughput.  `run(k)` therefore replays captured units of `graph_steps` consecutive
+    # steps.  Everything a step hands to the next one (observations, adjacency, NetMon states, node tables)
+    # lives in static tensors that the unit reads first and refreshes last; the three host counters that
+    # change between replays (env / policy Philox steps, replay ring index) are shadowed by device scalars.
+    def _carried(self):
+        env, be = self.env, self.base_env
+        obs_a, obs_g = self.obs
+        pk = getattr(obs_g, "_gm_pk", None)
+        d = dict(obs_a=obs_a, obs_g=obs_g, adj=self.adj, cur=env.current_netmon_state, node_obs=be._out["node_obs"],
+                 node_agent=be._out["node_agent"])
+        if env.last_netmon_state is not None:
+            d["last"] = env.last_netmon_state
+        if pk is not None:
+            d["pk"] = pk[0]
+        return d, (pk[1] if pk is not None else None)
+
+    def _adopt(self, t, math):
+        """Point every cross-step reference at the tensors in `t`."""
+        env, be = self.env, self.base_env
+        if "pk" in t:
+            t["obs_g"]._gm_pk = (t["pk"], math)
+        self.obs, self.adj = (t["obs_a"], t["obs_g"]), t["adj"]
+        env.current_netmon_state = t["cur"]
+        env.netmon.state = t["cur"]
+        if "last" in t:
+            env.last_netmon_state = t["last"]
+        be._out["node_obs"], be._out["node_agent"] = t["node_obs"], t["node_agent"]
+
+    def _counters(self):
+        return (self.episode_step, self.base_env._calls, self.policy._step,
+                (self.buff.index, self.buff.count) if self.buff is not None else None)
+
+    def _set_counters(self, c):
+        self.episode_step, self.base_env._calls, self.policy._step = c[0], c[1], c[2]
+        if self.buff is not None:
+            self.buff.index, self.buff.count = c[3]
+
+    def _sync_device_counters(self):
+        self.base_env._dev_step.set(self.base_env._calls)
+        self.policy._dev_step.set(self.policy._step)
+        if self.buff is not None:
+            self.buff._dev_index.set(self.buff.index)
+
+    def _capture_unit(self, n, slot=None):
+        """Capture n consecutive steps (from the current, static state) into a CUDA graph."""
+        from . import _lib
+
+        if self.base_env._dev_step is None:
+            self.base_env._dev_step = _lib.DeviceCounter(self.device)
+            self.policy._dev_step = _lib.DeviceCounter(self.device)
+            if self.buff is not None:
+                self.buff._dev_index = _lib.DeviceCounter(self.device)
+        cur, math = self._carried()
+        if self._static is None:  # static copies of the carried state; from now on the rollout lives in them
+            self._static = {k: v.clone() for k, v in cur.items()}
+            self._adopt(self._static, math)
+        saved = self._counters()
+        saved_cursor = self._h_cursor if self.host_draws else 0
+        if slot is not None:
+            self._h_cursor = slot * n  # this unit consumes the host draw slices [slot*n, slot*n + n)
+        self._sync_device_counters()
+        torch.cuda.synchronize()
+        launches0 = _lib.lib().gm_kernel_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._graph_pool):
+            for _ in range(n):
+                self._step_eager()
+            self.join_streams()
+            out, _ = self._carried()
+            for k, v in self._static.items():
+                v.copy_(out[k])
+        if self._graph_pool is None:
+            self._graph_pool = g.pool()
+        # capture executes nothing: remember by how much the host bookkeeping moved, then restore it and the
+        # static references
+        after = self._counters()
+        g.gm_delta = (after[0] - saved[0], after[1] - saved[1], after[2] - saved[2])
+        g.gm_launches = _lib.lib().gm_kernel_launch_count() - launches0
+        self._set_counters(saved)
+        if self.host_draws:
+            self._h_cursor = saved_cursor
+        self._adopt(self._static, math)
+        return g
+
+    def _enter_static(self):
+        """After eager steps the carried state lives in fresh tensors: move it into the static ones."""
+        cur, math = self._carried()
+        if cur["obs_a"] is not self._static["obs_a"]:
+            for k, v in self._static.items():
+                v.copy_(cur[k])
+            self._adopt(self._static, math)
+
+    def _replay_unit(self, g, n):
+        self._sync_device_counters()
+        g.replay()
+        self.graph_launches += g.gm_launches
+        c = self._counters()
+        buf = None
+        if self.buff is not None:
+            buf = ((c[3][0] + n * self.B) % self.buff.buffer_size, min(self.buff.buffer_size, c[3][1] + n * self.B))
+        d = g.gm_delta
+        self._set_counters((c[0] + d[0], c[1] + d[1], c[2] + d[2], buf))
+        if self.host_draws:
+            self._h_cursor += n
+
+    def run(self, steps):
+        """Advance `steps` rollout steps, through captured graph units where an episode allows it."""
+        n = self.graph_steps
+        done = 0
+        while done < steps:
+            if self._graphs and self._graph_tables is not self.base_env._pool:
+                self._graphs.clear()  # the topology tables moved (new pool): the captured units are stale
+            left_in_episode = self.cfg["episode_steps"] - (self.episode_step if self.episode_step is not None else 0)
+            usable = (n > 0 and self.episode_step is not None and self.episode_step > 0 and steps - done >= n
+                      and left_in_episode > n)  # a unit never contains an episode's first or last step
+            if usable and self.host_draws and self._h_cursor % n != 0:
+                # units consume whole, aligned blocks of the host draw table: skip to the next block (the table
+                # holds independent draws, skipping some changes nothing statistically)
+                self._h_cursor += n - self._h_cursor % n
+            if not usable:
+                self._step_eager()
+                done += 1
+                continue
+            slot = (self._h_cursor // n) % (self._h_steps // n) if self.host_draws else 0
+            if slot not in self._graphs:
+                self._graphs[slot] = self._capture_unit(n, slot if self.host_draws else None)
+                self._graph_tables = self.base_env._pool
+            self._enter_static()
+            self._replay_unit(self._graphs[slot], n)
+            done += n
+
+    def precapture(self):
+        """Capture every graph unit up front (one per block of the host draw table, or a single one) so that no
+        capture happens inside a timed region.  Needs a state in the middle of an episode."""
+        n = self.graph_steps
+        if n <= 0:
+            return
+        while self.episode_step is None or self.episode_step == 0 or self.cfg["episode_steps"] - self.episode_step <= n:
+            self._step_eager()
+        slots = range(self._h_steps // n) if self.host_draws else [0]
+        for slot in slots:
+            if slot not in self._graphs:
+                self._graphs[slot] = self._capture_unit(n, slot if self.host_draws else None)
+                self._graph_tables = self.base_env._pool
+
+    def step(self):
+        return self._step_eager()
 
     def profile_stages(self, iters=10):
         """Per-stage device time of one step (CUDA events on the launching stream), plus the time of

@@ -41,7 +41,7 @@ typedef enum {
 
 GM_API const char* gm_last_error(void);
 /* ABI version, bumped on any signature/struct change. */
-GM_API int gm_abi_version(void);   /* currently 3 */
+GM_API int gm_abi_version(void);   /* currently 4 */
 /* 0 if a CUDA device with compute capability 10.x is present, else GM_ERR_NO_DEVICE. */
 GM_API int gm_device_check(void);
 
@@ -114,6 +114,9 @@ typedef struct gm_routing_io {
     const int32_t* draw_target;  /*        packet in id order (routing.py:130-135).        */
     const double* draw_size;     /*        All three NULL => device Philox4x32-10 draws.    */
     uint64_t philox_seed, philox_step;
+    /* optional device counter added to philox_step (u64): lets a captured CUDA graph replay the call with a
+     * step that advances between replays (the host updates the counter, the baked argument is the offset) */
+    const uint64_t* philox_step_dev;
     /* outputs (device); any may be NULL and is then not produced */
     float* obs;                  /* [B,A,W] routing.py:269-358; W = 6N+10 (+5k for env_var 2, +N*N+N*(4N+8) for 3) */
     int8_t* adj;                 /* [B,A,A]      routing.py:522-539 */
@@ -264,12 +267,13 @@ GM_API int64_t gm_dqn_workspace_bytes(const gm_dqn_params* p, int64_t rows);
  *   obs_g_pk: optional tile-packed copy of obs_g written by gm_netmon_forward (same math mode).
  *   action_mask u8[rows,n_actions] or NULL: masked actions get Q = -inf (policy.py:42-43)
  *   rand_action i32[rows], rand_u f64[rows]: host-supplied draws (policy.py:46-47), both NULL
- *   => device Philox(seed, step).  act[r] = rand_u<eps ? rand_action : argmax (first max).
+ *   => device Philox(seed, step + *philox_step_dev) (philox_step_dev: optional device counter, see
+ *   gm_routing_io).  act[r] = rand_u<eps ? rand_action : argmax (first max).
  *   q_out f32[rows,n_actions] or NULL; act_out i32[rows]. */
 GM_API int gm_dqn_act(const gm_dqn_params* p, int64_t rows, const float* obs_a, int32_t Da, int64_t lda,
                const float* obs_g, int32_t Dg, int64_t ldg, const void* obs_g_pk, const uint8_t* action_mask,
                double epsilon, const int32_t* rand_action, const double* rand_u,
-               uint64_t philox_seed, uint64_t philox_step, float* q_out, int32_t* act_out,
+               uint64_t philox_seed, uint64_t philox_step, const uint64_t* philox_step_dev, float* q_out, int32_t* act_out,
                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ======================================================================== */
@@ -291,9 +295,10 @@ typedef struct gm_replay_field {
     int32_t rows, pad;
     int64_t row_bytes, ring_pitch, ring_offset;
 } gm_replay_field;
-/* copy n consecutive transitions into ring slots (index+i) % capacity */
+/* copy n consecutive transitions into ring slots (index + *index_dev + i) % capacity
+ * (index_dev: optional device counter for CUDA-graph replays, may be NULL) */
 GM_API int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t capacity,
-                     int64_t index, int64_t n, void* stream);
+                     int64_t index, const int64_t* index_dev, int64_t n, void* stream);
 /* gather n transitions ring[indices[i]] -> dst[i] with the dtype conversions of
  * ReplayBuffer._get_transition_batch; indices i64[n] on device */
 GM_API int gm_replay_sample(const gm_replay_field* fields, int32_t n_fields, const int64_t* indices,
