@@ -94,6 +94,7 @@ class Rollout:
         self.graph_steps = int(graph_steps)
         self._graphs, self._graph_pool, self._static, self._graph_tables = {}, None, None, None
         self.graph_launches = 0  # kernels of this library launched through graph replays
+        self._h_trace = None     # optional list: indices of the host draw table consumed so far (tests)
         if host_draws and self.graph_steps > 0:
             assert host_draw_steps % self.graph_steps == 0, "host draw table must hold whole graph units"
         self.episode_step = None
@@ -146,6 +147,8 @@ class Rollout:
         if self.host_draws:
             i = self._h_cursor % self._h_steps
             self._h_cursor += 1
+            if self._h_trace is not None and not torch.cuda.is_current_stream_capturing():
+                self._h_trace.append(i)
             d = {k: v[i].to(self.device, non_blocking=True) for k, v in self._h.items()}
             with torch.no_grad():
                 _, actions = self.model.act(obs[0], obs[1], epsilon=self.policy._epsilon, rand_action=d["ra"].reshape(-1),
@@ -285,6 +288,8 @@ class Rollout:
         d = g.gm_delta
         self._set_counters((c[0] + d[0], c[1] + d[1], c[2] + d[2], buf))
         if self.host_draws:
+            if self._h_trace is not None:
+                self._h_trace.extend((self._h_cursor + k) % self._h_steps for k in range(n))
             self._h_cursor += n
 
     def run(self, steps):
