@@ -43,12 +43,33 @@ __global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t i
         // 16-byte aligned source, destination only 8-byte aligned (the graph part of a joint observation row
         // starts 520 bytes into the ring row): one 16-byte load, two 8-byte stores
         const int64_t upr = rb / 16, total = n * runs * upr;
-        for (int64_t t = tid0; t < total; t += nthreads) {
+        auto addr2 = [&](int64_t t, const uint4*& s, uint2*& d) {
             int64_t u = t % upr, q = t / upr;
             int64_t row = q % runs, i = q / runs;
             int64_t slot = (index + i) % capacity;
-            const uint4 v = *(const uint4*)((const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * 16);
-            uint2* d = (uint2*)((char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * 16);
+            s = (const uint4*)((const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * 16);
+            d = (uint2*)((char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * 16);
+        };
+        int64_t t = tid0;
+        for (; t + 3 * nthreads < total; t += 4 * nthreads) {
+            const uint4* s[4];
+            uint2* d[4];
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) addr2(t + k * nthreads, s[k], d[k]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = __ldcs(s[k]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                __stcs(d[k], make_uint2(v[k].x, v[k].y));
+                __stcs(d[k] + 1, make_uint2(v[k].z, v[k].w));
+            }
+        }
+        for (; t < total; t += nthreads) {
+            const uint4* s;
+            uint2* d;
+            addr2(t, s, d);
+            const uint4 v = *s;
             d[0] = make_uint2(v.x, v.y);
             d[1] = make_uint2(v.z, v.w);
         }
@@ -57,14 +78,39 @@ __global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t i
     const int unit = (align_bits % 16 == 0) ? 16 : (align_bits % 8 == 0) ? 8 : (align_bits % 4 == 0) ? 4 : 1;
     const int64_t upr = rb / unit;  // units per run
     const int64_t total = n * runs * upr;
-    for (int64_t t = tid0; t < total; t += nthreads) {
+    auto addr = [&](int64_t t, const char*& s, char*& d) {
         int64_t u = t % upr, q = t / upr;
         int64_t row = q % runs, i = q / runs;
         int64_t slot = (index + i) % capacity;
-        const char* s = (const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * unit;
-        char* d = (char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * unit;
-        if (unit == 16) *(uint4*)d = *(const uint4*)s;
-        else if (unit == 8) *(uint2*)d = *(const uint2*)s;
+        s = (const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * unit;
+        d = (char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * unit;
+    };
+    if (unit == 16) {  // bulk of the bytes: four independent 16-byte loads in flight per thread
+        int64_t t = tid0;
+        for (; t + 3 * nthreads < total; t += 4 * nthreads) {
+            const char* s[4];
+            char* d[4];
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) addr(t + k * nthreads, s[k], d[k]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[k] = __ldcs((const uint4*)s[k]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) __stcs((uint4*)d[k], v[k]);
+        }
+        for (; t < total; t += nthreads) {
+            const char* s;
+            char* d;
+            addr(t, s, d);
+            *(uint4*)d = *(const uint4*)s;
+        }
+        return;
+    }
+    for (int64_t t = tid0; t < total; t += nthreads) {
+        const char* s;
+        char* d;
+        addr(t, s, d);
+        if (unit == 8) *(uint2*)d = *(const uint2*)s;
         else if (unit == 4) *(uint32_t*)d = *(const uint32_t*)s;
         else *d = *s;
     }
@@ -113,7 +159,7 @@ int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t ca
         F.f[i] = fields[i];
         maxb = max(maxb, fields[i].elem_bytes * n);
     }
-    int64_t blocks = std::min<int64_t>((maxb / 16 + 255) / 256 + 1, 148 * 4);
+    int64_t blocks = std::min<int64_t>((maxb / 64 + 255) / 256 + 1, 148 * 4);
     dim3 grid((unsigned)blocks, n_fields);
     replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, index_dev, n);
     GM_LAUNCH_CHECK();
