@@ -285,30 +285,44 @@ def main():
         return
 
     pk = peaks()
+    traffic = {}
+    try:  # DRAM bytes from the committed ncu --set full capture of this workload (cfg2, B=4096 only)
+        if a.workload == "cfg2" and B == 4096:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        traffic = {}
     H, K = c["H"], c["K"]
     flops_step = gemm_flops(N, A, H, K, c["enc"], c["dqn"]) * B
     gemm_ms = stage["gemm_ms"]
-    env_ms = stage["env_step_ms"]
+    env_ms = stage["env_kernel_ms"] if stage.get("env_kernel_ms", 0) > 0 else stage["env_step_ms"]
+    agg_ms = stage.get("aggregate_kernel_ms", 0.0) / max(stage.get("aggregate_kernel_launches_per_step", 1.0), 1.0)
     env_bytes = env_step_bytes(N, A) * B
     roof_env = dict(bound="hbm", kernel="routing_kernel<STEP>", achieved=env_bytes / (env_ms * 1e-3) / 1e9,
-                    peak=pk["hbm_gbs"], unit="GB/s", frac=env_bytes / (env_ms * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None,
+                    peak=pk["hbm_gbs"], unit="GB/s", frac=env_bytes / (env_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                    traffic=traffic.get("routing_step_bytes_per_launch"), algorithmic_bytes_per_launch=env_bytes,
                     peak_source=pk["source"], bytes_per_env_step=env_step_bytes(N, A), ms_per_launch=env_ms)
     tf = flops_step / (gemm_ms * 1e-3) / 1e12
     passes = {"fp32": 1, "bf16x3": 3, "bf16": 1}[a.math]
     roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
-                     frac=tf / pk["bf16_tflops_sustained"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
+                     frac=tf / pk["bf16_tflops_sustained"], traffic=traffic.get("linear_tc_bytes_per_step"),
+                     traffic_note="DRAM read+write bytes of the step's 9 launches (ncu, cold caches)" if traffic else None,
+                     peak_source=pk["source"] + " (sustained bf16)",
                      flops_per_env_step=flops_step // B, ms_per_step_in_gemms=gemm_ms,
                      launches_per_step=stage.get("gemm_launches_per_step"),
                      note=f"achieved = algorithmic dense-GEMM flops of one step (2mnk, fp32 semantics) / summed CUDA-event time of the "
                           f"step's GEMM launches; the tensor pipe executes {passes}x that in bf16 MMAs",
                      tensor_pipe_tflops_executed=tf * passes)
+    agg_bytes = 8 * N * H * B  # read h + write M per iteration
+    roof_agg = dict(bound="hbm", kernel="aggregate_pk_kernel", achieved=(agg_bytes / (agg_ms * 1e-3) / 1e9) if agg_ms > 0 else None,
+                    peak=pk["hbm_gbs"], unit="GB/s", frac=(agg_bytes / (agg_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if agg_ms > 0 else None,
+                    traffic=traffic.get("aggregate_pk_bytes_per_launch"), algorithmic_bytes_per_launch=agg_bytes, ms_per_launch=agg_ms)
     dominant = roof_gemm if gemm_ms >= env_ms else roof_env
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
                 ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype={"fp32": "f32", "bf16x3": "f32 (tcgen05 bf16 hi/lo split x3, fp32 accumulate; env state int32/f64)",
                        "bf16": "bf16 (single pass, fp32 accumulate) -- reduced precision"}[a.math],
                 data="synthetic", config=config, agent_steps_per_sec=value * A, host_issue_ms_per_step=host_issue_ms, gpu_launches=int(launches), clocks=clocks, e2e=e2e,
-                roofline=dominant, roofline_env_step=roof_env, roofline_gemm=roof_gemm, stage_ms=stage)
+                roofline=dominant, roofline_env_step=roof_env, roofline_aggregate=roof_agg, roofline_gemm=roof_gemm, stage_ms=stage)
     if not a.no_cpu_baseline and world == 1:
         try:
             cb, _, _ = cpu_arm(a.workload, steps=10**6, warmup=1, budget_s=15.0)

@@ -76,7 +76,7 @@ _SIGS = {
     "gm_device_check": (C.c_int, []),
     "gm_kernel_launch_count": (C.c_int64, []),
     "gm_profile_enable": (None, [C.c_int]),
-    "gm_profile_collect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gm_profile_collect": (C.c_int, [C.c_void_p, C.c_void_p]),  # double ms[8], int32 launches[8]
     "gm_mt_seed": (None, [C.c_void_p, C.c_uint32]),
     "gm_mt_u32": (C.c_uint32, [C.c_void_p]),
     "gm_mt_random": (C.c_double, [C.c_void_p]),

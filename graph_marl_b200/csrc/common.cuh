@@ -44,6 +44,22 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
         gm::count_launch();                                                            \
     } while (0)
 
+// optional per-launch timing with CUDA events on the launching stream (gm_profile_enable / gm_profile_collect)
+enum { PROF_TC = 0, PROF_ENV = 1, PROF_AGG = 2, PROF_READOUT = 3, PROF_REPLAY = 4, PROF_CATEGORIES = 8 };
+extern bool g_profile;
+void profile_begin(int category, cudaStream_t s);
+void profile_end(cudaStream_t s);
+struct ProfileScope {
+    cudaStream_t s;
+    bool on;
+    ProfileScope(int category, cudaStream_t stream) : s(stream), on(g_profile) {
+        if (on) profile_begin(category, s);
+    }
+    ~ProfileScope() {
+        if (on) profile_end(s);
+    }
+};
+
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int kNumSMs = 148;
 

@@ -698,10 +698,6 @@ int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, 
     return GM_OK;
 }
 
-// ---- optional per-launch timing of the tensor-core kernel (CUDA events on the launching stream) ----------
-static bool g_tc_profile = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_tc_events;
-
 static int tc_cluster_size() {
     static int csz = -1;
     if (csz < 0) {
@@ -747,18 +743,9 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
     const int units = ((a.m_tiles + csz - 1) / csz) * a.n_tiles;
     const int n_clusters = std::min(units, csz > 1 ? max_clusters[csz] : kNumSMs);
     cfg.gridDim = dim3(n_clusters * csz);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_tc_profile) {
-        GM_CUDA(cudaEventCreate(&e0));
-        GM_CUDA(cudaEventCreate(&e1));
-        GM_CUDA(cudaEventRecord(e0, s));
-    }
+    ProfileScope prof(PROF_TC, s);
     GM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     count_launch();
-    if (g_tc_profile) {
-        GM_CUDA(cudaEventRecord(e1, s));
-        g_tc_events.emplace_back(e0, e1);
-    }
     return GM_OK;
 }
 
@@ -824,18 +811,9 @@ static int launch_ws(TcArgs a, const TcWsPlan& plan, cudaStream_t s) {
     a.a_stages = plan.a_stages;
     const int n_clusters = std::min(a.m_tiles, max_clusters[plan.csz]);
     cfg.gridDim = dim3(n_clusters * plan.csz);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_tc_profile) {
-        GM_CUDA(cudaEventCreate(&e0));
-        GM_CUDA(cudaEventCreate(&e1));
-        GM_CUDA(cudaEventRecord(e0, s));
-    }
+    ProfileScope prof(PROF_TC, s);
     GM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     count_launch();
-    if (g_tc_profile) {
-        GM_CUDA(cudaEventRecord(e1, s));
-        g_tc_events.emplace_back(e0, e1);
-    }
     return GM_OK;
 }
 
@@ -909,25 +887,3 @@ int linear_tc(const LinearArgs& l, int math, void* ws, int64_t ws_bytes, cudaStr
 }
 
 }  // namespace gm
-
-extern "C" {
-
-void gm_profile_enable(int on) { gm::g_tc_profile = on != 0; }
-
-int gm_profile_collect(double* tc_ms, int32_t* tc_launches) {
-    double total = 0.0;
-    for (auto& ev : gm::g_tc_events) {
-        GM_CUDA(cudaEventSynchronize(ev.second));
-        float ms = 0.f;
-        GM_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
-        total += ms;
-        cudaEventDestroy(ev.first);
-        cudaEventDestroy(ev.second);
-    }
-    if (tc_ms) *tc_ms = total;
-    if (tc_launches) *tc_launches = (int32_t)gm::g_tc_events.size();
-    gm::g_tc_events.clear();
-    return GM_OK;
-}
-
-}  // extern "C"

@@ -110,7 +110,24 @@ __global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restri
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) x[i] = 0.f;
-    for (int q = 0; q < dg; q++) {
+    // first four list entries with all eight 16-byte loads in flight, then the (rare) rest; ascending list order
+    {
+        float4 a[4], c[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4* src = (const float4*)(hb + (size_t)lst[q < dg ? q : 0] * ldh);
+            a[q] = q < dg ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+            c[q] = q < dg ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q < dg) {
+                x[0] += a[q].x; x[1] += a[q].y; x[2] += a[q].z; x[3] += a[q].w;
+                x[4] += c[q].x; x[5] += c[q].y; x[6] += c[q].z; x[7] += c[q].w;
+            }
+        }
+    }
+    for (int q = 4; q < dg; q++) {
         const float4* src = (const float4*)(hb + (size_t)lst[q] * ldh);
         float4 a = __ldg(src), c = __ldg(src + 1);
         x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += c.x; x[5] += c.y; x[6] += c.z; x[7] += c.w;
@@ -663,8 +680,11 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         for (int it = 0; it < K; it++) {  // :509-554
             const bool final_it = it == K - 1;
             if (final_it) last = h;
-            aggregate_pk_kernel<<<agg_blocks, 256, 0, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
-                                                           p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16);
+            {
+                ProfileScope prof(PROF_AGG, s);
+                aggregate_pk_kernel<<<agg_blocks, 256, 0, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
+                                                               p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16);
+            }
             GM_LAUNCH_CHECK();
             float* hn = final_it ? state_out : hbuf[cur ^ 1];  // the last cell writes the new state in place (:562-564)
             float* cn = final_it ? state_out + H : cbuf[cur ^ 1];
@@ -799,9 +819,12 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         int64_t rows = (int64_t)B * A;
         const int kbs = O / TC_BK;
         const unsigned blocks = (unsigned)((((rows + 7) / 8) * kbs + 7) / 8);
-        readout_agents_pk_kernel<<<blocks, 256, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index, agent_node, A, B,
-                                                        N, H, use_nbr, use_glob, max_degree, agent_out, agent_out_ld,
-                                                        (uint8_t*)agent_out_pk, math != GM_MATH_BF16);
+        {
+            ProfileScope prof(PROF_READOUT, s);
+            readout_agents_pk_kernel<<<blocks, 256, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index, agent_node, A,
+                                                            B, N, H, use_nbr, use_glob, max_degree, agent_out, agent_out_ld,
+                                                            (uint8_t*)agent_out_pk, math != GM_MATH_BF16);
+        }
         GM_LAUNCH_CHECK();
     } else if (agent_out) {
         GM_CHECK_ARG(agent_node && A > 0 && agent_out_ld >= O, "agent readout needs agent_node, A, ld >= %d", O);

@@ -161,7 +161,10 @@ int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int64_t ca
     }
     int64_t blocks = std::min<int64_t>((maxb / 64 + 255) / 256 + 1, 148 * 4);
     dim3 grid((unsigned)blocks, n_fields);
-    replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, index_dev, n);
+    {
+        ProfileScope prof(PROF_REPLAY, (cudaStream_t)stream);
+        replay_insert_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(F, capacity, index, index_dev, n);
+    }
     GM_LAUNCH_CHECK();
     return GM_OK;
 }

@@ -564,10 +564,12 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
             GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             routing_kernel<MODE_RESET><<<grid, block, smem, s>>>(dd, *io, L);
             break;
-        case MODE_STEP:
+        case MODE_STEP: {
             GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ProfileScope prof(PROF_ENV, s);
             routing_kernel<MODE_STEP><<<grid, block, smem, s>>>(dd, *io, L);
             break;
+        }
         default:
             GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             routing_kernel<MODE_OBSERVE><<<grid, block, smem, s>>>(dd, *io, L);

@@ -355,20 +355,21 @@ class Rollout:
             for (n0, e0), (n1, e1) in zip(self._marks[:-1], self._marks[1:]):
                 acc[n1 + "_ms"] = acc.get(n1 + "_ms", 0.0) + e0.elapsed_time(e1) / iters
             self._marks = None
-        # time spent inside the GEMM kernels of one step, from CUDA events recorded around every launch
+        # device time per kernel category of one step, from CUDA events recorded around every launch inside
+        # the library (independent of Python issue time; everything on one stream here)
         math = self.netmon.math
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int32 * 8)()
+        _lib.lib().gm_profile_enable(1)
+        for _ in range(iters):
+            self._step_eager()
+        _lib.lib().gm_profile_enable(0)
+        _lib.check(_lib.lib().gm_profile_collect(ms, cnt))
+        for i, nm in enumerate(["gemm", "env_kernel", "aggregate_kernel", "readout_kernel", "replay_kernel"]):
+            acc[nm + "_ms"] = ms[i] / iters
+            acc[nm + "_launches_per_step"] = cnt[i] / iters
         if math == "fp32":
             acc["gemm_ms"] = acc.get("netmon_ms", 0.0) + acc.get("dqn_act_ms", 0.0)  # stage time (SIMT GEMMs dominate it)
-            acc["gemm_launches_per_step"] = None
-        else:
-            tc_ms, tc_n = C.c_double(0.0), C.c_int32(0)
-            _lib.lib().gm_profile_enable(1)
-            for _ in range(iters):
-                self.step()
-            _lib.lib().gm_profile_enable(0)
-            _lib.check(_lib.lib().gm_profile_collect(C.byref(tc_ms), C.byref(tc_n)))
-            acc["gemm_ms"] = tc_ms.value / iters
-            acc["gemm_launches_per_step"] = tc_n.value / iters
         self.overlap_replay = overlap
         acc["gemm_kernel"] = {"fp32": "linear_simt_kernel (fp32 FFMA)", "bf16x3": "linear_tc_kernel (tcgen05, bf16 hi/lo split x3)",
                               "bf16": "linear_tc_kernel (tcgen05, single bf16 pass)"}[math]

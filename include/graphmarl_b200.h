@@ -312,11 +312,13 @@ GM_API int gm_linear(const float* A, int64_t lda, const float* W, const float* b
               int64_t ldc, int64_t M, int32_t N, int32_t K, int32_t activation, int32_t math,
               void* workspace, int64_t workspace_bytes, void* stream);
 GM_API int64_t gm_linear_workspace_bytes(int64_t M, int32_t N, int32_t K, int32_t math);
-/* Per-launch timing of the tcgen05 kernel (linear_tc_kernel) with CUDA events recorded on the
- * launching stream: enable, run, then collect the summed device time and the launch count
- * (collect synchronises on the recorded events and clears them). */
+/* Per-launch timing with CUDA events recorded on the launching stream: enable, run, then collect the
+ * summed device time ms[8] and the launch count launches[8] per kernel category (collect synchronises on
+ * the recorded events and clears them).  Categories: 0 tensor-core linear/cell/Q-head kernels, 1 routing
+ * env step, 2 aggregation, 3 agent readout, 4 replay insert. */
+#define GM_PROFILE_CATEGORIES 8
 GM_API void gm_profile_enable(int on);
-GM_API int gm_profile_collect(double* tc_ms, int32_t* tc_launches);
+GM_API int gm_profile_collect(double* ms, int32_t* launches);
 /* number of kernels this library launched since load (all streams), for bench accounting */
 GM_API int64_t gm_kernel_launch_count(void);
 
