@@ -161,7 +161,7 @@ def cpu_arm(cfg_name, steps, warmup, envs=None, budget_s=20.0):
         n += 1
     dt = time.perf_counter() - t0
     return dict(value=B * n / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{B} envs x {n} rollout steps of {cfg_name} (C env oracle on {cores} threads + numpy/BLAS NetMon+DQN, "
+                sample=f"{B} envs x {n} rollout steps of {cfg_name} (C env oracle on {cores} threads + torch CPU NetMon+DQN on {cores} threads, "
                        f"replay insert incl.), {dt:.1f} s"), dt / max(n, 1), B
 
 

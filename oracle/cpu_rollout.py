@@ -14,6 +14,66 @@ import numpy as np
 from . import netmon_oracle as NO
 from . import oracle as O
 
+try:  # multi-threaded CPU tensor ops for the timed baseline (the reference itself computes with torch on CPU)
+    import torch
+    import torch.nn.functional as F
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _t_mlp(x, w, prefix, on_output=True):
+    n = 0
+    while f"{prefix}linear_layers.{n}.weight" in w:
+        n += 1
+    for i in range(n):
+        x = F.linear(x, w[f"{prefix}linear_layers.{i}.weight"], w[f"{prefix}linear_layers.{i}.bias"])
+        if i < n - 1 or on_output:
+            x = F.leaky_relu(x, 0.01)
+    return x
+
+
+def _t_cell(x, h, c, w, p, rnn):
+    H = h.shape[-1]
+    if rnn == "lstm":  # torch.nn.LSTMCell math (model.py:491,543)
+        g = F.linear(x, w[p + "weight_ih"], w[p + "bias_ih"]) + F.linear(h, w[p + "weight_hh"], w[p + "bias_hh"])
+        i, f, gg, o = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+        c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        return torch.sigmoid(o) * torch.tanh(c2), c2
+    ig = F.layer_norm(F.linear(x, w[p + "weight_ih"]), (4 * H,), w[p + "ln_input.weight"], w[p + "ln_input.bias"], 1e-5)
+    hg = F.layer_norm(F.linear(h, w[p + "weight_hh"]), (4 * H,), w[p + "ln_hidden.weight"], w[p + "ln_hidden.bias"], 1e-5)
+    g = ig + hg + w[p + "bias_ih"]  # layernormlstm.py:24-42
+    i, f, gg, o = g[:, :H], g[:, H:2 * H], g[:, 2 * H:3 * H], g[:, 3 * H:]
+    c2 = F.layer_norm(torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg), (H,), w[p + "ln_cell.weight"], w[p + "ln_cell.bias"], 1e-5)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
+
+
+def netmon_step_shared_topology_torch(w, cfg, x, nbr_full, nbr_wo_self, state, agent_node):
+    """netmon_step_shared_topology with torch CPU tensors (same math, all host threads).  `w` holds torch
+    tensors, x / state / outputs are torch tensors, the index tables are int64 tensors."""
+    B, N, _ = x.shape
+    H, K, rnn = cfg["hidden"], cfg["iterations"], cfg["rnn_type"]
+    if state is None:
+        state = torch.zeros((B, N, 2 * H), dtype=torch.float32)
+    st = state.reshape(B * N, 2, H)
+    h = _t_mlp(x.reshape(B * N, -1), w, "encode.")
+    h, c = _t_cell(h, st[:, 0], st[:, 1], w, "rnn_obs.", rnn)
+    last = h
+    for it in range(K):
+        if it == K - 1:
+            last = h
+        hb = h.reshape(B, N, H)
+        M = hb[:, nbr_full[:, 0]]
+        for q in range(1, nbr_full.shape[1]):
+            M = M + hb[:, nbr_full[:, q]]
+        if cfg["agg_type"] == "mean":
+            M = M / float(nbr_full.shape[1])
+        h, c = _t_cell(M.reshape(B * N, H), h, c, w, "rnn_update.", rnn)
+    new_state = torch.stack((h, c), 1).reshape(B, N, 2 * H)
+    hb, lb = h.reshape(B, N, H), last.reshape(B, N, H)
+    out = torch.cat([hb] + [lb[:, nbr_wo_self[:, q]] for q in range(nbr_wo_self.shape[1])], dim=-1)
+    agent_out = torch.gather(out, 1, agent_node[:, :, None].expand(-1, -1, out.shape[-1]))
+    return out, new_state, agent_out
+
 
 def netmon_step_shared_topology(w, cfg, x, nbr_full, nbr_wo_self, state, agent_node):
     """netmon_oracle.netmon_forward for lstm/lnlstm + carryover + sum/mean + neighbour readout
@@ -51,7 +111,10 @@ class CpuRollout:
     """B independent envs on one shared topology, advanced by the oracle on the host cores."""
 
     def __init__(self, n_nodes, n_data, topo_seed, congestion, K, rnn, H, enc, dqn_units, num_envs, threads,
-                 weights_netmon, weights_dqn, replay_capacity=0, seed=0):
+                 weights_netmon, weights_dqn, replay_capacity=0, seed=0, backend="torch"):
+        self.backend = backend if torch is not None else "numpy"
+        if self.backend == "torch":
+            torch.set_num_threads(max(int(threads), 1))
         self.N, self.A, self.B = n_nodes, n_data, num_envs
         self.topo = O.generate_topology(n_nodes, seed=topo_seed)
         self.env = O.RoutingOracle(self.topo, n_data, enable_congestion=congestion, num_envs=num_envs, threads=threads)
@@ -62,6 +125,10 @@ class CpuRollout:
         full, wo = NO.adjacency_lists(self.topo["adj"])
         self.nbr_full = np.stack(full).astype(np.int64)
         self.nbr_wo = np.stack(wo).astype(np.int64)
+        if self.backend == "torch":
+            self.tw_nm = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in self.w_nm.items()}
+            self.tw_dq = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in self.w_dq.items()}
+            self.t_full, self.t_wo = torch.from_numpy(self.nbr_full), torch.from_numpy(self.nbr_wo)
         self.rng = np.random.default_rng(seed)
         self.state = None
         self.replay = None
@@ -85,9 +152,16 @@ class CpuRollout:
     def _observe(self):
         o = self.env.observe(adj=True, node_agent=True)
         prev_state = self.state
-        _, self.state, g = netmon_step_shared_topology(self.w_nm, self.cfg, o["node_obs"], self.nbr_full, self.nbr_wo,
-                                                       self.state, self.env.now)
-        self.joint = np.concatenate([o["obs"], g], axis=-1)
+        if self.backend == "torch":
+            with torch.no_grad():
+                _, self.state, g = netmon_step_shared_topology_torch(
+                    self.tw_nm, self.cfg, torch.from_numpy(o["node_obs"]), self.t_full, self.t_wo, self.state,
+                    torch.from_numpy(self.env.now.astype(np.int64)))
+            self.joint = torch.cat([torch.from_numpy(o["obs"]), g], dim=-1)
+        else:
+            _, self.state, g = netmon_step_shared_topology(self.w_nm, self.cfg, o["node_obs"], self.nbr_full, self.nbr_wo,
+                                                           self.state, self.env.now)
+            self.joint = np.concatenate([o["obs"], g], axis=-1)
         self.node_obs = o["node_obs"]
         return prev_state
 
@@ -98,7 +172,12 @@ class CpuRollout:
 
     def step(self, epsilon=1.0):
         B, A = self.B, self.A
-        q = NO.dqn_forward(self.w_dq, self.joint)
+        if self.backend == "torch":
+            with torch.no_grad():
+                hq = _t_mlp(self.joint.reshape(B * A, -1), self.tw_dq, "encoder.")
+                q = F.linear(hq, self.tw_dq["q_net.fc.weight"], self.tw_dq["q_net.fc.bias"]).reshape(B, A, -1).numpy()
+        else:
+            q = NO.dqn_forward(self.w_dq, self.joint)
         ra = self.rng.integers(0, 4, (B, A))
         ru = self.rng.random((B, A))
         act = NO.epsilon_greedy(q, epsilon, ra, ru)
@@ -108,9 +187,10 @@ class CpuRollout:
         if self.replay is not None:
             idx = (self.rindex + np.arange(B)) % self.rcap
             rp = self.replay
-            rp["obs"][idx], rp["next_obs"][idx] = obs, self.joint
+            as_np = (lambda t: t.numpy()) if self.backend == "torch" else (lambda t: t)
+            rp["obs"][idx], rp["next_obs"][idx] = as_np(obs), as_np(self.joint)
             rp["node_obs"][idx], rp["next_node_obs"][idx] = node_obs, self.node_obs
-            rp["node_state"][idx] = 0 if last_state is None else last_state
+            rp["node_state"][idx] = 0 if last_state is None else as_np(last_state)
             rp["action"][idx], rp["reward"][idx] = act, r["reward"]
             self.rindex = int((self.rindex + B) % self.rcap)
         return r["reward"]

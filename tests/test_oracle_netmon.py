@@ -77,3 +77,25 @@ def test_replay_index_sampling():
     assert np.array_equal(g["full_action"], g["tr_action"][src].astype(np.int64))
     assert g["full_adj"].dtype == np.float32 and np.array_equal(g["full_adj"], g["tr_adj"][src].astype(np.float32))
     assert np.array_equal(g["full_done"], g["tr_done"][src])
+
+
+def test_cpu_rollout_torch_backend_matches_numpy_backend():
+    """oracle/cpu_rollout.py (the timed CPU baseline): the multi-threaded torch backend computes the same
+    rollout as the numpy restatement (same seeds -> same draws; fp32 summation-order noise only)."""
+    import torch
+    from oracle.cpu_rollout import CpuRollout
+    from helpers import det_weights, dqn_shapes, netmon_shapes
+
+    N = A = 20
+    H, K, enc, dq = 32, 2, (48, 40), (36, 28)
+    w_nm = det_weights(netmon_shapes(4 * N + 8, H, list(enc), "lstm"), 3)
+    w_dq = det_weights(dqn_shapes(6 * N + 10 + 4 * H, list(dq), 4), 5)
+    mk = lambda be: CpuRollout(N, A, 923430603, True, K, "lstm", H, enc, dq, 6, 2, w_nm, w_dq, replay_capacity=12, seed=1, backend=be)
+    a, b = mk("numpy"), mk("torch")
+    a.reset(), b.reset()
+    for t in range(4):
+        ra, rb = a.step(epsilon=1.0), b.step(epsilon=1.0)  # epsilon 1: actions come from the shared draw stream
+        assert np.array_equal(ra, rb), t
+        assert np.array_equal(a.env.now, b.env.now) and np.array_equal(a.env.load, b.env.load)
+        assert np.abs(np.asarray(a.joint) - b.joint.numpy()).max() < 1e-5
+        assert np.abs(np.asarray(a.state) - b.state.numpy()).max() < 1e-5
