@@ -16,29 +16,28 @@ from .. import _lib
 
 
 class Node:
-    """A node in a network (network.py:9-18)."""
+    """Router: position, neighbour ids in creation order and incident edge ids (network.py:9-18)."""
+
+    __slots__ = ("x", "y", "neighbors", "edges")
 
     def __init__(self, x, y):
-        self.x = x
-        self.y = y
-        self.neighbors = []
-        self.edges = []
+        self.x, self.y = x, y
+        self.neighbors, self.edges = [], []
 
 
 class Edge:
-    """An edge in a network (network.py:21-39)."""
+    """Undirected link start-end with an integer length in steps (network.py:21-39)."""
+
+    __slots__ = ("start", "end", "length")
 
     def __init__(self, start, end, length):
-        self.start = start
-        self.end = end
-        self.length = length
+        self.start, self.end, self.length = start, end, length
 
     def get_other_node(self, node):
-        if self.start == node:
-            return self.end
-        elif self.end == node:
-            return self.start
-        raise ValueError(f"Is neither start nor end of edge {self.start}-{self.end}: {node}")
+        ends = (self.start, self.end)
+        if node not in ends:
+            raise ValueError(f"Is neither start nor end of edge {self.start}-{self.end}: {node}")
+        return ends[1] if node == ends[0] else ends[0]
 
 
 def generate_tables(n_nodes, seed, allow_reseed=False, exclude=None):
@@ -117,19 +116,23 @@ class Network:
 
     # ---- seed management (network.py:100-120, 353-371) --------------------------------------
     def build_seed_list(self, random_topology, n_random_seeds, exclude_seeds=None):
+        """Fixed topology: [init seed].  Random topologies: `n_random_seeds` distinct valid seeds drawn from
+        a stream seeded with the init seed, leaving the caller's global stream untouched; [] = unrestricted."""
         if not random_topology:
             return [self.topology_init_seed]
-        if n_random_seeds is None or n_random_seeds <= 0:
-            return []
-        old_rand_state = np.random.get_state()
-        np.random.seed(self.topology_init_seed)
-        seed_list = []
-        while len(seed_list) < n_random_seeds:
-            new_seed = self._create_valid_network(seeds_exclude=exclude_seeds)
-            if new_seed not in seed_list:
-                seed_list.append(new_seed)
-        np.random.set_state(old_rand_state)
-        return seed_list
+        wanted = n_random_seeds or 0
+        found = []
+        if wanted > 0:
+            saved = np.random.get_state()
+            try:
+                np.random.seed(self.topology_init_seed)
+                while len(found) < wanted:
+                    candidate = self._create_valid_network(seeds_exclude=exclude_seeds)
+                    if candidate not in found:
+                        found.append(candidate)
+            finally:
+                np.random.set_state(saved)
+        return found
 
     def freeze_sequential_topology_seeds(self):
         self.sequential_topology_seeds_frozen = True

@@ -14,48 +14,50 @@ import torch
 
 class NetMonWrapper:
     def __init__(self, env, netmon, startup_iterations, split_obs=False) -> None:
-        self.env = env
-        self.netmon = netmon
-        self.device = next(netmon.parameters()).device
-        self.node_obs = None
-        self.node_adj = None
-        self.node_agent_matrix = None
-        self.last_netmon_state = None
-        self.current_netmon_state = None
-        assert startup_iterations >= 1, "Number of startup iterations must be >= 1"
+        if startup_iterations < 1:
+            raise AssertionError("Number of startup iterations must be >= 1")
+        self.env, self.netmon = env, netmon
         self.startup_iterations = startup_iterations
-        self.frozen = False
         self.split_obs = split_obs  # batched mode: return (agent_obs, graph_obs) instead of the concat
+        self.device = next(netmon.parameters()).device
+        # attributes main.py / sl.py read (wrapper.py:13-19)
+        self.node_obs = self.node_adj = self.node_agent_matrix = None
+        self.last_netmon_state = self.current_netmon_state = None
+        self.frozen = False
         self.netmon_out = None
 
     def __getattr__(self, name):
-        return getattr(self.env, name)
+        # anything the wrapper does not define is the env's (wrapper.py:25-26)
+        env = self.__dict__.get("env")
+        if env is None:  # not constructed yet (copy / pickle probes)
+            raise AttributeError(name)
+        return getattr(env, name)
 
     def __str__(self) -> str:
-        return self.env.__str__() + os.linesep + "▲ environment is wrapped with NetMon (graph obs)"
+        return f"{self.env}{os.linesep}▲ environment is wrapped with NetMon (graph obs)"
 
     @property
     def _batched(self):
         return getattr(self.env, "batched", False)
 
-    def _join(self, obs, network_obs):
-        if self._batched:
-            return (obs, network_obs) if self.split_obs else torch.cat((obs, network_obs), dim=-1)
-        return np.concatenate((obs, network_obs), axis=-1)
+    def _with_graph_obs(self, obs):
+        """One NetMon pass on the env's current node view, appended to the agents' observations."""
+        graph_obs = self._netmon_step()
+        if not self._batched:
+            return np.concatenate((obs, graph_obs), axis=-1)
+        return (obs, graph_obs) if self.split_obs else torch.cat((obs, graph_obs), dim=-1)
 
     def reset(self):
         self.frozen = False
-        self.current_netmon_state = None
-        self.last_netmon_state = None
+        self.last_netmon_state = self.current_netmon_state = None
         obs, adj = self.env.reset()
-        for _ in range(self.startup_iterations):
-            network_obs = self._netmon_step()
-        return self._join(obs, network_obs), adj
+        for _ in range(self.startup_iterations - 1):  # warm-up passes; the last one below builds the obs
+            self._netmon_step()
+        return self._with_graph_obs(obs), adj
 
     def step(self, actions):
-        next_obs, next_adj, reward, done, info = self.env.step(actions)
-        next_network_obs = self._netmon_step()
-        return self._join(next_obs, next_network_obs), next_adj, reward, done, info
+        obs, adj, reward, done, info = self.env.step(actions)
+        return self._with_graph_obs(obs), adj, reward, done, info
 
     def freeze(self):
         """Disable message passing for the rest of the episode (wrapper.py:53-58)."""
