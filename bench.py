@@ -2,7 +2,7 @@
 """Benchmark of the rollout hot path (BASELINE.json metric: batched env-steps/sec incl. NetMon
 forward; % of HBM roofline for the env-step kernel).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2ln|cfg4]
 
 One "step" = one batched rollout step over B environment instances per GPU
 (src/main.py:673-737): DQN epsilon-greedy action selection -> Routing env step with agent and
@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg2ln", "cfg4"])
     ap.add_argument("--envs", type=int, default=0, help="env instances per GPU (default: BASELINE config size)")
     ap.add_argument("--math", default=os.environ.get("GM_BENCH_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="GEMM arithmetic: bf16x3 = tcgen05 with the fp32-accurate hi/lo split (default, parity mode), "
@@ -190,7 +190,7 @@ def main():
 
     c = CONFIGS[a.workload]
     N, A = c["n_nodes"], c["n_data"]
-    B = a.envs or (4096 if a.workload == "cfg2" else 1024)
+    B = a.envs or (4096 if a.workload in ("cfg2", "cfg2ln") else 1024)
     config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
                            f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
                            f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,

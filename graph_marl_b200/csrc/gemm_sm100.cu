@@ -182,6 +182,13 @@ __device__ __forceinline__ void ld_global_v8(const float* ptr, float* v) {
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(ptr));
 }
+// coherent (not .nc) form: for data this thread wrote earlier in the same kernel
+__device__ __forceinline__ void ld_global_v8_coherent(const float* ptr, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(ptr)
+                 : "memory");
+}
 __device__ __forceinline__ void st_global_v8(float* ptr, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
                  "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
@@ -227,10 +234,14 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     constexpr int W_PART_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_PART_BYTES + 2 * W_PART_BYTES;
     constexpr uint32_t IDESC = umma_idesc(BN);
+    constexpr bool LN = EPI == EPI_LNLSTM;
+    constexpr int ACC_COLS = LN ? 2 * BN : BN;  // LayerNormLSTM: separate accumulators for x W_ih^T and h W_hh^T
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
+    __shared__ float ln_stats[LN ? 2 : 1][LN ? BM : 1][4];  // per row: mean / rstd of the ih gates, of the hh gates
+    __shared__ float ln_cpart[LN ? 2 : 1][LN ? BM : 1][4];  // per row: partial sums of the two column halves (LN_H)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     }
     if (warp == MMA_WARP) {  // TMEM: ACC_STAGES x BN fp32 columns x 128 lanes
         uint32_t dst = smem_u32(&tmem_base_smem);
-        uint32_t cols = ACC_STAGES * BN;
+        uint32_t cols = ACC_STAGES * ACC_COLS;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -269,11 +280,13 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     const int n_tiles = p.n_tiles;
     const int n_clusters = (int)gridDim.x / csz, cluster_id = (int)blockIdx.x / csz;
     const int total_units = ((p.m_tiles + csz - 1) / csz) * n_tiles;
-    const int my_units = (total_units - cluster_id + n_clusters - 1) / n_clusters;
+    // LayerNormLSTM: a CTA owns whole M tiles (row statistics couple the N tiles of a row), csz == 1
+    const int my_units = LN ? ((p.m_tiles - cluster_id + n_clusters - 1) / n_clusters) * n_tiles
+                            : (total_units - cluster_id + n_clusters - 1) / n_clusters;
     const int kblocks = p.Kp / BK;
     const int kb_seg1 = p.K0p / BK;  // first k-block of segment 1
-    auto unit_mt = [&](int i) { return ((cluster_id + i * n_clusters) / n_tiles) * csz + rank; };
-    auto unit_nt = [&](int i) { return (cluster_id + i * n_clusters) % n_tiles; };
+    auto unit_mt = [&](int i) { return LN ? cluster_id + (i / n_tiles) * n_clusters : ((cluster_id + i * n_clusters) / n_tiles) * csz + rank; };
+    auto unit_nt = [&](int i) { return LN ? i % n_tiles : (cluster_id + i * n_clusters) % n_tiles; };
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ================= producer: fp32 activations -> bf16 hi/lo core matrices ================
@@ -385,7 +398,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 const uint32_t aph = (tcount / ACC_STAGES) & 1;
                 mbar_wait(bar_tempty + 8 * as, aph ^ 1);  // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t d = tmem_base + as * BN;
+                const uint32_t d0 = tmem_base + as * ACC_COLS;
                 for (int kb = 0; kb < kblocks; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -393,15 +406,18 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     tc_fence_after();
                     const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_PART_BYTES;
                     const uint32_t w_hi = a_hi + 2 * A_PART_BYTES, w_lo = w_hi + W_PART_BYTES;
+                    // LayerNormLSTM: segment 1 accumulates into its own BN columns
+                    const uint32_t d = d0 + ((LN && kb >= kb_seg1) ? BN : 0);
+                    const int kfirst = LN ? (kb != 0 && kb != kb_seg1) : kb;  // 0 on the first k-block of an accumulator
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ks++) {
                         const uint32_t o = ks * 256;  // two 128-byte core matrices per K=16 step
                         if (PASSES == 3) {  // small terms first, then hi*hi
-                            umma(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
+                            umma(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kfirst | ks) != 0);
                             umma(d, umma_desc(a_hi + o), umma_desc(w_lo + o), IDESC, 1);
                             umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, 1);
                         } else {
-                            umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
+                            umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, (kfirst | ks) != 0);
                         }
                     }
                     // smem stage reusable once these MMAs retire; with multicast weights every CTA of the
@@ -417,16 +433,22 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         // 8 warps: warp e reads TMEM lanes 32*(e%4).. (its hardware quadrant) and the column half e/4.
         const int quad = warp & 3, chalf = warp >> 2;
         const int r = quad * 32 + lane;  // accumulator lane == tile row
+        float ln_csum = 0.f;             // LayerNormLSTM: running sum of this thread's pre-LN cell values of the row
         for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
             const int as = tcount % ACC_STAGES;
             const uint32_t aph = (tcount / ACC_STAGES) & 1;
             const int mt = unit_mt((int)tcount), nt = unit_nt((int)tcount);
             const int64_t m = (int64_t)mt * BM + r;
             const bool live = m < p.M;
+            if constexpr (LN) {
+#include "gemm_sm100_lnlstm.inc"
+            } else {
 #include "gemm_sm100_epilogue.inc"
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * as);
+            }
         }
+        (void)ln_csum;
     }
 
     tc_fence_before();
@@ -434,7 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     if (p.csz > 1) cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
     if (warp == MMA_WARP) {
         tc_fence_after();
-        uint32_t cols = ACC_STAGES * BN;
+        uint32_t cols = ACC_STAGES * ACC_COLS;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
     }
 }
@@ -663,13 +685,74 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, const float* __res
     out[idx] = v;
 }
 
+// -------------------------------------------------------------------------------------------------
+// LayerNormLSTM packing (EPI_LNLSTM, H = 128).  Stage 1 builds, per segment (0: weight_ih, 1: weight_hh), the fp32
+// matrix Wx [H + 4H, H] that pack_w_kernel then splits like any linear layer with BN = 128:
+//   rows [0, H)       : centred Gram matrix G[n][k] = sum_j (W[j][n] - mean_n)(W[j][k] - mean_k), fp64 accumulation
+//   rows H + t*128 + c: weight row gate*H + unit, (half, gate, u) = (c/64, (c%64)/16, c%16), unit = t*32 + half*16 + u
+// -------------------------------------------------------------------------------------------------
+__global__ void lnlstm_stage_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, int H, float* __restrict__ wx) {
+    const int rows = 5 * H;
+    const int64_t total = 2ll * rows * H;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % H);
+        const int n = (int)((idx / H) % rows);
+        const int seg = (int)(idx / ((int64_t)H * rows));
+        const float* W = seg ? w_hh : w_ih;
+        float v;
+        if (n < H) {
+            double sn = 0.0, sk = 0.0, snk = 0.0;
+            for (int j = 0; j < 4 * H; j++) {
+                const double a = W[(int64_t)j * H + n], b = W[(int64_t)j * H + k];
+                sn += a; sk += b; snk += a * b;
+            }
+            v = (float)(snk - sn * sk / (4.0 * H));
+        } else {
+            const int tt = (n - H) / 128, c = (n - H) % 128;
+            const int half = c / 64, gate = (c % 64) / 16, u = c % 16;
+            v = W[(int64_t)(gate * H + tt * 32 + half * 16 + u) * H + k];
+        }
+        wx[idx] = v;
+    }
+}
+
+// params: [colsum(W_ih) H | colsum(W_hh) H | per chunk tile: ln_input.weight, ln_hidden.weight, ln_input.bias +
+// ln_hidden.bias + bias_ih (tile column order) | ln_cell.weight H | ln_cell.bias H]
+__global__ void lnlstm_params_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
+                                     const float* __restrict__ ln_in_w, const float* __restrict__ ln_in_b,
+                                     const float* __restrict__ ln_hid_w, const float* __restrict__ ln_hid_b,
+                                     const float* __restrict__ ln_cell_w, const float* __restrict__ ln_cell_b, int H,
+                                     float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_chunks = H / 32, total = 2 * H + n_chunks * 3 * 128 + 2 * H;
+    if (idx >= total) return;
+    if (idx < 2 * H) {
+        const float* W = idx < H ? w_ih : w_hh;
+        const int k = idx % H;
+        double s = 0.0;
+        for (int j = 0; j < 4 * H; j++) s += W[(int64_t)j * H + k];
+        out[idx] = (float)s;
+    } else if (idx < 2 * H + n_chunks * 3 * 128) {
+        const int e = idx - 2 * H, tt = e / 384, which = (e % 384) / 128, c = e % 128;
+        const int half = c / 64, gate = (c % 64) / 16, u = c % 16;
+        const int src = gate * H + tt * 32 + half * 16 + u;
+        out[idx] = which == 0 ? ln_in_w[src] : which == 1 ? ln_hid_w[src] : ln_in_b[src] + ln_hid_b[src] + b_ih[src];
+    } else {
+        const int e = idx - (2 * H + n_chunks * 3 * 128);
+        out[idx] = e < H ? ln_cell_w[e] : ln_cell_b[e - H];
+    }
+}
+
 }  // namespace tc
 
 // -------------------------------------------------------------------------------------------------
 int tc_pick_bn(int N, int epi) {
     if (epi == EPI_LSTM || epi == EPI_QHEAD) return 256;
+    if (epi == EPI_LNLSTM) return 128;
     return N <= 128 ? 128 : 256;
 }
+
+static int64_t lnlstm_param_floats(int H) { return 2 * H + (H / 32) * 3 * 128 + 2 * H; }
 
 TcShape tc_shape(int N, int K0, int K1, int epi, int H, int ws) {
     TcShape s;
@@ -678,10 +761,34 @@ TcShape tc_shape(int N, int K0, int K1, int epi, int H, int ws) {
     if (ws && tc_ws_plan(N, K0, K1, epi, H, &plan)) s.BN = plan.BN;
     s.K0p = (int)round_up(K0, tc::BK);  // segment 1 starts on a k-block boundary
     s.Kp = s.K0p + (int)round_up(K1, tc::BK);
-    s.n_tiles = (epi == EPI_LSTM) ? ceil_div(H, s.BN / 4) : ceil_div(N, s.BN);
+    s.n_tiles = (epi == EPI_LSTM) ? ceil_div(H, s.BN / 4) : (epi == EPI_LNLSTM) ? 1 + H / 32 : ceil_div(N, s.BN);
     s.w_bytes = (int64_t)s.n_tiles * (s.Kp / tc::BK) * 2 * s.BN * tc::BK * 2;
     s.packed_bytes = round_up(s.w_bytes + (int64_t)s.n_tiles * s.BN * 4, 256);
+    if (epi == EPI_LNLSTM)  // weights | LN parameters | fp32 staging of the two [5H, H] source matrices
+        s.packed_bytes = round_up(s.w_bytes + round_up(lnlstm_param_floats(H) * 4, 256) + 2ll * 5 * H * H * 4, 256);
     return s;
+}
+
+int tc_pack_lnlstm(const float* w_ih, const float* w_hh, const float* b_ih, const float* ln_in_w, const float* ln_in_b,
+                   const float* ln_hid_w, const float* ln_hid_b, const float* ln_cell_w, const float* ln_cell_b, int H, void* out,
+                   cudaStream_t s) {
+    GM_CHECK_ARG(H == 128, "fused LayerNormLSTM cell is built for hidden == 128, got %d", H);
+    GM_CHECK_ARG(w_ih && w_hh && b_ih && ln_in_w && ln_in_b && ln_hid_w && ln_hid_b && ln_cell_w && ln_cell_b,
+                 "LayerNormLSTM cell parameters missing");
+    TcShape sh = tc_shape(4 * H, H, H, EPI_LNLSTM, H, 0);
+    float* params = (float*)((char*)out + sh.w_bytes);
+    float* wx = (float*)((char*)params + round_up(lnlstm_param_floats(H) * 4, 256));
+    tc::lnlstm_stage_kernel<<<148 * 4, 256, 0, s>>>(w_ih, w_hh, H, wx);
+    GM_LAUNCH_CHECK();
+    tc::lnlstm_params_kernel<<<ceil_div((int)lnlstm_param_floats(H), 256), 256, 0, s>>>(w_ih, w_hh, b_ih, ln_in_w, ln_in_b, ln_hid_w,
+                                                                                         ln_hid_b, ln_cell_w, ln_cell_b, H, params);
+    GM_LAUNCH_CHECK();
+    int64_t total = (int64_t)sh.n_tiles * (sh.Kp / tc::BK) * sh.BN * (tc::BK / 8);
+    int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    tc::pack_w_kernel<<<blocks, 256, 0, s>>>(wx, H, wx + (int64_t)5 * H * H, H, 5 * H, H, H, sh.K0p, sh.Kp, sh.BN, sh.n_tiles, 0, H,
+                                             (uint8_t*)out);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
 }
 
 int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, const float* bias, const float* bias2, int N,
@@ -740,7 +847,11 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
     if (csz > 1 && max_clusters[csz] < 0) csz = 1;  // clusters of this size cannot be scheduled: plain launch
     attr[0].val.clusterDim.x = csz;
     a.csz = csz;
-    const int units = ((a.m_tiles + csz - 1) / csz) * a.n_tiles;
+    if (EPI == EPI_LNLSTM) csz = 1;
+    attr[0].val.clusterDim.x = csz;
+    a.csz = csz;
+    // LayerNormLSTM: a CTA owns whole M tiles
+    const int units = EPI == EPI_LNLSTM ? a.m_tiles : ((a.m_tiles + csz - 1) / csz) * a.n_tiles;
     const int n_clusters = std::min(units, csz > 1 ? max_clusters[csz] : kNumSMs);
     cfg.gridDim = dim3(n_clusters * csz);
     ProfileScope prof(PROF_TC, s);
@@ -759,7 +870,7 @@ bool tc_ws_plan(int N, int K0, int K1, int epi, int H, TcWsPlan* out) {
         const char* e = getenv("GM_TC_WS");
         enabled = e ? atoi(e) : 0;  // measured on B200: slower than the streaming kernel (multicast replicates the bytes in flight, HBM-latency bound)
     }
-    if (!enabled || epi == EPI_QHEAD) return false;
+    if (!enabled || epi == EPI_QHEAD || epi == EPI_LNLSTM) return false;
     const int cols = epi == EPI_LSTM ? 4 * H : N;
     const int Kp = (int)round_up(K0, tc::BK) + (int)round_up(K1, tc::BK);
     const int bns[2] = {128, 64};
@@ -833,6 +944,14 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     GM_CHECK_ARG(a.K1 == 0 || a.A1pk == nullptr || ((a.K1 % tc::BK) == 0 && ((uintptr_t)a.A1pk & 127) == 0),
                  "tile-packed segment 1: K %% 32 and 128-byte alignment");
     a.has_prod = (a.A0 != nullptr) || (a.K1 > 0 && a.A1 != nullptr);
+    if (epi == EPI_LNLSTM) {
+        GM_CHECK_ARG(a.H == 128 && a.K0 == 128 && a.K1 == 128 && !a.ws, "fused LayerNormLSTM cell needs hidden == 128 and two 128-wide segments");
+        GM_CHECK_ARG(a.c_in && a.h_out && a.c_out && (a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 &&
+                         (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out) & 31) == 0 && ((uintptr_t)a.Hpk & 127) == 0,
+                     "fused LayerNormLSTM epilogue needs 32-byte aligned state rows");
+        a.ln_params = (const float*)(a.Wp + sh.w_bytes);
+        return launch_tc<128, 3, EPI_LNLSTM>(a, s);  // always the three-pass product (LN amplifies rounding)
+    }
     if (epi == EPI_LSTM) {
         GM_CHECK_ARG(a.H % 64 == 0, "fused LSTM epilogue needs hidden %% 64 == 0, got %d", a.H);
         GM_CHECK_ARG((a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 &&

@@ -4,7 +4,7 @@
 
 namespace gm {
 
-enum { EPI_LINEAR = 0, EPI_LSTM = 1, EPI_QHEAD = 2 };
+enum { EPI_LINEAR = 0, EPI_LSTM = 1, EPI_QHEAD = 2, EPI_LNLSTM = 3 };
 constexpr int TC_MAX_ACT = 8;
 
 // "pk" = tile-packed split activations: an fp32 matrix [R, Kact] (Kact % 32 == 0) stored as bf16
@@ -32,6 +32,12 @@ struct TcArgs {
     const float* c_in; int64_t ldc_in;
     float* h_out; int64_t ldh; float* c_out; int64_t ldco; uint8_t* Hpk;
     int H;
+    // EPI_LNLSTM (H == 128, both segments 128 wide; layernormlstm.py:24-42): the two gate GEMMs keep SEPARATE
+    // accumulators (LN_4H is applied to x W_ih^T and h W_hh^T on their own).  A CTA owns whole M tiles and walks
+    // 1 + H/32 N tiles per M tile: tile 0 multiplies by the centred Gram matrices of the weights, from which the
+    // epilogue gets each row's LayerNorm mean / variance; tiles 1.. carry [i|f|g|o] of 32 hidden units each.
+    // Uses c_in / h_out / c_out / Hpk like EPI_LSTM (h_out, c_out double as scratch for the LN_H pass).
+    const float* ln_params;   // filled by tc_launch: column sums, per-tile LN affine, ln_cell affine
     // EPI_QHEAD (N <= 256): the layer's activated output never leaves the SM; the epilogue applies the
     // Q head q = y Wq^T + bq, the action mask, argmax and the epsilon mix (model.py:199-203, policy.py:42-51)
     const float* q_w; const float* q_b; int n_act;
@@ -60,5 +66,11 @@ TcShape tc_shape(int N, int K0, int K1, int epi, int H, int ws = 0);
 int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, const float* bias, const float* bias2, int N,
                     int K0, int K1, int epi, int H, void* out, cudaStream_t s, int ws = 0);
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
+
+// LayerNormLSTM cell (H == 128) -> packed weights for EPI_LNLSTM: tc_shape(4H, H, H, EPI_LNLSTM, H).packed_bytes
+// (Gram + gate tiles, LN parameters, and the staging area the packing kernels use), 256-byte aligned destination.
+int tc_pack_lnlstm(const float* w_ih, const float* w_hh, const float* b_ih, const float* ln_in_w, const float* ln_in_b,
+                   const float* ln_hid_w, const float* ln_hid_b, const float* ln_cell_w, const float* ln_cell_b, int H, void* out,
+                   cudaStream_t s);
 
 }  // namespace gm

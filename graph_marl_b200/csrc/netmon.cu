@@ -426,6 +426,7 @@ struct NetmonPack {
     int64_t enc[GM_MAX_LAYERS];
     int64_t obs, upd, total;
     bool fused_cells;
+    int cell_epi;  // EPI_LSTM, or EPI_LNLSTM (LayerNormLSTM with hidden 128)
     bool ws_enc[GM_MAX_LAYERS];  // layer runs on the weight-stationary cluster kernel (tile-packed input)
     bool ws_cells;
 };
@@ -435,7 +436,8 @@ static NetmonPack pack_layout(const gm_netmon_params* p) {
     int64_t off = 0;
     int kin = p->in_features;
     const int H = p->hidden;
-    L.fused_cells = p->rnn_type == GM_RNN_LSTM && p->rnn_carryover && (H % 64) == 0;
+    L.cell_epi = p->rnn_type == GM_RNN_LNLSTM ? EPI_LNLSTM : EPI_LSTM;
+    L.fused_cells = p->rnn_carryover && ((p->rnn_type == GM_RNN_LSTM && (H % 64) == 0) || (p->rnn_type == GM_RNN_LNLSTM && H == 128));
     TcWsPlan plan;
     for (int l = 0; l < p->n_enc_layers; l++) {
         L.enc[l] = off;
@@ -447,8 +449,8 @@ static NetmonPack pack_layout(const gm_netmon_params* p) {
     L.obs = L.upd = off;
     L.ws_cells = false;
     if (L.fused_cells) {
-        L.ws_cells = tc_ws_plan(4 * H, H, H, EPI_LSTM, H, &plan);
-        int64_t cell = tc_shape(4 * H, H, H, EPI_LSTM, H, L.ws_cells).packed_bytes;
+        L.ws_cells = tc_ws_plan(4 * H, H, H, L.cell_epi, H, &plan);
+        int64_t cell = tc_shape(4 * H, H, H, L.cell_epi, H, L.ws_cells).packed_bytes;
         L.obs = off;
         L.upd = off + cell;
         off += 2 * cell;
@@ -466,7 +468,16 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
             return rc;
         kin = p->enc_units[l];
     }
-    if (L.fused_cells) {
+    if (L.fused_cells && L.cell_epi == EPI_LNLSTM) {
+        const gm_cell_params* cells[2] = {&p->rnn_obs, &p->rnn_update};
+        const int64_t offs[2] = {L.obs, L.upd};
+        for (int i = 0; i < 2; i++) {
+            const gm_cell_params& c = *cells[i];
+            if ((rc = tc_pack_lnlstm(c.w_ih, c.w_hh, c.b_ih, c.ln_in_w, c.ln_in_b, c.ln_hid_w, c.ln_hid_b, c.ln_cell_w, c.ln_cell_b,
+                                     p->hidden, (char*)out + offs[i], s)))
+                return rc;
+        }
+    } else if (L.fused_cells) {
         const int H = p->hidden;
         if ((rc = tc_pack_weights(p->rnn_obs.w_ih, H, p->rnn_obs.w_hh, H, p->rnn_obs.b_ih, p->rnn_obs.b_hh, 4 * H, H, H, EPI_LSTM, H,
                                   (char*)out + L.obs, s, L.ws_cells)))
@@ -577,9 +588,12 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     NetmonWs w = carve(p, R, B, workspace);
     void* lin_ws = (char*)workspace + w.bytes - (32 << 20);
     int64_t lin_ws_bytes = workspace_bytes - (w.bytes - (32 << 20));
-    const int math = p->rnn_type == GM_RNN_LNLSTM ? GM_MATH_FP32 : p->math;
-    const bool tc = tc_math(math);
     const NetmonPack PL = pack_layout(p);
+    // LayerNormLSTM amplifies rounding: its fused tensor-core cell always forms the three-pass product;
+    // shapes the fused cell is not built for run in fp32
+    const int math = (p->rnn_type == GM_RNN_LNLSTM && !PL.fused_cells) ? GM_MATH_FP32
+                     : (p->rnn_type == GM_RNN_LNLSTM && p->math == GM_MATH_BF16) ? GM_MATH_BF16X3 : p->math;
+    const bool tc = tc_math(math);
     const char* packed = (const char*)p->packed;
     if (tc && packed == nullptr) {  // no cached pack: build it in the workspace tail
         char* dst = (char*)round_up((int64_t)((char*)workspace + w.bytes), 256);
@@ -657,7 +671,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn; a.Hpk = hn_pk;
             a.H = H; a.M = R; a.N = 4 * H;
             a.ws = PL.ws_cells;
-            return tc_launch(a, math, EPI_LSTM, s);
+            return tc_launch(a, math, PL.cell_epi, s);
         };
         // rnn_obs (:491): x = encoder output, (h, c) = carried state.  The weight-stationary kernel takes
         // tile-packed operands only, so the carried h is split once by a small kernel; otherwise the

@@ -24,6 +24,9 @@ CONFIGS = {
     # BASELINE.json configs[1]: routing single graph, seed 923430603, DQN + NetMon, 4096 envs
     "cfg2": dict(n_nodes=20, n_data=20, topo_seed=923430603, congestion=True, K=3, rnn="lstm", H=128,
                  enc=(512, 256), dqn=(512, 256), episode_steps=300),
+    # configs[1] with the LayerNormLSTM cell BASELINE.json's north_star names (src/layernormlstm.py)
+    "cfg2ln": dict(n_nodes=20, n_data=20, topo_seed=923430603, congestion=True, K=3, rnn="lnlstm", H=128,
+                   enc=(512, 256), dqn=(512, 256), episode_steps=300),
     # BASELINE.json configs[3]: synthetic large graph 200 nodes / 100 agents, lnlstm, K=4
     "cfg4": dict(n_nodes=200, n_data=100, topo_seed=476, congestion=True, K=4, rnn="lnlstm", H=128,
                  enc=(512, 256), dqn=(512, 256), episode_steps=300),
@@ -159,7 +162,7 @@ class Rollout:
         self._mark("dqn_act")
         next_obs_a, next_adj, reward, done, info = self.base_env.step(actions)
         self._mark("env_step")
-        next_obs = env._join(next_obs_a, env._netmon_step())
+        next_obs = env._with_graph_obs(next_obs_a)
         self._mark("netmon")
         next_info = env.get_netmon_info()
         self.episode_step += 1

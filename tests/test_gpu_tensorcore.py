@@ -86,6 +86,50 @@ def test_netmon_fused_cells_against_fp64_oracle(K, agg, B, N, math, tol):
         assert np.abs(nm.state.cpu().numpy() - ref_state0).max() < tol
 
 
+@pytest.mark.parametrize("K,agg,B,N,A", [(3, "sum", 96, 20, 20), (1, "mean", 7, 20, 11), (4, "sum", 5, 200, 100)])
+def test_netmon_fused_layernorm_cell_against_fp64_oracle(K, agg, B, N, A):
+    """LayerNormLSTM cell on the tensor cores (EPI_LNLSTM: Gram-matrix row statistics + two accumulators per tile).
+    Stated tolerance: 1e-3 max abs on the new state and the readout, single step from an identical state
+    ('lnlstm atol 1e-3'; the fp32 reference itself sits 5e-6 from fp64 here)."""
+    from oracle import netmon_oracle as NO
+    from oracle import oracle as O
+    from graph_marl_b200.model import NetMon
+
+    Dn, H, tol = 4 * N + 8, 128, 1e-3
+    cfg = dict(hidden=H, iterations=K, rnn_type="lnlstm", rnn_carryover=True, agg_type=agg, output_neighbor_hidden=True,
+               output_global_hidden=False, enc=[512, 256], wseed=41)
+    nm, w = _netmon(cfg, Dn, "bf16x3")
+    topo = O.generate_topology(N, seed=923430603 if N == 20 else 476)
+    rng = np.random.default_rng(5)
+    x = ((rng.random((B, N, Dn)) < 0.05).astype(np.float32) + rng.random((B, N, Dn)).astype(np.float32) * (rng.random((B, N, Dn)) < 0.02))
+    mask = np.broadcast_to(topo["adj"], (B, N, N)).astype(np.float32)
+    st = (rng.standard_normal((B, N, 2 * H)) * 0.3).astype(np.float32)
+    agent_node = rng.integers(0, N, (B, A)).astype(np.int32)
+    ref_out, ref_state, ref_agent = NO.netmon_forward(w, cfg, x, mask, st, agent_node=agent_node, dtype=np.float64)
+    with torch.no_grad():
+        nbr, deg, dm = NetMon.lists_from_mask(torch.from_numpy(mask[:1].copy()).cuda())
+        nm.state = torch.from_numpy(st).cuda()
+        no, ao = nm.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, agent_node=torch.from_numpy(agent_node).cuda(),
+                                  want_node_out=True, want_agent_pk=True)
+        got_state = nm.state.cpu().numpy()
+        eh = np.abs(got_state[..., :H] - ref_state[..., :H]).max()
+        ec = np.abs(got_state[..., H:] - ref_state[..., H:]).max()
+        assert eh < tol and ec < tol, (eh, ec)
+        assert np.abs(no.cpu().numpy() - ref_out).max() < tol
+        assert np.abs(ao.cpu().numpy() - ref_agent).max() < tol
+        # zero initial state (h = 0: the hidden-side gate vector is constant, LayerNorm divides by sqrt(eps))
+        ref0, ref_state0, _ = NO.netmon_forward(w, cfg, x, mask, None, dtype=np.float64)
+        nm.state = None
+        out0 = nm(torch.from_numpy(x).cuda(), torch.from_numpy(mask.copy()).cuda(), None, no_agent_mapping=True)
+        assert np.abs(out0.cpu().numpy() - ref0).max() < tol
+        assert np.abs(nm.state.cpu().numpy() - ref_state0).max() < tol
+        # same inputs through the fp32 SIMT path of the library: both implementations agree
+        nm32, _ = _netmon(cfg, Dn, "fp32")
+        nm32.state = torch.from_numpy(st).cuda()
+        no32, _ = nm32.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, want_node_out=True)
+        assert np.abs(no32.cpu().numpy() - no.cpu().numpy()).max() < tol
+
+
 def test_packed_weight_cache_follows_parameter_updates():
     cfg = dict(hidden=64, iterations=1, rnn_type="lstm", rnn_carryover=True, agg_type="sum", output_neighbor_hidden=True,
                output_global_hidden=False, enc=[32], wseed=3)
