@@ -2,7 +2,7 @@
 """Benchmark of the rollout hot path (BASELINE.json metric: batched env-steps/sec incl. NetMon
 forward; % of HBM roofline for the env-step kernel).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2ln|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg2ln|cfg3|cfg4]
 
 One "step" = one batched rollout step over B environment instances per GPU
 (src/main.py:673-737): DQN epsilon-greedy action selection -> Routing env step with agent and
@@ -161,7 +161,7 @@ def cpu_arm(cfg_name, steps, warmup, envs=None, budget_s=20.0):
         n += 1
     dt = time.perf_counter() - t0
     return dict(value=B * n / dt, unit=UNIT, cores=cores, kind="port",
-                sample=f"{B} envs x {n} rollout steps of {cfg_name} (C env oracle on {cores} threads + torch CPU NetMon+DQN on {cores} threads, "
+                sample=f"{B} envs x {n} rollout steps of {cfg_name}{' (CPU arm: one shared topology instead of the pool)' if c.get('random_topology') else ''} (C env oracle on {cores} threads + torch CPU NetMon+DQN on {cores} threads, "
                        f"replay insert incl.), {dt:.1f} s"), dt / max(n, 1), B
 
 
@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg2ln", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg2ln", "cfg3", "cfg4"])
     ap.add_argument("--envs", type=int, default=0, help="env instances per GPU (default: BASELINE config size)")
     ap.add_argument("--math", default=os.environ.get("GM_BENCH_MATH", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="GEMM arithmetic: bf16x3 = tcgen05 with the fp32-accurate hi/lo split (default, parity mode), "
@@ -190,7 +190,16 @@ def main():
 
     c = CONFIGS[a.workload]
     N, A = c["n_nodes"], c["n_data"]
-    B = a.envs or (4096 if a.workload in ("cfg2", "cfg2ln") else 1024)
+    B = a.envs or {"cfg2": 4096, "cfg2ln": 4096, "cfg3": 2048}.get(a.workload, 1024)
+    # every step of a captured unit keeps its own observation / state tensors alive in the graph's pool:
+    # bound the unit so that those stay under ~24 GB (cfg4 at 8192 envs holds ~15 GB per step)
+    step_bytes = 4 * B * (1.5 * A * (6 * N + 10 + 4 * c["H"]) + N * (4 * N + 8) + 2 * N * c["H"])
+    a.graph_steps = int(max(1, min(a.graph_steps, 24e9 // step_bytes))) if a.graph_steps > 0 else a.graph_steps
+    if a.graph_steps > 2 and c["episode_steps"] <= 100:
+        # short episodes: units cover the steps between an episode's first and last one (those two run eagerly);
+        # pick the unit length that leaves the fewest eager steps
+        inner = c["episode_steps"] - 2
+        a.graph_steps = min(range(max(2, a.graph_steps // 2), a.graph_steps + 1), key=lambda g: (inner % g, -g))
     config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
                            f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
                            f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,

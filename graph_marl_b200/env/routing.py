@@ -232,7 +232,10 @@ class Routing(NetworkEnv):
                 tabs.append(net.tables)
             self._pool = TopologyPool(tabs, self.device)
             idx = np.arange(B, dtype=np.int32)
-        self._topo_index = torch.from_numpy(idx).to(self.device)
+        if self._topo_index is not None and self._topo_index.shape[0] == B:
+            self._topo_index.copy_(torch.from_numpy(idx))  # same device address: captured CUDA graphs keep reading it
+        else:
+            self._topo_index = torch.from_numpy(idx).to(self.device)
 
     def reset(self):
         _lib.require_device()
@@ -373,7 +376,9 @@ class Routing(NetworkEnv):
         """Shortest-path weights as float32 (routing.py:237-254)."""
         if not self.batched:
             return np.asarray(self.network.shortest_paths_weights, dtype=np.float32)
-        a = self._pool.apsp.float()
+        if getattr(self._pool, "apsp_f32", None) is None:
+            self._pool.apsp_f32 = self._pool.apsp.float()
+        a = self._pool.apsp_f32
         return a[self._topo_index.long()] if self._topo_index is not None else a.expand(self.num_envs, -1, -1)
 
     def get_state(self):

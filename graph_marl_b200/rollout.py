@@ -27,6 +27,10 @@ CONFIGS = {
     # configs[1] with the LayerNormLSTM cell BASELINE.json's north_star names (src/layernormlstm.py)
     "cfg2ln": dict(n_nodes=20, n_data=20, topo_seed=923430603, congestion=True, K=3, rnn="lnlstm", H=128,
                    enc=(512, 256), dqn=(512, 256), episode_steps=300),
+    # BASELINE.json configs[2]: no congestion, a random topology per env and episode out of a pool built with the
+    # reference generator (network.py:100-120), 50-step episodes, K=1 (16384 envs over 8 GPUs = 2048 per GPU)
+    "cfg3": dict(n_nodes=20, n_data=20, topo_seed=476, random_topology=True, n_topologies=4096, congestion=False, K=1,
+                 rnn="lstm", H=128, enc=(512, 256), dqn=(512, 256), episode_steps=50),
     # BASELINE.json configs[3]: synthetic large graph 200 nodes / 100 agents, lnlstm, K=4
     "cfg4": dict(n_nodes=200, n_data=100, topo_seed=476, congestion=True, K=4, rnn="lnlstm", H=128,
                  enc=(512, 256), dqn=(512, 256), episode_steps=300),
@@ -64,7 +68,10 @@ class Rollout:
         N, A = c["n_nodes"], c["n_data"]
         torch.manual_seed(seed)
         np.random.seed(seed)
-        net = Network(N, random_topology=False, topology_init_seed=c["topo_seed"])
+        if c.get("random_topology"):
+            net = Network(N, random_topology=True, n_random_seeds=c["n_topologies"], topology_init_seed=c["topo_seed"])
+        else:
+            net = Network(N, random_topology=False, topology_init_seed=c["topo_seed"])
         self.base_env = Routing(net, A, 1, enable_congestion=c["congestion"], num_envs=num_envs, device=device,
                                 seed=seed, batched=True)
         Dn, Da = 4 * N + 8, 6 * N + 10
@@ -77,7 +84,10 @@ class Rollout:
         self.policy = EpsilonGreedy(self.env, self.model, 4, args, seed=seed)
         self.buff = None
         if with_replay:
-            cap = replay_capacity or 8 * num_envs
+            # default ring: 8 batched steps, capped at ~48 GB of HBM (a cfg4 transition is ~3 MB), never below 2 steps
+            per_transition = 4 * (2 * A * Dj + 2 * N * Dn + N * self.netmon.get_state_size() + N * N) + 2 * (A * A + N * N + N * A)
+            steps_fit = max(2, min(8, int(48e9 // (per_transition * num_envs))))
+            cap = replay_capacity or steps_fit * num_envs
             self.buff = ReplayBuffer(seed, cap, A, Dj, 0, N, Dn, self.netmon.get_state_size(), N, device=device)
         self.sizes = dict(N=N, A=A, Dn=Dn, Da=Da, Dj=Dj, H=c["H"], K=c["K"])
         self.host_draws = host_draws
@@ -129,7 +139,12 @@ class Rollout:
 
     def reset(self):
         self.obs, self.adj = self.env.reset()
-        self.node_aux = self.env.get_node_aux()
+        aux = self.env.get_node_aux()
+        if (self.node_aux is not None and self.node_aux.shape == aux.shape and self.node_aux.is_contiguous()
+                and aux.data_ptr() != self.node_aux.data_ptr()):
+            self.node_aux.copy_(aux)  # per-env topologies: refresh in place, captured graph units hold this address
+        else:
+            self.node_aux = aux
         self.episode_step = 0
 
     def _mark(self, name):

@@ -62,3 +62,41 @@ def test_graph_units_respect_episode_boundaries():
         assert np.array_equal(sa[k], sb[k]), k
     assert torch.equal(a.env.current_netmon_state, b.env.current_netmon_state)
     assert a.episode_step == b.episode_step
+    for name in ("obs", "node_aux", "node_adj", "reward", "node_state"):  # units captured before a reset stay valid after it
+        assert torch.equal(getattr(a.buff, name), getattr(b.buff, name)), name
+
+
+@pytest.mark.parametrize("rnn,H,enc", [("lstm", 64, (64,)), ("lnlstm", 128, (64, 128))])
+def test_random_topology_pool_rollout_graph_equals_eager(rnn, H, enc):
+    """BASELINE config 3 shape: every env draws a topology from a pool at each episode start (the pool and the
+    per-env index tensor keep their device addresses, so captured units stay valid across resets)."""
+    from graph_marl_b200.rollout import Rollout
+
+    cfg = dict(n_nodes=20, n_data=20, topo_seed=476, random_topology=True, n_topologies=7, congestion=False, K=1, rnn=rnn,
+               H=H, enc=enc, dqn=(64,), episode_steps=9)
+    mk = lambda g: Rollout(cfg, num_envs=40, math="bf16x3", seed=11, replay_capacity=40 * 8, graph_steps=g)
+    a, b = mk(0), mk(3)
+    # the topology draws come from the global numpy stream (network.py:229-238): give both runs the same one
+    for ro in (a, b):
+        np.random.seed(5)
+        ro.reset()
+    assert a.base_env._pool.T == 7 and len(set(a.base_env._topo_index.cpu().tolist())) > 1
+    assert torch.equal(a.base_env._topo_index, b.base_env._topo_index)
+    for ro in (a, b):
+        np.random.seed(6)
+        ro.run(25)
+    torch.cuda.synchronize()
+    assert b._graphs, "no CUDA graph unit was captured"
+    assert torch.equal(a.base_env._topo_index, b.base_env._topo_index)
+    sa, sb = a.base_env.get_state(), b.base_env.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert torch.equal(a.obs[0], b.obs[0]) and torch.equal(a.obs[1], b.obs[1])
+    assert torch.equal(a.env.current_netmon_state, b.env.current_netmon_state)
+    bad = []
+    for name in ("obs", "next_obs", "node_adj", "node_aux", "reward", "node_state", "node_obs", "action"):
+        x, y = getattr(a.buff, name), getattr(b.buff, name)
+        if not torch.equal(x, y):
+            d = (x.float() - y.float()).abs().reshape(x.shape[0], -1).max(dim=1)[0]
+            bad.append((name, int((d > 0).sum()), float(d.max()), (d > 0).nonzero().flatten()[:8].tolist()))
+    assert not bad, bad
