@@ -22,6 +22,8 @@ SOURCES = ["runtime.cu", "routing_env.cu", "simple_env.cu", "netmon.cu", "gemm_d
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-x", "cu",
               "--expt-relaxed-constexpr", "-I", INCLUDE]
+# e.g. GM_NVCC_EXTRA="-DGM_TC_PROBES=1" builds the timing probes of gemm_sm100.cu (GM_TC_DEBUG / GM_LN_DEBUG)
+NVCC_FLAGS += os.environ.get("GM_NVCC_EXTRA", "").split()
 
 
 def _nvcc():

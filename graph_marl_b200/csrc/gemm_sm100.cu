@@ -42,6 +42,11 @@
 #ifndef GM_LSTM_SHARED_RCP
 #define GM_LSTM_SHARED_RCP 1
 #endif
+// Timing probes (build with -DGM_TC_PROBES=1): GM_TC_DEBUG / GM_LN_DEBUG then switch off parts of the kernels to
+// measure what bounds them.  Results are WRONG while a probe is active; the default build has none of this code.
+#ifndef GM_TC_PROBES
+#define GM_TC_PROBES 0
+#endif
 #ifndef GM_LSTM_UNROLL
 #define GM_LSTM_UNROLL 1
 #endif
@@ -230,6 +235,7 @@ __device__ __forceinline__ int ptr_align_floats(const float* p, int64_t ld) {
 __device__ __forceinline__ uint32_t core_off(int r, int kc) { return (uint32_t)((r >> 3) * SBO_BYTES + kc * 128 + (r & 7) * 16); }
 
 template <int BN, int PASSES, int EPI>
+// 18 warps: 5 on one SM sub-partition (16K registers each) -> 96 registers per thread at most
 __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     constexpr int W_PART_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = 2 * A_PART_BYTES + 2 * W_PART_BYTES;
@@ -240,8 +246,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
-    __shared__ float ln_stats[LN ? 2 : 1][LN ? BM : 1][4];  // per row: mean / rstd of the ih gates, of the hh gates
-    __shared__ float ln_cpart[LN ? 2 : 1][LN ? BM : 1][4];  // per row: partial sums of the two column halves (LN_H)
+    // LayerNormLSTM: warps 8-15 are epilogue warps too (no fp32 operands, hence no producers): 4 column quarters per row
+    constexpr int EPI_W = LN ? EPI_WARPS + PROD_WARPS : EPI_WARPS;
+    __shared__ float ln_part[LN ? 2 : 1][LN ? BM : 1][4][2];  // per row and column quarter: partial sum / centred sum of squares
+    __shared__ float ln_cpart[LN ? 2 : 1][LN ? BM : 1][8];    // per row: the quarters' partial sums of the LN_H pass
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         }
         for (int a = 0; a < ACC_STAGES; a++) {
             mbar_init(bar_tfull + 8 * a, 1);                // tcgen05.commit
-            mbar_init(bar_tempty + 8 * a, EPI_WARPS * 32);  // every epilogue thread
+            mbar_init(bar_tempty + 8 * a, EPI_W * 32);  // every epilogue thread
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -288,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     auto unit_mt = [&](int i) { return LN ? cluster_id + (i / n_tiles) * n_clusters : ((cluster_id + i * n_clusters) / n_tiles) * csz + rank; };
     auto unit_nt = [&](int i) { return LN ? i % n_tiles : (cluster_id + i * n_clusters) % n_tiles; };
 
-    if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    if (!LN && warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ================= producer: fp32 activations -> bf16 hi/lo core matrices ================
         // Warp pw owns tile rows [16pw, 16pw+16) as two 8-row groups.  Lane = (r8 = lane/4, part = lane%4):
         // one 32-byte load per lane = 8 rows x one 128-byte line per warp instruction, and lanes
@@ -411,6 +419,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     const int kfirst = LN ? (kb != 0 && kb != kb_seg1) : kb;  // 0 on the first k-block of an accumulator
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ks++) {
+#if GM_TC_PROBES
+                        if ((LN && (p.accumulate & 2)) || (p.a_stages & 2)) break;  // timing probes: no MMAs
+#endif
                         const uint32_t o = ks * 256;  // two 128-byte core matrices per K=16 step
                         if (PASSES == 3) {  // small terms first, then hi*hi
                             umma(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kfirst | ks) != 0);
@@ -434,6 +445,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         const int quad = warp & 3, chalf = warp >> 2;
         const int r = quad * 32 + lane;  // accumulator lane == tile row
         float ln_csum = 0.f;             // LayerNormLSTM: running sum of this thread's pre-LN cell values of the row
+        float* const ln_craw = (float*)(smem + STAGES * STAGE_BYTES);  // LayerNormLSTM only: [BN][BM] behind the ring
         for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
             const int as = tcount % ACC_STAGES;
             const uint32_t aph = (tcount / ACC_STAGES) & 1;
@@ -441,14 +453,32 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
             const int64_t m = (int64_t)mt * BM + r;
             const bool live = m < p.M;
             if constexpr (LN) {
+#if GM_TC_PROBES
+                if (p.accumulate & 1) {  // GM_LN_DEBUG timing probe: no epilogue work
+                    mbar_wait(bar_tfull + 8 * as, aph);
+                    tc_fence_after();
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * as);
+                    continue;
+                }
+#endif
 #include "gemm_sm100_lnlstm.inc"
             } else {
+#if GM_TC_PROBES
+                if ((p.a_stages & 1) && EPI != EPI_QHEAD) {  // GM_TC_DEBUG timing probe: no epilogue work
+                    mbar_wait(bar_tfull + 8 * as, aph);
+                    tc_fence_after();
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * as);
+                    continue;
+                }
+#endif
 #include "gemm_sm100_epilogue.inc"
                 tc_fence_before();
                 mbar_arrive(bar_tempty + 8 * as);
             }
         }
-        (void)ln_csum;
+        (void)ln_csum; (void)ln_craw;
     }
 
     tc_fence_before();
@@ -817,7 +847,8 @@ static int tc_cluster_size() {
 
 template <int BN, int PASSES, int EPI>
 static int launch_tc(TcArgs a, cudaStream_t s) {
-    constexpr int smem = tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2);
+    constexpr int smem = tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2) +
+                         (EPI == EPI_LNLSTM ? BN * tc::BM * 4 : 0);  // + pre-LN cell values of one M tile
     static bool configured = false;
     static int max_clusters[5] = {0, 0, 0, 0, 0};
     auto kern = tc::linear_tc_kernel<BN, PASSES, EPI>;
@@ -848,6 +879,13 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
     attr[0].val.clusterDim.x = csz;
     a.csz = csz;
     if (EPI == EPI_LNLSTM) csz = 1;
+#if GM_TC_PROBES
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("GM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+        a.a_stages = dbg;  // the field is unused by this kernel otherwise
+    }
+#endif
     attr[0].val.clusterDim.x = csz;
     a.csz = csz;
     // LayerNormLSTM: a CTA owns whole M tiles
@@ -946,10 +984,18 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     a.has_prod = (a.A0 != nullptr) || (a.K1 > 0 && a.A1 != nullptr);
     if (epi == EPI_LNLSTM) {
         GM_CHECK_ARG(a.H == 128 && a.K0 == 128 && a.K1 == 128 && !a.ws, "fused LayerNormLSTM cell needs hidden == 128 and two 128-wide segments");
+        GM_CHECK_ARG(a.A0pk && a.A1pk, "fused LayerNormLSTM cell takes tile-packed operands only (its producer warps run the epilogue)");
         GM_CHECK_ARG(a.c_in && a.h_out && a.c_out && (a.ldc_in & 7) == 0 && (a.ldh & 7) == 0 && (a.ldco & 7) == 0 &&
                          (((uintptr_t)a.c_in | (uintptr_t)a.h_out | (uintptr_t)a.c_out) & 31) == 0 && ((uintptr_t)a.Hpk & 127) == 0,
                      "fused LayerNormLSTM epilogue needs 32-byte aligned state rows");
         a.ln_params = (const float*)(a.Wp + sh.w_bytes);
+#if GM_TC_PROBES
+        {
+            static int dbg = -1;
+            if (dbg < 0) { const char* e = getenv("GM_LN_DEBUG"); dbg = e ? atoi(e) : 0; }
+            a.accumulate = dbg;
+        }
+#endif
         return launch_tc<128, 3, EPI_LNLSTM>(a, s);  // always the three-pass product (LN amplifies rounding)
     }
     if (epi == EPI_LSTM) {

@@ -678,8 +678,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         // producer warps split it on the fly.
         const int kbs = H / TC_BK;
         int rc;
-        if (PL.ws_cells) {
-            GM_CHECK_ARG(xpk != nullptr, "weight-stationary cells need a tile-packed encoder output");
+        if (PL.ws_cells || PL.cell_epi == EPI_LNLSTM) {
+            GM_CHECK_ARG(xpk != nullptr, "weight-stationary / LayerNormLSTM cells need a tile-packed encoder output");
             const unsigned blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
             split_pk_kernel<<<blocks, 256, 0, s>>>(st_in, S, hpk[1], R, H, math != GM_MATH_BF16);
             GM_LAUNCH_CHECK();
