@@ -234,7 +234,7 @@ __device__ __forceinline__ int ptr_align_floats(const float* p, int64_t ld) {
 // byte offset of the 16-byte chunk (row r, k-chunk kc) inside one bf16 part of a [128 x 32] block
 __device__ __forceinline__ uint32_t core_off(int r, int kc) { return (uint32_t)((r >> 3) * SBO_BYTES + kc * 128 + (r & 7) * 16); }
 
-template <int BN, int PASSES, int EPI>
+template <int BN, int PASSES, int EPI, int NCG>
 // 18 warps: 5 on one SM sub-partition (16K registers each) -> 96 registers per thread at most
 __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     constexpr int W_PART_BYTES = BN * BK * 2;
@@ -246,8 +246,11 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
-    // LayerNormLSTM: warps 8-15 are epilogue warps too (no fp32 operands, hence no producers): 4 column quarters per row
-    constexpr int EPI_W = LN ? EPI_WARPS + PROD_WARPS : EPI_WARPS;
+    // NCG == 4 ("wide" epilogue): warps 8-15 are epilogue warps too (no fp32 operands, hence no producers), four
+    // column groups per TMEM quadrant
+    static_assert(NCG == 2 || NCG == 4, "2 or 4 column groups");
+    static_assert(!LN || NCG == 4, "the LayerNormLSTM epilogue is written for four column quarters");
+    constexpr int EPI_W = NCG == 4 ? EPI_WARPS + PROD_WARPS : EPI_WARPS;  // NCG == 4: no producers (all operands tile-packed)
     __shared__ float ln_part[LN ? 2 : 1][LN ? BM : 1][4][2];  // per row and column quarter: partial sum / centred sum of squares
     __shared__ float ln_cpart[LN ? 2 : 1][LN ? BM : 1][8];    // per row: the quarters' partial sums of the LN_H pass
 
@@ -296,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     auto unit_mt = [&](int i) { return LN ? cluster_id + (i / n_tiles) * n_clusters : ((cluster_id + i * n_clusters) / n_tiles) * csz + rank; };
     auto unit_nt = [&](int i) { return LN ? i % n_tiles : (cluster_id + i * n_clusters) % n_tiles; };
 
-    if (!LN && warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    if (NCG == 2 && warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ================= producer: fp32 activations -> bf16 hi/lo core matrices ================
         // Warp pw owns tile rows [16pw, 16pw+16) as two 8-row groups.  Lane = (r8 = lane/4, part = lane%4):
         // one 32-byte load per lane = 8 rows x one 128-byte line per warp instruction, and lanes
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         }
     } else {
         // ================= epilogue: TMEM -> registers -> global ==========================================
-        // 8 warps: warp e reads TMEM lanes 32*(e%4).. (its hardware quadrant) and the column half e/4.
+        // warp e reads TMEM lanes 32*(e%4).. (its hardware quadrant) and the column group e/4 (of NCG).
         const int quad = warp & 3, chalf = warp >> 2;
         const int r = quad * 32 + lane;  // accumulator lane == tile row
         float ln_csum = 0.f;             // LayerNormLSTM: running sum of this thread's pre-LN cell values of the row
@@ -506,6 +509,7 @@ constexpr int WS_THREADS = 32 * 10, WS_MMA_WARP = 8, WS_COPY_WARP = 9, WS_MAX_A_
 
 template <int BN, int PASSES, int EPI>
 __global__ void __launch_bounds__(WS_THREADS, 1) linear_ws_kernel(const TcArgs p) {
+    constexpr int NCG = 2;  // 8 epilogue warps
     constexpr int W_PART_BYTES = BN * BK * 2;
     constexpr int W_KB_BYTES = 2 * W_PART_BYTES, A_STAGE_BYTES = 2 * A_PART_BYTES;
     constexpr int ACC_STAGES = (512 / BN) > 4 ? 4 : (512 / BN);
@@ -845,13 +849,13 @@ static int tc_cluster_size() {
     return csz;
 }
 
-template <int BN, int PASSES, int EPI>
+template <int BN, int PASSES, int EPI, int NCG = 2>
 static int launch_tc(TcArgs a, cudaStream_t s) {
     constexpr int smem = tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2) +
                          (EPI == EPI_LNLSTM ? BN * tc::BM * 4 : 0);  // + pre-LN cell values of one M tile
     static bool configured = false;
     static int max_clusters[5] = {0, 0, 0, 0, 0};
-    auto kern = tc::linear_tc_kernel<BN, PASSES, EPI>;
+    auto kern = tc::linear_tc_kernel<BN, PASSES, EPI, NCG>;
     if (!configured) {
         GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -996,7 +1000,7 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
             a.accumulate = dbg;
         }
 #endif
-        return launch_tc<128, 3, EPI_LNLSTM>(a, s);  // always the three-pass product (LN amplifies rounding)
+        return launch_tc<128, 3, EPI_LNLSTM, 4>(a, s);  // always the three-pass product (LN amplifies rounding)
     }
     if (epi == EPI_LSTM) {
         GM_CHECK_ARG(a.H % 64 == 0, "fused LSTM epilogue needs hidden %% 64 == 0, got %d", a.H);
@@ -1026,6 +1030,13 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
             return GM_ERR_CUDA;
         }
         return rc;
+    }
+    // all operands tile-packed: the producer warps have nothing to do and run the epilogue too (GM_TC_WIDE=0: off)
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("GM_TC_WIDE"); wide = e ? atoi(e) : 1; }
+    if (wide && !a.has_prod && passes == 3) {
+        if (epi == EPI_LSTM) return launch_tc<256, 3, EPI_LSTM, 4>(a, s);
+        if (epi == EPI_LINEAR) return sh.BN == 128 ? launch_tc<128, 3, EPI_LINEAR, 4>(a, s) : launch_tc<256, 3, EPI_LINEAR, 4>(a, s);
     }
     if (epi == EPI_LSTM) return passes == 3 ? launch_tc<256, 3, EPI_LSTM>(a, s) : launch_tc<256, 1, EPI_LSTM>(a, s);
     if (epi == EPI_QHEAD) return passes == 3 ? launch_tc<256, 3, EPI_QHEAD>(a, s) : launch_tc<256, 1, EPI_QHEAD>(a, s);
