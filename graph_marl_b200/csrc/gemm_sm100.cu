@@ -56,6 +56,7 @@ namespace gm {
 namespace tc {
 
 constexpr int BM = TC_BM, BK = TC_BK, STAGES = 4, ACC_STAGES = 2;
+constexpr int PAIR_STAGES = 6;  // 2-CTA pairs stage half a weight tile per CTA: 32 KiB per stage at BN = 256
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
 constexpr int MMA_WARP = 16, W_WARP = 17;
 constexpr int THREADS = 32 * 18;
@@ -143,6 +144,51 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__host__ __device__ constexpr uint32_t umma_idesc_m(int BN, int M) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// cta_group::2: one instruction drives the tensor cores of both SMs of the pair (M = 256: rows 0-127 from the leader's
+// shared memory / TMEM, rows 128-255 from the peer's; each CTA holds half of the B rows)
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives (once) on the mbarrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+// arrive on the mbarrier at this CTA-relative address in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -234,16 +280,24 @@ __device__ __forceinline__ int ptr_align_floats(const float* p, int64_t ld) {
 // byte offset of the 16-byte chunk (row r, k-chunk kc) inside one bf16 part of a [128 x 32] block
 __device__ __forceinline__ uint32_t core_off(int r, int kc) { return (uint32_t)((r >> 3) * SBO_BYTES + kc * 128 + (r & 7) * 16); }
 
-template <int BN, int PASSES, int EPI, int NCG>
+// PAIR: the CTAs of a 2-CTA cluster (one TPC) run ONE tcgen05.mma.cta_group::2 (M = 256) per step: each CTA stages the
+// activation block of its own M tile and HALF of the weight tile (rows rank*BN/2 ..), the tensor cores of both SMs
+// read the two halves from both shared memories.  Weight bytes per CTA and shared-memory operand reads per MMA
+// halve.  Only the leader (cluster rank 0) issues MMAs; the peer's MMA thread relays "my stage is full" to the
+// leader, both CTAs' epilogue threads release the accumulator stage on the leader's barrier.
+template <int BN, int PASSES, int EPI, int NCG, bool PAIR>
 // 18 warps: 5 on one SM sub-partition (16K registers each) -> 96 registers per thread at most
 __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
-    constexpr int W_PART_BYTES = BN * BK * 2;
+    constexpr int W_PART_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;  // this CTA's rows of one bf16 part of a weight stage
+    constexpr int W_SRC_PART_BYTES = BN * BK * 2;                // one bf16 part of the packed weight tile in global memory
     constexpr int STAGE_BYTES = 2 * A_PART_BYTES + 2 * W_PART_BYTES;
-    constexpr uint32_t IDESC = umma_idesc(BN);
+    constexpr int NST = PAIR ? PAIR_STAGES : STAGES;
+    constexpr uint32_t IDESC = PAIR ? umma_idesc_m(BN, 2 * BM) : umma_idesc(BN);
+    static_assert(!PAIR || EPI != EPI_LNLSTM, "the LayerNormLSTM mode owns whole M tiles per CTA");
     constexpr bool LN = EPI == EPI_LNLSTM;
     constexpr int ACC_COLS = LN ? 2 * BN : BN;  // LayerNormLSTM: separate accumulators for x W_ih^T and h W_hh^T
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * ACC_STAGES];
+    __shared__ __align__(8) uint64_t bars[3 * NST + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
     // NCG == 4 ("wide" epilogue): warps 8-15 are epilogue warps too (no fp32 operands, hence no producers), four
@@ -256,26 +310,34 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
-    const uint32_t bar_tfull = smem_u32(&bars[2 * STAGES]), bar_tempty = smem_u32(&bars[2 * STAGES + ACC_STAGES]);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NST]);
+    const uint32_t bar_tfull = smem_u32(&bars[2 * NST]), bar_tempty = smem_u32(&bars[2 * NST + ACC_STAGES]);
+    const uint32_t bar_pfull = smem_u32(&bars[2 * NST + 2 * ACC_STAGES]);  // PAIR, leader: the peer's stage is full
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) {
+        for (int s = 0; s < NST; s++) {
             // the copy thread's expect_tx arrive, plus the 256 producer threads when a segment is fp32
             mbar_init(bar_full + 8 * s, 1 + (p.has_prod ? PROD_WARPS * 32 : 0));
-            mbar_init(bar_empty + 8 * s, p.csz);  // one tcgen05.commit per CTA of the cluster (weights are multicast)
+            // one tcgen05.commit per CTA of the cluster when weights are multicast; the leader's commit alone for a pair
+            mbar_init(bar_empty + 8 * s, PAIR ? 1 : p.csz);
+            mbar_init(bar_pfull + 8 * s, 1);
         }
         for (int a = 0; a < ACC_STAGES; a++) {
-            mbar_init(bar_tfull + 8 * a, 1);                // tcgen05.commit
-            mbar_init(bar_tempty + 8 * a, EPI_W * 32);  // every epilogue thread
+            mbar_init(bar_tfull + 8 * a, 1);                              // tcgen05.commit
+            mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * EPI_W * 32);  // every epilogue thread (of both CTAs of a pair)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {  // TMEM: ACC_STAGES x BN fp32 columns x 128 lanes
         uint32_t dst = smem_u32(&tmem_base_smem);
         uint32_t cols = ACC_STAGES * ACC_COLS;
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -343,8 +405,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 for (int u = 0; u < 3; u++) {
                     const uint32_t it = base + u;
                     if (it >= total_it) break;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
                     fetch(it + 2, buf[(u + 2) % 3]);
                     const int kb = (int)(it % kblocks);
                     const bool mine = (kb >= kb_seg1) ? prod1 : prod0;
@@ -376,16 +438,21 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 const int mt = unit_mt(u), nt = unit_nt(u);
                 const bool tile_live = mt < p.m_tiles;  // a dead tile of the last group copies no activations
                 for (int kb = 0; kb < kblocks; kb++, it++) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
                     const bool seg1 = kb >= kb_seg1;
                     const uint8_t* apk = seg1 ? p.A1pk : p.A0pk;
                     if (!tile_live) apk = nullptr;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);  // every CTA of the cluster has retired its MMAs on this stage
                     mbar_arrive_expect_tx(bar_full + 8 * s, w_bytes + (apk ? a_bytes : 0u));
-                    const uint8_t* src = p.Wp + ((size_t)nt * kblocks + kb) * (2 * W_PART_BYTES);
+                    const uint8_t* src = p.Wp + ((size_t)nt * kblocks + kb) * (2 * W_SRC_PART_BYTES);
                     const uint32_t w_dst = smem_base + s * STAGE_BYTES + 2 * A_PART_BYTES;
-                    if (csz == 1) {
+                    if (PAIR) {  // this CTA's half of the rows of each part
+#pragma unroll
+                        for (int part = 0; part < (PASSES == 3 ? 2 : 1); part++)
+                            bulk_g2s(w_dst + part * W_PART_BYTES, src + part * W_SRC_PART_BYTES + rank * W_PART_BYTES, W_PART_BYTES,
+                                     bar_full + 8 * s);
+                    } else if (csz == 1) {
                         bulk_g2s(w_dst, src, w_bytes, bar_full + 8 * s);
                     } else {
 #pragma unroll
@@ -402,18 +469,30 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer ==================================================================
-        if (lane == 0) {
+        if (PAIR && rank != 0) {
+            // peer of a pair: no MMAs to issue; tell the leader whenever a stage of THIS CTA is full
+            if (lane == 0) {
+                const uint32_t total_it = (uint32_t)my_units * (uint32_t)kblocks;
+                for (uint32_t it = 0; it < total_it; it++) {
+                    const int s = it % NST;
+                    mbar_wait(bar_full + 8 * s, (it / NST) & 1);
+                    mbar_arrive_remote(bar_pfull + 8 * s, 0);
+                }
+            }
+        } else if (lane == 0) {
             uint32_t it = 0;
             for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
                 const int as = tcount % ACC_STAGES;
                 const uint32_t aph = (tcount / ACC_STAGES) & 1;
-                mbar_wait(bar_tempty + 8 * as, aph ^ 1);  // epilogue drained this accumulator
+                if (PAIR) mbar_wait_cluster(bar_tempty + 8 * as, aph ^ 1);  // both CTAs' epilogues drained this accumulator
+                else mbar_wait(bar_tempty + 8 * as, aph ^ 1);               // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t d0 = tmem_base + as * ACC_COLS;
                 for (int kb = 0; kb < kblocks; kb++, it++) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
                     mbar_wait(bar_full + 8 * s, ph);
+                    if (PAIR) mbar_wait_cluster(bar_pfull + 8 * s, ph);  // ... and the peer's half of the operands
                     tc_fence_after();
                     const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_PART_BYTES;
                     const uint32_t w_hi = a_hi + 2 * A_PART_BYTES, w_lo = w_hi + W_PART_BYTES;
@@ -426,7 +505,15 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                         if ((LN && (p.accumulate & 2)) || (p.a_stages & 2)) break;  // timing probes: no MMAs
 #endif
                         const uint32_t o = ks * 256;  // two 128-byte core matrices per K=16 step
-                        if (PASSES == 3) {  // small terms first, then hi*hi
+                        if (PAIR) {
+                            if (PASSES == 3) {
+                                umma2(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kfirst | ks) != 0);
+                                umma2(d, umma_desc(a_hi + o), umma_desc(w_lo + o), IDESC, 1);
+                                umma2(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, 1);
+                            } else {
+                                umma2(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, (kfirst | ks) != 0);
+                            }
+                        } else if (PASSES == 3) {  // small terms first, then hi*hi
                             umma(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kfirst | ks) != 0);
                             umma(d, umma_desc(a_hi + o), umma_desc(w_lo + o), IDESC, 1);
                             umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, 1);
@@ -435,11 +522,13 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                         }
                     }
                     // smem stage reusable once these MMAs retire; with multicast weights every CTA of the
-                    // cluster must know, because peers write into this CTA's stage
-                    if (csz == 1) umma_commit(bar_empty + 8 * s);
+                    // cluster must know, because peers write into this CTA's stage; in a pair both CTAs' stages retire
+                    if (PAIR) umma2_commit_mc(bar_empty + 8 * s, 3);
+                    else if (csz == 1) umma_commit(bar_empty + 8 * s);
                     else umma_commit_mc(bar_empty + 8 * s, mc_mask);
                 }
-                umma_commit(bar_tfull + 8 * as);  // accumulator complete
+                if (PAIR) umma2_commit_mc(bar_tfull + 8 * as, 3);  // accumulator complete in both CTAs
+                else umma_commit(bar_tfull + 8 * as);              // accumulator complete
             }
         }
     } else {
@@ -478,7 +567,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 #endif
 #include "gemm_sm100_epilogue.inc"
                 tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * as);
+                if (PAIR && rank != 0) mbar_arrive_remote(bar_tempty + 8 * as, 0);  // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(bar_tempty + 8 * as);
             }
         }
         (void)ln_csum; (void)ln_craw;
@@ -490,7 +580,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     if (warp == MMA_WARP) {
         tc_fence_after();
         uint32_t cols = ACC_STAGES * ACC_COLS;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
     }
 }
 
@@ -849,20 +940,22 @@ static int tc_cluster_size() {
     return csz;
 }
 
-template <int BN, int PASSES, int EPI, int NCG = 2>
+template <int BN, int PASSES, int EPI, int NCG = 2, bool PAIR = false>
 static int launch_tc(TcArgs a, cudaStream_t s) {
-    constexpr int smem = tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2) +
-                         (EPI == EPI_LNLSTM ? BN * tc::BM * 4 : 0);  // + pre-LN cell values of one M tile
+    constexpr int smem = PAIR ? tc::PAIR_STAGES * (2 * tc::A_PART_BYTES + 2 * (BN / 2) * tc::BK * 2)
+                              : tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2) +
+                                    (EPI == EPI_LNLSTM ? BN * tc::BM * 4 : 0);  // + pre-LN cell values of one M tile
     static bool configured = false;
     static int max_clusters[5] = {0, 0, 0, 0, 0};
-    auto kern = tc::linear_tc_kernel<BN, PASSES, EPI, NCG>;
+    auto kern = tc::linear_tc_kernel<BN, PASSES, EPI, NCG, PAIR>;
     if (!configured) {
         GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    // weight stages are multicast to the CTAs of a cluster (each CTA fetches 1/csz of every weight tile)
-    int csz = std::min(tc_cluster_size(), std::max(1, a.m_tiles));
-    while (csz > 1 && csz > a.m_tiles) csz >>= 1;
+    // weight stages are multicast to the CTAs of a cluster (each CTA fetches 1/csz of every weight tile);
+    // PAIR: always a 2-CTA cluster driving one cta_group::2 MMA
+    int csz = PAIR ? 2 : std::min(tc_cluster_size(), std::max(1, a.m_tiles));
+    while (!PAIR && csz > 1 && csz > a.m_tiles) csz >>= 1;
     if (csz == 3) csz = 2;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
@@ -879,6 +972,7 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
         if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
         max_clusters[csz] = n;
     }
+    if (PAIR && max_clusters[csz] < 0) return 1;    // caller falls back to the single-CTA kernel
     if (csz > 1 && max_clusters[csz] < 0) csz = 1;  // clusters of this size cannot be scheduled: plain launch
     attr[0].val.clusterDim.x = csz;
     a.csz = csz;
@@ -1000,7 +1094,7 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
             a.accumulate = dbg;
         }
 #endif
-        return launch_tc<128, 3, EPI_LNLSTM, 4>(a, s);  // always the three-pass product (LN amplifies rounding)
+        return launch_tc<128, 3, EPI_LNLSTM, 4, false>(a, s);  // always the three-pass product (LN amplifies rounding)
     }
     if (epi == EPI_LSTM) {
         GM_CHECK_ARG(a.H % 64 == 0, "fused LSTM epilogue needs hidden %% 64 == 0, got %d", a.H);
@@ -1031,9 +1125,21 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
         }
         return rc;
     }
-    // all operands tile-packed: the producer warps have nothing to do and run the epilogue too (GM_TC_WIDE=0: off)
+    // 2-CTA pairs (cta_group::2, M = 256): half the weight bytes and shared-memory operand reads per CTA.  Measured on
+    // B200 at this workload's shapes: correct but 5-15 % slower than the single-CTA kernel (the relay of "peer stage
+    // full" and the two-CTA accumulator release lengthen the per-stage loop), so it is an option: GM_TC_PAIR=1
+    static int pair = -1;
+    if (pair < 0) { const char* e = getenv("GM_TC_PAIR"); pair = e ? atoi(e) : 0; }
+    if (pair && passes == 3 && sh.BN == 256 && a.m_tiles >= 2) {
+        int rc = 1;
+        if (epi == EPI_LSTM) rc = launch_tc<256, 3, EPI_LSTM, 2, true>(a, s);
+        else if (epi == EPI_QHEAD) rc = launch_tc<256, 3, EPI_QHEAD, 2, true>(a, s);
+        else if (epi == EPI_LINEAR) rc = launch_tc<256, 3, EPI_LINEAR, 2, true>(a, s);
+        if (rc != 1) return rc;  // 1: 2-CTA clusters cannot be scheduled here
+    }
+    // all operands tile-packed: the producer warps have nothing to do and run the epilogue too (GM_TC_WIDE=1: on)
     static int wide = -1;
-    if (wide < 0) { const char* e = getenv("GM_TC_WIDE"); wide = e ? atoi(e) : 1; }
+    if (wide < 0) { const char* e = getenv("GM_TC_WIDE"); wide = e ? atoi(e) : 0; }
     if (wide && !a.has_prod && passes == 3) {
         if (epi == EPI_LSTM) return launch_tc<256, 3, EPI_LSTM, 4>(a, s);
         if (epi == EPI_LINEAR) return sh.BN == 128 ? launch_tc<128, 3, EPI_LINEAR, 4>(a, s) : launch_tc<256, 3, EPI_LINEAR, 4>(a, s);
