@@ -32,6 +32,11 @@ struct TcArgs {
     const float* c_in; int64_t ldc_in;
     float* h_out; int64_t ldh; float* c_out; int64_t ldco; uint8_t* Hpk;
     int H;
+    // cell state handed from one cell launch to the next may live in a BLOCKED layout (c_in_blocked / c_out_blocked):
+    // [32-row group][8-unit chunk][32 rows][8 floats], offset tc_blocked_off(row, unit, H).  The epilogue thread of
+    // row r reads / writes 32 bytes per chunk, so a warp instruction covers 1 KiB of contiguous memory (8 full
+    // lines) instead of 32 bytes in each of 32 lines -- L2 throughput here is bound by requests, not bytes.
+    int c_in_blocked, c_out_blocked;
     // EPI_LNLSTM (H == 128, both segments 128 wide; layernormlstm.py:24-42): the two gate GEMMs keep SEPARATE
     // accumulators (LN_4H is applied to x W_ih^T and h W_hh^T on their own).  A CTA owns whole M tiles and walks
     // 1 + H/32 N tiles per M tile: tile 0 multiplies by the centred Gram matrices of the weights, from which the
@@ -47,6 +52,11 @@ struct TcArgs {
     int ws;  // use the weight-stationary cluster kernel (tc_ws_plan must hold; weights packed with ws = 1)
     int m_tiles, n_tiles, has_prod, csz, a_stages;  // filled by tc_launch
 };
+
+__host__ __device__ inline int64_t tc_blocked_off(int64_t row, int unit, int H) {
+    return ((row >> 5) * (H >> 3) + (unit >> 3)) * 256 + (row & 31) * 8 + (unit & 7);
+}
+inline int64_t tc_blocked_floats(int64_t rows, int H) { return ((rows + 31) / 32) * 32 * (int64_t)H; }
 
 struct TcShape {
     int BN, K0p, Kp, n_tiles;

@@ -512,7 +512,8 @@ static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
     };
     w.act0 = take(R * maxw); w.act1 = take(R * maxw);
     w.g0 = take(R * G); w.g1 = take(R * G);
-    w.hA = take(R * H); w.hB = take(R * H); w.cA = take(R * H); w.cB = take(R * H);
+    w.hA = take(R * H); w.hB = take(R * H);
+    w.cA = take(tc_blocked_floats(R, H)); w.cB = take(tc_blocked_floats(R, H));  // the fused cells keep c blocked (gemm_sm100.cuh)
     w.M = take(R * H);
     w.gmean = take((int64_t)max(B, 1) * H);
     w.pk0 = w.pk1 = w.e_pk = w.m_pk = w.h_pk0 = w.h_pk1 = nullptr;
@@ -659,6 +660,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         // tile-packed by bulk copy, the new h leaves both as fp32 (state, readout, aggregation) and
         // tile-packed (next cell). =====
         uint8_t* hpk[2] = {w.h_pk0, w.h_pk1};
+        // ldcp / ldcn < 0: that cell-state buffer is one of the workspace's blocked buffers (cA / cB)
         auto cell = [&](int64_t woff, const uint8_t* xin_pk, const float* xin, const uint8_t* hp_pk, const float* hp, int64_t ldhp,
                         const float* cprev, int64_t ldcp, float* hn, int64_t ldhn, float* cn, int64_t ldcn, uint8_t* hn_pk) -> int {
             TcArgs a{};
@@ -667,8 +669,9 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             if (hp_pk) a.A1pk = hp_pk; else { a.A1 = hp; a.lda1 = ldhp; }
             a.K1 = H;
             a.Wp = (const uint8_t*)packed + woff;
-            a.c_in = cprev; a.ldc_in = ldcp;
-            a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn; a.Hpk = hn_pk;
+            a.c_in = cprev; a.ldc_in = ldcp < 0 ? H : ldcp; a.c_in_blocked = ldcp < 0;
+            a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn < 0 ? H : ldcn; a.c_out_blocked = ldcn < 0;
+            a.Hpk = hn_pk;
             a.H = H; a.M = R; a.N = 4 * H;
             a.ws = PL.ws_cells;
             return tc_launch(a, math, PL.cell_epi, s);
@@ -683,9 +686,9 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             const unsigned blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
             split_pk_kernel<<<blocks, 256, 0, s>>>(st_in, S, hpk[1], R, H, math != GM_MATH_BF16);
             GM_LAUNCH_CHECK();
-            rc = cell(PL.obs, xpk, e, hpk[1], nullptr, 0, st_in + H, S, hbuf[0], H, cbuf[0], H, hpk[0]);
+            rc = cell(PL.obs, xpk, e, hpk[1], nullptr, 0, st_in + H, S, hbuf[0], H, cbuf[0], -1, hpk[0]);
         } else {
-            rc = cell(PL.obs, xpk, e, nullptr, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], H, hpk[0]);
+            rc = cell(PL.obs, xpk, e, nullptr, st_in, S, st_in + H, S, hbuf[0], H, cbuf[0], -1, hpk[0]);
         }
         if (rc) return rc;
         h = hbuf[0]; c = cbuf[0];
@@ -703,7 +706,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             float* hn = final_it ? state_out : hbuf[cur ^ 1];  // the last cell writes the new state in place (:562-564)
             float* cn = final_it ? state_out + H : cbuf[cur ^ 1];
             int64_t ldn = final_it ? S : H;
-            rc = cell(PL.upd, w.m_pk, nullptr, hpk[cur], nullptr, 0, c, H, hn, ldn, cn, ldn, final_it ? nullptr : hpk[cur ^ 1]);
+            rc = cell(PL.upd, w.m_pk, nullptr, hpk[cur], nullptr, 0, c, -1, hn, ldn, cn, final_it ? ldn : -1, final_it ? nullptr : hpk[cur ^ 1]);
             if (rc) return rc;
             h = hn; c = cn; ldh_cur = ldn; cur ^= 1;
         }
