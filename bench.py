@@ -165,7 +165,29 @@ def cpu_arm(cfg_name, steps, warmup, envs=None, budget_s=20.0):
                        f"replay insert incl.), {dt:.1f} s"), dt / max(n, 1), B
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout, but C libraries (NCCL's version banner, the CUDA runtime)
+    write to file descriptor 1 as they please: keep a private copy of the real stdout for the JSON line and point
+    fd 1 (and sys.stdout) at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -216,7 +238,7 @@ def main():
                     data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (numpy)"),
                     cpu_baseline=cb, gpu_launches=0,
                     e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line), flush=True)
+        _emit(line)
         return
 
     import torch
@@ -338,7 +360,7 @@ def main():
             line["cpu_baseline"] = cb
         except Exception as ex:  # the baseline must never hide the GPU number
             line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=len(os.sched_getaffinity(0)), kind="port", sample=f"failed: {ex}")
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
