@@ -235,7 +235,7 @@ def main():
         cb, sec_per_step, Bc = cpu_arm(a.workload, a.steps, a.warmup)
         line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
                     ms_per_step=sec_per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                    data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (numpy)"),
+                    data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (oracle port: C env + torch CPU tensors)"),
                     cpu_baseline=cb, gpu_launches=0,
                     e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         _emit(line)
