@@ -61,3 +61,51 @@ def test_shard_envs_properties():
             spans = [shard_envs(total, world, r) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == total
             assert sum(h - l for l, h in spans) == total
+
+
+def _learner_worker(rank, world, port, out):
+    import torch.nn.functional as F
+
+    from graph_marl_b200.learner_sync import allreduce_gradients, broadcast_weights
+    from graph_marl_b200.model import DQN
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)  # different initial weights per rank
+    model = DQN(12, (16, 8), 4, F.leaky_relu)
+    broadcast_weights([model], src=0)
+    w_after = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    torch.manual_seed(7 + rank)  # different data per rank (its own replay shard)
+    x = torch.randn(5, 3, 12)
+    loss = model(x, None).pow(2).mean()
+    loss.backward()
+    local = torch.cat([p.grad.reshape(-1) for p in model.parameters()]).clone()
+    n = allreduce_gradients(model.parameters(), average=True)
+    reduced = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (w_after, local, reduced, n))
+    if rank == 0:
+        out.put(gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_learner_weight_broadcast_and_fused_gradient_allreduce():
+    """the only collectives of a multi-GPU job are the start-up weight broadcast and the learner's fused
+    gradient all-reduce (gloo here, NCCL on the GPUs)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_learner_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (w0, g0, r0, n0), (w1, g1, r1, n1) = res
+    assert torch.equal(w0, w1)                       # identical replicas after the broadcast
+    assert not torch.equal(g0, g1)                   # ranks saw different data
+    assert torch.allclose(r0, (g0 + g1) / 2, atol=1e-7) and torch.equal(r0, r1)
+    assert n0 == n1 == w0.numel()
