@@ -91,17 +91,23 @@ __device__ __forceinline__ uint32_t agg_pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// A block owns `rows_per_block` consecutive rows (whole graphs when the host can arrange it, a multiple of 8) and its
+// warps walk the (8-row group, k-block) tasks of those rows: every 128-byte line of h that the block gathers is
+// fetched from L2 once and re-read by the other list members (a row is in ~4 lists) from L1.
 __global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
                                                            int B, int N, int H, const int* __restrict__ nbr,
                                                            const int* __restrict__ deg, int DM,
-                                                           const int* __restrict__ list_index, int mean, int write_lo) {
+                                                           const int* __restrict__ list_index, int mean, int write_lo,
+                                                           int rows_per_block) {
     const int lane = threadIdx.x & 31;
     const int kbs = H / TC_BK;
-    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t R = (int64_t)B * N;
-    const int64_t row = (gw / kbs) * 8 + (lane >> 2);
-    const int kb = (int)(gw % kbs), part = lane & 3;
-    if (row >= R) return;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+    const int tasks = (rows_per_block >> 3) * kbs;
+    for (int t = threadIdx.x >> 5; t < tasks; t += (int)(blockDim.x >> 5)) {
+    const int64_t row = row0 + (t / kbs) * 8 + (lane >> 2);
+    const int kb = t % kbs, part = lane & 3;
+    if (row >= R) continue;
     const int b = (int)(row / N), v = (int)(row - (int64_t)b * N);
     const int li = list_index ? list_index[b] : b;
     const int* lst = nbr + ((size_t)li * N + v) * DM;
@@ -149,6 +155,20 @@ __global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restri
     uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16;
     *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// rows a block of aggregate_pk_kernel owns: whole graphs, a multiple of 8 rows, about 40-80 rows (GM_AGG_ROWS overrides)
+static int aggregate_rows_per_block(int N) {
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("GM_AGG_ROWS"); forced = e ? atoi(e) : 0; }
+    if (forced > 0) return (forced + 7) / 8 * 8;
+    int g = N;  // smallest whole-graph row count divisible by 8: N * 8 / gcd(N, 8)
+    for (int d = 8; d > 1; d >>= 1) if (N % d == 0) { g = N * (8 / d); break; }
+    if (N % 2 != 0) g = N * 8;
+    int rows = g;
+    while (rows < 40) rows += g;
+    return rows;
 }
 
 // fp32 rows [R, H] (row stride ld) -> tile-packed bf16 hi/lo (the carried hidden state for the
@@ -693,14 +713,16 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         if (rc) return rc;
         h = hbuf[0]; c = cbuf[0];
         int cur = 0;
-        const unsigned agg_blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
         for (int it = 0; it < K; it++) {  // :509-554
             const bool final_it = it == K - 1;
             if (final_it) last = h;
             {
                 ProfileScope prof(PROF_AGG, s);
-                aggregate_pk_kernel<<<agg_blocks, 256, 0, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
-                                                               p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16);
+                const int rpb = aggregate_rows_per_block(N);
+                static int agg_threads = -1;
+                if (agg_threads < 0) { const char* e = getenv("GM_AGG_THREADS"); agg_threads = e ? atoi(e) : 256; }
+                aggregate_pk_kernel<<<(unsigned)((R + rpb - 1) / rpb), agg_threads, 0, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
+                                                                                    p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
             }
             GM_LAUNCH_CHECK();
             float* hn = final_it ? state_out : hbuf[cur ^ 1];  // the last cell writes the new state in place (:562-564)
