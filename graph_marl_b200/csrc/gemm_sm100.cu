@@ -935,7 +935,7 @@ static int tc_cluster_size() {
     if (csz < 0) {
         const char* e = getenv("GM_TC_CLUSTER");
         csz = e ? atoi(e) : 1;  // measured on B200: multicast of the weight stages (2, 4) brings no gain at these shapes
-        if (csz != 1 && csz != 2 && csz != 4) csz = 1;
+        if (csz != 1 && csz != 2 && csz != 4 && csz != 8) csz = 1;
     }
     return csz;
 }
@@ -946,7 +946,7 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
                               : tc::STAGES * (2 * tc::A_PART_BYTES + 2 * BN * tc::BK * 2) +
                                     (EPI == EPI_LNLSTM ? BN * tc::BM * 4 : 0);  // + pre-LN cell values of one M tile
     static bool configured = false;
-    static int max_clusters[5] = {0, 0, 0, 0, 0};
+    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto kern = tc::linear_tc_kernel<BN, PASSES, EPI, NCG, PAIR>;
     if (!configured) {
         GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -957,6 +957,7 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
     int csz = PAIR ? 2 : std::min(tc_cluster_size(), std::max(1, a.m_tiles));
     while (!PAIR && csz > 1 && csz > a.m_tiles) csz >>= 1;
     if (csz == 3) csz = 2;
+    if (csz > 4 && csz < 8) csz = 4;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     cfg.blockDim = dim3(tc::THREADS);
