@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         }
         for (int a = 0; a < ACC_STAGES; a++) {
             mbar_init(bar_tfull + 8 * a, 1);                              // tcgen05.commit
-            mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * EPI_W * 32);  // every epilogue thread (of both CTAs of a pair)
+            // every epilogue thread; in a pair one elected lane per epilogue warp of both CTAs (remote arrives are not free)
+            mbar_init(bar_tempty + 8 * a, PAIR ? 2 * EPI_W : EPI_W * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -561,14 +562,26 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     mbar_wait(bar_tfull + 8 * as, aph);
                     tc_fence_after();
                     tc_fence_before();
-                    mbar_arrive(bar_tempty + 8 * as);
+                    if (PAIR) {
+                        __syncwarp();
+                        if (lane == 0) { if (rank != 0) mbar_arrive_remote(bar_tempty + 8 * as, 0); else mbar_arrive(bar_tempty + 8 * as); }
+                    } else {
+                        mbar_arrive(bar_tempty + 8 * as);
+                    }
                     continue;
                 }
 #endif
 #include "gemm_sm100_epilogue.inc"
                 tc_fence_before();
-                if (PAIR && rank != 0) mbar_arrive_remote(bar_tempty + 8 * as, 0);  // the leader's MMA thread waits for both CTAs
-                else mbar_arrive(bar_tempty + 8 * as);
+                if (PAIR) {  // the leader's MMA thread waits for the epilogue warps of both CTAs: one arrive per warp
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (rank != 0) mbar_arrive_remote(bar_tempty + 8 * as, 0);
+                        else mbar_arrive(bar_tempty + 8 * as);
+                    }
+                } else {
+                    mbar_arrive(bar_tempty + 8 * as);
+                }
             }
         }
         (void)ln_csum; (void)ln_craw;
