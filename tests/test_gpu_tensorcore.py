@@ -86,7 +86,10 @@ def test_netmon_fused_cells_against_fp64_oracle(K, agg, B, N, math, tol):
         assert np.abs(nm.state.cpu().numpy() - ref_state0).max() < tol
 
 
-@pytest.mark.parametrize("K,agg,B,N,A", [(3, "sum", 96, 20, 20), (1, "mean", 7, 20, 11), (4, "sum", 5, 200, 100)])
+# the last case gives every CTA 2-3 M tiles (320 tiles over 148 SMs): both epilogue groups and the reuse of the
+# resident activation blocks are exercised
+@pytest.mark.parametrize("K,agg,B,N,A", [(3, "sum", 96, 20, 20), (1, "mean", 7, 20, 11), (4, "sum", 5, 200, 100),
+                                         (2, "sum", 2048, 20, 20)])
 def test_netmon_fused_layernorm_cell_against_fp64_oracle(K, agg, B, N, A):
     """LayerNormLSTM cell on the tensor cores (EPI_LNLSTM: Gram-matrix row statistics + two accumulators per tile).
     Stated tolerance: 1e-3 max abs on the new state and the readout, single step from an identical state
