@@ -55,6 +55,15 @@ namespace gm {
 
 namespace tc {
 
+// GM_TC_PROBES: per-tile timeline of CTA 0 (SM clock) into the buffer GM_TC_TRACE_PTR points at: 8 slots per tile
+// [0] MMA: accumulator free  [1] MMA: first stage full  [2] MMA: last k-block issued  [3] epilogue: accumulator full
+// [4] epilogue: done  [5] copies: last stage of the tile requested
+#if GM_TC_PROBES
+#define GM_TRACE(ptr, tile, slot) do { if ((ptr) && blockIdx.x == 0 && (tile) < 64) ((long long*)(ptr))[(tile) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define GM_TRACE(ptr, tile, slot) do { } while (0)
+#endif
+
 constexpr int BM = TC_BM, BK = TC_BK, STAGES = 4, ACC_STAGES = 2;
 constexpr int PAIR_STAGES = 6;  // 2-CTA pairs stage half a weight tile per CTA: 32 KiB per stage at BN = 256
 constexpr int EPI_WARPS = 8, PROD_WARPS = 8;
@@ -265,6 +274,40 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ row, int k,
     }
 }
 
+// Bare MUFU forms (no range fix-up code around them: the callers clamp the arguments).  The LSTM-cell epilogues work in
+// base 2: the packed biases / LayerNorm parameters of the gates are pre-scaled by -log2(e) (i, f, o) and +2 log2(e) (g),
+// so a gate costs one FFMA, one FMNMX, one EX2 and one FADD before the shared reciprocal.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kGateI = -kLog2e, kGateG = 2.f * kLog2e;  // exponent scale of the sigmoid gates / of the tanh gate
+constexpr float kExpClamp = 29.f;                         // 1 + 2^29 per factor keeps the four-factor product finite
+// (h, c') of one hidden unit from the four gate EXPONENT arguments ei = -log2e*(i), ef, eo (sigmoid gates), eg = 2 log2e*(g)
+// and the previous cell value: sig(i), sig(f), sig(o), tanh(g) from four exponentials and ONE reciprocal -- with
+// A = 1+2^ei, F = 1+2^ef, O = 1+2^eo, G = 1+2^eg and R = 1/(A F O G): sig(i) = R F O G, sig(f) = R A O G,
+// sig(o) = R A F G, tanh(g) = 1 - 2 R A F O.  Saturation error of the clamp < 4e-9.
+__device__ __forceinline__ void lstm_unit(float ei, float ef, float eg, float eo, float c_prev, float& c_new, float& sig_o) {
+    const float A = 1.f + ex2_approx(fminf(ei, kExpClamp)), F = 1.f + ex2_approx(fminf(ef, kExpClamp));
+    const float O = 1.f + ex2_approx(fminf(eo, kExpClamp)), G = 1.f + ex2_approx(fminf(eg, kExpClamp));
+    const float AF = A * F, OG = O * G;
+    const float R = rcp_approx(AF * OG);
+    const float t1 = R * OG, t2 = R * AF;
+    const float i_ = t1 * F, f_ = t1 * A;
+    sig_o = t2 * G;
+    const float g_ = fmaf(t2 * O, -2.f, 1.f);
+    c_new = fmaf(f_, c_prev, i_ * g_);
+}
+__device__ __forceinline__ float tanh_base2(float x) {  // tanh(x) = 1 - 2 / (1 + 2^(2 log2e x))
+    return fmaf(rcp_approx(1.f + ex2_approx(fminf(x * kGateG, kExpClamp))), -2.f, 1.f);
+}
 // fast transcendental forms for the fused LSTM epilogue (abs. error ~1e-7, inside the stated tolerance)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
@@ -466,6 +509,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                         bulk_g2s(smem_base + s * STAGE_BYTES, apk + blk * TC_PK_BLOCK, a_bytes, bar_full + 8 * s);
                     }
                 }
+                GM_TRACE(p.trace, u, 5);
             }
         }
     } else if (warp == MMA_WARP) {
@@ -488,6 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 if (PAIR) mbar_wait_cluster(bar_tempty + 8 * as, aph ^ 1);  // both CTAs' epilogues drained this accumulator
                 else mbar_wait(bar_tempty + 8 * as, aph ^ 1);               // epilogue drained this accumulator
                 tc_fence_after();
+                GM_TRACE(p.trace, tcount, 0);
                 const uint32_t d0 = tmem_base + as * ACC_COLS;
                 for (int kb = 0; kb < kblocks; kb++, it++) {
                     const int s = it % NST;
@@ -495,6 +540,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     mbar_wait(bar_full + 8 * s, ph);
                     if (PAIR) mbar_wait_cluster(bar_pfull + 8 * s, ph);  // ... and the peer's half of the operands
                     tc_fence_after();
+                    if (kb == 0) GM_TRACE(p.trace, tcount, 1);
                     const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_PART_BYTES;
                     const uint32_t w_hi = a_hi + 2 * A_PART_BYTES, w_lo = w_hi + W_PART_BYTES;
                     // LayerNormLSTM: segment 1 accumulates into its own BN columns
@@ -528,6 +574,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     else if (csz == 1) umma_commit(bar_empty + 8 * s);
                     else umma_commit_mc(bar_empty + 8 * s, mc_mask);
                 }
+                GM_TRACE(p.trace, tcount, 2);
                 if (PAIR) umma2_commit_mc(bar_tfull + 8 * as, 3);  // accumulator complete in both CTAs
                 else umma_commit(bar_tfull + 8 * as);              // accumulator complete
             }
@@ -572,6 +619,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 }
 #endif
 #include "gemm_sm100_epilogue.inc"
+                if (threadIdx.x == 0) GM_TRACE(p.trace, tcount, 4);
                 tc_fence_before();
                 if (PAIR) {  // the leader's MMA thread waits for the epilogue warps of both CTAs: one arrive per warp
                     __syncwarp();
@@ -820,6 +868,8 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, const float* __res
     }
     float v = 0.f;
     if (n_src >= 0 && n_src < N) v = (b ? b[n_src] : 0.f) + (b2 ? b2[n_src] : 0.f);
+    // the LSTM epilogue works on base-2 exponent arguments: bias of gate g (tanh) scaled by 2 log2e, the others by -log2e
+    if (lstm) v *= (row / (BN / 4) == 2) ? kGateG : kGateI;
     out[idx] = v;
 }
 
@@ -874,7 +924,9 @@ __global__ void lnlstm_params_kernel(const float* __restrict__ w_ih, const float
         const int e = idx - 2 * H, tt = e / 384, which = (e % 384) / 128, c = e % 128;
         const int half = c / 64, gate = (c % 64) / 16, u = c % 16;
         const int src = gate * H + tt * 32 + half * 16 + u;
-        out[idx] = which == 0 ? ln_in_w[src] : which == 1 ? ln_hid_w[src] : ln_in_b[src] + ln_hid_b[src] + b_ih[src];
+        // pre-scaled to base-2 exponent arguments like the LSTM biases (gate 2 = tanh gate)
+        const float sc = gate == 2 ? kGateG : kGateI;
+        out[idx] = sc * (which == 0 ? ln_in_w[src] : which == 1 ? ln_hid_w[src] : ln_in_b[src] + ln_hid_b[src] + b_ih[src]);
     } else {
         const int e = idx - (2 * H + n_chunks * 3 * 128);
         out[idx] = e < H ? ln_cell_w[e] : ln_cell_b[e - H];
@@ -996,6 +1048,11 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("GM_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
         a.a_stages = dbg;  // the field is unused by this kernel otherwise
+        static long long trace_ptr = -1;
+        if (trace_ptr < 0) { const char* e = getenv("GM_TC_TRACE_PTR"); trace_ptr = e ? strtoll(e, nullptr, 0) : 0; }
+        static int trace_epi = -2;
+        if (trace_epi == -2) { const char* e = getenv("GM_TC_TRACE_EPI"); trace_epi = e ? atoi(e) : -1; }
+        a.trace = (EPI == trace_epi) ? (void*)trace_ptr : nullptr;
     }
 #endif
     attr[0].val.clusterDim.x = csz;

@@ -49,6 +49,7 @@ struct TcArgs {
     const uint8_t* action_mask; double epsilon; const int* rand_action; const double* rand_u;
     uint64_t philox_seed, philox_step; const uint64_t* philox_step_dev;
     float* q_out; int* act_out;
+    void* trace;  // GM_TC_PROBES builds only: per-tile timeline buffer (see gemm_sm100.cu)
     int ws;  // use the weight-stationary cluster kernel (tc_ws_plan must hold; weights packed with ws = 1)
     int m_tiles, n_tiles, has_prod, csz, a_stages;  // filled by tc_launch
 };
