@@ -57,7 +57,7 @@ namespace tc {
 
 // GM_TC_PROBES: per-tile timeline of CTA 0 (SM clock) into the buffer GM_TC_TRACE_PTR points at: 8 slots per tile
 // [0] MMA: accumulator free  [1] MMA: first stage full  [2] MMA: last k-block issued  [3] epilogue: accumulator full
-// [4] epilogue: done  [5] copies: last stage of the tile requested
+// [4] epilogue: done  [5] copies: last stage of the tile requested  [6] LSTM epilogue: first 8-unit step loaded  [7] ... done
 #if GM_TC_PROBES
 #define GM_TRACE(ptr, tile, slot) do { if ((ptr) && blockIdx.x == 0 && (tile) < 64) ((long long*)(ptr))[(tile) * 8 + (slot)] = clock64(); } while (0)
 #else

@@ -15,9 +15,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = buf.cpu().numpy().reshape(64, 8)
 t0 = t[0, 0]
-names = ["mma:acc_free", "mma:first_full", "mma:issued", "epi:acc_full", "epi:done", "copy:issued"]
+names = ["mma:acc_free", "mma:first_full", "mma:issued", "epi:acc_full", "epi:done", "copy:issued", "epi:step0_loaded", "epi:step0_done"]
 print("tile " + " ".join(f"{n:>15s}" for n in names) + "   (SM clocks relative to tile 0 acc_free; last traced launch)")
 for i in range(64):
     if t[i, 0] == 0:
         break
-    print(f"{i:4d} " + " ".join(f"{int(t[i, k] - t0):15d}" for k in range(6)))
+    print(f"{i:4d} " + " ".join(f"{int(t[i, k] - t0):15d}" for k in range(8)))
