@@ -146,9 +146,8 @@ __global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restri
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        __nv_bfloat16 a = __float2bfloat16_rn(x[2 * i]), c = __float2bfloat16_rn(x[2 * i + 1]);
-        hi[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(c) << 16);
-        lo[i] = agg_pack2(x[2 * i] - __bfloat162float(a), x[2 * i + 1] - __bfloat162float(c));
+        hi[i] = agg_pack2(x[2 * i], x[2 * i + 1]);
+        lo[i] = agg_pack2(x[2 * i] - __uint_as_float(hi[i] << 16), x[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
     }
     const int64_t mt = row / TC_BM;
     const int r = (int)(row - mt * TC_BM);
@@ -187,9 +186,8 @@ __global__ void __launch_bounds__(256) split_pk_kernel(const float* __restrict__
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        __nv_bfloat16 p0 = __float2bfloat16_rn(x[2 * i]), p1 = __float2bfloat16_rn(x[2 * i + 1]);
-        hi[i] = (uint32_t)__bfloat16_as_ushort(p0) | ((uint32_t)__bfloat16_as_ushort(p1) << 16);
-        lo[i] = agg_pack2(x[2 * i] - __bfloat162float(p0), x[2 * i + 1] - __bfloat162float(p1));
+        hi[i] = agg_pack2(x[2 * i], x[2 * i + 1]);
+        lo[i] = agg_pack2(x[2 * i] - __uint_as_float(hi[i] << 16), x[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
     }
     const int64_t mt = row / TC_BM;
     const int r = (int)(row - mt * TC_BM);
@@ -414,9 +412,8 @@ __global__ void __launch_bounds__(256) readout_agents_pk_kernel(
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            __nv_bfloat16 a = __float2bfloat16_rn(x[2 * i]), c = __float2bfloat16_rn(x[2 * i + 1]);
-            hi[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(c) << 16);
-            lo[i] = agg_pack2(x[2 * i] - __bfloat162float(a), x[2 * i + 1] - __bfloat162float(c));
+            hi[i] = agg_pack2(x[2 * i], x[2 * i + 1]);
+            lo[i] = agg_pack2(x[2 * i] - __uint_as_float(hi[i] << 16), x[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
         }
         const int64_t mt = row / TC_BM;
         const int r = (int)(row - mt * TC_BM);
