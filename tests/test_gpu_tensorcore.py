@@ -182,7 +182,7 @@ def test_dqn_tensorcore_q_values(math, tol):
 def test_optional_kernel_variants_match(switch):
     """The optional variants of the tcgen05 kernel give the same NetMon outputs as the default streaming kernel:
     GM_TC_WS=1 (weights resident in smem, activations multicast to a 4-CTA cluster), GM_TC_PAIR=1 (2-CTA pairs driving
-    tcgen05.mma.cta_group::2, M = 256, half a weight tile per CTA), GM_TC_WIDE=1 (16 epilogue warps for all-tile-packed
+    tcgen05.mma.cta_group::2, M = 256, half a weight tile per CTA), GM_TC_WIDE=0 (8 instead of 16 epilogue warps for all-tile-packed
     layers), GM_TC_CLUSTER=2 (weight stages multicast over a 2-CTA cluster).  Run in a subprocess because the switches
     are read once per process."""
     import os, subprocess, sys, textwrap
@@ -213,6 +213,6 @@ def test_optional_kernel_variants_match(switch):
         assert e1 < 1e-4 and e2 < 1e-4, (e1, e2)
         print("ok", e1, e2)
     """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, **{switch: "2" if switch == "GM_TC_CLUSTER" else "1"})
+    env = dict(os.environ, **{switch: {"GM_TC_CLUSTER": "2", "GM_TC_WIDE": "0"}.get(switch, "1")})
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
