@@ -33,86 +33,67 @@ __global__ void replay_insert_kernel(ReplayFields F, int64_t capacity, int64_t i
         }
         return;
     }
+    // One warp per contiguous run (a transition, or one row of a transition's 2-D block): the three 64-bit divisions
+    // that locate a run are paid once per warp and run, the lanes then stride over its 16 / 8 / 4 / 1-byte units with
+    // up to four independent loads in flight.
     const bool two_d = fd.rows > 0;
     const int64_t rb = two_d ? fd.row_bytes : eb;           // contiguous run
     const int64_t runs = two_d ? fd.rows : 1;               // runs per transition
     const uintptr_t src_bits = (uintptr_t)fd.src | (uintptr_t)rb;
     const uintptr_t dst_bits = (uintptr_t)fd.ring | (uintptr_t)eb | (two_d ? ((uintptr_t)fd.ring_pitch | (uintptr_t)fd.ring_offset) : 0);
     const uintptr_t align_bits = src_bits | dst_bits;
-    if (align_bits % 16 != 0 && src_bits % 16 == 0 && dst_bits % 8 == 0) {
-        // 16-byte aligned source, destination only 8-byte aligned (the graph part of a joint observation row
-        // starts 520 bytes into the ring row): one 16-byte load, two 8-byte stores
-        const int64_t upr = rb / 16, total = n * runs * upr;
-        auto addr2 = [&](int64_t t, const uint4*& s, uint2*& d) {
-            int64_t u = t % upr, q = t / upr;
-            int64_t row = q % runs, i = q / runs;
-            int64_t slot = (index + i) % capacity;
-            s = (const uint4*)((const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * 16);
-            d = (uint2*)((char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * 16);
-        };
-        int64_t t = tid0;
-        for (; t + 3 * nthreads < total; t += 4 * nthreads) {
-            const uint4* s[4];
-            uint2* d[4];
-            uint4 v[4];
+    // 16-byte aligned source with a destination that is only 8-byte aligned (the graph part of a joint observation
+    // row starts 520 bytes into the ring row): 16-byte loads, two 8-byte stores each
+    const bool split_store = align_bits % 16 != 0 && src_bits % 16 == 0 && dst_bits % 8 == 0;
+    const int unit = split_store ? 16 : (align_bits % 16 == 0) ? 16 : (align_bits % 8 == 0) ? 8 : (align_bits % 4 == 0) ? 4 : 1;
+    const int upr = (int)(rb / unit);  // units per run
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = tid0 >> 5, nwarps = nthreads >> 5;
+    for (int64_t q = warp0; q < n * runs; q += nwarps) {
+        const int64_t i = q / runs, row = q - i * runs;
+        const int64_t slot = (index + i) % capacity;
+        const char* s = (const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb;
+        char* d = (char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0);
+        if (unit == 16) {
+            int u = lane;
+            for (; u + 96 < upr; u += 128) {
+                uint4 v[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) addr2(t + k * nthreads, s[k], d[k]);
+                for (int k = 0; k < 4; k++) v[k] = __ldcs((const uint4*)s + u + 32 * k);
 #pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = __ldcs(s[k]);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                __stcs(d[k], make_uint2(v[k].x, v[k].y));
-                __stcs(d[k] + 1, make_uint2(v[k].z, v[k].w));
+                for (int k = 0; k < 4; k++) {
+                    if (split_store) {
+                        uint2* d2 = (uint2*)(d + (size_t)(u + 32 * k) * 16);
+                        __stcs(d2, make_uint2(v[k].x, v[k].y));
+                        __stcs(d2 + 1, make_uint2(v[k].z, v[k].w));
+                    } else {
+                        __stcs((uint4*)d + u + 32 * k, v[k]);
+                    }
+                }
             }
+            for (; u < upr; u += 32) {
+                const uint4 v = __ldcs((const uint4*)s + u);
+                if (split_store) {
+                    uint2* d2 = (uint2*)(d + (size_t)u * 16);
+                    __stcs(d2, make_uint2(v.x, v.y));
+                    __stcs(d2 + 1, make_uint2(v.z, v.w));
+                } else {
+                    __stcs((uint4*)d + u, v);
+                }
+            }
+        } else if (unit == 8) {
+            int u = lane;
+            for (; u + 32 < upr; u += 64) {
+                const uint2 v0 = __ldcs((const uint2*)s + u), v1 = __ldcs((const uint2*)s + u + 32);
+                __stcs((uint2*)d + u, v0);
+                __stcs((uint2*)d + u + 32, v1);
+            }
+            for (; u < upr; u += 32) __stcs((uint2*)d + u, __ldcs((const uint2*)s + u));
+        } else if (unit == 4) {
+            for (int u = lane; u < upr; u += 32) ((uint32_t*)d)[u] = ((const uint32_t*)s)[u];
+        } else {
+            for (int u = lane; u < upr; u += 32) d[u] = s[u];
         }
-        for (; t < total; t += nthreads) {
-            const uint4* s;
-            uint2* d;
-            addr2(t, s, d);
-            const uint4 v = *s;
-            d[0] = make_uint2(v.x, v.y);
-            d[1] = make_uint2(v.z, v.w);
-        }
-        return;
-    }
-    const int unit = (align_bits % 16 == 0) ? 16 : (align_bits % 8 == 0) ? 8 : (align_bits % 4 == 0) ? 4 : 1;
-    const int64_t upr = rb / unit;  // units per run
-    const int64_t total = n * runs * upr;
-    auto addr = [&](int64_t t, const char*& s, char*& d) {
-        int64_t u = t % upr, q = t / upr;
-        int64_t row = q % runs, i = q / runs;
-        int64_t slot = (index + i) % capacity;
-        s = (const char*)fd.src + ((fd.broadcast ? 0 : i) * runs + row) * rb + u * unit;
-        d = (char*)fd.ring + slot * eb + (two_d ? fd.ring_offset + row * fd.ring_pitch : 0) + u * unit;
-    };
-    if (unit == 16) {  // bulk of the bytes: four independent 16-byte loads in flight per thread
-        int64_t t = tid0;
-        for (; t + 3 * nthreads < total; t += 4 * nthreads) {
-            const char* s[4];
-            char* d[4];
-            uint4 v[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) addr(t + k * nthreads, s[k], d[k]);
-#pragma unroll
-            for (int k = 0; k < 4; k++) v[k] = __ldcs((const uint4*)s[k]);
-#pragma unroll
-            for (int k = 0; k < 4; k++) __stcs((uint4*)d[k], v[k]);
-        }
-        for (; t < total; t += nthreads) {
-            const char* s;
-            char* d;
-            addr(t, s, d);
-            *(uint4*)d = *(const uint4*)s;
-        }
-        return;
-    }
-    for (int64_t t = tid0; t < total; t += nthreads) {
-        const char* s;
-        char* d;
-        addr(t, s, d);
-        if (unit == 8) *(uint2*)d = *(const uint2*)s;
-        else if (unit == 4) *(uint32_t*)d = *(const uint32_t*)s;
-        else *d = *s;
     }
 }
 
