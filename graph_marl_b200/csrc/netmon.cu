@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restri
     const int64_t row = row0 + (t / kbs) * 8 + (lane >> 2);
     const int kb = t % kbs, part = lane & 3;
     if (row >= R) continue;
-    const int b = (int)(row / N), v = (int)(row - (int64_t)b * N);
+    const unsigned row32 = (unsigned)row;  // the host checks B*N < 2^31
+    const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
     const int li = list_index ? list_index[b] : b;
     const int* lst = nbr + ((size_t)li * N + v) * DM;
     const int dg = deg[(size_t)li * N + v];
@@ -369,12 +370,14 @@ __global__ void __launch_bounds__(256) readout_agents_pk_kernel(
     const int lane = threadIdx.x & 31;
     const int O = H + (use_glob ? H : 0) + (use_nbr ? max_degree * H : 0);
     const int kbs = O / TC_BK;
-    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t rows = (int64_t)B * A;
-    const int64_t row = (gw / kbs) * 8 + (lane >> 2);
-    const int kb = (int)(gw % kbs), part = lane & 3;
+    // 32-bit index arithmetic (the host checks B*A*kbs < 2^31): 64-bit divisions made this kernel ALU-bound
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned rows = (unsigned)B * (unsigned)A;
+    const unsigned rg = gw / (unsigned)kbs;
+    const unsigned row = rg * 8 + (lane >> 2);
+    const int kb = (int)(gw - rg * (unsigned)kbs), part = lane & 3;
     if (row >= rows) return;
-    const int b = (int)(row / A);
+    const int b = (int)(row / (unsigned)A);
     const int v = agent_node[row];
     const int col = kb * TC_BK + part * 8;
     int seg = col / H;
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(256) readout_agents_pk_kernel(
         for (int i = 0; i < 8; i++) x[i] = 0.f;
     }
     if (out) {
-        float4* o = (float4*)(out + row * ldo + col);
+        float4* o = (float4*)(out + (int64_t)row * ldo + col);
         o[0] = make_float4(x[0], x[1], x[2], x[3]);
         o[1] = make_float4(x[4], x[5], x[6], x[7]);
     }
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(256) readout_agents_pk_kernel(
             hi[i] = agg_pack2(x[2 * i], x[2 * i + 1]);
             lo[i] = agg_pack2(x[2 * i] - __uint_as_float(hi[i] << 16), x[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
         }
-        const int64_t mt = row / TC_BM;
+        const unsigned mt = row / TC_BM;
         const int r = (int)(row - mt * TC_BM);
         uint8_t* dst = out_pk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16;
         *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -852,6 +855,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                          (agent_out == nullptr || (agent_out_ld >= O && (agent_out_ld & 3) == 0 && ((uintptr_t)agent_out & 15) == 0)) &&
                          (ldh_cur & 3) == 0,
                      "tile-packed agent readout needs agent_node, hidden %% 32 == 0 and 16-byte aligned rows");
+        GM_CHECK_ARG((int64_t)B * A * (O / TC_BK) < (1ll << 31) && (int64_t)B * N < (1ll << 31), "batch too large for the 32-bit row arithmetic of the readout / aggregation kernels");
         int64_t rows = (int64_t)B * A;
         const int kbs = O / TC_BK;
         const unsigned blocks = (unsigned)((((rows + 7) / 8) * kbs + 7) / 8);
