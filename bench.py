@@ -217,11 +217,12 @@ def main():
     # bound the unit so that those stay under ~24 GB (cfg4 at 8192 envs holds ~15 GB per step)
     step_bytes = 4 * B * (1.5 * A * (6 * N + 10 + 4 * c["H"]) + N * (4 * N + 8) + 2 * N * c["H"])
     a.graph_steps = int(max(1, min(a.graph_steps, 24e9 // step_bytes))) if a.graph_steps > 0 else a.graph_steps
-    if a.graph_steps > 2 and c["episode_steps"] <= 100:
-        # short episodes: units cover the steps between an episode's first and last one (those two run eagerly);
-        # pick the unit length that leaves the fewest eager steps
-        inner = c["episode_steps"] - 2
-        a.graph_steps = min(range(max(2, a.graph_steps // 2), a.graph_steps + 1), key=lambda g: (inner % g, -g))
+    if a.graph_steps > 2 and c["episode_steps"] % a.graph_steps != 0:
+        # units that tile the episode exactly leave only the reset outside the captured graphs: prefer the largest
+        # divisor of the episode length in [graph_steps / 2, graph_steps]
+        divs = [g for g in range(max(2, a.graph_steps // 2), a.graph_steps + 1) if c["episode_steps"] % g == 0]
+        if divs:
+            a.graph_steps = divs[-1]
     config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
                            f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
                            f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,

@@ -145,6 +145,10 @@ class Rollout:
             self.node_aux.copy_(aux)  # per-env topologies: refresh in place, captured graph units hold this address
         else:
             self.node_aux = aux
+        # the state "before the first step" is all zeros (wrapper.py:40-41, main.py:692-696 store 0 then): keep it as a
+        # tensor so that an episode's first step is not a special case for the captured graph units
+        if self.env.last_netmon_state is None and self.env.current_netmon_state is not None:
+            self.env.last_netmon_state = torch.zeros_like(self.env.current_netmon_state)
         self.episode_step = 0
 
     def _mark(self, name):
@@ -311,15 +315,18 @@ class Rollout:
             self._h_cursor += n
 
     def run(self, steps):
-        """Advance `steps` rollout steps, through captured graph units where an episode allows it."""
+        """Advance `steps` rollout steps, through captured graph units where an episode allows it.  A unit is n
+        consecutive steps of one episode; the unit that ends an episode is its own captured variant (the episode-end flag
+        of its last replay insert is part of the captured work).  Resets run eagerly."""
         n = self.graph_steps
         done = 0
         while done < steps:
             if self._graphs and self._graph_tables is not self.base_env._pool:
                 self._graphs.clear()  # the topology tables moved (new pool): the captured units are stale
-            left_in_episode = self.cfg["episode_steps"] - (self.episode_step if self.episode_step is not None else 0)
-            usable = (n > 0 and self.episode_step is not None and self.episode_step > 0 and steps - done >= n
-                      and left_in_episode > n)  # a unit never contains an episode's first or last step
+            if self.episode_step is None or self.episode_step >= self.cfg["episode_steps"]:
+                self.reset()
+            left_in_episode = self.cfg["episode_steps"] - self.episode_step
+            usable = n > 0 and steps - done >= n and left_in_episode >= n
             if usable and self.host_draws and self._h_cursor % n != 0:
                 # units consume whole, aligned blocks of the host draw table: skip to the next block (the table
                 # holds independent draws, skipping some changes nothing statistically)
@@ -329,26 +336,44 @@ class Rollout:
                 done += 1
                 continue
             slot = (self._h_cursor // n) % (self._h_steps // n) if self.host_draws else 0
-            if slot not in self._graphs:
-                self._graphs[slot] = self._capture_unit(n, slot if self.host_draws else None)
+            key = (slot, left_in_episode == n)
+            if key not in self._graphs:
+                self._graphs[key] = self._capture_unit(n, slot if self.host_draws else None)
                 self._graph_tables = self.base_env._pool
             self._enter_static()
-            self._replay_unit(self._graphs[slot], n)
+            self._replay_unit(self._graphs[key], n)
             done += n
 
     def precapture(self):
-        """Capture every graph unit up front (one per block of the host draw table, or a single one) so that no
-        capture happens inside a timed region.  Needs a state in the middle of an episode."""
+        """Capture every graph unit up front (one per block of the host draw table, or a single one; each as a mid-episode
+        and, when the episode length is a multiple of the unit, as an episode-ending variant) so that no capture happens
+        inside a timed region."""
         n = self.graph_steps
         if n <= 0:
             return
-        while self.episode_step is None or self.episode_step == 0 or self.cfg["episode_steps"] - self.episode_step <= n:
-            self._step_eager()
+        E = self.cfg["episode_steps"]
         slots = range(self._h_steps // n) if self.host_draws else [0]
-        for slot in slots:
-            if slot not in self._graphs:
-                self._graphs[slot] = self._capture_unit(n, slot if self.host_draws else None)
-                self._graph_tables = self.base_env._pool
+
+        def advance_until(cond):
+            guard = 0
+            while not cond():
+                if self.episode_step is None or self.episode_step >= E:
+                    self.reset()
+                    continue
+                self._step_eager()
+                guard += 1
+                assert guard <= 2 * E + 2
+
+        variants = [False] + ([True] if E % n == 0 and E >= 2 * n else [])
+        for tail in variants:
+            if tail:
+                advance_until(lambda: self.episode_step is not None and E - self.episode_step == n)
+            else:
+                advance_until(lambda: self.episode_step is not None and E - self.episode_step > n)
+            for slot in slots:
+                if (slot, tail) not in self._graphs:
+                    self._graphs[(slot, tail)] = self._capture_unit(n, slot if self.host_draws else None)
+                    self._graph_tables = self.base_env._pool
 
     def step(self):
         return self._step_eager()
