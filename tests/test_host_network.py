@@ -88,6 +88,16 @@ def test_all_eval_seeds_and_n200():
         Network(50, random_topology=False, topology_init_seed=476).reset()
 
 
+def test_eval_seeds_constant_is_the_reference_list():
+    """env/constants.py derives EVAL_SEEDS with the native generator instead of hard-coding it."""
+    from graph_marl_b200.env.constants import EVAL_SEEDS
+
+    g = load_golden("topology")
+    state = np.random.get_state()[1].copy()
+    assert EVAL_SEEDS == [int(x) for x in g["eval_seeds"]] and EVAL_SEEDS[350] == 923430603
+    assert np.array_equal(np.random.get_state()[1], state)  # the caller's global stream is untouched
+
+
 def test_random_topology_chain_pool_and_sequential():
     g = load_golden("topology")
     ex = [int(x) for x in g["eval_seeds"]]

@@ -461,6 +461,65 @@ def gen_netmon():
     save("netmon", **out)
 
 
+def gen_sl():
+    """BASELINE config 5 (sl.py): the test split's first 32 graphs exactly as sl.py:575-592 +
+    build_dataset (:230-281) draws them (EVAL_SEEDS in order, one env.reset() per sample), the
+    per-node labels / targets of get_sl_sample (:174-219), and NetMonSL.forward's NetMon call
+    (:153-157: eye node-agent matrix, state None at sequence start, the SAME node obs fed for
+    `sequence_length` steps, :481-493) at the paper dims for K in {1,2,4}."""
+    torch.set_num_threads(1)
+    np.random.seed(5)
+    n_graphs, seq = 32, 8
+    net = Network(20, random_topology=True, sequential_topology_seeds=True, provided_seeds=EVAL_SEEDS)
+    env = Routing(net, 20, 1)
+    env.network.G_weight_key = "weight"
+    env.reset()
+    X, ADJ, LAB, TGT, TGT_ALL, SEEDS = [], [], [], [], [], []
+    for s in range(n_graphs):
+        if s:
+            env.reset()
+        n = env.get_num_nodes()
+        lab = np.zeros(n)
+        for v in range(n):
+            path = env.network.shortest_paths[v][0]
+            if len(path) > 1:
+                for e_idx, e in enumerate(env.network.nodes[v].edges):
+                    if env.network.edges[e].get_other_node(v) == path[1]:
+                        lab[v] = e_idx + 1
+                        break
+                else:
+                    raise AssertionError("no edge towards the next hop")
+        apsp = np.array([[env.network.shortest_paths_weights[i][j] for j in range(n)] for i in range(n)])
+        X.append(env.get_node_observation()), ADJ.append(env.get_nodes_adjacency())
+        LAB.append(lab), TGT.append(apsp[:, 0]), TGT_ALL.append(apsp)
+        SEEDS.append(env.network.current_topology_seed)
+    X, ADJ = np.stack(X).astype(np.float32), np.stack(ADJ)
+    out = dict(node_obs=X, node_adj=ADJ.astype(np.int8), labels=np.stack(LAB).astype(np.int8),
+               targets=np.stack(TGT).astype(np.int32), targets_all=np.stack(TGT_ALL).astype(np.int32),
+               seeds=np.array(SEEDS, dtype=np.int64), seq=np.array([seq]))
+    eye = torch.eye(20).repeat(n_graphs, 1, 1)
+    names = []
+    for K in (1, 2, 4):
+        nm = NetMon(X.shape[-1], 128, (512, 256), K, F.leaky_relu, rnn_type="lstm", rnn_carryover=True,
+                    agg_type="sum", output_neighbor_hidden=True, output_global_hidden=False)
+        wseed = 7000 + K
+        det_weights(nm, wseed)
+        nm.eval()
+        nm.state = None
+        with torch.no_grad():
+            for t in range(seq):
+                o = nm(torch.from_numpy(X), torch.from_numpy(ADJ).float(), eye)
+                if t == 0:
+                    out[f"k{K}_out_first"] = o[:4].numpy().copy()
+        name = f"k{K}"
+        out[name + "_cfg"] = np.array([128, K, 1, 1, 0, wseed, 512, 256], dtype=np.int64)
+        out[name + "_out_last"] = o.numpy().copy()
+        out[name + "_state_last"] = nm.state[:4].numpy().copy()
+        names.append(f"{name}|lstm|sum")
+    out["case_names"] = np.array(names)
+    save("sl_netmon", **out)
+
+
 def gen_dqn_policy():
     torch.set_num_threads(1)
     act = F.leaky_relu
@@ -589,7 +648,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     gens = dict(topology=gen_topology, rng=gen_rng, routing=gen_routing, simple=gen_simple,
-                netmon=gen_netmon, dqn=gen_dqn_policy, replay=gen_replay, wrapper=gen_wrapper)
+                netmon=gen_netmon, sl=gen_sl, dqn=gen_dqn_policy, replay=gen_replay, wrapper=gen_wrapper)
     for k, fn in gens.items():
         if a.only and k not in a.only.split(","):
             continue
