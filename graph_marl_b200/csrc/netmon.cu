@@ -94,25 +94,56 @@ __device__ __forceinline__ uint32_t agg_pack2(float a, float b) {
 // A block owns `rows_per_block` consecutive rows (whole graphs when the host can arrange it, a multiple of 8) and its
 // warps walk the (8-row group, k-block) tasks of those rows: every 128-byte line of h that the block gathers is
 // fetched from L2 once and re-read by the other list members (a row is in ~4 lists) from L1.
-__global__ void __launch_bounds__(256) aggregate_pk_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
+// STAGED: the block first copies the neighbour lists and degrees of its rows into shared memory (one coalesced pass),
+// so a task's dependent chain is "hidden rows -> store" instead of "list_index -> list/degree -> hidden rows -> store";
+// with ~2.5 task rounds per warp the kernel is bound by that chain, not by bytes (ncu: DRAM 20 %, L2 18 %).
+template <bool STAGED>
+__global__ void __launch_bounds__(STAGED ? 320 : 256) aggregate_pk_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
                                                            int B, int N, int H, const int* __restrict__ nbr,
                                                            const int* __restrict__ deg, int DM,
                                                            const int* __restrict__ list_index, int mean, int write_lo,
                                                            int rows_per_block) {
+    extern __shared__ int agg_lists[];  // STAGED: lists i32[rows_per_block][DM] | degrees i32[rows_per_block]
     const int lane = threadIdx.x & 31;
     const int kbs = H / TC_BK;
     const int64_t R = (int64_t)B * N;
     const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
     const int tasks = (rows_per_block >> 3) * kbs;
+    if (STAGED) {
+        int* s_deg = agg_lists + rows_per_block * DM;
+        for (int t = threadIdx.x; t < rows_per_block * DM; t += (int)blockDim.x) {
+            const int r = t / DM, q = t - r * DM;
+            const int64_t row = row0 + r;
+            int val = 0;
+            if (row < R) {
+                const unsigned row32 = (unsigned)row;
+                const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
+                const size_t node = (size_t)(list_index ? list_index[b] : b) * N + v;
+                val = nbr[node * DM + q];
+                if (q == 0) s_deg[r] = deg[node];
+            }
+            agg_lists[t] = val;
+        }
+        __syncthreads();
+    }
     for (int t = threadIdx.x >> 5; t < tasks; t += (int)(blockDim.x >> 5)) {
-    const int64_t row = row0 + (t / kbs) * 8 + (lane >> 2);
+    const int rl = (t / kbs) * 8 + (lane >> 2);
+    const int64_t row = row0 + rl;
     const int kb = t % kbs, part = lane & 3;
     if (row >= R) continue;
     const unsigned row32 = (unsigned)row;  // the host checks B*N < 2^31
-    const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
-    const int li = list_index ? list_index[b] : b;
-    const int* lst = nbr + ((size_t)li * N + v) * DM;
-    const int dg = deg[(size_t)li * N + v];
+    const int b = (int)(row32 / (unsigned)N);
+    const int* lst;
+    int dg;
+    if (STAGED) {
+        lst = agg_lists + rl * DM;
+        dg = agg_lists[rows_per_block * DM + rl];
+    } else {
+        const int v = (int)(row32 - (unsigned)b * (unsigned)N);
+        const int li = list_index ? list_index[b] : b;
+        lst = nbr + ((size_t)li * N + v) * DM;
+        dg = deg[(size_t)li * N + v];
+    }
     const float* hb = h + (size_t)b * N * ldh + kb * TC_BK + part * 8;
     float x[8];
 #pragma unroll
@@ -721,8 +752,15 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                 const int rpb = aggregate_rows_per_block(N);
                 static int agg_threads = -1;
                 if (agg_threads < 0) { const char* e = getenv("GM_AGG_THREADS"); agg_threads = e ? atoi(e) : 256; }
-                aggregate_pk_kernel<<<(unsigned)((R + rpb - 1) / rpb), agg_threads, 0, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
-                                                                                    p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
+                static int agg_staged = -1;
+                if (agg_staged < 0) { const char* e = getenv("GM_AGG_STAGE_LISTS"); agg_staged = e ? atoi(e) : 1; }
+                const unsigned agg_blocks = (unsigned)((R + rpb - 1) / rpb);
+                if (agg_staged)
+                    aggregate_pk_kernel<true><<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
+                        h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
+                else
+                    aggregate_pk_kernel<false><<<agg_blocks, agg_threads, 0, s>>>(
+                        h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
             }
             GM_LAUNCH_CHECK();
             float* hn = final_it ? state_out : hbuf[cur ^ 1];  // the last cell writes the new state in place (:562-564)
