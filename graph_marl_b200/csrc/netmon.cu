@@ -189,6 +189,90 @@ __global__ void __launch_bounds__(STAGED ? 320 : 256) aggregate_pk_kernel(const 
     }
 }
 
+// Same result as aggregate_pk_kernel<true>, different lane mapping: a load instruction covers 4 rows x one full 128-byte
+// line (lane = (r4 = lane/8, c = lane%8) owns the 4-float chunk c of rows r4 and 4+r4 of the 8-row group) instead of
+// 8 rows x half of every 32-byte sector, which halves the L1 wavefronts of the gather (ncu: the L1 data pipe, 53 % busy,
+// was the most loaded unit of the 8-row mapping).  A lane then holds half of a 16-byte core-matrix row for two rows and
+// stores 8 bytes per row and hi/lo plane; a store instruction still fills whole 32-byte sectors.
+__global__ void __launch_bounds__(256, 5) aggregate_pk4_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
+                                                            int B, int N, int H, const int* __restrict__ nbr,
+                                                            const int* __restrict__ deg, int DM,
+                                                            const int* __restrict__ list_index, int mean, int write_lo,
+                                                            int rows_per_block) {
+    extern __shared__ int agg_lists[];  // lists i32[rows_per_block][DM] | degrees i32[rows_per_block]
+    const int lane = threadIdx.x & 31;
+    const int kbs = H / TC_BK;
+    const int64_t R = (int64_t)B * N;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+    const int tasks = (rows_per_block >> 3) * kbs;
+    int* s_deg = agg_lists + rows_per_block * DM;
+    for (int t = threadIdx.x; t < rows_per_block * DM; t += (int)blockDim.x) {
+        const int r = t / DM, q = t - r * DM;
+        const int64_t row = row0 + r;
+        int val = 0;
+        if (row < R) {
+            const unsigned row32 = (unsigned)row;
+            const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
+            const size_t node = (size_t)(list_index ? list_index[b] : b) * N + v;
+            val = nbr[node * DM + q];
+            if (q == 0) s_deg[r] = deg[node];
+        } else if (q == 0) {
+            s_deg[r] = 0;
+        }
+        agg_lists[t] = val;
+    }
+    __syncthreads();
+    const int r4 = lane >> 3, c = lane & 7;
+    for (int t = threadIdx.x >> 5; t < tasks; t += (int)(blockDim.x >> 5)) {
+        const int g8 = (t / kbs) * 8, kb = t % kbs;
+        if (row0 + g8 >= R) continue;
+        float4 x[2];
+        const int* lst[2];
+        const float* hb[2];
+        int dg[2];
+        float4 a[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int rl = g8 + 4 * j + r4;
+            const unsigned row32 = (unsigned)(row0 + rl);  // the host checks B*N < 2^31
+            const unsigned b = min(row32 / (unsigned)N, (unsigned)(B - 1));
+            lst[j] = agg_lists + rl * DM;
+            dg[j] = s_deg[rl];  // 0 beyond the last row
+            hb[j] = h + (size_t)b * N * ldh + kb * TC_BK + c * 4;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                a[j][q] = q < dg[j] ? __ldg((const float4*)(hb[j] + (size_t)lst[j][q] * ldh)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // ascending list order; "+ 0" of an absent entry is skipped like in the 8-row kernel
+                if (q < dg[j]) { x[j].x += a[j][q].x; x[j].y += a[j][q].y; x[j].z += a[j][q].z; x[j].w += a[j][q].w; }
+            }
+            for (int q = 4; q < dg[j]; q++) {
+                const float4 e = __ldg((const float4*)(hb[j] + (size_t)lst[j][q] * ldh));
+                x[j].x += e.x; x[j].y += e.y; x[j].z += e.z; x[j].w += e.w;
+            }
+            if (mean) {
+                const float d = (float)max(dg[j], 1);
+                x[j].x = x[j].x / d; x[j].y = x[j].y / d; x[j].z = x[j].z / d; x[j].w = x[j].w / d;
+            }
+            const int64_t row = row0 + g8 + 4 * j + r4;
+            if (row >= R) continue;
+            const uint32_t hi0 = agg_pack2(x[j].x, x[j].y), hi1 = agg_pack2(x[j].z, x[j].w);
+            const uint32_t lo0 = agg_pack2(x[j].x - __uint_as_float(hi0 << 16), x[j].y - __uint_as_float(hi0 & 0xffff0000u));
+            const uint32_t lo1 = agg_pack2(x[j].z - __uint_as_float(hi1 << 16), x[j].w - __uint_as_float(hi1 & 0xffff0000u));
+            const int64_t mt = row / TC_BM;
+            const int r = (int)(row - mt * TC_BM);
+            uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
+                           (r & 7) * 16 + (c & 1) * 8;
+            *(uint2*)dst = make_uint2(hi0, hi1);
+            if (write_lo) *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
+        }
+    }
+}
+
 // rows a block of aggregate_pk_kernel owns: whole graphs, a multiple of 8 rows, about 40-80 rows (GM_AGG_ROWS overrides)
 static int aggregate_rows_per_block(int N) {
     static int forced = -1;
@@ -755,7 +839,12 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                 static int agg_staged = -1;
                 if (agg_staged < 0) { const char* e = getenv("GM_AGG_STAGE_LISTS"); agg_staged = e ? atoi(e) : 1; }
                 const unsigned agg_blocks = (unsigned)((R + rpb - 1) / rpb);
-                if (agg_staged)
+                static int agg_map = -1;
+                if (agg_map < 0) { const char* e = getenv("GM_AGG_MAP"); agg_map = e ? atoi(e) : 8; }
+                if (agg_map == 4)
+                    aggregate_pk4_kernel<<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
+                        h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
+                else if (agg_staged)
                     aggregate_pk_kernel<true><<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
                         h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
                 else

@@ -161,22 +161,54 @@ __device__ __forceinline__ void emit_f32_block(float* g, int total, int W, float
     }
 }
 
-// byte block [total] at g, value(idx) computed per byte; 4 bytes per store where aligned
-template <class ByteFn>
-__device__ __forceinline__ void emit_i8_block(int8_t* g, int total, int lane, ByteFn fn) {
-    int head = (int)((4 - ((uintptr_t)g & 3u)) & 3u);
-    if (head > total) head = total;
-    if (lane < head) g[lane] = fn(lane);
-    int body = (total - head) >> 2;
-    uint32_t* g4 = (uint32_t*)(g + head);
-    for (int q = lane; q < body; q += 32) {
-        int i0 = head + 4 * q;
-        uint32_t w = (uint32_t)(uint8_t)fn(i0) | ((uint32_t)(uint8_t)fn(i0 + 1) << 8) |
-                     ((uint32_t)(uint8_t)fn(i0 + 2) << 16) | ((uint32_t)(uint8_t)fn(i0 + 3) << 24);
-        g4[q] = w;
+// ---- int8 matrices with rows of A bytes; a lane owns whole rows, four bytes per store when rows are 4-byte aligned ----
+// (a flat per-byte form with a division and three table lookups per byte cost 37 % of the kernel's issue samples).
+// Separate functions: they run last, nothing of the kernel's state is live across them, and inlining them pushed
+// the step kernel over its 72-register budget.
+__device__ __forceinline__ void put_row4(int8_t* row, bool aligned, int A, int j0, uint32_t w) {
+    if (aligned) {
+        *(uint32_t*)(row + j0) = w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (j0 + u < A) row[j0 + u] = (int8_t)((w >> (8 * u)) & 0xffu);
     }
-    int tail0 = head + 4 * body;
-    if (lane < total - tail0) g[tail0 + lane] = fn(tail0 + lane);
+}
+
+// agent adjacency (routing.py:522-539): adj[i,j] = node_adj[now_i, now_j]; the lane keeps now_i and its three
+// neighbours in registers, now_j comes from shared memory as a broadcast
+__device__ __noinline__ void emit_adj_rows(const int* now, const int* __restrict__ nb, int8_t* g, int A, int lane) {
+    const bool aligned = (A & 3) == 0 && ((uintptr_t)g & 3u) == 0;
+#pragma unroll 1
+    for (int i = lane; i < A; i += 32) {
+        const int ni = now[i];
+        const int n0 = nb[ni * 3], n1 = nb[ni * 3 + 1], n2 = nb[ni * 3 + 2];
+#pragma unroll 1
+        for (int j0 = 0; j0 < A; j0 += 4) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int nj = now[min(j0 + u, A - 1)];
+                w |= (uint32_t)((nj == ni) | (nj == n0) | (nj == n1) | (nj == n2)) << (8 * u);
+            }
+            put_row4(g + (size_t)i * A, aligned, A, j0, w);
+        }
+    }
+}
+
+// node-agent matrix (routing.py:256-267): M[n,a] = (now_a == n), lane = node
+__device__ __noinline__ void emit_node_agent_rows(const int* now, int8_t* g, int N, int A, int lane) {
+    const bool aligned = (A & 3) == 0 && ((uintptr_t)g & 3u) == 0;
+#pragma unroll 1
+    for (int n = lane; n < N; n += 32) {
+#pragma unroll 1
+        for (int a0 = 0; a0 < A; a0 += 4) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) w |= (uint32_t)(now[min(a0 + u, A - 1)] == n) << (8 * u);
+            put_row4(g + (size_t)n * A, aligned, A, a0, w);
+        }
+    }
 }
 
 template <int MODE>
@@ -504,21 +536,8 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                        });
     }
 
-    // ---- agent adjacency (routing.py:522-539): adj[i,j] = node_adj[now_i, now_j] ----------
-    if (io.adj) {
-        emit_i8_block(io.adj + (size_t)b * A * A, A * A, lane, [&](int idx) -> int8_t {
-            int i = idx / A, j = idx - i * A;
-            int ni = v.now[i], nj = v.now[j];
-            return (int8_t)((ni == nj) || nb[ni * 3] == nj || nb[ni * 3 + 1] == nj || nb[ni * 3 + 2] == nj);
-        });
-    }
-    // ---- node-agent matrix (routing.py:256-267) ----------------------------------------------
-    if (io.node_agent) {
-        emit_i8_block(io.node_agent + (size_t)b * N * A, N * A, lane, [&](int idx) -> int8_t {
-            int n = idx / A, a = idx - n * A;
-            return (int8_t)(v.now[a] == n);
-        });
-    }
+    if (io.adj) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, A, lane);
+    if (io.node_agent) emit_node_agent_rows(v.now, io.node_agent + (size_t)b * N * A, N, A, lane);
 }
 
 static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_io* io, void* stream) {

@@ -178,13 +178,15 @@ def test_dqn_tensorcore_q_values(math, tol):
         assert np.array_equal(a2.cpu().numpy(), g["q"].argmax(-1))
 
 
-@pytest.mark.parametrize("switch", ["GM_TC_WS", "GM_TC_PAIR", "GM_TC_WIDE", "GM_TC_CLUSTER"])
+@pytest.mark.parametrize("switch", ["GM_TC_WS", "GM_TC_PAIR", "GM_TC_WIDE", "GM_TC_CLUSTER", "GM_AGG_MAP=4", "GM_AGG_MAP=8",
+                                    "GM_AGG_STAGE_LISTS=0"])
 def test_optional_kernel_variants_match(switch):
     """The optional variants of the tcgen05 kernel give the same NetMon outputs as the default streaming kernel:
     GM_TC_WS=1 (weights resident in smem, activations multicast to a 4-CTA cluster), GM_TC_PAIR=1 (2-CTA pairs driving
     tcgen05.mma.cta_group::2, M = 256, half a weight tile per CTA), GM_TC_WIDE=0 (8 instead of 16 epilogue warps for all-tile-packed
-    layers), GM_TC_CLUSTER=2 (weight stages multicast over a 2-CTA cluster).  Run in a subprocess because the switches
-    are read once per process."""
+    layers), GM_TC_CLUSTER=2 (weight stages multicast over a 2-CTA cluster); GM_AGG_MAP=4|8 / GM_AGG_STAGE_LISTS=0: the lane
+    mappings of the aggregation kernel (on a batch whose last block, 8-row group and M tile are all partial).  Run in a
+    subprocess because the switches are read once per process."""
     import os, subprocess, sys, textwrap
 
     code = textwrap.dedent("""
@@ -193,11 +195,11 @@ def test_optional_kernel_variants_match(switch):
         from helpers import det_weights, netmon_shapes
         from graph_marl_b200.model import NetMon
         from oracle import netmon_oracle as NO, oracle as O
-        N, H, K, B = 20, 128, 3, 300
+        N, H, K, B = 20, 128, 3, %d
         Dn = 4 * N + 8
-        cfg = dict(hidden=H, iterations=K, rnn_type="lstm", rnn_carryover=True, agg_type="sum", output_neighbor_hidden=True,
+        cfg = dict(hidden=H, iterations=K, rnn_type="lstm", rnn_carryover=True, agg_type=%r, output_neighbor_hidden=True,
                    output_global_hidden=False, enc=[512, 256], wseed=5)
-        nm = NetMon(Dn, H, cfg["enc"], K, F.leaky_relu, output_neighbor_hidden=True, math="bf16x3")
+        nm = NetMon(Dn, H, cfg["enc"], K, F.leaky_relu, output_neighbor_hidden=True, math="bf16x3", agg_type=cfg["agg_type"])
         w = det_weights(netmon_shapes(Dn, H, cfg["enc"], "lstm"), 5)
         nm.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}); nm = nm.cuda().eval()
         topo = O.generate_topology(N, seed=923430603)
@@ -212,7 +214,12 @@ def test_optional_kernel_variants_match(switch):
         e1, e2 = np.abs(out.cpu().numpy() - ref).max(), np.abs(nm.state.cpu().numpy() - ref_state).max()
         assert e1 < 1e-4 and e2 < 1e-4, (e1, e2)
         print("ok", e1, e2)
-    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, **{switch: {"GM_TC_CLUSTER": "2", "GM_TC_WIDE": "0"}.get(switch, "1")})
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+            301 if switch.startswith("GM_AGG") else 300, "mean" if switch == "GM_AGG_MAP=4" else "sum")
+    if "=" in switch:
+        switch, value = switch.split("=")
+    else:
+        value = {"GM_TC_CLUSTER": "2", "GM_TC_WIDE": "0"}.get(switch, "1")
+    env = dict(os.environ, **{switch: value})
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
