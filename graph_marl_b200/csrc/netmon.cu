@@ -273,6 +273,259 @@ __global__ void __launch_bounds__(256, 5) aggregate_pk4_kernel(const float* __re
     }
 }
 
+// Bulk-staged aggregation: a block owns whole graphs, so every neighbour of its rows is one of its rows.  One thread pulls the
+// block's hidden rows (contiguous when ldh == H: ONE cp.async.bulk, TMA bulk copy, completing on an mbarrier) into shared
+// memory while the others stage the neighbour lists; the sums then read shared memory only.  h crosses L2 -> SM once (not
+// once per list that names the row), no warp ever waits on a dependent global gather, and the only long latency of a block
+// is the bulk copy, overlapped across the 8-10 resident blocks of an SM.  Lane mapping as in aggregate_pk4_kernel: a
+// quarter-warp reads one row's contiguous 128 bytes (conflict-free LDS.128), a lane stores 8 bytes per row and plane.
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(256, 5) aggregate_pk_bulk_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
+                                                                   int B, int N, int H, const int* __restrict__ nbr,
+                                                                   const int* __restrict__ deg, int DM,
+                                                                   const int* __restrict__ list_index, int mean, int write_lo,
+                                                                   int rows_per_block) {
+    extern __shared__ __align__(128) uint8_t agg_sm[];  // mbarrier (16 B) | rows f32[rpb][H] | lists i32[rpb][DM] | degrees i32[rpb]
+    float* s_h = (float*)(agg_sm + 16);
+    int* s_lst = (int*)(agg_sm + 16 + (size_t)rows_per_block * H * 4);
+    int* s_deg = s_lst + rows_per_block * DM;
+    const int lane = threadIdx.x & 31;
+    const int kbs = H / TC_BK;
+    const int64_t R = (int64_t)B * N;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
+    const int nrows = (int)min((int64_t)rows_per_block, R - row0);
+    const uint32_t bar = agg_smem_u32(agg_sm);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t row_bytes = (uint32_t)H * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)nrows) : "memory");
+        if (ldh == H) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(agg_smem_u32(s_h)),
+                         "l"(h + row0 * ldh), "r"(row_bytes * (uint32_t)nrows), "r"(bar)
+                         : "memory");
+        } else {
+            for (int r = 0; r < nrows; r++)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 agg_smem_u32(s_h + (size_t)r * H)),
+                             "l"(h + (row0 + r) * ldh), "r"(row_bytes), "r"(bar)
+                             : "memory");
+        }
+    }
+    for (int t = threadIdx.x; t < rows_per_block * DM; t += (int)blockDim.x) {
+        const int r = t / DM, q = t - r * DM;
+        int val = 0;
+        if (r < nrows) {
+            const unsigned row32 = (unsigned)(row0 + r);  // the host checks B*N < 2^31
+            const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
+            const size_t node = (size_t)(list_index ? list_index[b] : b) * N + v;
+            val = nbr[node * DM + q];
+            if (q == 0) s_deg[r] = deg[node];
+        } else if (q == 0) {
+            s_deg[r] = 0;
+        }
+        s_lst[t] = val;
+    }
+    __syncthreads();  // lists staged; the mbarrier's initialisation is visible to every thread
+    {
+        uint32_t done = 0, spins = 0;
+        while (!done) {  // bounded: a protocol bug traps instead of hanging the GPU
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(bar)
+                         : "memory");
+            if (!done && ++spins > (1u << 26)) __trap();
+        }
+    }
+    const int r4 = lane >> 3, c = lane & 7;
+    const int tasks = ((nrows + 7) >> 3) * kbs;
+    for (int t = threadIdx.x >> 5; t < tasks; t += (int)(blockDim.x >> 5)) {
+        const int g8 = (t / kbs) * 8, kb = t % kbs;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int rl = g8 + 4 * j + r4;
+            if (rl >= nrows) continue;
+            const int* lst = s_lst + rl * DM;
+            const int dg = s_deg[rl];
+            const float* hb = s_h + (size_t)(rl / N) * N * H + kb * TC_BK + c * 4;  // rows of this row's graph
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < dg; q++) {  // ascending list order = the reference's bmm row order
+                const float4 e = *(const float4*)(hb + (size_t)lst[q] * H);
+                x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
+            }
+            if (mean) {
+                const float d = (float)max(dg, 1);
+                x.x = x.x / d; x.y = x.y / d; x.z = x.z / d; x.w = x.w / d;
+            }
+            const uint32_t hi0 = agg_pack2(x.x, x.y), hi1 = agg_pack2(x.z, x.w);
+            const uint32_t lo0 = agg_pack2(x.x - __uint_as_float(hi0 << 16), x.y - __uint_as_float(hi0 & 0xffff0000u));
+            const uint32_t lo1 = agg_pack2(x.z - __uint_as_float(hi1 << 16), x.w - __uint_as_float(hi1 & 0xffff0000u));
+            const int64_t row = row0 + rl;
+            const int64_t mt = row / TC_BM;
+            const int r = (int)(row - mt * TC_BM);
+            uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
+                           (r & 7) * 16 + (c & 1) * 8;
+            *(uint2*)dst = make_uint2(hi0, hi1);
+            if (write_lo) *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
+        }
+    }
+}
+
+// Persistent, pipelined form of the bulk-staged aggregation: one CTA per SM slot walks its row blocks through a 3-stage
+// shared-memory ring.  Warp 0 is the producer: lane 0 posts the stage's transaction count and issues the bulk copy of the
+// block's hidden rows, all 32 lanes stage the neighbour lists / degrees with ordinary loads (their two dependent latencies
+// are the producer's, not the consumers'), then arrive on the stage's "full" mbarrier.  The other warps consume: wait for
+// "full", form the sums from shared memory, store the packed tile rows, release the stage on its "empty" mbarrier.  No
+// consumer warp ever waits on global memory, so loads of block i+1, i+2 overlap the arithmetic and stores of block i.
+constexpr int AGG_STAGES = 3;
+
+__device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {  // bounded: a protocol bug traps instead of hanging the GPU
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();
+    }
+}
+
+__global__ void __launch_bounds__(352, 3) aggregate_pk_pipe_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
+                                                                   int B, int N, int H, const int* __restrict__ nbr,
+                                                                   const int* __restrict__ deg, int DM,
+                                                                   const int* __restrict__ list_index, int mean, int write_lo,
+                                                                   int rows_per_block, int n_blocks, int stage_bytes) {
+    extern __shared__ __align__(128) uint8_t agg_sm[];  // full[3], empty[3] mbarriers | 3 x (rows f32[rpb][H] | lists | degrees)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_cons = (int)(blockDim.x >> 5) - 1;
+    const int kbs = H / TC_BK;
+    const int64_t R = (int64_t)B * N;
+    const uint32_t full0 = agg_smem_u32(agg_sm), empty0 = full0 + 8 * AGG_STAGES;
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < AGG_STAGES; st++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(full0 + 8 * st), "r"(32) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * st), "r"(n_cons) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int it = 0;
+    if (warp == 0) {  // ---- producer ----
+        // a block holds whole graphs and a graph's lists / degrees are contiguous: when they are 16-byte granular they move
+        // as bulk copies too, and the producer touches global memory only for the (prefetched) list index of each graph
+        const int gpb = rows_per_block / N;  // graphs per block (<= 32)
+        const bool bulk_lists = ((N * DM) & 3) == 0 && (N & 3) == 0 && (((uintptr_t)nbr | (uintptr_t)deg) & 15) == 0;
+        auto graph_list = [&](int blk) -> int {  // lane g: list index of the block's g-th graph (or -1)
+            const int b = blk * gpb + lane;
+            if (blk >= n_blocks || lane >= gpb || b >= B) return -1;
+            return list_index ? list_index[b] : b;
+        };
+        int li_next = graph_list(blockIdx.x);
+        for (int blk = blockIdx.x; blk < n_blocks; blk += (int)gridDim.x, it++) {
+            const int st = it % AGG_STAGES;
+            const uint32_t ph = (uint32_t)(it / AGG_STAGES) & 1u;
+            const int li_mine = li_next;
+            li_next = graph_list(blk + (int)gridDim.x);
+            if (it >= AGG_STAGES) agg_mbar_wait(empty0 + 8 * st, ph ^ 1u);
+            uint8_t* base = agg_sm + 128 + (size_t)st * stage_bytes;
+            float* s_h = (float*)base;
+            int* s_lst = (int*)(base + (size_t)rows_per_block * H * 4);
+            int* s_deg = s_lst + rows_per_block * DM;
+            const int64_t row0 = (int64_t)blk * rows_per_block;
+            const int nrows = (int)min((int64_t)rows_per_block, R - row0);
+            const int ngraphs = nrows / N;
+            const uint32_t bar = full0 + 8 * st;
+            const uint32_t row_bytes = (uint32_t)H * 4u;
+            if (lane == 0) {
+                const uint32_t tx = row_bytes * (uint32_t)nrows + (bulk_lists ? (uint32_t)ngraphs * (uint32_t)(N * (DM + 1)) * 4u : 0u);
+                asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(tx) : "memory");
+                if (ldh == H) {
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     agg_smem_u32(s_h)),
+                                 "l"(h + row0 * ldh), "r"(row_bytes * (uint32_t)nrows), "r"(bar)
+                                 : "memory");
+                } else {
+                    for (int r = 0; r < nrows; r++)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                         agg_smem_u32(s_h + (size_t)r * H)),
+                                     "l"(h + (row0 + r) * ldh), "r"(row_bytes), "r"(bar)
+                                     : "memory");
+                }
+            }
+            __syncwarp();  // the transaction count is posted before any other lane's copy can complete
+            if (bulk_lists) {
+                if (lane < ngraphs) {
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     agg_smem_u32(s_lst + lane * N * DM)),
+                                 "l"(nbr + (size_t)li_mine * N * DM), "r"((uint32_t)(N * DM) * 4u), "r"(bar)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     agg_smem_u32(s_deg + lane * N)),
+                                 "l"(deg + (size_t)li_mine * N), "r"((uint32_t)N * 4u), "r"(bar)
+                                 : "memory");
+                }
+            } else {
+                for (int g = 0; g < ngraphs; g++) {
+                    const int li = __shfl_sync(FULL, li_mine, g);
+                    const int* src = nbr + (size_t)li * N * DM;
+                    for (int t = lane; t < N * DM; t += 32) s_lst[g * N * DM + t] = src[t];
+                    for (int t = lane; t < N; t += 32) s_deg[g * N + t] = deg[(size_t)li * N + t];
+                }
+            }
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");  // release: the lists are visible
+        }
+        return;
+    }
+    // ---- consumers ----
+    const int cw = warp - 1;
+    const int r4 = lane >> 3, c = lane & 7;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += (int)gridDim.x, it++) {
+        const int st = it % AGG_STAGES;
+        const uint32_t ph = (uint32_t)(it / AGG_STAGES) & 1u;
+        const uint8_t* base = agg_sm + 128 + (size_t)st * stage_bytes;
+        const float* s_h = (const float*)base;
+        const int* s_lst = (const int*)(base + (size_t)rows_per_block * H * 4);
+        const int* s_deg = s_lst + rows_per_block * DM;
+        const int64_t row0 = (int64_t)blk * rows_per_block;
+        const int nrows = (int)min((int64_t)rows_per_block, R - row0);
+        const int tasks = ((nrows + 7) >> 3) * kbs;
+        agg_mbar_wait(full0 + 8 * st, ph);
+        for (int t = cw; t < tasks; t += n_cons) {
+            const int g8 = (t / kbs) * 8, kb = t % kbs;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int rl = g8 + 4 * j + r4;
+                if (rl >= nrows) continue;
+                const int* lst = s_lst + rl * DM;
+                const int dg = s_deg[rl];
+                const float* hb = s_h + (size_t)(rl / N) * N * H + kb * TC_BK + c * 4;  // rows of this row's graph
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < dg; q++) {  // ascending list order = the reference's bmm row order
+                    const float4 e = *(const float4*)(hb + (size_t)lst[q] * H);
+                    x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
+                }
+                if (mean) {
+                    const float d = (float)max(dg, 1);
+                    x.x = x.x / d; x.y = x.y / d; x.z = x.z / d; x.w = x.w / d;
+                }
+                const uint32_t hi0 = agg_pack2(x.x, x.y), hi1 = agg_pack2(x.z, x.w);
+                const uint32_t lo0 = agg_pack2(x.x - __uint_as_float(hi0 << 16), x.y - __uint_as_float(hi0 & 0xffff0000u));
+                const uint32_t lo1 = agg_pack2(x.z - __uint_as_float(hi1 << 16), x.w - __uint_as_float(hi1 & 0xffff0000u));
+                const int64_t row = row0 + rl;
+                const int64_t mt = row / TC_BM;
+                const int r = (int)(row - mt * TC_BM);
+                uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
+                               (r & 7) * 16 + (c & 1) * 8;
+                *(uint2*)dst = make_uint2(hi0, hi1);
+                if (write_lo) *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * st) : "memory");
+    }
+}
+
 // rows a block of aggregate_pk_kernel owns: whole graphs, a multiple of 8 rows, about 40-80 rows (GM_AGG_ROWS overrides)
 static int aggregate_rows_per_block(int N) {
     static int forced = -1;
@@ -841,7 +1094,35 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                 const unsigned agg_blocks = (unsigned)((R + rpb - 1) / rpb);
                 static int agg_map = -1;
                 if (agg_map < 0) { const char* e = getenv("GM_AGG_MAP"); agg_map = e ? atoi(e) : 8; }
-                if (agg_map == 4)
+                const size_t bulk_smem = 16 + (size_t)rpb * H * 4 + (size_t)rpb * (DM + 1) * sizeof(int);
+                const int pipe_stage = (int)round_up((int64_t)rpb * H * 4 + (int64_t)rpb * (DM + 1) * (int64_t)sizeof(int), 128);
+                const size_t pipe_smem = 128 + (size_t)AGG_STAGES * pipe_stage;
+                if (agg_map == 2 && rpb % N == 0 && rpb / N <= 32 && pipe_smem <= 72 * 1024 && ((uintptr_t)h & 15) == 0) {
+                    static int pipe_threads = -1, pipe_ctas = -1;
+                    if (pipe_threads < 0) {
+                        const char* e = getenv("GM_AGG_PIPE_WARPS");  // consumer warps per CTA
+                        int cw = e ? atoi(e) : 10;
+                        cw = cw < 1 ? 1 : (cw > 10 ? 10 : cw);
+                        const char* f = getenv("GM_AGG_PIPE_CTAS");  // CTAs per SM
+                        pipe_ctas = f ? atoi(f) : 3;
+                        pipe_ctas = pipe_ctas < 1 ? 1 : (pipe_ctas > 3 ? 3 : pipe_ctas);
+                        GM_CUDA(cudaFuncSetAttribute(aggregate_pk_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                        pipe_threads = 32 * (cw + 1);
+                    }
+                    int sms = 148;
+                    {
+                        int dev = 0;
+                        cudaGetDevice(&dev);
+                        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                    }
+                    const unsigned grid = std::min<unsigned>(agg_blocks, (unsigned)(sms * pipe_ctas));
+                    aggregate_pk_pipe_kernel<<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
+                                                                                   p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
+                                                                                   (int)agg_blocks, pipe_stage);
+                } else if (agg_map == 1 && rpb % N == 0 && bulk_smem <= 48 * 1024 && ((uintptr_t)h & 15) == 0 && agg_threads <= 256)
+                    aggregate_pk_bulk_kernel<<<agg_blocks, agg_threads, bulk_smem, s>>>(
+                        h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
+                else if (agg_map == 4)
                     aggregate_pk4_kernel<<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
                         h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
                 else if (agg_staged)
