@@ -478,8 +478,14 @@ __global__ void __launch_bounds__(352, 3) aggregate_pk_pipe_kernel(const float* 
         return;
     }
     // ---- consumers ----
+    // A task = one 8-row group x `kc` consecutive k-blocks: the row's list, degree, graph base and tile address are formed
+    // once per row and reused for every k-block, divisions are replaced by shifts / a multiply-high, all shared-memory
+    // offsets are 32-bit (the first form of this loop issued ~380 instructions per 8x32 unit, 66 % issue-slot utilisation).
     const int cw = warp - 1;
     const int r4 = lane >> 3, c = lane & 7;
+    const int kc = (kbs & 1) == 0 ? 2 : 1;
+    const int kgroups = kbs / kc;
+    const unsigned n_magic = (unsigned)((0x100000000ull + (unsigned)N - 1u) / (unsigned)N);  // rl / N = umulhi(rl, magic), rl < 2^16
     for (int blk = blockIdx.x; blk < n_blocks; blk += (int)gridDim.x, it++) {
         const int st = it % AGG_STAGES;
         const uint32_t ph = (uint32_t)(it / AGG_STAGES) & 1u;
@@ -489,36 +495,53 @@ __global__ void __launch_bounds__(352, 3) aggregate_pk_pipe_kernel(const float* 
         const int* s_deg = s_lst + rows_per_block * DM;
         const int64_t row0 = (int64_t)blk * rows_per_block;
         const int nrows = (int)min((int64_t)rows_per_block, R - row0);
-        const int tasks = ((nrows + 7) >> 3) * kbs;
+        const int tasks = ((nrows + 7) >> 3) * kgroups;
         agg_mbar_wait(full0 + 8 * st, ph);
         for (int t = cw; t < tasks; t += n_cons) {
-            const int g8 = (t / kbs) * 8, kb = t % kbs;
+            const int grp = t / kgroups;
+            const int kb0 = (t - grp * kgroups) * kc;
 #pragma unroll
             for (int j = 0; j < 2; j++) {
-                const int rl = g8 + 4 * j + r4;
+                const int rl = grp * 8 + 4 * j + r4;
                 if (rl >= nrows) continue;
-                const int* lst = s_lst + rl * DM;
                 const int dg = s_deg[rl];
-                const float* hb = s_h + (size_t)(rl / N) * N * H + kb * TC_BK + c * 4;  // rows of this row's graph
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int q = 0; q < dg; q++) {  // ascending list order = the reference's bmm row order
-                    const float4 e = *(const float4*)(hb + (size_t)lst[q] * H);
-                    x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
-                }
-                if (mean) {
-                    const float d = (float)max(dg, 1);
-                    x.x = x.x / d; x.y = x.y / d; x.z = x.z / d; x.w = x.w / d;
-                }
-                const uint32_t hi0 = agg_pack2(x.x, x.y), hi1 = agg_pack2(x.z, x.w);
-                const uint32_t lo0 = agg_pack2(x.x - __uint_as_float(hi0 << 16), x.y - __uint_as_float(hi0 & 0xffff0000u));
-                const uint32_t lo1 = agg_pack2(x.z - __uint_as_float(hi1 << 16), x.w - __uint_as_float(hi1 & 0xffff0000u));
+                const int gbase = (N == 1 ? rl : (int)__umulhi((unsigned)rl, n_magic)) * N;  // first row of this row's graph
                 const int64_t row = row0 + rl;
-                const int64_t mt = row / TC_BM;
-                const int r = (int)(row - mt * TC_BM);
-                uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
-                               (r & 7) * 16 + (c & 1) * 8;
-                *(uint2*)dst = make_uint2(hi0, hi1);
-                if (write_lo) *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
+                const int r = (int)(row & (TC_BM - 1));
+                uint8_t* drow = Mpk + (size_t)(row / TC_BM) * kbs * TC_PK_BLOCK + (r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
+                                (r & 7) * 16 + (c & 1) * 8;
+                const bool four = DM == 4 && dg == 4;
+                int4 l4 = make_int4(0, 0, 0, 0);
+                if (four) l4 = *(const int4*)(s_lst + rl * 4);
+                for (int kk = 0; kk < kc; kk++) {
+                    const int kb = kb0 + kk;
+                    const float* hb = s_h + (gbase * H + kb * TC_BK + c * 4);
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (four) {  // ascending list order = the reference's bmm row order
+                        const float4 e0 = *(const float4*)(hb + l4.x * H), e1 = *(const float4*)(hb + l4.y * H);
+                        const float4 e2 = *(const float4*)(hb + l4.z * H), e3 = *(const float4*)(hb + l4.w * H);
+                        x.x = (((x.x + e0.x) + e1.x) + e2.x) + e3.x; x.y = (((x.y + e0.y) + e1.y) + e2.y) + e3.y;
+                        x.z = (((x.z + e0.z) + e1.z) + e2.z) + e3.z; x.w = (((x.w + e0.w) + e1.w) + e2.w) + e3.w;
+                    } else {
+                        const int* lst = s_lst + rl * DM;
+                        for (int q = 0; q < dg; q++) {
+                            const float4 e = *(const float4*)(hb + lst[q] * H);
+                            x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
+                        }
+                    }
+                    if (mean) {
+                        const float d = (float)max(dg, 1);
+                        x.x = x.x / d; x.y = x.y / d; x.z = x.z / d; x.w = x.w / d;
+                    }
+                    const uint32_t hi0 = agg_pack2(x.x, x.y), hi1 = agg_pack2(x.z, x.w);
+                    uint8_t* dst = drow + (size_t)kb * TC_PK_BLOCK;
+                    *(uint2*)dst = make_uint2(hi0, hi1);
+                    if (write_lo) {
+                        const uint32_t lo0 = agg_pack2(x.x - __uint_as_float(hi0 << 16), x.y - __uint_as_float(hi0 & 0xffff0000u));
+                        const uint32_t lo1 = agg_pack2(x.z - __uint_as_float(hi1 << 16), x.w - __uint_as_float(hi1 & 0xffff0000u));
+                        *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -1093,7 +1116,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                 if (agg_staged < 0) { const char* e = getenv("GM_AGG_STAGE_LISTS"); agg_staged = e ? atoi(e) : 1; }
                 const unsigned agg_blocks = (unsigned)((R + rpb - 1) / rpb);
                 static int agg_map = -1;
-                if (agg_map < 0) { const char* e = getenv("GM_AGG_MAP"); agg_map = e ? atoi(e) : 8; }
+                if (agg_map < 0) { const char* e = getenv("GM_AGG_MAP"); agg_map = e ? atoi(e) : 2; }  // 2: pipelined (default), 1: bulk-staged, 4 / 8: gather kernels
                 const size_t bulk_smem = 16 + (size_t)rpb * H * 4 + (size_t)rpb * (DM + 1) * sizeof(int);
                 const int pipe_stage = (int)round_up((int64_t)rpb * H * 4 + (int64_t)rpb * (DM + 1) * (int64_t)sizeof(int), 128);
                 const size_t pipe_smem = 128 + (size_t)AGG_STAGES * pipe_stage;

@@ -220,6 +220,8 @@ def test_optional_kernel_variants_match(switch):
             (2101 if switch.endswith(":wrap") else 301) if switch.startswith("GM_AGG") else 300,
             "mean" if switch.endswith(":mean") else "sum")
     extra = {"GM_AGG_PIPE_CTAS": "1", "GM_AGG_PIPE_WARPS": "3"} if switch.endswith(":wrap") else {}
+    if switch.startswith("GM_AGG_STAGE_LISTS"):
+        extra["GM_AGG_MAP"] = "8"  # the gather kernel (the default is the pipelined kernel, GM_AGG_MAP=2)
     switch = switch.split(":")[0]
     if "=" in switch:
         switch, value = switch.split("=")
