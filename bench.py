@@ -345,7 +345,7 @@ def main():
                           f"step's GEMM launches; the tensor pipe executes {passes}x that in bf16 MMAs",
                      tensor_pipe_tflops_executed=tf * passes)
     agg_bytes = 8 * N * H * B  # read h + write M per iteration
-    roof_agg = dict(bound="hbm", kernel="aggregate_pk_kernel", achieved=(agg_bytes / (agg_ms * 1e-3) / 1e9) if agg_ms > 0 else None,
+    roof_agg = dict(bound="hbm", kernel="aggregate_pk_pipe_kernel", achieved=(agg_bytes / (agg_ms * 1e-3) / 1e9) if agg_ms > 0 else None,
                     peak=pk["hbm_gbs"], unit="GB/s", frac=(agg_bytes / (agg_ms * 1e-3) / 1e9 / pk["hbm_gbs"]) if agg_ms > 0 else None,
                     traffic=traffic.get("aggregate_pk_bytes_per_launch"), algorithmic_bytes_per_launch=agg_bytes, ms_per_launch=agg_ms)
     dominant = roof_gemm if gemm_ms >= env_ms else roof_env

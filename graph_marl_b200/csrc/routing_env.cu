@@ -177,8 +177,23 @@ __device__ __forceinline__ void put_row4(int8_t* row, bool aligned, int A, int j
 
 // agent adjacency (routing.py:522-539): adj[i,j] = node_adj[now_i, now_j]; the lane keeps now_i and its three
 // neighbours in registers, now_j comes from shared memory as a broadcast
-__device__ __noinline__ void emit_adj_rows(const int* now, const int* __restrict__ nb, int8_t* g, int A, int lane) {
+__device__ __noinline__ void emit_adj_rows(const int* now, const int* __restrict__ nb, int8_t* g, int N, int A, int lane) {
     const bool aligned = (A & 3) == 0 && ((uintptr_t)g & 3u) == 0;
+    if (aligned && N <= 32 && ((uintptr_t)now & 15u) == 0) {
+        // small graphs: the row's node set {now_i} + neighbours as a 32-bit mask, now_j four at a time (LDS.128)
+#pragma unroll 1
+        for (int i = lane; i < A; i += 32) {
+            const int ni = now[i];
+            const uint32_t m = (1u << ni) | (1u << nb[ni * 3]) | (1u << nb[ni * 3 + 1]) | (1u << nb[ni * 3 + 2]);
+            uint32_t* gr = (uint32_t*)(g + (size_t)i * A);
+#pragma unroll 1
+            for (int j0 = 0; j0 < A; j0 += 4) {
+                const int4 nj = *(const int4*)(now + j0);
+                gr[j0 >> 2] = ((m >> nj.x) & 1u) | (((m >> nj.y) & 1u) << 8) | (((m >> nj.z) & 1u) << 16) | (((m >> nj.w) & 1u) << 24);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int i = lane; i < A; i += 32) {
         const int ni = now[i];
@@ -199,6 +214,18 @@ __device__ __noinline__ void emit_adj_rows(const int* now, const int* __restrict
 // node-agent matrix (routing.py:256-267): M[n,a] = (now_a == n), lane = node
 __device__ __noinline__ void emit_node_agent_rows(const int* now, int8_t* g, int N, int A, int lane) {
     const bool aligned = (A & 3) == 0 && ((uintptr_t)g & 3u) == 0;
+    if (aligned && ((uintptr_t)now & 15u) == 0) {
+#pragma unroll 1
+        for (int n = lane; n < N; n += 32) {
+            uint32_t* gr = (uint32_t*)(g + (size_t)n * A);
+#pragma unroll 1
+            for (int a0 = 0; a0 < A; a0 += 4) {
+                const int4 na = *(const int4*)(now + a0);
+                gr[a0 >> 2] = (uint32_t)(na.x == n) | ((uint32_t)(na.y == n) << 8) | ((uint32_t)(na.z == n) << 16) | ((uint32_t)(na.w == n) << 24);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int n = lane; n < N; n += 32) {
 #pragma unroll 1
@@ -536,7 +563,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                        });
     }
 
-    if (io.adj) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, A, lane);
+    if (io.adj) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, N, A, lane);
     if (io.node_agent) emit_node_agent_rows(v.now, io.node_agent + (size_t)b * N * A, N, A, lane);
 }
 

@@ -9,7 +9,7 @@ python bench.py --steps 20 --warmup 3 --no-cpu-baseline --graph-steps 0 > /dev/n
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --graph-steps 0 > gpurun_out/ncu_launches_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k "regex:routing_kernel|aggregate_pk_kernel" -s 60 -c 8 -f -o gpurun_out/envagg_$TAG \
+    -k "regex:routing_kernel|aggregate_pk" -s 8 -c 8 -f -o gpurun_out/envagg_$TAG \
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --graph-steps 0 > gpurun_out/ncu_envagg_$TAG.log 2>&1
 ncu -i gpurun_out/envagg_$TAG.ncu-rep --page raw --csv > gpurun_out/envagg_${TAG}_raw.csv 2>/dev/null
 tail -c 600 gpurun_out/bench_$TAG.json; echo; ls -la gpurun_out/*$TAG*
