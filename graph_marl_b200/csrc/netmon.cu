@@ -391,11 +391,15 @@ __device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// HC / DMC: compile-time hidden size / list width (0 = use the runtime arguments); the <128, 4> instance turns the row, tile and
+// task index arithmetic of the consumer loop into shifts.
+template <int HC, int DMC>
 __global__ void __launch_bounds__(352, 3) aggregate_pk_pipe_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
-                                                                   int B, int N, int H, const int* __restrict__ nbr,
-                                                                   const int* __restrict__ deg, int DM,
+                                                                   int B, int N, int H_rt, const int* __restrict__ nbr,
+                                                                   const int* __restrict__ deg, int DM_rt,
                                                                    const int* __restrict__ list_index, int mean, int write_lo,
                                                                    int rows_per_block, int n_blocks, int stage_bytes) {
+    const int H = HC ? HC : H_rt, DM = DMC ? DMC : DM_rt;
     extern __shared__ __align__(128) uint8_t agg_sm[];  // full[3], empty[3] mbarriers | 3 x (rows f32[rpb][H] | lists | degrees)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_cons = (int)(blockDim.x >> 5) - 1;
@@ -1129,7 +1133,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                         const char* f = getenv("GM_AGG_PIPE_CTAS");  // CTAs per SM
                         pipe_ctas = f ? atoi(f) : 3;
                         pipe_ctas = pipe_ctas < 1 ? 1 : (pipe_ctas > 3 ? 3 : pipe_ctas);
-                        GM_CUDA(cudaFuncSetAttribute(aggregate_pk_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                        GM_CUDA(cudaFuncSetAttribute(aggregate_pk_pipe_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+                        GM_CUDA(cudaFuncSetAttribute(aggregate_pk_pipe_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
                         pipe_threads = 32 * (cw + 1);
                     }
                     int sms = 148;
@@ -1139,9 +1144,16 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
                     }
                     const unsigned grid = std::min<unsigned>(agg_blocks, (unsigned)(sms * pipe_ctas));
-                    aggregate_pk_pipe_kernel<<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
-                                                                                   p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
-                                                                                   (int)agg_blocks, pipe_stage);
+                    static int pipe_generic = -1;
+                    if (pipe_generic < 0) { const char* e = getenv("GM_AGG_PIPE_GENERIC"); pipe_generic = e ? atoi(e) : 0; }
+                    if (H == 128 && DM == 4 && !pipe_generic)
+                        aggregate_pk_pipe_kernel<128, 4><<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
+                                                                                               p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
+                                                                                               (int)agg_blocks, pipe_stage);
+                    else
+                        aggregate_pk_pipe_kernel<0, 0><<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
+                                                                                             p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
+                                                                                             (int)agg_blocks, pipe_stage);
                 } else if (agg_map == 1 && rpb % N == 0 && bulk_smem <= 48 * 1024 && ((uintptr_t)h & 15) == 0 && agg_threads <= 256)
                     aggregate_pk_bulk_kernel<<<agg_blocks, agg_threads, bulk_smem, s>>>(
                         h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
