@@ -7,8 +7,14 @@
 // Data layout (HBM, fp32): rows r = b*N + v; state [R, ns*H] with h in the first H floats
 // of a node's row and c in the next H (model.py:417-449); adjacency as padded ascending
 // neighbour lists (self included when the mask has it) instead of the reference's dense
-// [B,N,N] float mask, so aggregation is a coalesced row gather + register sum and the
-// readout is a pure gather.
+// [B,N,N] float mask, so aggregation is a sum over short lists and the readout is a pure gather.
+//
+// Aggregation on the tensor-core path (tile-packed output, one of four kernels, see the launch site):
+//   aggregate_pk_pipe_kernel  default: persistent CTAs, TMA bulk copies of whole graphs' hidden rows / lists into a
+//                             3-stage shared-memory ring (producer warp + mbarriers), sums from shared memory
+//   aggregate_pk_bulk_kernel  one block per row block, one bulk copy, no ring           (GM_AGG_MAP=1)
+//   aggregate_pk_kernel       L2 gather, 8 rows x 32 columns per warp; the fallback for graphs that do not fit the ring
+//   aggregate_pk4_kernel      L2 gather, 4 rows x one full line per load instruction    (GM_AGG_MAP=4)
 #include <cuda_bf16.h>
 
 #include "common.cuh"
