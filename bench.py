@@ -131,26 +131,51 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _init_weights(c):
+    """Default-initialised NetMon / DQN parameters under the reference's state_dict names (model.py:256-401, 187-203),
+    built from plain torch.nn layers: the CPU arm shares no code with the package it is compared with."""
+    import torch
+    import torch.nn as nn
+
+    torch.manual_seed(0)
+    N, H = c["n_nodes"], c["H"]
+    w_nm, w_dq = {}, {}
+    prev = 4 * N + 8
+    for i, u in enumerate(list(c["enc"]) + [H]):
+        l = nn.Linear(prev, u)
+        w_nm[f"encode.linear_layers.{i}.weight"], w_nm[f"encode.linear_layers.{i}.bias"] = l.weight, l.bias
+        prev = u
+    for cell in ("rnn_obs", "rnn_update"):
+        m = nn.LSTMCell(H, H)
+        w_nm[f"{cell}.weight_ih"], w_nm[f"{cell}.weight_hh"], w_nm[f"{cell}.bias_ih"] = m.weight_ih, m.weight_hh, m.bias_ih
+        if c["rnn"] == "lnlstm":
+            for ln, width in (("ln_input", 4 * H), ("ln_hidden", 4 * H), ("ln_cell", H)):
+                w_nm[f"{cell}.{ln}.weight"], w_nm[f"{cell}.{ln}.bias"] = torch.ones(width), torch.zeros(width)
+        else:
+            w_nm[f"{cell}.bias_hh"] = m.bias_hh
+    prev = 6 * N + 10 + 4 * H
+    for i, u in enumerate(c["dqn"]):
+        l = nn.Linear(prev, u)
+        w_dq[f"encoder.linear_layers.{i}.weight"], w_dq[f"encoder.linear_layers.{i}.bias"] = l.weight, l.bias
+        prev = u
+    q = nn.Linear(prev, 4)
+    w_dq["q_net.fc.weight"], w_dq["q_net.fc.bias"] = q.weight, q.bias
+    f = lambda d: {k: v.detach().numpy().copy() for k, v in d.items()}
+    return f(w_nm), f(w_dq)
+
+
 def cpu_arm(cfg_name, steps, warmup, envs=None, budget_s=20.0):
     """The oracle's rollout step on the host cores, bounded sample of the same workload."""
-    import numpy as np
-    import torch
-    import torch.nn.functional as F
-
-    from graph_marl_b200.model import DQN, NetMon
-    from graph_marl_b200.rollout import CONFIGS
+    from graph_marl_b200.rollout import CONFIGS  # the workload table only (sizes, seeds): no kernels, no classes
     from oracle.cpu_rollout import CpuRollout
 
     c = CONFIGS[cfg_name]
     cores = len(os.sched_getaffinity(0))
-    torch.manual_seed(0)
     N, A = c["n_nodes"], c["n_data"]
-    nm = NetMon(4 * N + 8, c["H"], c["enc"], c["K"], F.leaky_relu, rnn_type=c["rnn"], output_neighbor_hidden=True)
-    dq = DQN(6 * N + 10 + 4 * c["H"], c["dqn"], 4, F.leaky_relu)
+    w_nm, w_dq = _init_weights(c)
     B = envs or (64 * cores if N <= 50 else 2 * cores)
     ro = CpuRollout(N, A, c["topo_seed"], c["congestion"], c["K"], c["rnn"], c["H"], c["enc"], c["dqn"], B, cores,
-                    {k: v.numpy() for k, v in nm.state_dict().items()}, {k: v.numpy() for k, v in dq.state_dict().items()},
-                    replay_capacity=4 * B)
+                    w_nm, w_dq, replay_capacity=4 * B)
     ro.reset()
     for _ in range(max(1, min(warmup, 2))):
         ro.step()
@@ -163,6 +188,21 @@ def cpu_arm(cfg_name, steps, warmup, envs=None, budget_s=20.0):
     return dict(value=B * n / dt, unit=UNIT, cores=cores, kind="port",
                 sample=f"{B} envs x {n} rollout steps of {cfg_name}{' (CPU arm: one shared topology instead of the pool)' if c.get('random_topology') else ''} (C env oracle on {cores} threads + torch CPU NetMon+DQN on {cores} threads, "
                        f"replay insert incl.), {dt:.1f} s"), dt / max(n, 1), B
+
+
+def reference_arm(cfg_name, seconds=8.0):
+    """The UNMODIFIED Python reference (staged at baseline/_ref/src) running its own rollout loop, one process per
+    host core (baseline/ref_rollout.py).  None when the staged copy is absent or the workload is not config 2's."""
+    try:
+        from baseline import ref_rollout
+        from graph_marl_b200.rollout import CONFIGS
+
+        c = CONFIGS[cfg_name]
+        if not ref_rollout.available() or c.get("random_topology"):
+            return None
+        return ref_rollout.time_reference(c, seconds=seconds, warmup_steps=5 if c["n_nodes"] <= 50 else 1)
+    except Exception as ex:  # never hide the GPU number behind the baseline
+        return dict(value=None, unit=UNIT, kind="reference", sample=f"failed: {ex}")
 
 
 _REAL_STDOUT = None
@@ -201,6 +241,12 @@ def main():
     ap.add_argument("--graph-steps", type=int, default=int(os.environ.get("GM_BENCH_GRAPH_STEPS", "10")),
                     help="rollout steps per captured CUDA graph unit (0 = launch every kernel from Python)")
     ap.add_argument("--no-replay", action="store_true")
+    ap.add_argument("--replay", default="compact", choices=["compact", "dense"],
+                    help="replay ring format: compact (env records + NetMon state, dense fields rebuilt when sampled; default) "
+                         "or dense (the reference's 17 dense fields per transition)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --envs (default: the config's size) per GPU; strong: the config's TOTAL env count "
+                         "(cfg2 4096, cfg3 16384) sharded over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--per-kernel", action="store_true", help="also print a per-stage CUDA-event breakdown to stderr")
     a = ap.parse_args()
@@ -213,6 +259,13 @@ def main():
     c = CONFIGS[a.workload]
     N, A = c["n_nodes"], c["n_data"]
     B = a.envs or {"cfg2": 4096, "cfg2ln": 4096, "cfg3": 2048}.get(a.workload, 1024)
+    B_weak = B
+    if a.scaling == "strong":
+        from graph_marl_b200.rollout import shard_envs
+
+        total = a.envs or {"cfg2": 4096, "cfg2ln": 4096, "cfg3": 16384, "cfg4": 8192}[a.workload]
+        lo, hi = shard_envs(total, world, rank)
+        B = hi - lo
     # every step of a captured unit keeps its own observation / state tensors alive in the graph's pool:
     # bound the unit so that those stay under ~24 GB (cfg4 at 8192 envs holds ~15 GB per step)
     step_bytes = 4 * B * (1.5 * A * (6 * N + 10 + 4 * c["H"]) + N * (4 * N + 8) + 2 * N * c["H"])
@@ -225,20 +278,28 @@ def main():
             a.graph_steps = divs[-1]
     config = dict(workload=f"{a.workload}: routing N={N} A={A} topo_seed={c['topo_seed']} congestion={c['congestion']} "
                            f"episode={c['episode_steps']} NetMon H={c['H']} enc={list(c['enc'])} K={c['K']} {c['rnn']} sum "
-                           f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=B * world, math=a.math,
-                  replay_insert=not a.no_replay, replay_overlap="side stream, joined before the end event",
+                           f"+ DQN {list(c['dqn'])}", envs_per_gpu=B, envs_total=(B * world if a.scaling == "weak" else total), math=a.math,
+                  replay_insert=not a.no_replay,
+                  replay_format=("compact: env records before/after + actions/reward/done + NetMon state per transition, dense fields rebuilt by get_batch"
+                                 if a.replay == "compact" else "dense: the reference's 17 fields per transition"),
+                  replay_overlap=("main stream (two small launches)" if a.replay == "compact" else "side stream, joined before the end event"),
                   cuda_graph_steps=a.graph_steps, sharding=f"env instances, {world} rank(s), no collective",
                   l2="per-step working set (obs + node_obs + NetMon activations + replay slots) exceeds the 126 MB L2")
 
     if a.impl == "reference":
         if rank != 0:
             return
-        cb, sec_per_step, Bc = cpu_arm(a.workload, a.steps, a.warmup)
+        cb, sec_per_step, Bc = cpu_arm(a.workload, a.steps, a.warmup, envs=(B_weak if N <= 50 else None), budget_s=60.0)
+        cbr = reference_arm(a.workload)
         line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=sec_per_step * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                    data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (oracle port: C env + torch CPU tensors)"),
+                    ms_per_step=sec_per_step * 1e3, higher_is_better=True, scaling=a.scaling, vs_baseline=None, dtype="f32",
+                    data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (oracle port: C env + torch CPU tensors)",
+                                replay_format="dense: the reference's 17 fields per transition (numpy ring)", replay_overlap="none (host)",
+                                cuda_graph_steps=0),
                     cpu_baseline=cb, gpu_launches=0,
                     e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        if cbr is not None:
+            line["cpu_baseline_reference"] = cbr  # the unmodified Python reference beside the (faster) port
         _emit(line)
         return
 
@@ -287,7 +348,8 @@ def main():
 
     # ---- device-resident arm ---------------------------------------------------------------
     G = a.graph_steps
-    ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank, graph_steps=G)
+    ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank, graph_steps=G,
+                 replay=a.replay)
     ro.reset()
     sampler = ClockSampler(local) if rank == 0 else None
     value, ms, launches, w0, w1 = timed(ro, a.steps, max(a.warmup, 3), host=False)
@@ -301,7 +363,7 @@ def main():
 
     # ---- end-to-end arm: host-supplied draws in, reward out, every step --------------------------
     ro = Rollout(a.workload, num_envs=B, device=dev, math=a.math, with_replay=not a.no_replay, seed=1000 + rank,
-                 host_draws=True, graph_steps=G,
+                 host_draws=True, graph_steps=G, replay=a.replay,
                  host_draw_steps=((a.steps + 2 * max(a.warmup, 10) + 4 * max(G, 1)) // max(G, 1) + 1) * max(G, 1))
     ro.reset()
     value_e, ms_e, _, _, _ = timed(ro, a.steps, max(a.warmup, 3), host=True)
@@ -350,7 +412,7 @@ def main():
                     traffic=traffic.get("aggregate_pk_bytes_per_launch"), algorithmic_bytes_per_launch=agg_bytes, ms_per_launch=agg_ms)
     dominant = roof_gemm if gemm_ms >= env_ms else roof_env
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
-                ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=ms / a.steps, higher_is_better=True, scaling=a.scaling, vs_baseline=None,
                 dtype={"fp32": "f32", "bf16x3": "f32 (tcgen05 bf16 hi/lo split x3, fp32 accumulate; env state int32/f64)",
                        "bf16": "bf16 (single pass, fp32 accumulate) -- reduced precision"}[a.math],
                 data="synthetic", config=config, agent_steps_per_sec=value * A, host_issue_ms_per_step=host_issue_ms, gpu_launches=int(launches), clocks=clocks, e2e=e2e,
@@ -359,6 +421,9 @@ def main():
         try:
             cb, _, _ = cpu_arm(a.workload, steps=10**6, warmup=1, budget_s=15.0)
             line["cpu_baseline"] = cb
+            cbr = reference_arm(a.workload, seconds=6.0)
+            if cbr is not None:
+                line["cpu_baseline_reference"] = cbr
         except Exception as ex:  # the baseline must never hide the GPU number
             line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=len(os.sched_getaffinity(0)), kind="port", sample=f"failed: {ex}")
     _emit(line)

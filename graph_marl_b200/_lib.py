@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libgraphmarl_b200.so")
 GM_MAX_LAYERS = 8
 GM_REPLAY_MAX_FIELDS = 24
 GM_MT_STATE_WORDS = 625
+GM_PCG64_STATE_WORDS = 6
 RNN_TYPES = {"lstm": 0, "lnlstm": 1, "gru": 2, "none": 3}
 AGG_TYPES = {"sum": 0, "mean": 1}
 ACTIVATIONS = {"leaky_relu": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "elu": 4}
@@ -112,6 +113,9 @@ _SIGS = {
                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_replay_insert": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_replay_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gm_pcg64_seed": (None, [C.c_void_p, C.c_uint64]),
+    "gm_pcg64_choice": (None, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "gm_replay_sample_indices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "gm_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_linear_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

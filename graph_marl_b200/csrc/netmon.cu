@@ -997,12 +997,10 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     GM_CHECK_ARG(H > 0 && H <= 256, "hidden size %d: need 1..256", H);
     GM_CHECK_ARG(L >= 1 && L <= GM_MAX_LAYERS && p->enc_units[L - 1] == H, "encoder must end in %d units", H);
     GM_CHECK_ARG(p->rnn_type >= GM_RNN_LSTM && p->rnn_type <= GM_RNN_NONE, "rnn_type %d", p->rnn_type);
-    GM_CHECK_ARG(!(p->rnn_type == GM_RNN_GRU && !p->rnn_carryover),
-                 "gru without carryover is not built (the reference scrambles its state rows, model.py:571)");
     GM_CHECK_ARG(K >= 1 || p->rnn_type == GM_RNN_NONE, "iterations must be >= 1 (model.py:564 fails for 0)");
     GM_CHECK_ARG(max_degree <= DM, "max_degree %d > DM %d", max_degree, DM);
     const bool lstm_like = p->rnn_type == GM_RNN_LSTM || p->rnn_type == GM_RNN_LNLSTM;
-    const int ns = lstm_like ? (p->rnn_carryover ? 2 : 4) : (p->rnn_type == GM_RNN_GRU ? 1 : 1);
+    const int ns = lstm_like ? (p->rnn_carryover ? 2 : 4) : (p->rnn_type == GM_RNN_GRU ? (p->rnn_carryover ? 1 : 2) : 1);
     const int S = ns * H;
     const int64_t R = (int64_t)B * N;
     GM_CHECK_ARG(workspace_bytes >= gm_netmon_workspace_bytes(p, R), "workspace too small");
@@ -1229,14 +1227,17 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     }
     // h0/c0 for the no-carry state live in hbuf[0]/cbuf[0]; keep them untouched in that mode
     const bool nocarry = lstm_like && !p->rnn_carryover;
+    const bool gru_nocarry = p->rnn_type == GM_RNN_GRU && !p->rnn_carryover;
     float* h0_keep = nullptr; float* c0_keep = nullptr;
-    if (nocarry) {
+    if (nocarry || gru_nocarry) {
         h0_keep = w.act0; c0_keep = w.act1;  // encoder buffers are free now (e was consumed)
         int64_t tot = R * H;
         copy_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(hbuf[0], H, h0_keep, H, R, H);
         GM_LAUNCH_CHECK();
-        copy_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(cbuf[0], H, c0_keep, H, R, H);
-        GM_LAUNCH_CHECK();
+        if (nocarry) {
+            copy_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(cbuf[0], H, c0_keep, H, R, H);
+            GM_LAUNCH_CHECK();
+        }
     }
 
     // ---- K x (aggregate, rnn_update) (model.py:509-554) ----------------------------------
@@ -1258,6 +1259,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         const float* hp = h; int64_t ldhp = H;
         const float* cpv = c; int64_t ldcp = H;
         if (nocarry && it == 0) { hp = st_in + 2 * H; ldhp = S; cpv = st_in + 3 * H; ldcp = S; }  // :538-539
+        if (gru_nocarry && it == 0) { hp = st_in + H; ldhp = S; }                                  // :546-547
         int nxt = cur ^ 1;
         int rc = run_cell(p->rnn_update, w.M, H, hp, ldhp, cpv, ldcp, hbuf[nxt], H, cbuf[nxt], H, nullptr, 0, nullptr, 0);
         if (rc) return rc;
@@ -1276,6 +1278,12 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             }
             copy_rows_kernel<<<g, 256, 0, s>>>(h, H, state_out + o, S, R, H); GM_LAUNCH_CHECK();
             copy_rows_kernel<<<g, 256, 0, s>>>(c, H, state_out + o + H, S, R, H); GM_LAUNCH_CHECK();
+        } else if (gru_nocarry) {
+            // model.py:571 stacks (h0, h1) as [2,1,R,H]; _state_reshape_out (:449) then transposes the two LEADING
+            // axes only, so the flat state buffer is all of h0 followed by all of h1 (not interleaved per row).
+            // Reproduced, not fixed: the next step reads row r as [state0 | state1] = flat[r*2H : (r+1)*2H].
+            copy_rows_kernel<<<g, 256, 0, s>>>(h0_keep, H, state_out, H, R, H); GM_LAUNCH_CHECK();
+            copy_rows_kernel<<<g, 256, 0, s>>>(h, H, state_out + R * H, H, R, H); GM_LAUNCH_CHECK();
         } else {
             copy_rows_kernel<<<g, 256, 0, s>>>(h, H, state_out, S, R, H); GM_LAUNCH_CHECK();
         }

@@ -334,6 +334,28 @@ class Routing(NetworkEnv):
         self._calls -= 1
         return out
 
+    def observe_records(self, records, topo_index=None):
+        """Observations of ARBITRARY packed env records (uint8 [n, state_stride], e.g. gathered from the compact
+        replay ring) on this env's topology pool: the same emitters as reset()/step(), nothing is advanced.
+        Returns dict(obs, adj, node_obs, node_agent, agent_node)."""
+        _lib.require_device()
+        n = records.shape[0]
+        assert records.dtype == torch.uint8 and records.shape[1] == self._layout["stride"] and records.is_contiguous()
+        N, A, dev = self._N, self._A, self.device
+        e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        out = dict(obs=e((n, A, self.obs_width()), torch.float32), adj=e((n, A, A), torch.int8),
+                   node_obs=e((n, N, 4 * N + 8), torch.float32), node_agent=e((n, N, A), torch.int8),
+                   agent_node=e((n, A), torch.int32))
+        d = self._desc()
+        d.B, d.state = n, records.data_ptr()
+        d.topo_index = None if topo_index is None else topo_index.data_ptr()
+        io = _lib.RoutingIO()
+        for k, v in out.items():
+            setattr(io, k, v.data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().gm_routing_observe(C.byref(d), C.byref(io), _lib.current_stream()))
+        return out
+
     def _ret(self, t):
         return t if self.batched else t[0].cpu().numpy()
 

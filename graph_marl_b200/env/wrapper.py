@@ -13,12 +13,15 @@ import torch
 
 
 class NetMonWrapper:
-    def __init__(self, env, netmon, startup_iterations, split_obs=False) -> None:
+    def __init__(self, env, netmon, startup_iterations, split_obs=False, graph_obs_fp32=True) -> None:
         if startup_iterations < 1:
             raise AssertionError("Number of startup iterations must be >= 1")
         self.env, self.netmon = env, netmon
         self.startup_iterations = startup_iterations
         self.split_obs = split_obs  # batched mode: return (agent_obs, graph_obs) instead of the concat
+        # batched split mode on the tensor-core path: False = the graph observation is produced once, tile-packed
+        # (model.PackedRows), for a DQN of the same math mode; nothing writes or reads its fp32 rows
+        self.graph_obs_fp32 = graph_obs_fp32
         self.device = next(netmon.parameters()).device
         # attributes main.py / sl.py read (wrapper.py:13-19)
         self.node_obs = self.node_adj = self.node_agent_matrix = None
@@ -60,7 +63,19 @@ class NetMonWrapper:
         return self._with_graph_obs(obs), adj, reward, done, info
 
     def freeze(self):
-        """Disable message passing for the rest of the episode (wrapper.py:53-58)."""
+        """Disable message passing for the rest of the episode (wrapper.py:53-58).  The frozen path serves
+        `netmon_out` (the node readout of the latest NetMon step) at the agents' new nodes; the lean batched mode
+        only reads out the agents' rows, so the node readout is rebuilt here by repeating that step from the state
+        before it (same kernels, same inputs: the state it reproduces is the current one)."""
+        if not self.frozen and self.netmon_out is None and self.current_netmon_state is not None:
+            env = self.env
+            nbr_all, deg, list_index = env.get_adjacency_lists()
+            with torch.no_grad():
+                keep = self.netmon.state
+                self.netmon.state = self.last_netmon_state
+                self.netmon_out, _ = self.netmon.forward_lists(env._out["node_obs"], nbr_all, deg, list_index,
+                                                               nbr_all.shape[-1] - 1, want_node_out=True)
+                self.netmon.state = keep
         self.frozen = True
 
     def get_netmon_info(self):
@@ -88,7 +103,7 @@ class NetMonWrapper:
         if self.frozen:
             # wrapper.py:67-75: agents keep reading the frozen node outputs at their new position
             if self.netmon_out is None:
-                raise RuntimeError("freeze() needs the node readout: construct NetMonWrapper with split_obs=False")
+                raise RuntimeError("freeze() before the first NetMon step")
             idx = agent_node.long().unsqueeze(-1).expand(-1, -1, self.netmon_out.shape[-1])
             return self._ret(torch.gather(self.netmon_out, 1, idx))
         if not self._batched:
@@ -102,6 +117,6 @@ class NetMonWrapper:
             lean = self._batched and self.split_obs
             self.netmon_out, agent_out = self.netmon.forward_lists(
                 node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=not lean,
-                want_agent_pk=lean)
+                want_agent_pk=lean, want_agent_fp32=self.graph_obs_fp32 or not lean)
             self.current_netmon_state = self.netmon.state
         return self._ret(agent_out)

@@ -51,6 +51,21 @@ def _rows2d(t):
     return t.reshape(-1, D).float().contiguous()
 
 
+class PackedRows:
+    """Activation rows that exist ONLY as tile-packed bf16 hi/lo blocks (csrc/gemm_sm100.cuh), i.e. the graph
+    observation of the batched rollout when nothing needs its fp32 rows: NetMon's agent readout writes it, the
+    tensor-core DQN of the same math mode pulls it with bulk copies."""
+
+    is_cuda = True
+
+    def __init__(self, buf, shape, math):
+        self.buf, self.shape, self.math = buf, tuple(shape), math
+
+    @property
+    def device(self):
+        return self.buf.device
+
+
 class _PackedWeights:
     """Cache of the tensor-core weight pack (bf16 hi/lo tiles) of a module; rebuilt whenever a
     parameter's storage or version counter changes (optimizer step, load_state_dict, .to())."""
@@ -177,14 +192,18 @@ class DQN(nn.Module):
         rows = a2.shape[0]
         g2, Dg = None, 0
         g_pk = None
-        if obs_g is not None:
+        if isinstance(obs_g, PackedRows):
+            if obs_g.math != self.math or self.math == "fp32":
+                raise _lib.GraphMarlError(f"graph observation is tile-packed for math={obs_g.math}, the DQN runs {self.math}")
+            Dg, g_pk = obs_g.shape[-1], obs_g.buf
+        elif obs_g is not None:
             Dg = obs_g.shape[-1]
             g2 = _rows2d(obs_g)
             pk = getattr(obs_g, "_gm_pk", None)  # tile-packed copy written by NetMon's readout (same math mode)
             if pk is not None and pk[1] == self.math and self.math != "fp32":
                 g_pk = pk[0]
         dev = obs_a.device
-        p = self._params(split=Da if g2 is not None else 0)
+        p = self._params(split=Da if Dg > 0 else 0)
         nbytes = _lib.lib().gm_dqn_workspace_bytes(C.byref(p), rows)
         ws = self._ws.get(nbytes, dev)
         q = torch.empty((rows, self.num_actions), dtype=torch.float32, device=dev) if want_q else None
@@ -324,10 +343,12 @@ class NetMon(nn.Module):
         return H + (H if self.output_global_hidden else 0) + (max_degree * H if self.output_neighbor_hidden else 0)
 
     def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
-                      want_node_out=False, agent_out=None, want_agent_pk=False):
+                      want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True):
         """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
         nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
-        Updates self.state; returns (node_out | None, agent_out | None)."""
+        Updates self.state; returns (node_out | None, agent_out | None).  want_agent_fp32=False with
+        want_agent_pk (tensor-core modes): the agents' graph observation is written ONCE, tile-packed, and
+        returned as PackedRows (no fp32 rows)."""
         _lib.require_device()
         if not x.is_cuda:
             raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
@@ -345,14 +366,16 @@ class NetMon(nn.Module):
         node_out = torch.empty((B, N, O), dtype=torch.float32, device=dev) if want_node_out else None
         A = 0
         ld = O
+        agent_pk = None
         if agent_node is not None:
             A = agent_node.shape[-1]
-            if agent_out is None:
+            if want_agent_pk and self.math != "fp32" and self.hidden_features % 32 == 0:
+                agent_pk = torch.empty(int(_lib.lib().gm_packed_activation_bytes(B * A, O)), dtype=torch.uint8, device=dev)
+            pk_only = agent_pk is not None and not want_agent_fp32 and agent_out is None
+            if agent_out is None and not pk_only:
                 agent_out = torch.empty((B, A, O), dtype=torch.float32, device=dev)
-            ld = agent_out.stride(-2)
-        agent_pk = None
-        if want_agent_pk and agent_node is not None and self.math != "fp32" and self.hidden_features % 32 == 0:
-            agent_pk = torch.empty(int(_lib.lib().gm_packed_activation_bytes(B * A, O)), dtype=torch.uint8, device=dev)
+            if agent_out is not None:
+                ld = agent_out.stride(-2)
         DM = nbr_all.shape[-1]
         if list_index is None and nbr_all.shape[0] != B:
             if nbr_all.shape[0] != 1:
@@ -366,6 +389,8 @@ class NetMon(nn.Module):
                 _lib.current_stream()))
         self.state = st_out
         if agent_pk is not None:
+            if agent_out is None:
+                return node_out, PackedRows(agent_pk, (B, A, O), self.math)
             agent_out._gm_pk = (agent_pk, self.math)  # consumed by DQN.act of the same math mode
         return node_out, (agent_out if agent_node is not None else None)
 
@@ -447,12 +472,14 @@ class NetMon(nn.Module):
         if lstm_like:
             new = torch.stack((h1, c1)) if self.rnn_carryover else torch.stack((h0, c0, h1, c1))
         elif self.rnn_type == "gru":
-            if not self.rnn_carryover:
-                raise NotImplementedError("gru without carryover (reference state layout is scrambled, model.py:571)")
             new = h1.unsqueeze(0)
         else:
             new = h.unsqueeze(0)
-        self.state = new.transpose(0, 1).reshape(B, N, -1)
+        if self.rnn_type == "gru" and not self.rnn_carryover:
+            # model.py:571 + :449: [2,1,R,H] transposed on its two leading axes only -> all of h0, then all of h1
+            self.state = torch.cat((h0.reshape(-1), h1.reshape(-1))).reshape(B, N, -1)
+        else:
+            self.state = new.transpose(0, 1).reshape(B, N, -1)
         hb = h.reshape(B, N, -1)
         parts = [hb]
         if self.output_global_hidden:

@@ -29,10 +29,55 @@ ADD_ORDER = ["obs", "action", "reward", "next_obs", "adj", "next_adj", "done", "
              "next_node_adj", "next_node_agent_matrix"]
 
 
-class ReplayBuffer(object):
+class _RingSampler(object):
+    """Index streams of get_batch (replaybuffer.py:101, 111-130).  Host mode draws from numpy's
+    `default_rng(seed)` like the reference; `device_sampler=True` keeps a bit-identical PCG64 stream in HBM
+    (csrc/replay_sampler.cu) so that a batch of sequences is sampled without any host round trip (`idx` of the
+    returned batches is then a device tensor)."""
+
+    def _init_sampler(self, seed, device_sampler):
+        self._random_generator = np.random.default_rng(seed)
+        self._pcg_dev = None
+        if device_sampler:
+            st = np.zeros(_lib.GM_PCG64_STATE_WORDS, np.uint64)
+            _lib.lib().gm_pcg64_seed(_lib.ptr(st), int(seed) & (2**64 - 1))
+            self._pcg_dev = torch.from_numpy(st.view(np.int64)).to(self.device)
+
+    def _index_rows(self, batch_size, sequence_length):
+        """[max(sequence_length, 1), batch_size] ring slots: numpy int64 (host mode) or a device tensor."""
+        T = max(int(sequence_length), 1)
+        if self._pcg_dev is not None:
+            _lib.require_device()
+            out = torch.empty((T, batch_size), dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().gm_replay_sample_indices(self._pcg_dev.data_ptr(), self.count, self.index,
+                                                               batch_size, int(sequence_length), out.data_ptr(),
+                                                               _lib.current_stream()))
+            return out
+        if sequence_length <= 1:
+            return self._random_generator.choice(self.count, batch_size, replace=True, p=None)[None]
+        buffer_start = self.index % self.count
+        batch_sequence_start = self._random_generator.choice(self.count - sequence_length, batch_size,
+                                                             replace=True, p=None)
+        batch_sequence_start = (buffer_start + batch_sequence_start) % self.count
+        return np.stack([(batch_sequence_start + offset) % self.count for offset in range(sequence_length)])
+
+    def get_batch(self, batch_size, device, sequence_length=0) -> Iterator[TransitionBatch]:
+        rows = self._index_rows(batch_size, sequence_length)
+        for offset in range(rows.shape[0]):
+            yield self._get_transition_batch(rows[offset], device)
+
+    def _device_indices(self, indices):
+        if torch.is_tensor(indices):
+            return indices.to(device=self.device, dtype=torch.int64).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)).to(self.device)
+
+
+
+class ReplayBuffer(_RingSampler):
     def __init__(self, seed, buffer_size, n_agents, observation_size, agent_state_size, n_nodes=0,
                  node_observation_size=0, node_state_size=0, node_aux_size=0, half_precision=False,
-                 device="cuda"):
+                 device="cuda", device_sampler=False):
         self.buffer_size = int(buffer_size)
         self.count = 0
         self.index = 0
@@ -52,7 +97,7 @@ class ReplayBuffer(object):
             setattr(self, name, torch.zeros((self.buffer_size, *shape), dtype=dt, device=self.device))
         self._consts = {}
         self._dev_index = None  # _lib.DeviceCounter in CUDA-graph mode (rollout.Rollout)
-        self._random_generator = np.random.default_rng(seed)
+        self._init_sampler(seed, device_sampler)
         # dtype conversion of _get_transition_batch (replaybuffer.py:132-187)
         self._out_dtype = {n: torch.float32 for n in shapes}
         self._out_dtype.update(action=torch.int64, done=torch.bool, episode_done=torch.bool)
@@ -149,23 +194,10 @@ class ReplayBuffer(object):
         self.index = (self.index + n) % self.buffer_size
 
     # ---- sample ------------------------------------------------------------------------------
-    def get_batch(self, batch_size, device, sequence_length=0) -> Iterator[TransitionBatch]:
-        if sequence_length <= 1:
-            indices = self._random_generator.choice(self.count, batch_size, replace=True, p=None)
-            yield self._get_transition_batch(indices, device)
-            return
-        buffer_start = self.index % self.count
-        batch_sequence_start = self._random_generator.choice(self.count - sequence_length, batch_size,
-                                                             replace=True, p=None)
-        batch_sequence_start = (buffer_start + batch_sequence_start) % self.count
-        for offset in range(sequence_length):
-            indices = (batch_sequence_start + offset) % self.count
-            yield self._get_transition_batch(indices, device)
-
     def _get_transition_batch(self, indices, device) -> TransitionBatch:
         _lib.require_device()
         n = len(indices)
-        idx = torch.as_tensor(np.ascontiguousarray(indices, dtype=np.int64)).to(self.device)
+        idx = self._device_indices(indices)
         names = [f for f in TransitionBatch._fields if f != "idx"]
         fields = (_lib.ReplayField * len(names))()
         outs = {}
@@ -195,9 +227,153 @@ class ReplayBuffer(object):
         dev = torch.device(device)
         return TransitionBatch(indices, *[outs[f].to(dev, non_blocking=True) for f in names])
 
-    def get_recent_indices(self, last_n):
-        if last_n is None:
-            return np.arange(self.count), np.arange(self.count)
-        m = min(self.count, last_n)
-        x = self.index - m + np.arange(m)
-        return x, x % self.count
+
+class CompactReplayBuffer(_RingSampler):
+    """Compact replay format for the batched rollout: a transition keeps only what cannot be recomputed
+
+        rec / next_rec   the packed Routing env record before / after the step (csrc/routing_env.cu layout)
+        topo             topology-pool index of the env
+        action i8[A], reward f32[A], done[A], episode_done, node_state f32[N,S]
+
+    (23 kB instead of the reference's 141 kB at BASELINE config 2) and `get_batch` rebuilds all 17 fields of the
+    reference's TransitionBatch (replaybuffer.py:132-187) on the device: the dense one-hot `obs` / `node_obs` /
+    `adj` / `node_agent_matrix` rows of both sides of the transition come from the env's own observation emitters
+    run on the gathered records (gm_routing_observe), `node_adj` / `node_aux` from the topology pool, and the
+    graph-observation tail of `obs` / `next_obs` from two NetMon steps starting at `node_state` -- the same
+    recomputation the learner performs anyway before it uses them (main.py:854-880, 909-915).  With unchanged NetMon
+    weights every field is bit-identical to what the dense ring returns (tests/test_gpu_rollout.py).
+
+    `env` is the batched NetMonWrapper over Routing that produces the transitions.  Insert is two small launches per
+    batched step: `stage()` BEFORE env.step (the records are advanced in place) and `commit()` after it."""
+
+    FIELDS = ("rec", "next_rec", "topo", "action", "reward", "done", "episode_done", "node_state")
+
+    def __init__(self, seed, buffer_size, env, device_sampler=False):
+        self.env = env
+        be = env.get()
+        self.device = be.device
+        self.buffer_size = int(buffer_size)
+        self.count = 0
+        self.index = 0
+        A, N = be._A, be._N
+        S = env.netmon.get_state_size()
+        stride = be._layout["stride"]
+        z = lambda shape, dt: torch.zeros((self.buffer_size, *shape), dtype=dt, device=self.device)
+        self.rec, self.next_rec = z((stride,), torch.uint8), z((stride,), torch.uint8)
+        self.topo = z((), torch.int32)
+        self.action, self.reward, self.done = z((A,), torch.int8), z((A,), torch.float32), z((A,), torch.bool)
+        self.episode_done = z((), torch.bool)
+        self.node_state = z((N, S), torch.float32)
+        self._zero_topo = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        self._flags = {v: torch.full((1,), v, dtype=torch.bool, device=self.device) for v in (False, True)}
+        self._dev_index = None  # _lib.DeviceCounter in CUDA-graph mode (rollout.Rollout)
+        self._staged = False
+        self._init_sampler(seed, device_sampler)
+
+    def bytes_per_transition(self):
+        return sum(getattr(self, f)[0].numel() * getattr(self, f).element_size() for f in self.FIELDS)
+
+    def _insert(self, items, n):
+        """items: (ring, source tensor [n or 1 rows], convert, broadcast)."""
+        fields = (_lib.ReplayField * _lib.GM_REPLAY_MAX_FIELDS)()
+        keep = []
+        for k, (ring, src, convert, bcast) in enumerate(items):
+            f = fields[k]
+            f.ring, f.src, f.elem_bytes = ring.data_ptr(), src.data_ptr(), ring[0].numel() * ring.element_size()
+            f.convert, f.broadcast = convert, bcast
+            keep.append(src)
+        index, index_dev = self.index, None
+        if self._dev_index is not None:
+            index, index_dev = self._dev_index.offset(self.index) % self.buffer_size, self._dev_index.ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gm_replay_insert(fields, len(items), self.buffer_size, index, index_dev, n,
+                                                   _lib.current_stream()))
+        return keep
+
+    def stage(self, num):
+        """Before env.step: the records (and topology indices) that produced the current observations."""
+        _lib.require_device()
+        be = self.env.get()
+        n = int(num)
+        assert n == be.num_envs and n <= self.buffer_size
+        ti = be._topo_index
+        items = [(self.rec, be._state, 0, 0), (self.topo, self._zero_topo if ti is None else ti, 0, 1 if ti is None else 0)]
+        self._keep0 = self._insert(items, n)
+        self._staged = True
+
+    def commit(self, action, reward, done, episode_done, node_state, num):
+        """After env.step (+ the NetMon step): completes the `num` transitions staged at the ring head."""
+        assert self._staged, "CompactReplayBuffer.commit() without stage()"
+        be = self.env.get()
+        n = int(num)
+        action = action.reshape(n, -1)
+        conv = 4 if action.dtype == torch.int32 else 0
+        if not conv and action.dtype != torch.int8:
+            action = action.to(torch.int8)
+        done_b = done.contiguous().view(torch.bool) if done.dtype in (torch.uint8, torch.int8) else done.to(torch.bool).contiguous()
+        if torch.is_tensor(episode_done):
+            ep, ep_b = episode_done.to(torch.bool).reshape(-1).contiguous(), 0 if episode_done.numel() == n else 1
+        else:
+            ep, ep_b = self._flags[bool(episode_done)], 1
+        if node_state is None or (isinstance(node_state, (int, float)) and node_state == 0):
+            ns, ns_b = torch.zeros_like(self.node_state[:1]), 1  # main.py:692-696 stores 0 before the first step
+        else:
+            ns, ns_b = node_state.reshape(n, *self.node_state.shape[1:]).contiguous(), 0
+        items = [(self.next_rec, be._state, 0, 0), (self.action, action.contiguous(), conv, 0),
+                 (self.reward, reward.reshape(n, -1).contiguous(), 0, 0), (self.done, done_b.reshape(n, -1), 0, 0),
+                 (self.episode_done, ep, 0, ep_b), (self.node_state, ns, 0, ns_b)]
+        self._keep1 = self._insert(items, n)
+        self._staged = False
+        self.count = min(self.buffer_size, self.count + n)
+        self.index = (self.index + n) % self.buffer_size
+
+    # ---- sample: gather the compact fields, rebuild the reference's 17 dense fields ----------------
+    def _gather(self, idx):
+        n = idx.shape[0]
+        spec = [("rec", torch.uint8, 0), ("next_rec", torch.uint8, 0), ("topo", torch.int32, 0), ("action", torch.int64, 2),
+                ("reward", torch.float32, 0), ("done", torch.bool, 0), ("episode_done", torch.bool, 0),
+                ("node_state", torch.float32, 0)]
+        fields = (_lib.ReplayField * len(spec))()
+        out = {}
+        for k, (name, od, conv) in enumerate(spec):
+            ring = getattr(self, name)
+            out[name] = torch.empty((n, *ring.shape[1:]), dtype=od, device=self.device)
+            fields[k].ring, fields[k].dst, fields[k].convert = ring.data_ptr(), out[name].data_ptr(), conv
+            fields[k].elem_bytes = ring[0].numel() * ring.element_size()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().gm_replay_sample(fields, len(spec), idx.data_ptr(), n, _lib.current_stream()))
+        return out
+
+    def _get_transition_batch(self, indices, device) -> TransitionBatch:
+        _lib.require_device()
+        env, be = self.env, self.env.get()
+        nm, pool = env.netmon, be._pool
+        idx = self._device_indices(indices)
+        g = self._gather(idx)
+        n = idx.shape[0]
+        topo = g["topo"]
+        cur = be.observe_records(g["rec"], topo)
+        nxt = be.observe_records(g["next_rec"], topo)
+        be.get_nodes_adjacency(), be.get_node_aux()  # materialise the pool's dense tables
+        tl = topo.long()
+        node_adj = pool.node_adj.index_select(0, tl).float()
+        node_aux = pool.apsp_f32.index_select(0, tl)
+        # graph-observation tails: NetMon from the stored state on the current, then on the next node view
+        saved = nm.state
+        with torch.no_grad():
+            nm.state = g["node_state"]
+            md = pool.nbr_all.shape[-1] - 1
+            _, tail = nm.forward_lists(cur["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=cur["agent_node"])
+            _, ntail = nm.forward_lists(nxt["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=nxt["agent_node"])
+        nm.state = saved
+        A = be._A
+        f = dict(
+            obs=torch.cat((cur["obs"], tail), -1), action=g["action"], reward=g["reward"],
+            next_obs=torch.cat((nxt["obs"], ntail), -1), adj=cur["adj"].float(), next_adj=nxt["adj"].float(),
+            done=g["done"], episode_done=g["episode_done"],
+            agent_state=torch.empty((n, A, 0), dtype=torch.float32, device=self.device),
+            node_obs=cur["node_obs"], node_adj=node_adj, node_state=g["node_state"], node_aux=node_aux,
+            node_agent_matrix=cur["node_agent"].float(), next_node_obs=nxt["node_obs"], next_node_adj=node_adj,
+            next_node_agent_matrix=nxt["node_agent"].float())
+        dev = torch.device(device)
+        return TransitionBatch(indices, *[f[k].to(dev, non_blocking=True) for k in TransitionBatch._fields if k != "idx"])

@@ -16,9 +16,9 @@ import torch.nn.functional as F
 from .env.network import Network
 from .env.routing import Routing
 from .env.wrapper import NetMonWrapper
-from .model import DQN, NetMon
+from .model import DQN, NetMon, PackedRows
 from .policy import EpsilonGreedy
-from .replaybuffer import ReplayBuffer
+from .replaybuffer import CompactReplayBuffer, ReplayBuffer
 
 CONFIGS = {
     # BASELINE.json configs[1]: routing single graph, seed 923430603, DQN + NetMon, 4096 envs
@@ -62,7 +62,9 @@ def aggregate_throughput(units_per_rank, ms_local, world_size):
 class Rollout:
     def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
                  epsilon=1.0, seed=0, with_replay=True, host_draws=False, overlap_replay=True, host_draw_steps=64,
-                 graph_steps=0):
+                 graph_steps=0, replay="compact", device_sampler=False):
+        """replay: "compact" (default; replaybuffer.CompactReplayBuffer: env records + NetMon state, dense fields are
+        rebuilt when sampled) or "dense" (the reference's 17 dense fields per transition, replaybuffer.ReplayBuffer)."""
         c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
         self.cfg, self.B, self.device = c, num_envs, torch.device(device)
         N, A = c["n_nodes"], c["n_data"]
@@ -77,7 +79,12 @@ class Rollout:
         Dn, Da = 4 * N + 8, 6 * N + 10
         self.netmon = NetMon(Dn, c["H"], c["enc"], c["K"], F.leaky_relu, rnn_type=c["rnn"], agg_type="sum",
                              output_neighbor_hidden=True, math=math).to(device).eval()
-        self.env = NetMonWrapper(self.base_env, self.netmon, 1, split_obs=True)
+        assert replay in ("compact", "dense")
+        self.compact = bool(with_replay) and replay == "compact"
+        # the compact ring does not store the graph observation (it is recomputed when sampled): on the tensor-core
+        # path it then exists only tile-packed, written once by the readout and pulled by the DQN's bulk copies
+        lean_graph_obs = (self.compact or not with_replay) and math != "fp32" and c["H"] % 32 == 0
+        self.env = NetMonWrapper(self.base_env, self.netmon, 1, split_obs=True, graph_obs_fp32=not lean_graph_obs)
         Dj = Da + self.netmon.get_out_features()
         self.model = DQN(Dj, c["dqn"], 4, F.leaky_relu, math=math).to(device).eval()
         args = SimpleNamespace(epsilon=epsilon, step_before_train=10**9, epsilon_update_freq=100, epsilon_decay=0.996)
@@ -88,7 +95,11 @@ class Rollout:
             per_transition = 4 * (2 * A * Dj + 2 * N * Dn + N * self.netmon.get_state_size() + N * N) + 2 * (A * A + N * N + N * A)
             steps_fit = max(2, min(8, int(48e9 // (per_transition * num_envs))))
             cap = replay_capacity or steps_fit * num_envs
-            self.buff = ReplayBuffer(seed, cap, A, Dj, 0, N, Dn, self.netmon.get_state_size(), N, device=device)
+            if self.compact:
+                self.buff = CompactReplayBuffer(seed, cap, self.env, device_sampler=device_sampler)
+            else:
+                self.buff = ReplayBuffer(seed, cap, A, Dj, 0, N, Dn, self.netmon.get_state_size(), N, device=device,
+                                         device_sampler=device_sampler)
         self.sizes = dict(N=N, A=A, Dn=Dn, Da=Da, Dj=Dj, H=c["H"], K=c["K"])
         self.host_draws = host_draws
         if host_draws:
@@ -102,7 +113,8 @@ class Rollout:
             self._h_reward = pin((B, A), torch.float32)
             self._h_steps, self._h_cursor = T, 0
             self.refresh_host_draws()
-        self.overlap_replay = overlap_replay and with_replay
+        # the dense insert (141 kB per transition) is worth a side stream; the compact one is two small launches
+        self.overlap_replay = overlap_replay and with_replay and not self.compact
         self._replay_stream = torch.cuda.Stream(device=self.device) if self.overlap_replay else None
         self.graph_steps = int(graph_steps)
         self._graphs, self._graph_pool, self._static, self._graph_tables = {}, None, None, None
@@ -179,6 +191,8 @@ class Rollout:
         else:
             actions = self.policy(obs, adj)
         self._mark("dqn_act")
+        if self.compact:
+            self.buff.stage(self.B)  # the env records are advanced in place: snapshot them into the ring first
         next_obs_a, next_adj, reward, done, info = self.base_env.step(actions)
         self._mark("env_step")
         next_obs = env._with_graph_obs(next_obs_a)
@@ -186,7 +200,9 @@ class Rollout:
         next_info = env.get_netmon_info()
         self.episode_step += 1
         episode_done = self.episode_step >= c["episode_steps"]
-        if self.buff is not None:
+        if self.compact:
+            self.buff.commit(actions, reward, done, episode_done, last_state, num=self.B)
+        elif self.buff is not None:
             node_state = last_state if last_state is not None else 0
             if self.overlap_replay:
                 # the insert is off the critical path (nothing in the next step reads the ring): run it on a
@@ -214,21 +230,31 @@ class Rollout:
     def _carried(self):
         env, be = self.env, self.base_env
         obs_a, obs_g = self.obs
-        pk = getattr(obs_g, "_gm_pk", None)
-        d = dict(obs_a=obs_a, obs_g=obs_g, adj=self.adj, cur=env.current_netmon_state, node_obs=be._out["node_obs"],
+        d = dict(obs_a=obs_a, adj=self.adj, cur=env.current_netmon_state, node_obs=be._out["node_obs"],
                  node_agent=be._out["node_agent"])
+        if isinstance(obs_g, PackedRows):  # graph observation exists only tile-packed
+            d["pk"] = obs_g.buf
+            self._pk_shape = obs_g.shape
+            pk = (obs_g.buf, obs_g.math)
+        else:
+            d["obs_g"] = obs_g
+            pk = getattr(obs_g, "_gm_pk", None)
+            if pk is not None:
+                d["pk"] = pk[0]
         if env.last_netmon_state is not None:
             d["last"] = env.last_netmon_state
-        if pk is not None:
-            d["pk"] = pk[0]
         return d, (pk[1] if pk is not None else None)
 
     def _adopt(self, t, math):
         """Point every cross-step reference at the tensors in `t`."""
         env, be = self.env, self.base_env
-        if "pk" in t:
-            t["obs_g"]._gm_pk = (t["pk"], math)
-        self.obs, self.adj = (t["obs_a"], t["obs_g"]), t["adj"]
+        if "obs_g" not in t:
+            obs_g = PackedRows(t["pk"], self._pk_shape, math)
+        else:
+            obs_g = t["obs_g"]
+            if "pk" in t:
+                obs_g._gm_pk = (t["pk"], math)
+        self.obs, self.adj = (t["obs_a"], obs_g), t["adj"]
         env.current_netmon_state = t["cur"]
         env.netmon.state = t["cur"]
         if "last" in t:
@@ -245,6 +271,9 @@ class Rollout:
             self.buff.index, self.buff.count = c[3]
 
     def _sync_device_counters(self):
+        # a replay insert still pending on the side stream reads the ring-index counter (and the static
+        # observation tensors): the main stream must not overwrite either before that insert has run
+        self.join_streams()
         self.base_env._dev_step.set(self.base_env._calls)
         self.policy._dev_step.set(self.policy._step)
         if self.buff is not None:
@@ -295,6 +324,7 @@ class Rollout:
         """After eager steps the carried state lives in fresh tensors: move it into the static ones."""
         cur, math = self._carried()
         if cur["obs_a"] is not self._static["obs_a"]:
+            self.join_streams()  # pending side-stream inserts may still read the static tensors
             for k, v in self._static.items():
                 v.copy_(cur[k])
             self._adopt(self._static, math)

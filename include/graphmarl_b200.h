@@ -41,7 +41,7 @@ typedef enum {
 
 GM_API const char* gm_last_error(void);
 /* ABI version, bumped on any signature/struct change. */
-GM_API int gm_abi_version(void);   /* currently 4 */
+GM_API int gm_abi_version(void);   /* currently 5 */
 /* 0 if a CUDA device with compute capability 10.x is present, else GM_ERR_NO_DEVICE. */
 GM_API int gm_device_check(void);
 
@@ -303,6 +303,20 @@ GM_API int gm_replay_insert(const gm_replay_field* fields, int32_t n_fields, int
  * ReplayBuffer._get_transition_batch; indices i64[n] on device */
 GM_API int gm_replay_sample(const gm_replay_field* fields, int32_t n_fields, const int64_t* indices,
                      int64_t n, void* stream);
+
+/* Index streams of ReplayBuffer.get_batch (src/replaybuffer.py:101, :111-130): numpy's
+ * default_rng(seed) (PCG64 seeded through SeedSequence) and Generator.choice(n, size, replace=True),
+ * restated bit-exactly.  `state` is GM_PCG64_STATE_WORDS uint64 (128-bit LCG state hi/lo, increment
+ * hi/lo, "has buffered uint32" flag, buffered uint32). */
+#define GM_PCG64_STATE_WORDS 6
+GM_API void gm_pcg64_seed(uint64_t* state, uint64_t seed);                             /* host: default_rng(seed) */
+GM_API void gm_pcg64_choice(uint64_t* state, int64_t n, int64_t size, int64_t* out);   /* host: rng.choice(n, size) */
+/* device-side sampler: the generator state lives in HBM (state_dev, seeded on the host and copied) and
+ * advances there; out i64[max(seq_len,1), batch] (device) receives the ring slots of get_batch:
+ * seq_len <= 1: choice(count, batch); else start = (index % count + choice(count - seq_len, batch)) % count
+ * and row o = (start + o) % count.  No host round trip. */
+GM_API int gm_replay_sample_indices(uint64_t* state_dev, int64_t count, int64_t index, int32_t batch,
+                             int32_t seq_len, int64_t* out, void* stream);
 
 /* ======================================================================== */
 /* building blocks exposed for tests / profiling                             */

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 G = load_golden("netmon")
 TOL_ROLLOUT = {"lstm": 1e-4, "gru": 1e-4, "none": 1e-4, "lnlstm": 2e-3}
-SKIP = {"gru_nocarry_k2"}  # reference state layout is scrambled (model.py:571); not built
+SKIP = set()  # gru_nocarry_k2: the reference's scrambled state layout (model.py:571, :449) is reproduced
 
 
 def _netmon(cfg, in_features, math="fp32"):
@@ -226,6 +226,98 @@ def test_wrapper_closed_loop_golden():
         assert np.abs(env.current_netmon_state.cpu().numpy()[0] - g["cur_state"][t][0]).max() < 1e-4
         node_obs, node_adj, nam = env.get_netmon_info()
         assert node_obs.shape == (20, 88) and node_adj.shape == (20, 20) and nam.shape == (20, 20)
+
+
+def test_replay_half_precision_golden():
+    """ReplayBuffer(half_precision=True) (replaybuffer.py:52-54): float fields are stored as fp16 (round to nearest
+    even, like numpy's assignment) and sampled back as fp32 (gm_replay_sample convert 3); flags / actions as usual."""
+    from graph_marl_b200.replaybuffer import ReplayBuffer
+
+    g = load_golden("replay_half")
+    seed, cap, A, D, S, N, Dn, Sn, Ax, n_add = [int(x) for x in g["cfg"]]
+    rb = ReplayBuffer(seed, cap, A, D, S, N, Dn, Sn, Ax, half_precision=True)
+    assert rb.obs.dtype == torch.float16 and rb.node_state.dtype == torch.float16 and rb.reward.dtype == torch.float16
+    T = lambda k, i: g["tr_" + k][i]
+    for i in range(n_add):
+        rb.add(T("obs", i), T("action", i), T("reward", i), T("next_obs", i), T("adj", i), T("next_adj", i),
+               T("done", i), bool(T("episode_done", i)), 0, T("node_state", i), T("node_aux", i), T("node_obs", i),
+               T("node_adj", i), T("node_agent", i), T("next_node_obs", i), T("next_node_adj", i),
+               T("next_node_agent", i))
+    b = next(rb.get_batch(6, "cuda"))
+    assert np.array_equal(b.idx, g["idx_full"])
+    for f in b._fields:
+        if f == "idx":
+            continue
+        got, ref = getattr(b, f).cpu().numpy(), g["full_" + f]
+        assert got.dtype == ref.dtype, f
+        assert np.array_equal(got, ref), f
+
+
+def test_wrapper_freeze_golden():
+    """NetMonWrapper.freeze() (wrapper.py:53-75) in compat mode against the reference: after the freeze the NetMon
+    state stops advancing and the agents read the frozen node readout at their new nodes; `env.data` exposes the
+    packets with the reference's attribute names (routing.py:12-40) for the heuristic policies (policy.py:90-139)."""
+    from graph_marl_b200.env.network import Network
+    from graph_marl_b200.env.routing import Routing
+    from graph_marl_b200.env.wrapper import NetMonWrapper
+    from graph_marl_b200.model import NetMon
+
+    g = load_golden("wrapper_freeze")
+    Dn, H, e1, K, wseed, startup = [int(x) for x in g["cfg"]]
+    nm = NetMon(Dn, H, (e1,), K, F.leaky_relu, rnn_type="lstm", output_neighbor_hidden=True)
+    nm.load_state_dict({k: torch.from_numpy(v) for k, v in det_weights(netmon_shapes(Dn, H, [e1], "lstm"), wseed).items()})
+    nm = nm.cuda().eval()
+    np.random.seed(77)
+    net = Network(20, random_topology=False, topology_init_seed=923430603)
+    env0 = Routing(net, 20, 1)
+    env = NetMonWrapper(env0, nm, startup)
+    obs, adj = env.reset()
+    assert np.abs(obs - g["joint_obs"][0]).max() < 1e-4
+    fz = int(g["freeze_at"][0])
+    for t in range(g["actions"].shape[0]):
+        if t == fz:
+            env.freeze()
+        obs, adj, rew, done, info = env.step(g["actions"][t])
+        assert np.array_equal(obs[:, :130], g["joint_obs"][t + 1][:, :130]), t
+        assert np.abs(obs - g["joint_obs"][t + 1]).max() < 1e-4, t
+        assert np.abs(env.current_netmon_state.cpu().numpy()[0] - g["cur_state"][t][0]).max() < 1e-4, t
+        assert np.array_equal(env.get_netmon_info()[2], g["node_agent"][t]), t
+        got = np.array([[p.now, p.target, p.edge, p.time, p.ttl, p.shortest_path_weight, p.start] for p in env0.data], dtype=np.int32)
+        assert np.array_equal(got, g["data"][t]), t
+    assert np.array_equal(g["cur_state"][fz - 1], g["cur_state"][-1])  # the recording itself: no step after the freeze
+    assert np.array_equal(np.array([p.size for p in env0.data]), g["sizes"])
+    assert [p.id for p in env0.data] == list(range(20))
+
+
+@pytest.mark.parametrize("math", ["fp32", "bf16x3"])
+def test_wrapper_freeze_batched_lean_mode(math):
+    """freeze() in the batched split mode the rollout uses (only the agents' rows are read out, tile-packed on the
+    tensor-core path): the node readout of the latest NetMon step is rebuilt when freeze() is called, and the frozen
+    graph observations equal those of a wrapper that kept the full node readout all along."""
+    from graph_marl_b200.env.network import Network
+    from graph_marl_b200.env.routing import Routing
+    from graph_marl_b200.env.wrapper import NetMonWrapper
+    from graph_marl_b200.model import NetMon
+
+    B, N, A, H = 37, 20, 20, 64
+    torch.manual_seed(3)
+    nm = NetMon(4 * N + 8, H, (96,), 2, F.leaky_relu, rnn_type="lstm", output_neighbor_hidden=True, math=math).cuda().eval()
+    mk = lambda split, fp32: NetMonWrapper(Routing(Network(N, random_topology=False, topology_init_seed=923430603), A, 1,
+                                                   num_envs=B, seed=5, batched=True), nm, 1, split_obs=split, graph_obs_fp32=fp32)
+    full, lean = mk(False, True), mk(True, False)
+    jo, _ = full.reset()
+    (la, lg), _ = lean.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(7):
+        if t == 3:
+            full.freeze(), lean.freeze()
+        act = torch.randint(0, 4, (B, A), device="cuda", generator=g, dtype=torch.int32)
+        jo, _, r0, _, _ = full.step(act)
+        (la, lg), _, r1, _, _ = lean.step(act)
+        assert torch.equal(r0, r1) and torch.equal(jo[..., :6 * N + 10], la)
+        if t >= 3:
+            assert torch.is_tensor(lg) and torch.equal(jo[..., 6 * N + 10:], lg), t
+            assert torch.equal(full.current_netmon_state, lean.current_netmon_state)
 
 
 def test_ci_known_answer_simple_env_training_reaches_reward_mean_1():

@@ -8,18 +8,28 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _mk(graph_steps, host_draws=False):
+def _mk(graph_steps, host_draws=False, replay="dense", B=96, **kw):
     from graph_marl_b200.rollout import Rollout
 
-    ro = Rollout("cfg2", num_envs=96, math="bf16x3", seed=7, replay_capacity=96 * 16, graph_steps=graph_steps,
-                 host_draws=host_draws, host_draw_steps=40)
+    ro = Rollout("cfg2", num_envs=B, math="bf16x3", seed=7, replay_capacity=B * 16, graph_steps=graph_steps,
+                 host_draws=host_draws, host_draw_steps=40, replay=replay, **kw)
     ro.reset()
     return ro
 
 
+def _graph_obs(ro):
+    g = ro.obs[1]
+    return g.buf if hasattr(g, "buf") else g
+
+
+DENSE_FIELDS = ("obs", "next_obs", "action", "reward", "done", "node_state", "node_obs", "next_node_agent_matrix")
+COMPACT_FIELDS = ("rec", "next_rec", "topo", "action", "reward", "done", "episode_done", "node_state")
+
+
+@pytest.mark.parametrize("replay", ["dense", "compact"])
 @pytest.mark.parametrize("host_draws", [False, True])
-def test_graph_replay_equals_eager(host_draws):
-    a, b = _mk(0, host_draws), _mk(5, host_draws)
+def test_graph_replay_equals_eager(host_draws, replay):
+    a, b = _mk(0, host_draws, replay), _mk(5, host_draws, replay)
     if host_draws:
         # graph units consume aligned blocks of the host draw table (skipping to the next block when needed):
         # record which table rows the graph run used and feed the eager run the same rows
@@ -37,13 +47,65 @@ def test_graph_replay_equals_eager(host_draws):
     sa, sb = a.base_env.get_state(), b.base_env.get_state()
     for k in sa:
         assert np.array_equal(sa[k], sb[k]), k
-    assert torch.equal(a.obs[0], b.obs[0]) and torch.equal(a.obs[1], b.obs[1]) and torch.equal(a.adj, b.adj)
+    assert torch.equal(a.obs[0], b.obs[0]) and torch.equal(_graph_obs(a), _graph_obs(b)) and torch.equal(a.adj, b.adj)
     assert torch.equal(a.env.current_netmon_state, b.env.current_netmon_state)
     assert torch.equal(a.env.last_netmon_state, b.env.last_netmon_state)
     assert (a.buff.index, a.buff.count) == (b.buff.index, b.buff.count)
-    for name in ("obs", "next_obs", "action", "reward", "done", "node_state", "node_obs", "next_node_agent_matrix"):
+    for name in (DENSE_FIELDS if replay == "dense" else COMPACT_FIELDS):
         assert torch.equal(getattr(a.buff, name), getattr(b.buff, name)), name
     assert (a.episode_step, a.base_env._calls, a.policy._step) == (b.episode_step, b.base_env._calls, b.policy._step)
+
+
+@pytest.mark.parametrize("math", ["bf16x3", "fp32"])
+def test_compact_ring_rebuilds_the_dense_transition(math):
+    """the compact ring (env records + NetMon state, 23 kB instead of 141 kB per transition at config 2)
+    must hand the learner the SAME TransitionBatch as the reference's dense ring: two runs from one seed, one per
+    format, sampled with the same index streams (single transitions, then 6-step sequences) -- all 17 fields
+    bit-identical, including the graph-observation tails the compact ring recomputes with NetMon."""
+    from graph_marl_b200.replaybuffer import TransitionBatch
+    from graph_marl_b200.rollout import Rollout
+
+    cfg = dict(n_nodes=20, n_data=20, topo_seed=476, random_topology=True, n_topologies=5, congestion=True, K=2, rnn="lstm",
+               H=64, enc=(96, 64), dqn=(64, 32), episode_steps=9)
+    mk = lambda fmt, **kw: Rollout(cfg, num_envs=24, math=math, seed=13, replay_capacity=24 * 12, replay=fmt, **kw)
+    runs = []
+    for fmt, kw in (("dense", {}), ("compact", {}), ("compact", dict(device_sampler=True))):
+        ro = mk(fmt, **kw)
+        np.random.seed(2)
+        ro.reset()
+        ro.run(22)  # crosses two episode ends: first steps (zero NetMon state), episode_done flags, new topologies
+        runs.append(ro)
+    d, c, cd = runs
+    assert c.buff.bytes_per_transition() * 5 < sum(getattr(d.buff, f)[0].numel() * getattr(d.buff, f).element_size()
+                                                  for f in TransitionBatch._fields if f != "idx")
+    assert (d.buff.index, d.buff.count) == (c.buff.index, c.buff.count) == (cd.buff.index, cd.buff.count)
+    for seq in (0, 6):
+        bd = list(d.buff.get_batch(16, "cuda", sequence_length=seq))
+        bc = list(c.buff.get_batch(16, "cuda", sequence_length=seq))
+        bx = list(cd.buff.get_batch(16, "cuda", sequence_length=seq))
+        assert len(bd) == len(bc) == len(bx) == max(seq, 1)
+        for x, y, z in zip(bd, bc, bx):
+            assert np.array_equal(x.idx, y.idx) and np.array_equal(x.idx, z.idx.cpu().numpy())  # device PCG64 == numpy
+            for f in TransitionBatch._fields[1:]:
+                u, v, w = getattr(x, f), getattr(y, f), getattr(z, f)
+                assert u.dtype == v.dtype and u.shape == v.shape, f
+                assert torch.equal(u, v) and torch.equal(u, w), (f, seq)
+    assert bd[0].obs.shape == (16, 20, 130 + 4 * 64)
+
+
+def test_eager_tail_then_graph_unit_keeps_the_ring_consistent():
+    """run(k) with k % graph_steps != 0 interleaves eager steps (insert on the side stream, reading the ring
+    index counter and the static tensors) with graph units that rewrite both: at a batch where the insert takes real
+    time the ring must still equal the eager run's."""
+    a, b = _mk(0, B=2048), _mk(5, B=2048)
+    for _ in range(4):
+        a.run(7)
+        b.run(7)
+    torch.cuda.synchronize()
+    assert b._graphs
+    assert (a.buff.index, a.buff.count) == (b.buff.index, b.buff.count)
+    for name in DENSE_FIELDS + ("adj", "node_agent_matrix"):
+        assert torch.equal(getattr(a.buff, name), getattr(b.buff, name)), name
 
 
 def test_graph_units_respect_episode_boundaries():
@@ -51,7 +113,7 @@ def test_graph_units_respect_episode_boundaries():
 
     cfg = dict(n_nodes=20, n_data=20, topo_seed=923430603, congestion=True, K=1, rnn="lstm", H=64, enc=(64,), dqn=(64,),
                episode_steps=12)
-    mk = lambda g: Rollout(cfg, num_envs=33, math="bf16x3", seed=3, replay_capacity=33 * 8, graph_steps=g)
+    mk = lambda g: Rollout(cfg, num_envs=33, math="bf16x3", seed=3, replay_capacity=33 * 8, graph_steps=g, replay="dense")
     a, b = mk(0), mk(4)
     a.reset(), b.reset()
     a.run(31)
@@ -74,7 +136,7 @@ def test_random_topology_pool_rollout_graph_equals_eager(rnn, H, enc):
 
     cfg = dict(n_nodes=20, n_data=20, topo_seed=476, random_topology=True, n_topologies=7, congestion=False, K=1, rnn=rnn,
                H=H, enc=enc, dqn=(64,), episode_steps=9)
-    mk = lambda g: Rollout(cfg, num_envs=40, math="bf16x3", seed=11, replay_capacity=40 * 8, graph_steps=g)
+    mk = lambda g: Rollout(cfg, num_envs=40, math="bf16x3", seed=11, replay_capacity=40 * 8, graph_steps=g, replay="dense")
     a, b = mk(0), mk(3)
     # the topology draws come from the global numpy stream (network.py:229-238): give both runs the same one
     for ro in (a, b):

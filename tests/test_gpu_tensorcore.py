@@ -17,8 +17,7 @@ from helpers import det_weights, dqn_shapes, netmon_case, netmon_shapes
 pytestmark = pytest.mark.gpu
 
 G = load_golden("netmon")
-LSTM_CASES = [str(x) for x in G["case_names"] if str(x).split("|")[1] in ("lstm", "gru", "none")
-              and str(x).split("|")[0] != "gru_nocarry_k2"]
+LSTM_CASES = [str(x) for x in G["case_names"] if str(x).split("|")[1] in ("lstm", "gru", "none")]
 
 
 def _netmon(cfg, in_features, math):
@@ -131,6 +130,28 @@ def test_netmon_fused_layernorm_cell_against_fp64_oracle(K, agg, B, N, A):
         nm32.state = torch.from_numpy(st).cuda()
         no32, _ = nm32.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, want_node_out=True)
         assert np.abs(no32.cpu().numpy() - no.cpu().numpy()).max() < tol
+
+
+@pytest.mark.parametrize("math,tol", [("bf16x3", 1e-3), ("fp32", 1e-3)])
+def test_netmon_layernorm_cell_single_step_from_reference_recording(math, tol):
+    """The LayerNormLSTM cell (tcgen05 EPI_LNLSTM for bf16x3, the FFMA path for fp32) against the UNMODIFIED reference:
+    every step of the `lnlstm_sum_k4_paper` recording restarted from the reference's own recorded state (single step
+    from identical state; SURVEY Appendix B tolerance 1e-3)."""
+    from graph_marl_b200.model import NetMon
+
+    name, cfg = netmon_case(G, [x for x in G["case_names"] if str(x).startswith("lnlstm_sum_k4_paper")][0])
+    X, ADJ, NAM = G["node_obs"], G["node_adj"], G["node_agent"]
+    nm, _ = _netmon(cfg, X.shape[-1], math)
+    with torch.no_grad():
+        for t in range(X.shape[0]):
+            nbr, deg, dm = NetMon.lists_from_mask(torch.from_numpy(ADJ[t]).float().cuda())
+            nm.state = torch.from_numpy(G[name + "_state"][t - 1]).cuda() if t else None
+            agent_node = torch.from_numpy(NAM[t].argmax(axis=1).astype(np.int32)).cuda()
+            _, ao = nm.forward_lists(torch.from_numpy(X[t]).cuda(), nbr, deg, None, 3, agent_node=agent_node,
+                                     want_agent_pk=(math != "fp32"))
+            err = np.abs(ao.cpu().numpy() - G[name + "_agent_out"][t]).max()
+            serr = np.abs(nm.state.cpu().numpy() - G[name + "_state"][t]).max()
+            assert err < tol and serr < tol, (t, err, serr)
 
 
 def test_packed_weight_cache_follows_parameter_updates():

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.gm_abi_version() == 4
+    assert L.gm_abi_version() == 5
 
 
 def test_native_mt19937_matches_numpy_legacy_stream():
@@ -57,6 +57,42 @@ def _check_net(net, edges, node_edges, apsp):
     assert np.array_equal(np.asarray(net.shortest_paths_weights), apsp)
     for i, nd in enumerate(net.nodes):
         assert [net.edges[e].get_other_node(i) for e in nd.edges] == sorted(nd.neighbors)
+
+
+def test_native_pcg64_matches_numpy_generator_choice():
+    """gm_pcg64_seed / gm_pcg64_choice (csrc/replay_sampler.cu) == np.random.default_rng(seed).choice(n, size): the
+    index stream of ReplayBuffer.get_batch (replaybuffer.py:101, 111-130), incl. the buffered 32-bit halves, the
+    Lemire rejection loop and n == 1 (consumes nothing); then the reference's own recorded index streams."""
+    L = _lib.lib()
+    for seed in (0, 1, 3, 12345, 2**32 + 5, 2**63 + 11, 923430603):
+        st = np.zeros(_lib.GM_PCG64_STATE_WORDS, np.uint64)
+        L.gm_pcg64_seed(_lib.ptr(st), seed)
+        g = np.random.default_rng(seed)
+        for n, size in ((10, 4), (1, 3), (4096 * 8, 32), (7, 5), (100000, 64), (3, 33), (2**32 - 1, 9), (2**31 + 7, 40)):
+            out = np.zeros(size, np.int64)
+            L.gm_pcg64_choice(_lib.ptr(st), n, size, _lib.ptr(out))
+            assert np.array_equal(out, g.choice(n, size, replace=True)), (seed, n, size)
+    from conftest import load_golden
+
+    g = load_golden("replay")
+    seed, cap = int(g["cfg"][0]), int(g["cfg"][1])
+    st = np.zeros(_lib.GM_PCG64_STATE_WORDS, np.uint64)
+    L.gm_pcg64_seed(_lib.ptr(st), seed)
+
+    def batch(count, index, size, seq):
+        out = np.zeros(size, np.int64)
+        if seq <= 1:
+            L.gm_pcg64_choice(_lib.ptr(st), count, size, _lib.ptr(out))
+            return out[None]
+        L.gm_pcg64_choice(_lib.ptr(st), count - seq, size, _lib.ptr(out))
+        start = (index % count + out) % count
+        return np.stack([(start + o) % count for o in range(seq)])
+
+    assert np.array_equal(batch(10, 10, 4, 0)[0], g["idx_partial"])
+    assert np.array_equal(batch(10, 10, 4, 3), g["idx_seq_partial"])
+    index, count = [int(x) for x in g["final_index_count"]]
+    assert np.array_equal(batch(count, index, 6, 0)[0], g["idx_full"])
+    assert np.array_equal(batch(count, index, 5, 4), g["idx_seq_full"])
 
 
 def test_fixed_seed_networks():

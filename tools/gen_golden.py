@@ -642,13 +642,82 @@ def gen_wrapper():
          **rec.arrays())
 
 
+def gen_freeze():
+    """NetMonWrapper.freeze() (wrapper.py:53-75): message passing stops, agents keep reading the frozen node
+    readout at their new positions; `data` read-back views (routing.py:12-40) for heuristic policies."""
+    torch.set_num_threads(1)
+    np.random.seed(77)
+    net = Network(20, random_topology=False, topology_init_seed=923430603)
+    env0 = Routing(net, 20, 1)
+    nm = NetMon(88, 16, (24,), 2, F.leaky_relu, rnn_type="lstm", output_neighbor_hidden=True)
+    det_weights(nm, 777)
+    nm.eval()
+    env = NetMonWrapper(env0, nm, 1)
+    rec = DrawRecorder(env0)
+    obs, adj = env.reset()
+    OBS, ACT, CUR, NAM, DATA = [obs], [], [], [], []
+    ar = np.random.RandomState(19)
+    for t in range(8):
+        rec.t = t
+        if t == 3:
+            env.freeze()
+        a = ar.randint(4, size=20).astype(np.int32)
+        obs, adj, rew, done, info = env.step(a)
+        OBS.append(obs), ACT.append(a), CUR.append(env.current_netmon_state.numpy().copy())
+        NAM.append(env.get_netmon_info()[2].copy())
+        DATA.append(np.array([[p.now, p.target, p.edge, p.time, p.ttl, p.shortest_path_weight, p.start]
+                              for p in env0.data], dtype=np.int32))
+    save("wrapper_freeze", joint_obs=np.stack(OBS), actions=np.stack(ACT), cur_state=np.stack(CUR),
+         node_agent=np.stack(NAM), data=np.stack(DATA), sizes=np.array([p.size for p in env0.data]),
+         freeze_at=np.array([3]), cfg=np.array([88, 16, 24, 2, 777, 1], dtype=np.int64), **rec.arrays())
+
+
+def gen_replay_half():
+    """ReplayBuffer(half_precision=True) (replaybuffer.py:52-54, 132-187): float fields stored as fp16 and
+    returned as fp32."""
+    rng = np.random.default_rng(12)
+    cap, A, D, S, N, Dn, Sn, Ax = 8, 3, 5, 0, 4, 6, 8, 4
+    rb = ReplayBuffer(5, cap, A, D, S, N, Dn, Sn, Ax, half_precision=True)
+    n_add = 11
+
+    def r(*shape):
+        return (rng.standard_normal(shape) * 3).astype(np.float32)
+
+    tr = dict(
+        obs=r(n_add, A, D), action=rng.integers(0, 4, (n_add, A)).astype(np.int32),
+        reward=r(n_add, A), next_obs=r(n_add, A, D),
+        adj=(rng.random((n_add, A, A)) < 0.5).astype(np.int8),
+        next_adj=(rng.random((n_add, A, A)) < 0.5).astype(np.int8),
+        done=rng.random((n_add, A)) < 0.2, episode_done=rng.random(n_add) < 0.1,
+        node_state=r(n_add, N, Sn), node_aux=r(n_add, N, Ax), node_obs=r(n_add, N, Dn),
+        node_adj=(rng.random((n_add, N, N)) < 0.5).astype(np.int8),
+        node_agent=(rng.random((n_add, N, A)) < 0.5).astype(np.int8),
+        next_node_obs=r(n_add, N, Dn),
+        next_node_adj=(rng.random((n_add, N, N)) < 0.5).astype(np.int8),
+        next_node_agent=(rng.random((n_add, N, A)) < 0.5).astype(np.int8),
+    )
+    for i in range(n_add):
+        rb.add(tr["obs"][i], tr["action"][i], tr["reward"][i], tr["next_obs"][i], tr["adj"][i],
+               tr["next_adj"][i], tr["done"][i], tr["episode_done"][i], 0, tr["node_state"][i],
+               tr["node_aux"][i], tr["node_obs"][i], tr["node_adj"][i], tr["node_agent"][i],
+               tr["next_node_obs"][i], tr["next_node_adj"][i], tr["next_node_agent"][i])
+    b = next(rb.get_batch(6, "cpu"))
+    samples = {"idx_full": np.asarray(b.idx)}
+    for f in b._fields:
+        if f != "idx":
+            samples["full_" + f] = getattr(b, f).numpy()
+    samples["cfg"] = np.array([5, cap, A, D, S, N, Dn, Sn, Ax, n_add], dtype=np.int64)
+    save("replay_half", **{("tr_" + k): v for k, v in tr.items()}, **samples)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     gens = dict(topology=gen_topology, rng=gen_rng, routing=gen_routing, simple=gen_simple,
-                netmon=gen_netmon, sl=gen_sl, dqn=gen_dqn_policy, replay=gen_replay, wrapper=gen_wrapper)
+                netmon=gen_netmon, sl=gen_sl, dqn=gen_dqn_policy, replay=gen_replay, wrapper=gen_wrapper,
+                freeze=gen_freeze, replay_half=gen_replay_half)
     for k, fn in gens.items():
         if a.only and k not in a.only.split(","):
             continue
