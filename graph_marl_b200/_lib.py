@@ -69,6 +69,25 @@ class ReplayField(C.Structure):
                 ("ring_offset", C.c_int64)]
 
 
+class MlpDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("in_features", C.c_int32), ("units", C.c_int32 * GM_MAX_LAYERS),
+                ("act", C.c_int32 * GM_MAX_LAYERS), ("math", C.c_int32), ("pad", C.c_int32),
+                ("w", C.c_void_p * GM_MAX_LAYERS), ("b", C.c_void_p * GM_MAX_LAYERS)]
+
+
+class MlpGrads(C.Structure):
+    _fields_ = [("w", C.c_void_p * GM_MAX_LAYERS), ("b", C.c_void_p * GM_MAX_LAYERS)]
+
+
+class CellGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w_ih", "w_hh", "b_ih", "b_hh")]
+
+
+class NetmonGrads(C.Structure):
+    _fields_ = [("enc_w", C.c_void_p * GM_MAX_LAYERS), ("enc_b", C.c_void_p * GM_MAX_LAYERS),
+                ("rnn_obs", CellGrads), ("rnn_update", CellGrads)]
+
+
 _lib = None
 
 _SIGS = {
@@ -116,6 +135,20 @@ _SIGS = {
     "gm_pcg64_seed": (None, [C.c_void_p, C.c_uint64]),
     "gm_pcg64_choice": (None, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "gm_replay_sample_indices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "gm_mlp_tape_floats": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "gm_mlp_train_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "gm_mlp_forward_train": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                       C.c_void_p]),
+    "gm_mlp_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gm_netmon_tape_floats": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "gm_netmon_train_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "gm_netmon_forward_train": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_void_p]),
+    "gm_netmon_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_linear_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

@@ -484,12 +484,16 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         }
         __syncwarp();
     }
-    // non-zero fields of node row j (routing.py:193-234) placed at column offset `base` of row r
-    auto node_row = [&](int r, int base, int j, auto put) {
-        put(r, base + j, 1.f);
-        put(r, base + N, (float)v.cnt[j]);
-        put(r, base + N + 1, (float)v.tl[j]);
-        for (int q = 0; q < 3; q++) {
+    // non-zero fields of node row j (routing.py:193-234) placed at column offset `base` of row r.  The row's 12
+    // fields are split over four lanes: part 0..2 = the node's q-th edge (one-hot, length, load), part 3 = the node's
+    // own fields; part < 0 = everything (the GLOBAL agent observation embeds whole node rows).
+    auto node_row = [&](int r, int base, int j, int part, auto put) {
+        if (part < 0 || part == 3) {
+            put(r, base + j, 1.f);
+            put(r, base + N, (float)v.cnt[j]);
+            put(r, base + N + 1, (float)v.tl[j]);
+        }
+        for (int q = (part < 0 || part == 3) ? 0 : part; q < ((part < 0) ? 3 : (part == 3 ? 0 : part + 1)); q++) {
             int k = ne[j * 3 + q], o = nb[j * 3 + q];
             int b2 = base + N + 2 + q * (N + 2);
             put(r, b2 + o, 1.f);
@@ -497,6 +501,74 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             put(r, b2 + N + 1, (float)v.load[k]);
         }
     };
+
+    // ---- store mode 3 ("direct"): no staging tile.  The env's dense blocks are zero-filled in HBM with 16-byte
+    // stores, then every row's few non-zero fields are written over them by the lane that owns the row, which keeps
+    // the row's packet / node view in registers (one pass, no per-tile re-scan, no bounds checks, no wait on a bulk
+    // store).  __syncwarp() orders a lane's field stores after the other lanes' zero stores to the same sectors; L2
+    // merges both before anything reaches DRAM.  Used for env_var 1 when both blocks are 16-byte granular.
+    if (store_mode == 3) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int W0 = 6 * N + 10, Wn = 4 * N + 8;
+        float* go = io.obs ? io.obs + (size_t)b * A * W0 : nullptr;
+        float* gn = io.node_obs ? io.node_obs + (size_t)b * N * Wn : nullptr;
+        if (go) {
+            float4* g4 = (float4*)go;
+            const int n4 = (A * W0) >> 2;
+#pragma unroll 4
+            for (int q = lane; q < n4; q += 32) g4[q] = z4;
+        }
+        if (gn) {
+            float4* g4 = (float4*)gn;
+            const int n4 = (N * Wn) >> 2;
+#pragma unroll 4
+            for (int q = lane; q < n4; q += 32) g4[q] = z4;
+        }
+        __syncwarp();
+        if (go) {
+            for (int i = lane; i < A; i += 32) {
+                float* r = go + (size_t)i * W0;
+                const int nw = v.now[i], e = v.edge[i];
+                r[nw] = 1.f;
+                r[N + v.target[i]] = 1.f;
+                if (e != -1) {
+                    const int4 ee = ed[e];
+                    r[2 * N] = 1.f;
+                    r[2 * N + 1 + ((ee.x == nw) ? ee.y : ee.x)] = 1.f;
+                }
+                r[3 * N + 1] = (float)v.time[i];
+                r[3 * N + 2] = (float)v.size[i];
+                r[3 * N + 3] = (float)i;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int k = ne[nw * 3 + q], o = nb[nw * 3 + q];
+                    float* rb = r + 3 * N + 4 + q * (N + 2);
+                    rb[o] = 1.f;
+                    rb[N] = (float)ed[k].z;
+                    rb[N + 1] = (float)v.load[k];
+                }
+            }
+        }
+        if (gn) {
+            for (int j = lane; j < N; j += 32) {
+                float* r = gn + (size_t)j * Wn;
+                r[j] = 1.f;
+                r[N] = (float)v.cnt[j];
+                r[N + 1] = (float)v.tl[j];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int k = ne[j * 3 + q], o = nb[j * 3 + q];
+                    float* rb = r + N + 2 + q * (N + 2);
+                    rb[o] = 1.f;
+                    rb[N] = (float)ed[k].z;
+                    rb[N + 1] = (float)v.load[k];
+                }
+            }
+        }
+        if (io.adj) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, N, A, lane);
+        if (io.node_agent) emit_node_agent_rows(v.now, io.node_agent + (size_t)b * N * A, N, A, lane);
+        return;
+    }
 
     // ---- agent observations (routing.py:277-358) ------------------------------------------
     // row = 6N+10 packet/edge fields | env_var 2: 5 fields of up to k neighbouring agents (:328-348)
@@ -506,27 +578,33 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         const int W = W0 + (d.env_var == 2 ? 5 * d.k : 0) + (d.env_var == 3 ? N * N + N * (4 * N + 8) : 0);
         emit_f32_block(io.obs + (size_t)b * A * W, A * W, W, stage, L.stage_floats, lane, store_mode,
                        [&](int r0, int r1, auto put) {
-                           for (int i = r0 + lane; i <= r1; i += 32) {
-                               int nw = v.now[i], e = v.edge[i];
-                               put(i, nw, 1.f);
-                               put(i, N + v.target[i], 1.f);
-                               if (e != -1) {
-                                   put(i, 2 * N, 1.f);
-                                   int4 ee = ed[e];
-                                   int prev = (ee.x == nw) ? ee.y : ee.x;
-                                   put(i, 2 * N + 1 + prev, 1.f);
-                               }
-                               put(i, 3 * N + 1, (float)v.time[i]);
-                               put(i, 3 * N + 2, (float)v.size[i]);
-                               put(i, 3 * N + 3, (float)i);
-                               for (int q = 0; q < 3; q++) {
+                           // four lanes per row (8 rows per pass): the ~16 fields of a row are written by four lanes
+                           // side by side instead of one lane after the other (a tile holds 7-9 rows at N = 20)
+                           const int part = lane & 3;
+                           for (int i = r0 + (lane >> 2); i <= r1; i += 8) {
+                               const int nw = v.now[i];
+                               if (part == 3) {
+                                   const int e = v.edge[i];
+                                   put(i, nw, 1.f);
+                                   put(i, N + v.target[i], 1.f);
+                                   if (e != -1) {
+                                       put(i, 2 * N, 1.f);
+                                       int4 ee = ed[e];
+                                       int prev = (ee.x == nw) ? ee.y : ee.x;
+                                       put(i, 2 * N + 1 + prev, 1.f);
+                                   }
+                                   put(i, 3 * N + 3, (float)i);
+                               } else {
+                                   const int q = part;
                                    int k = ne[nw * 3 + q], o = nb[nw * 3 + q];
                                    int base = 3 * N + 4 + q * (N + 2);
                                    put(i, base + o, 1.f);
                                    put(i, base + N, (float)ed[k].z);
                                    put(i, base + N + 1, (float)v.load[k]);
+                                   if (q == 0) put(i, 3 * N + 1, (float)v.time[i]);
+                                   if (q == 1) put(i, 3 * N + 2, (float)v.size[i]);
                                }
-                               if (d.env_var == 2) {
+                               if (d.env_var == 2 && part == 3) {
                                    int count = 0;
                                    for (int j = 0; j < A && count < d.k; j++) {
                                        if (j == i) continue;
@@ -544,10 +622,10 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                                    for (; count < d.k; count++)
                                        for (int q = 0; q < 5; q++) put(i, W0 + 5 * count + q, -1.f);
                                } else if (d.env_var == 3) {
-                                   for (int j = 0; j < N; j++) {
+                                   for (int j = part; j < N; j += 4) {
                                        put(i, W0 + j * N + j, 1.f);
                                        for (int q = 0; q < 3; q++) put(i, W0 + j * N + nb[j * 3 + q], 1.f);
-                                       node_row(i, W0 + N * N + j * (4 * N + 8), j, put);
+                                       node_row(i, W0 + N * N + j * (4 * N + 8), j, -1, put);
                                    }
                                }
                            }
@@ -559,7 +637,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         const int W = 4 * N + 8;
         emit_f32_block(io.node_obs + (size_t)b * N * W, N * W, W, stage, L.stage_floats, lane, store_mode,
                        [&](int r0, int r1, auto put) {
-                           for (int j = r0 + lane; j <= r1; j += 32) node_row(j, 0, j, put);
+                           for (int j = r0 + (lane >> 2); j <= r1; j += 8) node_row(j, 0, j, lane & 3, put);
                        });
     }
 
@@ -581,6 +659,20 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
     GM_CHECK_ARG(mode != MODE_STEP || io->actions, "step needs actions");
     GM_CHECK_ARG(io->info == nullptr || ((uintptr_t)io->info & 15) == 0, "info must be 16-byte aligned");
 
+    gm_routing_desc dd = *d;
+    static int store_env = -1;
+    if (store_env < 0) {
+        const char* e = getenv("GM_ROUTING_STORE_MODE");  // 1 staged + vector stores, 2 staged + bulk stores, 3 direct
+        store_env = e ? atoi(e) : 0;
+    }
+    // direct stores need env_var 1 and 16-byte granular per-env blocks (e.g. A = 35 is not: rows of 130 floats)
+    const bool direct_ok = d->env_var == 1 && (((int64_t)d->A * (6 * d->N + 10)) & 3) == 0 && (((int64_t)d->N * (4 * d->N + 8)) & 3) == 0 &&
+                           ((uintptr_t)io->obs & 15) == 0 && ((uintptr_t)io->node_obs & 15) == 0;
+    // default 2: the direct mode measured slower (37 vs 29 us per launch at config 2: its per-row field stores are 32
+    // different lines per warp instruction); kept as an option and parity-tested
+    if (dd.store_mode == 0) dd.store_mode = store_env ? store_env : 2;
+    if (dd.store_mode == 3 && !direct_ok) dd.store_mode = 2;
+
     // staging tile: 4 KiB per warp keeps >= 7 CTAs (28 warps) resident per SM, so 4096 envs run as ONE wave
     // (measured: 30.8 us vs 37.9 us with 16 KiB tiles; double-buffered tiles were slower, they halve residency)
     const int64_t W_obs = 6 * d->N + 10 + (d->env_var == 2 ? 5 * d->k : 0) + (d->env_var == 3 ? d->N * d->N + d->N * (4 * d->N + 8) : 0);
@@ -591,7 +683,7 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
         stage_cap = e ? atoi(e) : 4096;
         if (stage_cap < 1024 || stage_cap > 65536) stage_cap = 4096;
     }
-    int stage_bytes = (int)std::min<int64_t>(stage_cap, round_up(need, 256));
+    int stage_bytes = dd.store_mode == 3 ? 16 : (int)std::min<int64_t>(stage_cap, round_up(need, 256));  // direct mode stages nothing
     RoutingLayout L = make_layout(d->N, d->A, d->E, stage_bytes);
     GM_CHECK_ARG(d->state_stride == L.stride, "state_stride %d != %d", d->state_stride, L.stride);
     while (L.sm_per_warp * WARPS_PER_CTA > 200 * 1024 && stage_bytes > 2048) {
@@ -601,8 +693,6 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
     size_t smem = (size_t)L.sm_per_warp * WARPS_PER_CTA;
     GM_CHECK_ARG(smem <= 227 * 1024, "env too large for shared memory (%zu bytes)", smem);
 
-    gm_routing_desc dd = *d;
-    if (dd.store_mode == 0) dd.store_mode = 2;
     dim3 grid(ceil_div(d->B, WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
     cudaStream_t s = (cudaStream_t)stream;
     switch (mode) {

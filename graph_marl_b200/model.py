@@ -87,6 +87,132 @@ class _PackedWeights:
         return self.buf
 
 
+# ---- training path: device-side backward (csrc/train.cu) behind torch.autograd ---------------------
+# `loss.backward()` of the unmodified learner (main.py:1002, sl.py:392) reaches these nodes; each runs ONE C-ABI
+# call forward (writes a tape) and one backward (hand-written kernels).  A sequence of NetMon steps (main.py:840-915)
+# is a chain of _NetMonStep nodes: the state gradient d_state_in of step t+1 is the d_state_out of step t.
+GRAD_PATH_CALLS = {"device": 0, "torch": 0}  # how often grad-mode forwards ran the kernels / the torch-composed path
+_warned_torch_path = set()
+
+
+def _note_torch_path(who, why):
+    GRAD_PATH_CALLS["torch"] += 1
+    if (who, why) not in _warned_torch_path:
+        _warned_torch_path.add((who, why))
+        import warnings
+
+        warnings.warn(f"{who}: grad-mode forward runs the torch-composed path, not the CUDA kernels ({why})", stacklevel=3)
+
+
+class _MlpFn(torch.autograd.Function):
+    """y = MLP(x) through gm_mlp_forward_train / gm_mlp_backward.  `layers`: [(weight, bias, act_id)]."""
+
+    @staticmethod
+    def forward(ctx, spec, x, *params):
+        acts, math = spec
+        L = len(acts)
+        rows = x.shape[0]
+        d = _lib.MlpDesc()
+        d.n_layers, d.in_features, d.math = L, x.shape[1], _lib.MATH_MODES["bf16x3" if math == "bf16" else math]
+        for l in range(L):
+            w, b = params[2 * l], params[2 * l + 1]
+            d.units[l], d.act[l], d.w[l], d.b[l] = w.shape[0], acts[l], w.data_ptr(), b.data_ptr()
+        lib = _lib.lib()
+        tape = torch.empty(int(lib.gm_mlp_tape_floats(C.byref(d), rows)), dtype=torch.float32, device=x.device)
+        ws = torch.empty(int(lib.gm_mlp_train_workspace_bytes(C.byref(d), rows)), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.gm_mlp_forward_train(C.byref(d), rows, x.data_ptr(), x.stride(0), tape.data_ptr(), ws.data_ptr(),
+                                                ws.numel(), _lib.current_stream()))
+        ctx.save_for_backward(x, tape, *params)
+        ctx.spec = spec
+        out_w = params[2 * (L - 1)].shape[0]
+        return tape[tape.numel() - rows * out_w:].view(rows, out_w).clone()
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, tape, *params = ctx.saved_tensors
+        acts, math = ctx.spec
+        L = len(acts)
+        rows = x.shape[0]
+        d = _lib.MlpDesc()
+        d.n_layers, d.in_features, d.math = L, x.shape[1], _lib.MATH_MODES["bf16x3" if math == "bf16" else math]
+        g = _lib.MlpGrads()
+        grads = []
+        for l in range(L):
+            w, b = params[2 * l], params[2 * l + 1]
+            d.units[l], d.act[l], d.w[l], d.b[l] = w.shape[0], acts[l], w.data_ptr(), b.data_ptr()
+            gw = torch.empty_like(w) if ctx.needs_input_grad[2 + 2 * l] else None
+            gb = torch.empty_like(b) if ctx.needs_input_grad[3 + 2 * l] else None
+            g.w[l], g.b[l] = _lib.ptr(gw), _lib.ptr(gb)
+            grads += [gw, gb]
+        d_out = d_out.float().contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        lib = _lib.lib()
+        ws = torch.empty(int(lib.gm_mlp_train_workspace_bytes(C.byref(d), rows)), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.gm_mlp_backward(C.byref(d), rows, x.data_ptr(), x.stride(0), tape.data_ptr(), d_out.data_ptr(),
+                                           d_out.stride(0), _lib.ptr(dx), C.byref(g), ws.data_ptr(), ws.numel(),
+                                           _lib.current_stream()))
+        return (None, dx, *grads)
+
+
+class _NetMonStepFn(torch.autograd.Function):
+    """One NetMon step (model.py:476-631 without the node->agent bmm) through gm_netmon_forward_train /
+    gm_netmon_backward: (node_obs, state_in, parameters) -> (node_out, state_out)."""
+
+    @staticmethod
+    def forward(ctx, nm, x, nbr, deg, list_index, max_degree, state_in, *params):
+        B, N, _ = x.shape
+        dev = x.device
+        p = nm._params(packed=False)
+        lib = _lib.lib()
+        R = B * N
+        H = nm.hidden_features
+        tape = torch.empty(int(lib.gm_netmon_tape_floats(C.byref(p), R)), dtype=torch.float32, device=dev)
+        ws = torch.empty(int(lib.gm_netmon_train_workspace_bytes(C.byref(p), R)), dtype=torch.uint8, device=dev)
+        st_out = torch.empty((B, N, 2 * H), dtype=torch.float32, device=dev)
+        O = nm.out_width(max_degree)
+        node_out = torch.empty((B, N, O), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gm_netmon_forward_train(
+                C.byref(p), B, N, x.data_ptr(), nbr.data_ptr(), deg.data_ptr(), nbr.shape[-1], _lib.ptr(list_index),
+                _lib.ptr(state_in), st_out.data_ptr(), max_degree, node_out.data_ptr(), tape.data_ptr(), ws.data_ptr(),
+                ws.numel(), _lib.current_stream()))
+        ctx.nm, ctx.max_degree, ctx.has_state = nm, max_degree, state_in is not None
+        ctx.save_for_backward(x, nbr, deg, list_index if list_index is not None else x.new_empty(0),
+                              state_in if state_in is not None else x.new_empty(0), tape, *params)
+        return node_out, st_out
+
+    @staticmethod
+    def backward(ctx, d_node_out, d_state_out):
+        x, nbr, deg, list_index, state_in, tape, *params = ctx.saved_tensors
+        nm = ctx.nm
+        B, N, _ = x.shape
+        dev = x.device
+        H = nm.hidden_features
+        p = nm._params(packed=False)
+        g = _lib.NetmonGrads()
+        grads = [torch.empty_like(q) if ctx.needs_input_grad[7 + i] else None for i, q in enumerate(params)]
+        L = len(nm.encode.linear_layers)
+        for l in range(L):
+            g.enc_w[l], g.enc_b[l] = _lib.ptr(grads[2 * l]), _lib.ptr(grads[2 * l + 1])
+        for k, cell in enumerate((g.rnn_obs, g.rnn_update)):
+            base = 2 * L + 4 * k
+            cell.w_ih, cell.w_hh, cell.b_ih, cell.b_hh = (_lib.ptr(grads[base + j]) for j in range(4))
+        d_state_in = torch.empty((B, N, 2 * H), dtype=torch.float32, device=dev) if (ctx.has_state and ctx.needs_input_grad[6]) else None
+        dn = None if d_node_out is None else d_node_out.float().contiguous()
+        ds = None if d_state_out is None else d_state_out.float().contiguous()
+        lib = _lib.lib()
+        ws = torch.empty(int(lib.gm_netmon_train_workspace_bytes(C.byref(p), B * N)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.gm_netmon_backward(
+                C.byref(p), B, N, x.data_ptr(), nbr.data_ptr(), deg.data_ptr(), nbr.shape[-1],
+                list_index.data_ptr() if list_index.numel() else None, state_in.data_ptr() if ctx.has_state else None,
+                ctx.max_degree, tape.data_ptr(), _lib.ptr(dn), _lib.ptr(ds), _lib.ptr(d_state_in), C.byref(g), ws.data_ptr(),
+                ws.numel(), _lib.current_stream()))
+        return (None, None, None, None, None, None, d_state_in, *grads)
+
+
 class MLP(nn.Module):
     """model.py:13-42."""
 
@@ -218,8 +344,21 @@ class DQN(nn.Module):
         return (None if q is None else q.reshape(*lead, self.num_actions)), act.reshape(lead)
 
     def forward(self, x, mask):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return self.q_net(self.encoder(x))  # learner path (autograd)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # learner path (main.py:917): one autograd node whose forward / backward are gm_mlp_forward_train /
+            # gm_mlp_backward (encoder layers + the Q head as a last layer without activation)
+            if x.is_cuda and _act_name(self.activation_fn) in _lib.ACTIVATIONS:
+                _lib.require_device()
+                GRAD_PATH_CALLS["device"] += 1
+                act = _lib.ACTIVATIONS[_act_name(self.activation_fn)]
+                layers = list(self.encoder.linear_layers) + [self.q_net.fc]
+                acts = tuple([act] * len(self.encoder.linear_layers) + [-1])
+                params = [t for l in layers for t in (l.weight, l.bias)]
+                x2 = x.reshape(-1, x.shape[-1]).float().contiguous()
+                q = _MlpFn.apply((acts, self.math), x2, *params)
+                return q.reshape(*x.shape[:-1], self.num_actions)
+            _note_torch_path("DQN", "CPU tensors")
+            return self.q_net(self.encoder(x))
         q, _ = self.act(x.float())
         return q
 
@@ -311,7 +450,7 @@ class NetMon(nn.Module):
             c.b_hh = mod.bias_hh.data_ptr()
         return c
 
-    def _params(self):
+    def _params(self, packed=True):
         p = _lib.NetmonParams()
         layers = list(self.encode.linear_layers)
         p.in_features, p.hidden, p.n_enc_layers = self.in_features, self.hidden_features, len(layers)
@@ -327,7 +466,7 @@ class NetMon(nn.Module):
         p.math = _lib.MATH_MODES[self.math]
         p.rnn_obs = self._cell(getattr(self, "rnn_obs", None))
         p.rnn_update = self._cell(getattr(self, "rnn_update", None))
-        if self.math != "fp32" and layers[0].weight.is_cuda:
+        if packed and self.math != "fp32" and layers[0].weight.is_cuda:
             dev = layers[0].weight.device
 
             def pack(buf):
@@ -410,9 +549,42 @@ class NetMon(nn.Module):
                                                   ovf.data_ptr(), _lib.current_stream()))
         return nbr, deg, dm
 
+    def _device_backward_reason(self, x):
+        """None when the device-side backward (csrc/train.cu) covers this configuration, else why not."""
+        if not x.is_cuda:
+            return "CPU tensors"
+        if self.rnn_type != "lstm" or not self.rnn_carryover:
+            return f"rnn_type {self.rnn_type} / carryover {self.rnn_carryover}: the device backward is built for lstm with carry-over"
+        if self.output_global_hidden or self.iterations < 1:
+            return "global readout / zero iterations"
+        return None
+
     def forward(self, x, mask, node_agent_matrix, max_degree=None, no_agent_mapping=False):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            return self._forward_autograd(x, mask, node_agent_matrix, max_degree, no_agent_mapping)
+        if torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters())
+                                        or (self.state is not None and self.state.requires_grad)):
+            why = self._device_backward_reason(x)
+            if why is not None:
+                _note_torch_path("NetMon", why)
+                return self._forward_autograd(x, mask, node_agent_matrix, max_degree, no_agent_mapping)
+            _lib.require_device()
+            GRAD_PATH_CALLS["device"] += 1
+            B, N, _ = x.shape
+            with torch.no_grad():
+                nbr, deg, dm = self.lists_from_mask(mask)
+                if max_degree is None:
+                    max_degree = int(mask.sum(dim=-1).max().long().item()) - 1  # model.py:588-589
+            md = max(min(max_degree, dm), 0) if self.output_neighbor_hidden else 0
+            st = self.state
+            if st is not None:
+                st = st.to(x.device).float().reshape(B, N, self.state_size).contiguous()
+            layers = list(self.encode.linear_layers)
+            params = [t for l in layers for t in (l.weight, l.bias)]
+            for cell in (self.rnn_obs, self.rnn_update):
+                params += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+            node_out, self.state = _NetMonStepFn.apply(self, x.float().contiguous(), nbr, deg, None, md, st, *params)
+            if no_agent_mapping:
+                return node_out
+            return torch.bmm(node_out.transpose(1, 2), node_agent_matrix.to(node_out.dtype)).transpose(1, 2)
         _lib.require_device()
         if not x.is_cuda:
             raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")

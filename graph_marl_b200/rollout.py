@@ -120,6 +120,7 @@ class Rollout:
         self._graphs, self._graph_pool, self._static, self._graph_tables = {}, None, None, None
         self.graph_launches = 0  # kernels of this library launched through graph replays
         self._h_trace = None     # optional list: indices of the host draw table consumed so far (tests)
+        self._draw_bufs, self._copy_stream = None, None  # static per-step draw buffers of the captured units
         if host_draws and self.graph_steps > 0:
             assert host_draw_steps % self.graph_steps == 0, "host draw table must hold whole graph units"
         self.episode_step = None
@@ -169,8 +170,9 @@ class Rollout:
             e.record()
             self._marks.append((name, e))
 
-    def _step_eager(self):
-        """One batched rollout step (main.py:673-737)."""
+    def _step_eager(self, draws=None):
+        """One batched rollout step (main.py:673-737).  draws: device copies of this step's slice of the host draw table
+        that a copy stream already fetched (captured graph units prefetch all their slices, see _capture_unit)."""
         env, c = self.env, self.cfg
         if self.episode_step is None or self.episode_step >= c["episode_steps"]:
             self.reset()
@@ -183,7 +185,7 @@ class Rollout:
             self._h_cursor += 1
             if self._h_trace is not None and not torch.cuda.is_current_stream_capturing():
                 self._h_trace.append(i)
-            d = {k: v[i].to(self.device, non_blocking=True) for k, v in self._h.items()}
+            d = draws if draws is not None else {k: v[i].to(self.device, non_blocking=True) for k, v in self._h.items()}
             with torch.no_grad():
                 _, actions = self.model.act(obs[0], obs[1], epsilon=self.policy._epsilon, rand_action=d["ra"].reshape(-1),
                                             rand_u=d["ru"].reshape(-1), want_q=False)
@@ -300,9 +302,33 @@ class Rollout:
         torch.cuda.synchronize()
         launches0 = _lib.lib().gm_kernel_launch_count()
         g = torch.cuda.CUDAGraph()
+        if self.host_draws and (self._draw_bufs is None or len(self._draw_bufs) < n):
+            self._draw_bufs = [{k: torch.empty_like(v[0], device=self.device) for k, v in self._h.items()} for _ in range(n)]
+            self._copy_stream = torch.cuda.Stream(device=self.device)
         with torch.cuda.graph(g, pool=self._graph_pool):
-            for _ in range(n):
-                self._step_eager()
+            fetched = None
+            if self.host_draws:
+                # every step still copies ITS slice of the pinned host table, but on a copy stream that runs ahead of
+                # the compute: slice k lands in its own static buffer while steps < k execute; step k waits for event k
+                main, cs = torch.cuda.current_stream(), self._copy_stream
+                cs.wait_stream(main)
+                fetched = []
+                with torch.cuda.stream(cs):
+                    for k in range(n):
+                        i = (self._h_cursor + k) % self._h_steps
+                        for name, buf in self._draw_bufs[k].items():
+                            buf.copy_(self._h[name][i], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(cs)
+                        fetched.append(ev)
+            for k in range(n):
+                if fetched is not None:
+                    torch.cuda.current_stream().wait_event(fetched[k])
+                    self._step_eager(draws=self._draw_bufs[k])
+                else:
+                    self._step_eager()
+            if fetched is not None:
+                torch.cuda.current_stream().wait_stream(self._copy_stream)
             self.join_streams()
             out, _ = self._carried()
             for k, v in self._static.items():

@@ -96,7 +96,8 @@ typedef struct gm_routing_desc {
     int32_t action_mask;         /* enable_action_mask (routing.py:62) */
     int32_t ttl;                 /* ttl, 0 = disabled (routing.py:63) */
     int32_t state_stride;        /* bytes per env in `state`, from gm_routing_state_layout */
-    int32_t store_mode;          /* 0 auto, 1 smem staging + vector stores, 2 + cp.async.bulk */
+    int32_t store_mode;          /* 0 auto, 1 smem staging + vector stores, 2 smem staging + cp.async.bulk,
+                                    3 direct: zero-fill + per-row field stores (env_var 1, 16-byte granular blocks) */
     /* topology pool (device, int32) */
     const int32_t* node_edges;   /* [T,N,3] edge ids of node n sorted by neighbour id */
     const int32_t* node_nbrs;    /* [T,N,3] the neighbour reached by action 1..3 */
@@ -317,6 +318,60 @@ GM_API void gm_pcg64_choice(uint64_t* state, int64_t n, int64_t size, int64_t* o
  * and row o = (start + o) % count.  No host round trip. */
 GM_API int gm_replay_sample_indices(uint64_t* state_dev, int64_t count, int64_t index, int32_t batch,
                              int32_t seq_len, int64_t* out, void* stream);
+
+/* ======================================================================== */
+/* Training path: forward with a tape + backward (replaces the torch autograd */
+/* of the learner, src/main.py:830-1006, src/sl.py:366-428, over               */
+/* src/model.py:32-42, 199-203, 213-229, 476-631)                              */
+/* ======================================================================== */
+/* An MLP (model.py:13-42; the DQN of :187-203 = its encoder layers + the Q head as a last layer without
+ * activation).  act[l] = GM_ACT_* or -1 for identity. */
+typedef struct gm_mlp_desc {
+    int32_t n_layers, in_features;
+    int32_t units[GM_MAX_LAYERS];
+    int32_t act[GM_MAX_LAYERS];
+    int32_t math, pad;                  /* GM_MATH_FP32 | GM_MATH_BF16X3 (forward GEMMs; the backward GEMMs are fp32) */
+    const float* w[GM_MAX_LAYERS];      /* [units[l], in_l] row-major */
+    const float* b[GM_MAX_LAYERS];
+} gm_mlp_desc;
+typedef struct gm_mlp_grads {           /* device outputs, written (not accumulated); NULL = not wanted */
+    float* w[GM_MAX_LAYERS];
+    float* b[GM_MAX_LAYERS];
+} gm_mlp_grads;
+/* tape = the post-activation output of every layer, layer l at float offset rows * sum(units[0..l-1]); the last
+ * block is the module's output */
+GM_API int64_t gm_mlp_tape_floats(const gm_mlp_desc* m, int64_t rows);
+GM_API int64_t gm_mlp_train_workspace_bytes(const gm_mlp_desc* m, int64_t rows);
+GM_API int gm_mlp_forward_train(const gm_mlp_desc* m, int64_t rows, const float* x, int64_t ldx, float* tape,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+/* d_out f32[rows, units[last]] (row stride ldd) -> parameter gradients and, if d_x != NULL, d_x f32[rows, in_features] */
+GM_API int gm_mlp_backward(const gm_mlp_desc* m, int64_t rows, const float* x, int64_t ldx, const float* tape,
+                    const float* d_out, int64_t ldd, float* d_x, const gm_mlp_grads* grads, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
+typedef struct gm_cell_grads { float *w_ih, *w_hh, *b_ih, *b_hh; } gm_cell_grads;
+typedef struct gm_netmon_grads {
+    float* enc_w[GM_MAX_LAYERS];
+    float* enc_b[GM_MAX_LAYERS];
+    gm_cell_grads rnn_obs, rnn_update;
+} gm_netmon_grads;
+/* One NetMon step with a tape (rnn_type lstm with carry-over, agg sum | mean, K >= 1, no global readout; anything
+ * else returns GM_ERR_INVALID).  Arguments as gm_netmon_forward; node_out f32[B,N,O] (O = H (1 + max_degree) with the
+ * neighbour readout) or NULL; state_in f32[B,N,2H] or NULL (= zeros). */
+GM_API int64_t gm_netmon_tape_floats(const gm_netmon_params* p, int64_t rows);
+GM_API int64_t gm_netmon_train_workspace_bytes(const gm_netmon_params* p, int64_t rows);
+GM_API int gm_netmon_forward_train(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs,
+                            const int32_t* nbr_all, const int32_t* deg, int32_t DM, const int32_t* list_index,
+                            const float* state_in, float* state_out, int32_t max_degree, float* node_out, float* tape,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+/* Backward of that step: d_node_out f32[B,N,O] and / or d_state_out f32[B,N,2H] (gradients of the step's two outputs;
+ * either may be NULL = zero) -> d_state_in f32[B,N,2H] (may be NULL) and the parameter gradients (written, not
+ * accumulated: a sequence of steps sums them outside, as autograd does). */
+GM_API int gm_netmon_backward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs, const int32_t* nbr_all,
+                       const int32_t* deg, int32_t DM, const int32_t* list_index, const float* state_in,
+                       int32_t max_degree, const float* tape, const float* d_node_out, const float* d_state_out,
+                       float* d_state_in, const gm_netmon_grads* grads, void* workspace, int64_t workspace_bytes,
+                       void* stream);
 
 /* ======================================================================== */
 /* building blocks exposed for tests / profiling                             */

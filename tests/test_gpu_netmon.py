@@ -330,3 +330,25 @@ def test_ci_known_answer_simple_env_training_reaches_reward_mean_1():
 
     metrics = train_simple.main(["--total-steps", "5000", "--step-before-train", "1000", "--eval-episodes", "100"])
     assert metrics["reward_mean"] == 1.0
+
+
+def test_unmodified_reference_main_py_runs_on_the_package(tmp_path):
+    """The drop-in claim, demonstrated: the reference's own src/main.py (staged, unedited, at baseline/_ref/src) runs its
+    CI command (.github/workflows/train-example.yml:26-27, BASELINE config 1; --device=cuda because this package has no
+    CPU path) with env.* / model.NetMon,DQN,MLP / policy.EpsilonGreedy / replaybuffer / buffer aliased to graph_marl_b200
+    (tools/run_reference_driver.py) and prints the known answer `"reward_mean": 1.0`."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "baseline", "_ref", "src", "main.py")):
+        pytest.skip("baseline/_ref/src is not staged (run __graft_entry__.build() where /root/reference exists)")
+    cmd = [sys.executable, os.path.join(root, "tools", "run_reference_driver.py"), "main.py"] + (
+        "--model=dqn --hidden-dim=8 --random-topology=1 --mini-batch-size=32 --device=cuda --episode-steps=1 "
+        "--eval-episode-steps=1 --lr=0.001 --tau=0.01 --netmon --netmon-encoder-dim=4 --hidden-dim=4 --netmon-dim=2 "
+        "--netmon-iterations=1 --sequence-length=1 --step-before-train=1_000 --capacity=10_000 --eval-episodes=100 "
+        "--total-steps=5_000 --env-type=simple --epsilon=0.1 --epsilon-decay=1.0 --seed=0 --disable-progress").split()
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"reward_mean": 1.0' in r.stdout, r.stdout[-3000:]

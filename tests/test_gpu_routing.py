@@ -30,7 +30,7 @@ def _check_state(env, g, t):
         assert np.array_equal(s[k][0], g["s_" + k][t]), (k, t)
 
 
-@pytest.mark.parametrize("store_mode", [1, 2])
+@pytest.mark.parametrize("store_mode", [1, 2, 3])
 @pytest.mark.parametrize("case", CASES)
 def test_golden_trajectory(case, store_mode):
     g = load_golden(case)
