@@ -14,6 +14,7 @@ GM_MAX_LAYERS = 8
 GM_REPLAY_MAX_FIELDS = 24
 GM_MT_STATE_WORDS = 625
 GM_PCG64_STATE_WORDS = 6
+GM_NCCL_UNIQUE_ID_BYTES = 128
 RNN_TYPES = {"lstm": 0, "lnlstm": 1, "gru": 2, "none": 3}
 AGG_TYPES = {"sum": 0, "mean": 1}
 ACTIVATIONS = {"leaky_relu": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "elu": 4}
@@ -149,6 +150,12 @@ _SIGS = {
     "gm_netmon_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "gm_nccl_version": (C.c_int, []),
+    "gm_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "gm_nccl_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "gm_nccl_comm_destroy": (C.c_int, [C.c_void_p]),
+    "gm_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "gm_broadcast_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "gm_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_linear_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),

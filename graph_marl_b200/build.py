@@ -18,7 +18,7 @@ LIB = os.path.join(LIBDIR, "libgraphmarl_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["runtime.cu", "routing_env.cu", "simple_env.cu", "netmon.cu", "gemm_dispatch.cu", "linear_simt.cu",
-           "gemm_sm100.cu", "dqn.cu", "replay.cu", "replay_sampler.cu", "train.cu", "host_topology.cpp"]
+           "gemm_sm100.cu", "dqn.cu", "replay.cu", "replay_sampler.cu", "train.cu", "host_topology.cpp", "collective.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-x", "cu",
               "--expt-relaxed-constexpr", "-I", INCLUDE]
@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

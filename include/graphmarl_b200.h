@@ -374,6 +374,23 @@ GM_API int gm_netmon_backward(const gm_netmon_params* p, int32_t B, int32_t N, c
                        void* stream);
 
 /* ======================================================================== */
+/* Optional learner collective (hook between loss.backward() and             */
+/* optimizer.step(), src/main.py:1002-1004): one fused NCCL        */
+/* all-reduce of the flat fp32 gradient.  The rollout path has no collective. */
+/* ======================================================================== */
+#define GM_NCCL_UNIQUE_ID_BYTES 128
+/* NCCL is bound at run time (the libnccl.so.2 already mapped into the process, else the system one); 0 = unavailable */
+GM_API int gm_nccl_version(void);
+/* rank 0 creates the id (host bytes) and the host code hands it to every rank (any transport) */
+GM_API int gm_nccl_unique_id(uint8_t* id128);
+GM_API int gm_nccl_comm_create(int32_t world_size, int32_t rank, const uint8_t* id128, void** comm);
+GM_API int gm_nccl_comm_destroy(void* comm);
+/* flat f32[n] (device) <- sum (average = 0) or mean (average = 1) over the ranks, in place, asynchronous on stream */
+GM_API int gm_allreduce_grads(void* comm, float* flat, int64_t n, int32_t average, void* stream);
+/* start-up: every rank's flat parameter buffer <- rank root's */
+GM_API int gm_broadcast_weights(void* comm, float* flat, int64_t n, int32_t root, void* stream);
+
+/* ======================================================================== */
 /* building blocks exposed for tests / profiling                             */
 /* ======================================================================== */
 /* C[M,N] = act(A[M,K] * W[N,K]^T + bias) in the requested math mode */

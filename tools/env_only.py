@@ -1,0 +1,36 @@
+"""Env-step kernel alone (profiling / A-B timing): B envs of config 2, device Philox draws, random actions.
+usage: python tools/env_only.py [B] [iters] -- prints the CUDA-event time per launch and the HBM-roofline fraction."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from bench import env_step_bytes, peaks
+from graph_marl_b200.env.network import Network
+from graph_marl_b200.env.routing import Routing
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+N = A = 20
+env = Routing(Network(N, random_topology=False, topology_init_seed=923430603), A, 1, num_envs=B, seed=1, batched=True)
+env.reset()
+acts = [torch.randint(0, 4, (B, A), device="cuda", dtype=torch.int32) for _ in range(8)]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for i in range(10):
+    env.step(acts[i % 8])
+torch.cuda.synchronize()
+ts = []
+for i in range(iters):
+    flush.zero_()  # outputs of the previous launch leave L2, like in the rollout where GEMMs run in between
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    env.step(acts[i % 8])
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3)
+ts.sort()
+med = ts[len(ts) // 2]
+by = env_step_bytes(N, A) * B
+print(f"B={B} store_mode={os.environ.get('GM_ROUTING_STORE_MODE', 'default')} median {med:.2f} us  min {ts[0]:.2f} us  "
+      f"roofline frac (median) {by / (med * 1e-6) / 1e9 / peaks()['hbm_gbs']:.3f}")
