@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgraphmarl_b200.so")
+# GM_LIB_PATH: a probe / experiment build of the same sources (tools/env_only.py, tools/tc_trace.py); default in-tree
+LIB_PATH = os.environ.get("GM_LIB_PATH") or os.path.join(_HERE, "lib", "libgraphmarl_b200.so")
 
 GM_MAX_LAYERS = 8
 GM_REPLAY_MAX_FIELDS = 24
@@ -118,8 +119,8 @@ _SIGS = {
                                   C.c_void_p, C.c_void_p]),
     "gm_netmon_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
-                                    C.c_void_p]),
+                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64, C.c_void_p]),
     "gm_packed_activation_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "gm_netmon_map_to_agents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]),

@@ -644,164 +644,6 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// Weight-stationary cluster variant (all activations tile-packed).
-//
-// The layers of this workload have small weights and a huge M (rows = envs x nodes): streaming the
-// weight tile once per M tile makes linear_tc_kernel operand-bandwidth bound.  Here a cluster of csz
-// CTAs splits the N dimension: CTA `rank` keeps ITS BN-column slice of the packed weights resident in
-// shared memory for the whole kernel (<= 128 KiB), and the cluster walks the M tiles together: each
-// CTA bulk-copies 1/csz of every activation k-block and multicasts it to all CTAs of the cluster, so
-// an activation block is read from L2/HBM once per cluster and no weight byte moves after the prologue.
-// 10 warps: 8 epilogue (same code as linear_tc_kernel), 1 MMA thread, 1 copy thread.
-// -------------------------------------------------------------------------------------------------
-constexpr int WS_THREADS = 32 * 10, WS_MMA_WARP = 8, WS_COPY_WARP = 9, WS_MAX_A_STAGES = 8;
-
-template <int BN, int PASSES, int EPI>
-__global__ void __launch_bounds__(WS_THREADS, 1) linear_ws_kernel(const TcArgs p) {
-    constexpr int NCG = 2;  // 8 epilogue warps
-    constexpr int W_PART_BYTES = BN * BK * 2;
-    constexpr int W_KB_BYTES = 2 * W_PART_BYTES, A_STAGE_BYTES = 2 * A_PART_BYTES;
-    constexpr int ACC_STAGES = (512 / BN) > 4 ? 4 : (512 / BN);
-    constexpr uint32_t IDESC = umma_idesc(BN);
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[2 * WS_MAX_A_STAGES + 1 + 2 * 4];
-    __shared__ uint32_t tmem_base_smem;
-    __shared__ float qpart[1][1][TC_MAX_ACT];  // unused here (no fused Q head), referenced by the shared epilogue text
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a_stages = p.a_stages;
-    const int kblocks = p.Kp / BK;
-    const int kb_seg1 = p.K0p / BK;
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t a_ring = smem_base + (uint32_t)kblocks * W_KB_BYTES;  // activation ring sits behind the weights
-    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[WS_MAX_A_STAGES]);
-    const uint32_t bar_w = smem_u32(&bars[2 * WS_MAX_A_STAGES]);
-    const uint32_t bar_tfull = smem_u32(&bars[2 * WS_MAX_A_STAGES + 1]), bar_tempty = smem_u32(&bars[2 * WS_MAX_A_STAGES + 5]);
-    const int csz = p.csz;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < a_stages; s++) {
-            mbar_init(bar_afull + 8 * s, 1);     // own expect_tx arrive; the bytes come from every CTA's multicast share
-            mbar_init(bar_aempty + 8 * s, csz);  // one tcgen05.commit per CTA of the cluster
-        }
-        mbar_init(bar_w, 1);
-        for (int a = 0; a < ACC_STAGES; a++) {
-            mbar_init(bar_tfull + 8 * a, 1);
-            mbar_init(bar_tempty + 8 * a, EPI_WARPS * 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == WS_MMA_WARP) {
-        uint32_t dst = smem_u32(&tmem_base_smem);
-        uint32_t cols = ACC_STAGES * BN;
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (csz > 1) cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = tmem_base_smem;
-
-    const int rank = csz > 1 ? (int)cluster_ctarank() : 0;  // == this CTA's N tile
-    const uint16_t mc_mask = (uint16_t)((1u << csz) - 1u);
-    const int n_clusters = (int)gridDim.x / csz, cluster_id = (int)blockIdx.x / csz;
-    const int my_units = (p.m_tiles - cluster_id + n_clusters - 1) / n_clusters;  // M tiles of this cluster
-
-    if (warp == WS_COPY_WARP) {
-        if (lane == 0) {
-            // ---- the weight slice of this CTA: resident for the whole kernel --------------------
-            constexpr uint32_t w_kb = (PASSES == 3 ? 2 : 1) * W_PART_BYTES;
-            mbar_arrive_expect_tx(bar_w, (uint32_t)kblocks * w_kb);
-            for (int kb = 0; kb < kblocks; kb++)
-                bulk_g2s(smem_base + kb * W_KB_BYTES, p.Wp + ((size_t)rank * kblocks + kb) * W_KB_BYTES, w_kb, bar_w);
-            // ---- activation k-blocks: 1/csz each, multicast to the cluster -----------------------------
-            constexpr uint32_t a_bytes = (PASSES == 3 ? 2 : 1) * A_PART_BYTES;
-            const uint32_t slice = A_PART_BYTES / csz;
-            const int kb0_blocks = kb_seg1, kb1_blocks = kblocks - kb_seg1;
-            uint32_t it = 0;
-            for (int u = 0; u < my_units; u++) {
-                const int mt = cluster_id + u * n_clusters;
-                for (int kb = 0; kb < kblocks; kb++, it++) {
-                    const int sa = it % a_stages;
-                    const uint32_t pha = (it / a_stages) & 1;
-                    const bool seg1 = kb >= kb_seg1;
-                    const uint8_t* apk = seg1 ? p.A1pk : p.A0pk;
-                    const size_t blk = seg1 ? ((size_t)mt * kb1_blocks + (kb - kb_seg1)) : ((size_t)mt * kb0_blocks + kb);
-                    const uint8_t* src = apk + blk * TC_PK_BLOCK;
-                    mbar_wait(bar_aempty + 8 * sa, pha ^ 1);  // every CTA of the cluster retired its MMAs on this stage
-                    mbar_arrive_expect_tx(bar_afull + 8 * sa, a_bytes);
-                    const uint32_t dst = a_ring + sa * A_STAGE_BYTES;
-                    if (csz == 1) {
-                        bulk_g2s(dst, src, a_bytes, bar_afull + 8 * sa);
-                    } else {
-#pragma unroll
-                        for (int part = 0; part < (PASSES == 3 ? 2 : 1); part++)
-                            bulk_g2s_mc(dst + part * A_PART_BYTES + rank * slice, src + part * A_PART_BYTES + rank * slice, slice,
-                                        bar_afull + 8 * sa, mc_mask);
-                    }
-                }
-            }
-        }
-    } else if (warp == WS_MMA_WARP) {
-        if (lane == 0) {
-            mbar_wait(bar_w, 0);
-            uint32_t it = 0;
-            for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
-                const int as = tcount % ACC_STAGES;
-                const uint32_t aph = (tcount / ACC_STAGES) & 1;
-                mbar_wait(bar_tempty + 8 * as, aph ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + as * BN;
-                for (int kb = 0; kb < kblocks; kb++, it++) {
-                    const int sa = it % a_stages;
-                    mbar_wait(bar_afull + 8 * sa, (it / a_stages) & 1);
-                    tc_fence_after();
-                    const uint32_t a_hi = a_ring + sa * A_STAGE_BYTES, a_lo = a_hi + A_PART_BYTES;
-                    const uint32_t w_hi = smem_base + kb * W_KB_BYTES, w_lo = w_hi + W_PART_BYTES;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 16; ks++) {
-                        const uint32_t o = ks * 256;
-                        if (PASSES == 3) {
-                            umma(d, umma_desc(a_lo + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
-                            umma(d, umma_desc(a_hi + o), umma_desc(w_lo + o), IDESC, 1);
-                            umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, 1);
-                        } else {
-                            umma(d, umma_desc(a_hi + o), umma_desc(w_hi + o), IDESC, (kb | ks) != 0);
-                        }
-                    }
-                    if (csz == 1) umma_commit(bar_aempty + 8 * sa);
-                    else umma_commit_mc(bar_aempty + 8 * sa, mc_mask);
-                }
-                umma_commit(bar_tfull + 8 * as);
-            }
-        }
-    } else {
-        const int quad = warp & 3, chalf = warp >> 2;
-        const int r = quad * 32 + lane;
-        for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
-            const int as = tcount % ACC_STAGES;
-            const uint32_t aph = (tcount / ACC_STAGES) & 1;
-            const int mt = cluster_id + (int)tcount * n_clusters, nt = rank;
-            const int64_t m = (int64_t)mt * BM + r;
-            const bool live = m < p.M;
-#include "gemm_sm100_epilogue.inc"
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * as);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (csz > 1) cluster_sync_all();
-    if (warp == WS_MMA_WARP) {
-        tc_fence_after();
-        uint32_t cols = ACC_STAGES * BN;
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
-    }
-}
-
-// -------------------------------------------------------------------------------------------------
 // weight packing: fp32 W[N,K] (nn.Linear layout) -> bf16 hi/lo tiles in the UMMA canonical layout
 //   out[nt][kb][part][g][kc][r][e]  (g = 8-row group, kc = 8-element K chunk, r = row in group)
 // Packed K space: segment 0 = [0,K0p) (K0 real columns, zero padded), segment 1 from K0p.
@@ -1065,72 +907,11 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
 }
 
 
-// ---- weight-stationary plan ---------------------------------------------------------------------------
-// Splits the packed N columns over a cluster so that one slice (BN columns x Kp, hi+lo) fits in shared
-// memory next to >= 3 activation stages.  Returns false when the layer does not qualify.
-bool tc_ws_plan(int N, int K0, int K1, int epi, int H, TcWsPlan* out) {
-    static int enabled = -1;
-    if (enabled < 0) {
-        const char* e = getenv("GM_TC_WS");
-        enabled = e ? atoi(e) : 0;  // measured on B200: slower than the streaming kernel (multicast replicates the bytes in flight, HBM-latency bound)
-    }
-    if (!enabled || epi == EPI_QHEAD || epi == EPI_LNLSTM) return false;
-    const int cols = epi == EPI_LSTM ? 4 * H : N;
-    const int Kp = (int)round_up(K0, tc::BK) + (int)round_up(K1, tc::BK);
-    const int bns[2] = {128, 64};
-    for (int bi = 0; bi < 2; bi++) {
-        const int BN = bns[bi];
-        if (epi == EPI_LSTM && BN != 128) continue;  // instantiated for 32 hidden units x 4 gates per CTA
-        if (cols % BN != 0) continue;
-        const int csz = cols / BN;
-        if (csz != 1 && csz != 2 && csz != 4) continue;
-        const int64_t w_bytes = (int64_t)(Kp / tc::BK) * 2 * BN * tc::BK * 2;
-        const int64_t room = 227 * 1024 - 1024 - w_bytes;
-        const int stages = (int)std::min<int64_t>(room / (2 * tc::A_PART_BYTES), tc::WS_MAX_A_STAGES);
-        if (stages < 3) continue;
-        out->BN = BN; out->csz = csz; out->a_stages = stages;
-        out->smem = (int)(w_bytes + (int64_t)stages * 2 * tc::A_PART_BYTES);
-        return true;
-    }
-    return false;
-}
-
-template <int BN, int PASSES, int EPI>
-static int launch_ws(TcArgs a, const TcWsPlan& plan, cudaStream_t s) {
-    static int configured_smem = 0;
-    static int max_clusters[5] = {0, 0, 0, 0, 0};
-    auto kern = tc::linear_ws_kernel<BN, PASSES, EPI>;
-    if (configured_smem < plan.smem) {
-        GM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
-        if (plan.csz > 2) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), cudaGetLastError();
-        configured_smem = plan.smem;
-        for (int i = 0; i < 5; i++) max_clusters[i] = 0;
-    }
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
-    cfg.blockDim = dim3(tc::WS_THREADS);
-    cfg.dynamicSmemBytes = plan.smem;
-    cfg.stream = s;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = plan.csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (max_clusters[plan.csz] == 0) {
-        cfg.gridDim = dim3((kNumSMs / plan.csz) * plan.csz);
-        int n = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-        if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = -1; }
-        max_clusters[plan.csz] = n;
-    }
-    if (max_clusters[plan.csz] < 0) return 1;  // clusters of this shape cannot be scheduled: caller falls back
-    a.csz = plan.csz;
-    a.a_stages = plan.a_stages;
-    const int n_clusters = std::min(a.m_tiles, max_clusters[plan.csz]);
-    cfg.gridDim = dim3(n_clusters * plan.csz);
-    ProfileScope prof(PROF_TC, s);
-    GM_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
-    count_launch();
-    return GM_OK;
-}
+// A weight-stationary cluster kernel (one N slice of the weights resident per CTA, activation k-blocks multicast over the
+// cluster) was built and measured in round 1: slower than the streaming kernel at these shapes (multicast replicates
+// the bytes in flight) and removed in round 2.  The plan query stays so that callers' packing code
+// keeps one code path.
+bool tc_ws_plan(int, int, int, int, int, TcWsPlan*) { return false; }
 
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     if (a.M <= 0) return GM_OK;
@@ -1180,19 +961,7 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
         GM_CHECK_ARG(!a.accumulate || a.C != nullptr, "accumulate needs an fp32 output");
     }
     const int passes = math == GM_MATH_BF16 ? 1 : 3;
-    if (a.ws) {  // weight-stationary cluster variant: weights were packed for the plan's BN
-        TcWsPlan plan;
-        GM_CHECK_ARG(!a.has_prod && tc_ws_plan(a.N, a.K0, a.K1, epi, a.H, &plan), "layer does not qualify for the weight-stationary kernel");
-        int rc = 1;
-        if (epi == EPI_LSTM) rc = passes == 3 ? launch_ws<128, 3, EPI_LSTM>(a, plan, s) : launch_ws<128, 1, EPI_LSTM>(a, plan, s);
-        else if (plan.BN == 128) rc = passes == 3 ? launch_ws<128, 3, EPI_LINEAR>(a, plan, s) : launch_ws<128, 1, EPI_LINEAR>(a, plan, s);
-        else rc = passes == 3 ? launch_ws<64, 3, EPI_LINEAR>(a, plan, s) : launch_ws<64, 1, EPI_LINEAR>(a, plan, s);
-        if (rc == 1) {
-            set_error("cluster launch of the weight-stationary kernel is not possible on this device (set GM_TC_WS=0)");
-            return GM_ERR_CUDA;
-        }
-        return rc;
-    }
+    GM_CHECK_ARG(!a.ws, "the weight-stationary kernel was removed");
     // 2-CTA pairs (cta_group::2, M = 256): half the weight bytes and shared-memory operand reads per CTA.  Measured on
     // B200 at this workload's shapes: correct but 5-15 % slower than the single-CTA kernel (the relay of "peer stage
     // full" and the two-CTA accumulator release lengthen the per-stage loop), so it is an option: GM_TC_PAIR=1

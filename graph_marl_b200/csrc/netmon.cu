@@ -9,12 +9,12 @@
 // neighbour lists (self included when the mask has it) instead of the reference's dense
 // [B,N,N] float mask, so aggregation is a sum over short lists and the readout is a pure gather.
 //
-// Aggregation on the tensor-core path (tile-packed output, one of four kernels, see the launch site):
+// Aggregation on the tensor-core path (tile-packed output, see the launch site):
 //   aggregate_pk_pipe_kernel  default: persistent CTAs, TMA bulk copies of whole graphs' hidden rows / lists into a
 //                             3-stage shared-memory ring (producer warp + mbarriers), sums from shared memory
-//   aggregate_pk_bulk_kernel  one block per row block, one bulk copy, no ring           (GM_AGG_MAP=1)
 //   aggregate_pk_kernel       L2 gather, 8 rows x 32 columns per warp; the fallback for graphs that do not fit the ring
-//   aggregate_pk4_kernel      L2 gather, 4 rows x one full line per load instruction    (GM_AGG_MAP=4)
+//                             (GM_AGG_MAP=8 forces it).  Two more forms measured in round 1 (a 4-row-per-line gather and a
+//                             single-stage bulk-staged kernel, both slower) were removed in round 2.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -195,188 +195,7 @@ __global__ void __launch_bounds__(STAGED ? 320 : 256) aggregate_pk_kernel(const 
     }
 }
 
-// Same result as aggregate_pk_kernel<true>, different lane mapping: a load instruction covers 4 rows x one full 128-byte
-// line (lane = (r4 = lane/8, c = lane%8) owns the 4-float chunk c of rows r4 and 4+r4 of the 8-row group) instead of
-// 8 rows x half of every 32-byte sector, which halves the L1 wavefronts of the gather (ncu: the L1 data pipe, 53 % busy,
-// was the most loaded unit of the 8-row mapping).  A lane then holds half of a 16-byte core-matrix row for two rows and
-// stores 8 bytes per row and hi/lo plane; a store instruction still fills whole 32-byte sectors.
-__global__ void __launch_bounds__(256, 5) aggregate_pk4_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
-                                                            int B, int N, int H, const int* __restrict__ nbr,
-                                                            const int* __restrict__ deg, int DM,
-                                                            const int* __restrict__ list_index, int mean, int write_lo,
-                                                            int rows_per_block) {
-    extern __shared__ int agg_lists[];  // lists i32[rows_per_block][DM] | degrees i32[rows_per_block]
-    const int lane = threadIdx.x & 31;
-    const int kbs = H / TC_BK;
-    const int64_t R = (int64_t)B * N;
-    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
-    const int tasks = (rows_per_block >> 3) * kbs;
-    int* s_deg = agg_lists + rows_per_block * DM;
-    for (int t = threadIdx.x; t < rows_per_block * DM; t += (int)blockDim.x) {
-        const int r = t / DM, q = t - r * DM;
-        const int64_t row = row0 + r;
-        int val = 0;
-        if (row < R) {
-            const unsigned row32 = (unsigned)row;
-            const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
-            const size_t node = (size_t)(list_index ? list_index[b] : b) * N + v;
-            val = nbr[node * DM + q];
-            if (q == 0) s_deg[r] = deg[node];
-        } else if (q == 0) {
-            s_deg[r] = 0;
-        }
-        agg_lists[t] = val;
-    }
-    __syncthreads();
-    const int r4 = lane >> 3, c = lane & 7;
-    for (int t = threadIdx.x >> 5; t < tasks; t += (int)(blockDim.x >> 5)) {
-        const int g8 = (t / kbs) * 8, kb = t % kbs;
-        if (row0 + g8 >= R) continue;
-        float4 x[2];
-        const int* lst[2];
-        const float* hb[2];
-        int dg[2];
-        float4 a[2][4];
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int rl = g8 + 4 * j + r4;
-            const unsigned row32 = (unsigned)(row0 + rl);  // the host checks B*N < 2^31
-            const unsigned b = min(row32 / (unsigned)N, (unsigned)(B - 1));
-            lst[j] = agg_lists + rl * DM;
-            dg[j] = s_deg[rl];  // 0 beyond the last row
-            hb[j] = h + (size_t)b * N * ldh + kb * TC_BK + c * 4;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                a[j][q] = q < dg[j] ? __ldg((const float4*)(hb[j] + (size_t)lst[j][q] * ldh)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {  // ascending list order; "+ 0" of an absent entry is skipped like in the 8-row kernel
-                if (q < dg[j]) { x[j].x += a[j][q].x; x[j].y += a[j][q].y; x[j].z += a[j][q].z; x[j].w += a[j][q].w; }
-            }
-            for (int q = 4; q < dg[j]; q++) {
-                const float4 e = __ldg((const float4*)(hb[j] + (size_t)lst[j][q] * ldh));
-                x[j].x += e.x; x[j].y += e.y; x[j].z += e.z; x[j].w += e.w;
-            }
-            if (mean) {
-                const float d = (float)max(dg[j], 1);
-                x[j].x = x[j].x / d; x[j].y = x[j].y / d; x[j].z = x[j].z / d; x[j].w = x[j].w / d;
-            }
-            const int64_t row = row0 + g8 + 4 * j + r4;
-            if (row >= R) continue;
-            const uint32_t hi0 = agg_pack2(x[j].x, x[j].y), hi1 = agg_pack2(x[j].z, x[j].w);
-            const uint32_t lo0 = agg_pack2(x[j].x - __uint_as_float(hi0 << 16), x[j].y - __uint_as_float(hi0 & 0xffff0000u));
-            const uint32_t lo1 = agg_pack2(x[j].z - __uint_as_float(hi1 << 16), x[j].w - __uint_as_float(hi1 & 0xffff0000u));
-            const int64_t mt = row / TC_BM;
-            const int r = (int)(row - mt * TC_BM);
-            uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
-                           (r & 7) * 16 + (c & 1) * 8;
-            *(uint2*)dst = make_uint2(hi0, hi1);
-            if (write_lo) *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
-        }
-    }
-}
-
-// Bulk-staged aggregation: a block owns whole graphs, so every neighbour of its rows is one of its rows.  One thread pulls the
-// block's hidden rows (contiguous when ldh == H: ONE cp.async.bulk, TMA bulk copy, completing on an mbarrier) into shared
-// memory while the others stage the neighbour lists; the sums then read shared memory only.  h crosses L2 -> SM once (not
-// once per list that names the row), no warp ever waits on a dependent global gather, and the only long latency of a block
-// is the bulk copy, overlapped across the 8-10 resident blocks of an SM.  Lane mapping as in aggregate_pk4_kernel: a
-// quarter-warp reads one row's contiguous 128 bytes (conflict-free LDS.128), a lane stores 8 bytes per row and plane.
 __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__global__ void __launch_bounds__(256, 5) aggregate_pk_bulk_kernel(const float* __restrict__ h, int64_t ldh, uint8_t* __restrict__ Mpk,
-                                                                   int B, int N, int H, const int* __restrict__ nbr,
-                                                                   const int* __restrict__ deg, int DM,
-                                                                   const int* __restrict__ list_index, int mean, int write_lo,
-                                                                   int rows_per_block) {
-    extern __shared__ __align__(128) uint8_t agg_sm[];  // mbarrier (16 B) | rows f32[rpb][H] | lists i32[rpb][DM] | degrees i32[rpb]
-    float* s_h = (float*)(agg_sm + 16);
-    int* s_lst = (int*)(agg_sm + 16 + (size_t)rows_per_block * H * 4);
-    int* s_deg = s_lst + rows_per_block * DM;
-    const int lane = threadIdx.x & 31;
-    const int kbs = H / TC_BK;
-    const int64_t R = (int64_t)B * N;
-    const int64_t row0 = (int64_t)blockIdx.x * rows_per_block;
-    const int nrows = (int)min((int64_t)rows_per_block, R - row0);
-    const uint32_t bar = agg_smem_u32(agg_sm);
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t row_bytes = (uint32_t)H * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes * (uint32_t)nrows) : "memory");
-        if (ldh == H) {
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(agg_smem_u32(s_h)),
-                         "l"(h + row0 * ldh), "r"(row_bytes * (uint32_t)nrows), "r"(bar)
-                         : "memory");
-        } else {
-            for (int r = 0; r < nrows; r++)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 agg_smem_u32(s_h + (size_t)r * H)),
-                             "l"(h + (row0 + r) * ldh), "r"(row_bytes), "r"(bar)
-                             : "memory");
-        }
-    }
-    for (int t = threadIdx.x; t < rows_per_block * DM; t += (int)blockDim.x) {
-        const int r = t / DM, q = t - r * DM;
-        int val = 0;
-        if (r < nrows) {
-            const unsigned row32 = (unsigned)(row0 + r);  // the host checks B*N < 2^31
-            const int b = (int)(row32 / (unsigned)N), v = (int)(row32 - (unsigned)b * (unsigned)N);
-            const size_t node = (size_t)(list_index ? list_index[b] : b) * N + v;
-            val = nbr[node * DM + q];
-            if (q == 0) s_deg[r] = deg[node];
-        } else if (q == 0) {
-            s_deg[r] = 0;
-        }
-        s_lst[t] = val;
-    }
-    __syncthreads();  // lists staged; the mbarrier's initialisation is visible to every thread
-    {
-        uint32_t done = 0, spins = 0;
-        while (!done) {  // bounded: a protocol bug traps instead of hanging the GPU
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done)
-                         : "r"(bar)
-                         : "memory");
-            if (!done && ++spins > (1u << 26)) __trap();
-        }
-    }
-    const int r4 = lane >> 3, c = lane & 7;
-    const int tasks = ((nrows + 7) >> 3) * kbs;
-    for (int t = threadIdx.x >> 5; t < tasks; t += (int)(blockDim.x >> 5)) {
-        const int g8 = (t / kbs) * 8, kb = t % kbs;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int rl = g8 + 4 * j + r4;
-            if (rl >= nrows) continue;
-            const int* lst = s_lst + rl * DM;
-            const int dg = s_deg[rl];
-            const float* hb = s_h + (size_t)(rl / N) * N * H + kb * TC_BK + c * 4;  // rows of this row's graph
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < dg; q++) {  // ascending list order = the reference's bmm row order
-                const float4 e = *(const float4*)(hb + (size_t)lst[q] * H);
-                x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
-            }
-            if (mean) {
-                const float d = (float)max(dg, 1);
-                x.x = x.x / d; x.y = x.y / d; x.z = x.z / d; x.w = x.w / d;
-            }
-            const uint32_t hi0 = agg_pack2(x.x, x.y), hi1 = agg_pack2(x.z, x.w);
-            const uint32_t lo0 = agg_pack2(x.x - __uint_as_float(hi0 << 16), x.y - __uint_as_float(hi0 & 0xffff0000u));
-            const uint32_t lo1 = agg_pack2(x.z - __uint_as_float(hi1 << 16), x.w - __uint_as_float(hi1 & 0xffff0000u));
-            const int64_t row = row0 + rl;
-            const int64_t mt = row / TC_BM;
-            const int r = (int)(row - mt * TC_BM);
-            uint8_t* dst = Mpk + ((size_t)mt * kbs + kb) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + (c >> 1) * 128 +
-                           (r & 7) * 16 + (c & 1) * 8;
-            *(uint2*)dst = make_uint2(hi0, hi1);
-            if (write_lo) *(uint2*)(dst + TC_BM * TC_BK * 2) = make_uint2(lo0, lo1);
-        }
-    }
-}
 
 // Persistent, pipelined form of the bulk-staged aggregation: one CTA per SM slot walks its row blocks through a 3-stage
 // shared-memory ring.  Warp 0 is the producer: lane 0 posts the stage's transaction count and issues the bulk copy of the
@@ -989,8 +808,8 @@ int gm_netmon_map_to_agents(const float* node_out, const float* node_agent, int3
 int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs, const int32_t* nbr_all,
                       const int32_t* deg, int32_t DM, const int32_t* list_index, const float* state_in,
                       float* state_out, int32_t max_degree, float* node_out, const int32_t* agent_node, int32_t A,
-                      float* agent_out, int64_t agent_out_ld, void* agent_out_pk, void* workspace, int64_t workspace_bytes,
-                      void* stream) {
+                      float* agent_out, int64_t agent_out_ld, void* agent_out_pk, const void* state_h_pk_in, void* state_h_pk_out,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
     GM_CHECK_ARG(p && node_obs && nbr_all && deg && state_out && workspace, "null pointer");
     GM_CHECK_ARG(B > 0 && N > 0 && DM > 0, "bad sizes");
     const int H = p->hidden, K = p->iterations, L = p->n_enc_layers;
@@ -1034,6 +853,9 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     // Tensor-core path with fused cells: layer outputs stay tile-packed (bf16 hi/lo) and are pulled
     // by the next layer with bulk copies; the last layer feeds the rnn_obs cell the same way.
     const bool fused = tc && PL.fused_cells;
+    GM_CHECK_ARG(fused || (state_h_pk_in == nullptr && state_h_pk_out == nullptr),
+                 "a tile-packed hidden state is only carried by the fused tensor-core cells");
+    GM_CHECK_ARG((((uintptr_t)state_h_pk_in | (uintptr_t)state_h_pk_out) & 127) == 0, "tile-packed state must be 128-byte aligned");
     const float* x = node_obs;
     const uint8_t* xpk = nullptr;
     int64_t ldx = p->in_features;
@@ -1100,8 +922,13 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         // producer warps split it on the fly.
         const int kbs = H / TC_BK;
         int rc;
-        if (PL.ws_cells || PL.cell_epi == EPI_LNLSTM) {
-            GM_CHECK_ARG(xpk != nullptr, "weight-stationary / LayerNormLSTM cells need a tile-packed encoder output");
+        // the carried h as the previous step's last cell left it, tile-packed (state_h_pk_in): the cell then runs with
+        // every operand pulled by bulk copies (16 epilogue warps, no producer work); only valid with a given state
+        const uint8_t* hpk_in = state_in ? (const uint8_t*)state_h_pk_in : nullptr;
+        if (hpk_in && xpk) {
+            rc = cell(PL.obs, xpk, e, hpk_in, nullptr, 0, st_in + H, S, hbuf[0], H, cbuf[0], -1, hpk[0]);
+        } else if (PL.ws_cells || PL.cell_epi == EPI_LNLSTM) {
+            GM_CHECK_ARG(xpk != nullptr, "LayerNormLSTM cells need a tile-packed encoder output");
             const unsigned blocks = (unsigned)((((R + 7) / 8) * kbs + 7) / 8);
             split_pk_kernel<<<blocks, 256, 0, s>>>(st_in, S, hpk[1], R, H, math != GM_MATH_BF16);
             GM_LAUNCH_CHECK();
@@ -1124,8 +951,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                 if (agg_staged < 0) { const char* e = getenv("GM_AGG_STAGE_LISTS"); agg_staged = e ? atoi(e) : 1; }
                 const unsigned agg_blocks = (unsigned)((R + rpb - 1) / rpb);
                 static int agg_map = -1;
-                if (agg_map < 0) { const char* e = getenv("GM_AGG_MAP"); agg_map = e ? atoi(e) : 2; }  // 2: pipelined (default), 1: bulk-staged, 4 / 8: gather kernels
-                const size_t bulk_smem = 16 + (size_t)rpb * H * 4 + (size_t)rpb * (DM + 1) * sizeof(int);
+                if (agg_map < 0) { const char* e = getenv("GM_AGG_MAP"); agg_map = e ? atoi(e) : 2; }  // 2: pipelined (default), anything else: the L2 gather kernel
                 const int pipe_stage = (int)round_up((int64_t)rpb * H * 4 + (int64_t)rpb * (DM + 1) * (int64_t)sizeof(int), 128);
                 const size_t pipe_smem = 128 + (size_t)AGG_STAGES * pipe_stage;
                 if (agg_map == 2 && rpb % N == 0 && rpb / N <= 32 && pipe_smem <= 72 * 1024 && ((uintptr_t)h & 15) == 0) {
@@ -1158,12 +984,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                         aggregate_pk_pipe_kernel<0, 0><<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
                                                                                              p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
                                                                                              (int)agg_blocks, pipe_stage);
-                } else if (agg_map == 1 && rpb % N == 0 && bulk_smem <= 48 * 1024 && ((uintptr_t)h & 15) == 0 && agg_threads <= 256)
-                    aggregate_pk_bulk_kernel<<<agg_blocks, agg_threads, bulk_smem, s>>>(
-                        h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
-                else if (agg_map == 4)
-                    aggregate_pk4_kernel<<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
-                        h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
+                }
                 else if (agg_staged)
                     aggregate_pk_kernel<true><<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
                         h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb);
@@ -1175,7 +996,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             float* hn = final_it ? state_out : hbuf[cur ^ 1];  // the last cell writes the new state in place (:562-564)
             float* cn = final_it ? state_out + H : cbuf[cur ^ 1];
             int64_t ldn = final_it ? S : H;
-            rc = cell(PL.upd, w.m_pk, nullptr, hpk[cur], nullptr, 0, c, -1, hn, ldn, cn, final_it ? ldn : -1, final_it ? nullptr : hpk[cur ^ 1]);
+            rc = cell(PL.upd, w.m_pk, nullptr, hpk[cur], nullptr, 0, c, -1, hn, ldn, cn, final_it ? ldn : -1,
+                      final_it ? (uint8_t*)state_h_pk_out : hpk[cur ^ 1]);
             if (rc) return rc;
             h = hn; c = cn; ldh_cur = ldn; cur ^= 1;
         }

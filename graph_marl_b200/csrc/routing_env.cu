@@ -26,7 +26,7 @@ struct RoutingLayout {
     int sm_scratch, sm_stage, sm_per_warp, stage_floats;
 };
 
-static RoutingLayout make_layout(int N, int A, int E, int stage_bytes) {
+static RoutingLayout make_layout(int N, int A, int E, int stage_bytes, int stages = 1) {
     RoutingLayout L;
     L.VW = (N + 31) / 32;
     L.off_load = 8 * A;
@@ -39,11 +39,24 @@ static RoutingLayout make_layout(int N, int A, int E, int stage_bytes) {
     int scratch = 8 * N + 4 * N + 4 * A + A;
     L.sm_stage = (int)round_up(L.sm_scratch + scratch, 16);
     L.stage_floats = stage_bytes / 4;
-    L.sm_per_warp = (int)round_up(L.sm_stage + stage_bytes + 32, 16);
+    L.sm_per_warp = (int)round_up(L.sm_stage + stages * (stage_bytes + 32), 16);  // per env: record + scratch + staging tile(s)
     return L;
 }
 
 enum { MODE_RESET = 0, MODE_STEP = 1, MODE_OBSERVE = 2 };
+
+// -DGM_ROUTING_PROBES=1 (GM_NVCC_EXTRA): per-env SM-clock stamps at the phase boundaries of the step kernel, read back
+// with gm_routing_probe_read (tools/env_probe.py).  The default build contains none of this.
+#ifdef GM_ROUTING_PROBES
+constexpr int PROBE_ENVS = 16384, PROBE_N = 10;
+__device__ long long g_probe[PROBE_ENVS][PROBE_N];
+#define GM_PROBE(k)                                                                      \
+    do {                                                                                 \
+        if (MODE == MODE_STEP && lane == 0 && b < PROBE_ENVS) g_probe[b][(k) + (role ? 0 : 0)] = clock64(); \
+    } while (0)
+#else
+#define GM_PROBE(k) do {} while (0)
+#endif
 #ifndef GM_ROUTING_MIN_CTAS
 #define GM_ROUTING_MIN_CTAS 7
 #endif
@@ -238,36 +251,66 @@ __device__ __noinline__ void emit_node_agent_rows(const int* now, int8_t* g, int
     }
 }
 
-template <int MODE>
+// WPE = warps per env.  1: one warp owns the env from record load to the last observation byte.  2 (batches that
+// leave half of an SM's warp slots empty): the pair shares the env's shared-memory record; warp 0 advances it, then --
+// after a 64-thread named barrier -- emits the agent observations and adjacency while warp 1 builds the waiting-packet
+// sums, the node observations and the node-agent matrix (each warp has its own staging tile).
+// SIMPLE: the common configuration (env_var 1, staged bulk stores, no action mask, no evaluation extras) compiled
+// without the other variants' code: the general kernel is 5.4 K SASS instructions and 16 % of its stall samples were
+// instruction fetches (ncu, profiles/r2_env_step_ncu.md).
+template <int MODE, int WPE, bool SIMPLE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, GM_ROUTING_MIN_CTAS)
 routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLayout L) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.x * WARPS_PER_CTA + warp;
-    if (b >= d.B) return;  // whole warp exits together; no block-wide barrier is used below
+    const int role = WPE == 2 ? (warp & 1) : 0;
+    const int slot_in_cta = WPE == 2 ? (warp >> 1) : warp;
+    const int b = blockIdx.x * (WARPS_PER_CTA / WPE) + slot_in_cta;
+    if (b >= d.B) return;  // the env's warp(s) exit together; only pair-wide named barriers are used below
     if (MODE == MODE_RESET && io.env_mask != nullptr && io.env_mask[b] == 0) return;
 
     const int N = d.N, A = d.A, E = d.E;
+    const int env_var = SIMPLE ? 1 : d.env_var;
+    const bool use_mask = SIMPLE ? false : (d.action_mask != 0);
+    const bool eval_info = SIMPLE ? false : (io.eval_f64 != nullptr);
     const int topo = d.topo_index ? d.topo_index[b] : 0;
     const int* __restrict__ ne = d.node_edges + (size_t)topo * N * 3;
     const int* __restrict__ nb = d.node_nbrs + (size_t)topo * N * 3;
     const int4* __restrict__ ed = (const int4*)d.edges + (size_t)topo * E;
     const int* __restrict__ apsp = d.apsp + (size_t)topo * N * N;
 
-    uint8_t* sm = smem + (size_t)warp * L.sm_per_warp;
+    uint8_t* sm = smem + (size_t)slot_in_cta * L.sm_per_warp;
     EnvView v = make_view(sm, L, A, N);
     uint8_t* gstate = d.state + (size_t)b * L.stride;
 
+    GM_PROBE(0);
+    int n_resets = 0;
+    if (role == 0) {  // ======== warp 0 of the env: record load, reset / step, write-back ========
     // ---- load the env record ------------------------------------------------------
+    // (the first chunk of actions is requested before the record so that both DRAM round trips overlap; every record
+    // load of a 128-unit group is in flight before the first store waits -- the plain copy loop serialised three round
+    // trips: 3.6 K of a warp's 32 K clocks, tools/env_only.py with the probe build)
+    int act_first = 0;
+    if (MODE == MODE_STEP && lane < A) act_first = __ldg(io.actions + (size_t)b * A + lane);
     if (MODE != MODE_RESET) {
         const uint4* src = (const uint4*)gstate;
         uint4* dst = (uint4*)sm;
-        for (int q = lane; q < L.stride / 16; q += 32) dst[q] = src[q];
+        const int n16 = L.stride / 16;
+        for (int q0 = 0; q0 < n16; q0 += 128) {
+            uint4 t[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (q0 + 32 * k + lane < n16) t[k] = src[q0 + 32 * k + lane];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (q0 + 32 * k + lane < n16) dst[q0 + 32 * k + lane] = t[k];
+        }
     } else {
         uint4* dst = (uint4*)sm;
         for (int q = lane; q < L.stride / 16; q += 32) dst[q] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
+    GM_PROBE(1);
 
     const bool host_draws = io.draw_start != nullptr;
     const uint64_t pstep = io.philox_step + (io.philox_step_dev ? *io.philox_step_dev : 0ull);
@@ -285,7 +328,6 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         }
     };
 
-    int n_resets = 0;
     if (MODE == MODE_RESET) {
         // routing.py:160-178: agent_steps = 0, every edge load = 0 (record already zeroed),
         // packets 0..A-1 spawned from draw slots 0..A-1
@@ -301,7 +343,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     if (MODE == MODE_STEP) {
         const int* act = io.actions + (size_t)b * A;
         int blocked = 0, n_looped = 0, n_success = 0, n_dropped = 0;
-        if (io.sum_packets_per_node) {  // routing.py:384-386: waiting packets seen at the start of the step
+        if (!SIMPLE && io.sum_packets_per_node) {  // routing.py:384-386: waiting packets seen at the start of the step
             for (int i = lane; i < A; i += 32)
                 if (v.edge[i] == -1) atomicAdd(io.sum_packets_per_node + (size_t)b * N + v.now[i], 1);
         }
@@ -309,7 +351,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         for (int c0 = 0; c0 < A; c0 += 32) {
             int i = c0 + lane;
             bool in = i < A;
-            int a = in ? act[i] : 0;
+            int a = in ? (c0 == 0 ? act_first : act[i]) : 0;
             float rew = 0.f;
             uint8_t lp = 0;
             bool want = in && v.edge[i] == -1 && a != 0;
@@ -337,7 +379,8 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             if (in) { v.rew[i] = rew; v.looped[i] = lp; v.steps[i] += 1; }  // :371 agent_steps += 1
         }
         __syncwarp();
-        if (io.eval_f64) {  // routing.py:414-441, between the two loops
+        GM_PROBE(2);
+        if (eval_info) {  // routing.py:414-441, between the two loops
             for (int i = lane; i < A; i += 32) {
                 if (v.edge[i] != -1 && io.sum_packets_per_edge) atomicAdd(io.sum_packets_per_edge + (size_t)b * E + v.edge[i], 1);
                 if (io.packet_sizes) io.packet_sizes[(size_t)b * A + i] = v.size[i];
@@ -372,7 +415,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                 }
                 drop = (d.ttl > 0) && (tt <= 0);
                 bool on_edge_after = (e != -1) && !arrive;
-                if (d.action_mask) {  // :456-469
+                if (use_mask) {  // :456-469
                     uint32_t m = 0;
                     if (!on_edge_after) {
                         m = 1u;
@@ -438,7 +481,22 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         }
     }
 
-    // ---- write the record back ------------------------------------------------------
+    GM_PROBE(3);
+    }  // role 0
+
+    if (WPE == 2) {  // hand the advanced record (shared memory) to the env's second warp
+        __syncwarp();
+        if (slot_in_cta == 0) asm volatile("bar.sync 1, 64;" ::: "memory");  // literal ids: a register id reserves all 16 barriers
+        else asm volatile("bar.sync 2, 64;" ::: "memory");
+    }
+    const bool do_agent = WPE == 1 || role == 0, do_node = WPE == 1 || role == 1;
+
+    // While the observations are emitted the SM writes at the rate the L2 / HBM write path takes (27 B/clk per SM at
+    // config 2, all 28 warps in the same phase); everything below that is pure latency -- the record write-back, the
+    // small outputs, the waiting-packet sums -- is therefore issued BETWEEN the bulk stores of the two observation
+    // blocks, where it costs nothing, instead of in front of them (probe build: 2.5 K of a warp's 32 K clocks).
+    // ---- write the record back + small per-agent outputs (the env's first warp) ----------------------------------
+    auto finish_record = [&]() {
     if (MODE != MODE_OBSERVE) {
         uint4* dst = (uint4*)gstate;
         const uint4* src = (const uint4*)sm;
@@ -460,17 +518,18 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     // ---- small per-agent outputs --------------------------------------------------------
     if (io.agent_node)
         for (int i = lane; i < A; i += 32) io.agent_node[(size_t)b * A + i] = v.now[i];
-    if (io.action_mask_out)
+    if (!SIMPLE && io.action_mask_out)
         for (int i = lane; i < A; i += 32)
             *((uint32_t*)io.action_mask_out + (size_t)b * A + i) = *(uint32_t*)(v.mask + 4 * i);
+    };
 
-    float* stage = (float*)(sm + L.sm_stage);
-    const int store_mode = d.store_mode;
+    float* stage = (float*)(sm + L.sm_stage + (WPE == 2 && role == 1 ? L.stage_floats * 4 + 32 : 0));
+    const int store_mode = SIMPLE ? 2 : d.store_mode;
 
     // waiting packets per node: count and fp64 size sum in packet-id order (routing.py:200-205); needed by
     // the node observations and by the GLOBAL agent observation
-    const bool need_wait = io.node_obs != nullptr || (io.obs != nullptr && d.env_var == 3);
-    if (need_wait) {
+    const bool need_wait = (io.node_obs != nullptr && do_node) || (io.obs != nullptr && env_var == 3);
+    auto waiting_sums = [&]() {
         for (int j = lane; j < N; j += 32) { v.tl[j] = 0.0; v.cnt[j] = 0; }
         __syncwarp();
         for (int c0 = 0; c0 < A; c0 += 32) {
@@ -483,6 +542,13 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             });
         }
         __syncwarp();
+    };
+    // the GLOBAL agent observation embeds node rows and the direct store mode emits everything in one pass: both need the
+    // sums (and, to keep one code path, the record write-back) first
+    const bool early = !SIMPLE && (env_var == 3 || store_mode == 3);
+    if (early) {
+        if (role == 0) finish_record();
+        if (need_wait) waiting_sums();
     }
     // non-zero fields of node row j (routing.py:193-234) placed at column offset `base` of row r.  The row's 12
     // fields are split over four lanes: part 0..2 = the node's q-th edge (one-hot, length, load), part 3 = the node's
@@ -507,7 +573,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     // the row's packet / node view in registers (one pass, no per-tile re-scan, no bounds checks, no wait on a bulk
     // store).  __syncwarp() orders a lane's field stores after the other lanes' zero stores to the same sectors; L2
     // merges both before anything reaches DRAM.  Used for env_var 1 when both blocks are 16-byte granular.
-    if (store_mode == 3) {
+    if (!SIMPLE && store_mode == 3) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const int W0 = 6 * N + 10, Wn = 4 * N + 8;
         float* go = io.obs ? io.obs + (size_t)b * A * W0 : nullptr;
@@ -573,9 +639,9 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     // ---- agent observations (routing.py:277-358) ------------------------------------------
     // row = 6N+10 packet/edge fields | env_var 2: 5 fields of up to k neighbouring agents (:328-348)
     //                                | env_var 3: flattened node adjacency + node observations (:271-275,353-354)
-    if (io.obs) {
+    if (io.obs && do_agent) {
         const int W0 = 6 * N + 10;
-        const int W = W0 + (d.env_var == 2 ? 5 * d.k : 0) + (d.env_var == 3 ? N * N + N * (4 * N + 8) : 0);
+        const int W = W0 + (env_var == 2 ? 5 * d.k : 0) + (env_var == 3 ? N * N + N * (4 * N + 8) : 0);
         emit_f32_block(io.obs + (size_t)b * A * W, A * W, W, stage, L.stage_floats, lane, store_mode,
                        [&](int r0, int r1, auto put) {
                            // four lanes per row (8 rows per pass): the ~16 fields of a row are written by four lanes
@@ -604,7 +670,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                                    if (q == 0) put(i, 3 * N + 1, (float)v.time[i]);
                                    if (q == 1) put(i, 3 * N + 2, (float)v.size[i]);
                                }
-                               if (d.env_var == 2 && part == 3) {
+                               if (env_var == 2 && part == 3) {
                                    int count = 0;
                                    for (int j = 0; j < A && count < d.k; j++) {
                                        if (j == i) continue;
@@ -621,7 +687,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                                    }
                                    for (; count < d.k; count++)
                                        for (int q = 0; q < 5; q++) put(i, W0 + 5 * count + q, -1.f);
-                               } else if (d.env_var == 3) {
+                               } else if (env_var == 3) {
                                    for (int j = part; j < N; j += 4) {
                                        put(i, W0 + j * N + j, 1.f);
                                        for (int q = 0; q < 3; q++) put(i, W0 + j * N + nb[j * 3 + q], 1.f);
@@ -632,8 +698,15 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                        });
     }
 
+    if (do_agent) GM_PROBE(4);
+    if (!early) {
+        if (role == 0) finish_record();
+        GM_PROBE(5);
+        if (need_wait) waiting_sums();
+    }
+    if (do_node) GM_PROBE(6);
     // ---- node observations (routing.py:193-234), row width 4N+8 ------------------------
-    if (io.node_obs) {
+    if (io.node_obs && do_node) {
         const int W = 4 * N + 8;
         emit_f32_block(io.node_obs + (size_t)b * N * W, N * W, W, stage, L.stage_floats, lane, store_mode,
                        [&](int r0, int r1, auto put) {
@@ -641,8 +714,11 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                        });
     }
 
-    if (io.adj) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, N, A, lane);
-    if (io.node_agent) emit_node_agent_rows(v.now, io.node_agent + (size_t)b * N * A, N, A, lane);
+    if (do_node) GM_PROBE(7);
+    if (io.adj && do_agent) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, N, A, lane);
+    if (io.node_agent && do_node) emit_node_agent_rows(v.now, io.node_agent + (size_t)b * N * A, N, A, lane);
+    if (do_agent) GM_PROBE(8);
+    if (do_node) GM_PROBE(9);
 }
 
 static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_io* io, void* stream) {
@@ -684,33 +760,54 @@ static int launch_routing(int mode, const gm_routing_desc* d, const gm_routing_i
         if (stage_cap < 1024 || stage_cap > 65536) stage_cap = 4096;
     }
     int stage_bytes = dd.store_mode == 3 ? 16 : (int)std::min<int64_t>(stage_cap, round_up(need, 256));  // direct mode stages nothing
-    RoutingLayout L = make_layout(d->N, d->A, d->E, stage_bytes);
-    GM_CHECK_ARG(d->state_stride == L.stride, "state_stride %d != %d", d->state_stride, L.stride);
-    while (L.sm_per_warp * WARPS_PER_CTA > 200 * 1024 && stage_bytes > 2048) {
-        stage_bytes /= 2;
-        L = make_layout(d->N, d->A, d->E, stage_bytes);
+    // the common configuration runs the specialised instance; batches that would leave at least half of the warp slots
+    // of every SM empty (2 B <= SMs x 28) give each env two warps
+    const bool simple = d->env_var == 1 && dd.store_mode == 2 && !d->action_mask && io->eval_f64 == nullptr &&
+                        io->sum_packets_per_node == nullptr && io->action_mask_out == nullptr;
+    static int wpe_env = -1, sms = 0;
+    if (wpe_env < 0) {
+        const char* e = getenv("GM_ROUTING_WPE");
+        wpe_env = e ? atoi(e) : 0;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = kNumSMs;
     }
-    size_t smem = (size_t)L.sm_per_warp * WARPS_PER_CTA;
+    int wpe = (simple && 2ll * d->B <= (int64_t)sms * WARPS_PER_CTA * GM_ROUTING_MIN_CTAS) ? 2 : 1;
+    if (wpe_env == 1 || (wpe_env == 2 && simple)) wpe = wpe_env;
+    RoutingLayout L = make_layout(d->N, d->A, d->E, stage_bytes, wpe);
+    GM_CHECK_ARG(d->state_stride == L.stride, "state_stride %d != %d", d->state_stride, L.stride);
+    while (L.sm_per_warp * (WARPS_PER_CTA / wpe) > 200 * 1024 && stage_bytes > 2048) {
+        stage_bytes /= 2;
+        L = make_layout(d->N, d->A, d->E, stage_bytes, wpe);
+    }
+    size_t smem = (size_t)L.sm_per_warp * (WARPS_PER_CTA / wpe);
     GM_CHECK_ARG(smem <= 227 * 1024, "env too large for shared memory (%zu bytes)", smem);
 
-    dim3 grid(ceil_div(d->B, WARPS_PER_CTA)), block(WARPS_PER_CTA * 32);
+    dim3 grid(ceil_div(d->B, WARPS_PER_CTA / wpe)), block(WARPS_PER_CTA * 32);
     cudaStream_t s = (cudaStream_t)stream;
+#define GM_ROUTING_LAUNCH(MODE_, WPE_, SIMPLE_)                                                                              \
+    do {                                                                                                                     \
+        GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_, WPE_, SIMPLE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        routing_kernel<MODE_, WPE_, SIMPLE_><<<grid, block, smem, s>>>(dd, *io, L);                                          \
+    } while (0)
+#define GM_ROUTING_VARIANT(MODE_)                                 \
+    do {                                                          \
+        if (wpe == 2) GM_ROUTING_LAUNCH(MODE_, 2, true);          \
+        else if (simple) GM_ROUTING_LAUNCH(MODE_, 1, true);       \
+        else GM_ROUTING_LAUNCH(MODE_, 1, false);                  \
+    } while (0)
     switch (mode) {
-        case MODE_RESET:
-            GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_RESET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            routing_kernel<MODE_RESET><<<grid, block, smem, s>>>(dd, *io, L);
-            break;
+        case MODE_RESET: GM_ROUTING_VARIANT(MODE_RESET); break;
         case MODE_STEP: {
-            GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ProfileScope prof(PROF_ENV, s);
-            routing_kernel<MODE_STEP><<<grid, block, smem, s>>>(dd, *io, L);
+            GM_ROUTING_VARIANT(MODE_STEP);
             break;
         }
-        default:
-            GM_CUDA(cudaFuncSetAttribute(routing_kernel<MODE_OBSERVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            routing_kernel<MODE_OBSERVE><<<grid, block, smem, s>>>(dd, *io, L);
-            break;
+        default: GM_ROUTING_VARIANT(MODE_OBSERVE); break;
     }
+#undef GM_ROUTING_VARIANT
+#undef GM_ROUTING_LAUNCH
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -736,5 +833,13 @@ int gm_routing_step(const gm_routing_desc* d, const gm_routing_io* io, void* str
 int gm_routing_observe(const gm_routing_desc* d, const gm_routing_io* io, void* stream) {
     return gm::launch_routing(gm::MODE_OBSERVE, d, io, stream);
 }
+
+#ifdef GM_ROUTING_PROBES
+GM_API int gm_routing_probe_read(long long* out, int n_envs) {  // out[n_envs][PROBE_N], synchronises
+    GM_CUDA(cudaDeviceSynchronize());
+    GM_CUDA(cudaMemcpyFromSymbol(out, gm::g_probe, sizeof(long long) * gm::PROBE_N * n_envs));
+    return GM_OK;
+}
+#endif
 
 }  // extern "C"

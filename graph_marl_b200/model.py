@@ -498,9 +498,22 @@ class NetMon(nn.Module):
         p = self._params()
         ws = self._ws.get(_lib.lib().gm_netmon_workspace_bytes(C.byref(p), B * N), dev)
         st_in = None
+        hpk_in = None
         if self.state is not None and self.state.numel() > 0:
             st_in = self.state.to(dev).float().reshape(B, N, S).contiguous()
+            tag = getattr(self.state, "_gm_hpk", None)  # tile-packed h left by the step that produced this very tensor
+            if tag is not None and tag[1] == self.math and st_in.data_ptr() == self.state.data_ptr():
+                hpk_in = tag[0]
         st_out = torch.empty((B, N, S), dtype=torch.float32, device=dev)
+        # fused tensor-core cells (same condition as pack_layout() in csrc/netmon.cu) also leave h tile-packed
+        H = self.hidden_features
+        fused = self.math != "fp32" and self.rnn_carryover and self.iterations >= 1 and (
+            (self.rnn_type == "lstm" and H % 64 == 0) or (self.rnn_type == "lnlstm" and H == 128))
+        hpk_out = None
+        if fused:
+            hpk_out = torch.empty(int(_lib.lib().gm_packed_activation_bytes(B * N, H)), dtype=torch.uint8, device=dev)
+        else:
+            hpk_in = None
         O = self.out_width(max_degree)
         node_out = torch.empty((B, N, O), dtype=torch.float32, device=dev) if want_node_out else None
         A = 0
@@ -524,9 +537,11 @@ class NetMon(nn.Module):
             _lib.check(_lib.lib().gm_netmon_forward(
                 C.byref(p), B, N, x.data_ptr(), nbr_all.data_ptr(), deg.data_ptr(), DM, _lib.ptr(list_index),
                 _lib.ptr(st_in), st_out.data_ptr(), max_degree, _lib.ptr(node_out), _lib.ptr(agent_node), A,
-                _lib.ptr(agent_out) if agent_node is not None else None, ld, _lib.ptr(agent_pk), ws.data_ptr(), ws.numel(),
-                _lib.current_stream()))
+                _lib.ptr(agent_out) if agent_node is not None else None, ld, _lib.ptr(agent_pk), _lib.ptr(hpk_in),
+                _lib.ptr(hpk_out), ws.data_ptr(), ws.numel(), _lib.current_stream()))
         self.state = st_out
+        if hpk_out is not None:
+            st_out._gm_hpk = (hpk_out, self.math)
         if agent_pk is not None:
             if agent_out is None:
                 return node_out, PackedRows(agent_pk, (B, A, O), self.math)

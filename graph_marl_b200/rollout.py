@@ -245,6 +245,9 @@ class Rollout:
                 d["pk"] = pk[0]
         if env.last_netmon_state is not None:
             d["last"] = env.last_netmon_state
+        hpk = getattr(env.current_netmon_state, "_gm_hpk", None)  # tile-packed hidden half of the carried state
+        if hpk is not None:
+            d["cur_hpk"] = hpk[0]
         return d, (pk[1] if pk is not None else None)
 
     def _adopt(self, t, math):
@@ -257,6 +260,8 @@ class Rollout:
             if "pk" in t:
                 obs_g._gm_pk = (t["pk"], math)
         self.obs, self.adj = (t["obs_a"], obs_g), t["adj"]
+        if "cur_hpk" in t:
+            t["cur"]._gm_hpk = (t["cur_hpk"], env.netmon.math)
         env.current_netmon_state = t["cur"]
         env.netmon.state = t["cur"]
         if "last" in t:

@@ -228,14 +228,18 @@ GM_API int gm_adj_to_lists(const float* mask, int32_t B, int32_t N, int32_t DM, 
  *   agent_out_pk: optional (tensor-core modes) copy of agent_out as tile-packed bf16 hi/lo blocks
  *   (gm_packed_activation_bytes(B*A, O) bytes, 128-byte aligned) that gm_dqn_act can consume as
  *   obs_g_pk instead of re-reading the fp32 rows.
+ *   state_h_pk_in / state_h_pk_out: optional (fused tensor-core cells only; NULL otherwise) tile-packed copy of
+ *   the hidden half of the state (gm_packed_activation_bytes(B*N, H) bytes, 128-byte aligned).  The last cell of a
+ *   step writes state_h_pk_out next to state_out; handing it back as state_h_pk_in with the same state lets the next
+ *   step's rnn_obs cell pull h with bulk copies instead of re-splitting the fp32 rows.
  *   workspace: device scratch of gm_netmon_workspace_bytes (256-byte aligned). */
 GM_API int64_t gm_packed_activation_bytes(int64_t rows, int32_t width);
 GM_API int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const float* node_obs,
                       const int32_t* nbr_all, const int32_t* deg, int32_t DM,
                       const int32_t* list_index, const float* state_in, float* state_out,
                       int32_t max_degree, float* node_out, const int32_t* agent_node, int32_t A,
-                      float* agent_out, int64_t agent_out_ld, void* agent_out_pk, void* workspace,
-                      int64_t workspace_bytes, void* stream);
+                      float* agent_out, int64_t agent_out_ld, void* agent_out_pk, const void* state_h_pk_in,
+                      void* state_h_pk_out, void* workspace, int64_t workspace_bytes, void* stream);
 /* general node->agent mapping with an arbitrary (not one-hot) node_agent matrix f32[B,N,A]
  * (NetMon.output_to_network_obs, model.py:629-631; frozen wrapper path wrapper.py:67-75) */
 GM_API int gm_netmon_map_to_agents(const float* node_out, const float* node_agent, int32_t B, int32_t N,

@@ -199,17 +199,16 @@ def test_dqn_tensorcore_q_values(math, tol):
         assert np.array_equal(a2.cpu().numpy(), g["q"].argmax(-1))
 
 
-@pytest.mark.parametrize("switch", ["GM_TC_WS", "GM_TC_PAIR", "GM_TC_WIDE", "GM_TC_CLUSTER", "GM_AGG_MAP=1", "GM_AGG_MAP=1:mean",
-                                    "GM_AGG_MAP=2", "GM_AGG_MAP=2:mean", "GM_AGG_MAP=2:wrap", "GM_AGG_PIPE_GENERIC=1",
-                                    "GM_AGG_MAP=4:mean", "GM_AGG_MAP=8", "GM_AGG_STAGE_LISTS=0"])
+@pytest.mark.parametrize("switch", ["GM_TC_PAIR", "GM_TC_WIDE", "GM_TC_CLUSTER", "GM_AGG_MAP=2", "GM_AGG_MAP=2:mean", "GM_AGG_MAP=2:wrap",
+                                    "GM_AGG_PIPE_GENERIC=1", "GM_AGG_MAP=8:mean", "GM_AGG_MAP=8", "GM_AGG_STAGE_LISTS=0"])
 def test_optional_kernel_variants_match(switch):
     """The optional variants of the tcgen05 kernel give the same NetMon outputs as the default streaming kernel:
-    GM_TC_WS=1 (weights resident in smem, activations multicast to a 4-CTA cluster), GM_TC_PAIR=1 (2-CTA pairs driving
-    tcgen05.mma.cta_group::2, M = 256, half a weight tile per CTA), GM_TC_WIDE=0 (8 instead of 16 epilogue warps for all-tile-packed
-    layers), GM_TC_CLUSTER=2 (weight stages multicast over a 2-CTA cluster); GM_AGG_MAP=1|2|4|8 / GM_AGG_STAGE_LISTS=0: the
-    bulk-staged aggregation kernel, its persistent 3-stage pipelined form (":wrap": one CTA per SM and 1051 row blocks, so
-    every CTA goes round its stage ring twice and both mbarrier phases are used; GM_AGG_PIPE_GENERIC=1: its instance with
-    run-time strides instead of the <H=128, DM=4> one) and the gather kernels' lane mappings (on a batch whose last block, 8-row group and M tile are all partial).  Run in a
+    GM_TC_PAIR=1 (2-CTA pairs driving tcgen05.mma.cta_group::2, M = 256, half a weight tile per CTA), GM_TC_WIDE=0 (8 instead of
+    16 epilogue warps for all-tile-packed layers), GM_TC_CLUSTER=2 (weight stages multicast over a 2-CTA cluster);
+    GM_AGG_MAP=2|8 / GM_AGG_STAGE_LISTS=0: the persistent 3-stage pipelined aggregation kernel (":wrap": one CTA per SM and
+    1051 row blocks, so every CTA goes round its stage ring twice and both mbarrier phases are used; GM_AGG_PIPE_GENERIC=1: its
+    instance with run-time strides instead of the <H=128, DM=4> one) and the L2 gather kernel with / without staged lists (on a
+    batch whose last block, 8-row group and M tile are all partial).  Run in a
     subprocess because the switches are read once per process."""
     import os, subprocess, sys, textwrap
 
