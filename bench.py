@@ -289,17 +289,27 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cb, sec_per_step, Bc = cpu_arm(a.workload, a.steps, a.warmup, envs=(B_weak if N <= 50 else None), budget_s=60.0)
-        cbr = reference_arm(a.workload)
-        line = dict(metric=METRIC, value=cb["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                    ms_per_step=sec_per_step * 1e3, higher_is_better=True, scaling=a.scaling, vs_baseline=None, dtype="f32",
-                    data="synthetic", impl="reference", config=dict(config, envs_per_gpu=Bc, envs_total=Bc, math="fp32 (oracle port: C env + torch CPU tensors)",
+        # The reference's own CPU implementation of the path: the UNMODIFIED Python rollout loop (src/main.py:673-737,
+        # staged at baseline/_ref/src) with one process per host core -- the reference has no batching, every process
+        # advances one env instance.  The oracle port (C env + torch CPU tensors, all cores, the GPU arm's env count) is
+        # timed beside it and becomes the line's value only where the staged reference is absent.
+        cbr = reference_arm(a.workload, seconds=max(6.0, min(20.0, 0.4 * (a.steps + a.warmup))))
+        cb, sec_per_step, Bc = cpu_arm(a.workload, a.steps, a.warmup, envs=(B_weak if N <= 50 else None), budget_s=45.0)
+        use_ref = cbr is not None and cbr.get("value")
+        main = cbr if use_ref else cb
+        envs = main["cores"] if use_ref else Bc
+        line = dict(metric=METRIC, value=main["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                    ms_per_step=(envs / main["value"] * 1e3) if use_ref else sec_per_step * 1e3, higher_is_better=True,
+                    scaling=a.scaling, vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                    config=dict(config, envs_per_gpu=envs, envs_total=envs,
+                                math="fp32 (torch CPU)" if use_ref else "fp32 (oracle port: C env + torch CPU tensors)",
                                 replay_format="dense: the reference's 17 fields per transition (numpy ring)", replay_overlap="none (host)",
-                                cuda_graph_steps=0),
-                    cpu_baseline=cb, gpu_launches=0,
-                    e2e=dict(value=cb["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        if cbr is not None:
-            line["cpu_baseline_reference"] = cbr  # the unmodified Python reference beside the (faster) port
+                                cuda_graph_steps=0,
+                                sharding=(f"{envs} single-env processes (the reference is not batched), one per host core" if use_ref
+                                          else f"{Bc} envs batched over {cb['cores']} host threads")),
+                    cpu_baseline=main, gpu_launches=0,
+                    e2e=dict(value=main["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        line["cpu_baseline_port" if use_ref else "cpu_baseline_reference"] = cb if use_ref else cbr
         _emit(line)
         return
 
@@ -382,7 +392,8 @@ def main():
     traffic = {}
     try:  # DRAM bytes from the committed ncu --set full capture of this workload (cfg2, B=4096 only)
         if a.workload == "cfg2" and B == 4096:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if a.replay == "compact":
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         traffic = {}
     H, K = c["H"], c["K"]
@@ -419,11 +430,13 @@ def main():
                 roofline=dominant, roofline_env_step=roof_env, roofline_aggregate=roof_agg, roofline_gemm=roof_gemm, stage_ms=stage)
     if not a.no_cpu_baseline and world == 1:
         try:
-            cb, _, _ = cpu_arm(a.workload, steps=10**6, warmup=1, budget_s=15.0)
-            line["cpu_baseline"] = cb
-            cbr = reference_arm(a.workload, seconds=6.0)
-            if cbr is not None:
-                line["cpu_baseline_reference"] = cbr
+            cb, _, _ = cpu_arm(a.workload, steps=10**6, warmup=1, budget_s=12.0)
+            cbr = reference_arm(a.workload, seconds=8.0)
+            if cbr is not None and cbr.get("value"):
+                line["cpu_baseline"] = cbr       # the unmodified Python reference, one process per host core
+                line["cpu_baseline_port"] = cb   # the oracle port (C env + torch CPU tensors) on the same cores
+            else:
+                line["cpu_baseline"] = cb
         except Exception as ex:  # the baseline must never hide the GPU number
             line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=len(os.sched_getaffinity(0)), kind="port", sample=f"failed: {ex}")
     _emit(line)

@@ -189,6 +189,10 @@ class ReplayBuffer(_RingSampler):
                 # allocator from recycling the sources before the copy has run
                 for t in keep:
                     t.record_stream(cur)
+        # the sources of the last TWO inserts stay referenced: inside a captured graph unit (no record_stream) the
+        # allocator must not hand a source block to step k+2's main-stream work while insert k may still read it on the
+        # side stream -- the main stream joins the side stream only at the end of the unit
+        self._keep_prev = getattr(self, "_keep", None)
         self._keep = keep
         self.count = min(self.buffer_size, self.count + n)
         self.index = (self.index + n) % self.buffer_size

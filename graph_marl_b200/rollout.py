@@ -369,7 +369,12 @@ class Rollout:
         if self.buff is not None:
             buf = ((c[3][0] + n * self.B) % self.buff.buffer_size, min(self.buff.buffer_size, c[3][1] + n * self.B))
         d = g.gm_delta
-        self._set_counters((c[0] + d[0], c[1] + d[1], c[2] + d[2], buf))
+        self._set_counters((c[0] + d[0], c[1] + d[1], c[2], buf))
+        # epsilon is a launch argument, i.e. constant inside a captured unit: the decay schedule (policy.py:55-62) is
+        # applied here, step by step, and takes effect at the next unit (units are keyed by epsilon)
+        for _ in range(d[2]):
+            self.policy._step += 1
+            self.policy._decay()
         if self.host_draws:
             if self._h_trace is not None:
                 self._h_trace.extend((self._h_cursor + k) % self._h_steps for k in range(n))
@@ -397,7 +402,7 @@ class Rollout:
                 done += 1
                 continue
             slot = (self._h_cursor // n) % (self._h_steps // n) if self.host_draws else 0
-            key = (slot, left_in_episode == n)
+            key = (slot, left_in_episode == n, float(self.policy._epsilon))
             if key not in self._graphs:
                 self._graphs[key] = self._capture_unit(n, slot if self.host_draws else None)
                 self._graph_tables = self.base_env._pool
@@ -432,8 +437,9 @@ class Rollout:
             else:
                 advance_until(lambda: self.episode_step is not None and E - self.episode_step > n)
             for slot in slots:
-                if (slot, tail) not in self._graphs:
-                    self._graphs[(slot, tail)] = self._capture_unit(n, slot if self.host_draws else None)
+                key = (slot, tail, float(self.policy._epsilon))
+                if key not in self._graphs:
+                    self._graphs[key] = self._capture_unit(n, slot if self.host_draws else None)
                     self._graph_tables = self.base_env._pool
 
     def step(self):

@@ -2,6 +2,7 @@
 """Run an UNMODIFIED driver of the reference (src/main.py, src/sl.py) on the classes of graph_marl_b200.
 
     python tools/run_reference_driver.py main.py --env-type=simple --model=dqn --netmon ... --device=cuda
+    GM_DEFAULT_DEVICE=cuda python tools/run_reference_driver.py sl.py --iterations 200 ...      # sl.py has no --device
 
 The drivers are executed from the staged copy of the reference (baseline/_ref/src, written by
 __graft_entry__.build(); git-ignored, never edited).  Before the driver starts, the modules it imports for the
@@ -72,6 +73,12 @@ def main():
     if not os.path.exists(driver):
         raise SystemExit(f"{driver} is missing: run `python __graft_entry__.py` where /root/reference exists to stage it")
     install_aliases()
+    if os.environ.get("GM_DEFAULT_DEVICE"):
+        # sl.py has no --device flag: it builds its tensors on torch's default device (the CPU); this package has no CPU
+        # path, so the launcher moves the default device instead of editing the driver
+        import torch
+
+        torch.set_default_device(os.environ["GM_DEFAULT_DEVICE"])
     sys.argv = [driver] + sys.argv[2:]
     runpy.run_path(driver, run_name="__main__")
 
