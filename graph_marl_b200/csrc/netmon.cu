@@ -580,78 +580,75 @@ __global__ void readout_kernel(const float* __restrict__ h, int64_t ldh, const f
 
 // Agent readout for the tensor-core DQN: the same rows as readout_kernel(agent_node != NULL), written as fp32 rows
 // (optional) and / or tile-packed bf16 hi/lo (gemm_sm100.cuh) so the DQN's first layer pulls the graph observation
-// with bulk copies.  One warp = 8 agent rows x ALL k-blocks: lane = (r8, part) resolves its row's node and neighbour
-// slots ONCE (agent_node -> list -> degree is a dependent chain of three loads) and then walks the O / 32 k-blocks,
-// 32 bytes in and 2 x 16 bytes out per step, four steps in flight.  A warp instruction reads 8 rows x one 128-byte
-// line and fills 512 contiguous bytes of each plane.  (Round 1 ran one warp per (8 rows, ONE k-block) and repeated the
-// chain 16 times per row: 72 us for 252 MB at config 2, issue- and latency-bound.)
+// with bulk copies.  One warp = 8 agent rows x one H-wide SEGMENT of the row ([h_v | gmean_b | last[n_1] | ...]):
+// lane = (r8, part) resolves its segment's source row once (agent_node -> list -> degree is a dependent chain of
+// three loads) and then moves the segment's H / 32 k-blocks, 32 bytes in and 2 x 16 bytes out each, all in flight
+// together.  A warp instruction reads 8 rows x one 128-byte line and fills 512 contiguous bytes of each plane.
+// Measured at config 2 (event time per launch): one warp per (8 rows, ONE k-block) 60 us (the chain is repeated for
+// every k-block; issue slots 68 % busy), one warp per 8 WHOLE rows 75 us (too few warps to cover the gather latency).
 __global__ void __launch_bounds__(256) readout_agents_pk_kernel(
     const float* __restrict__ h, int64_t ldh, const float* __restrict__ last, int64_t ldl, const float* __restrict__ gmean,
     const int* __restrict__ nbr, const int* __restrict__ deg, int DM, const int* __restrict__ list_index,
     const int* __restrict__ agent_node, int A, int B, int N, int H, int use_nbr, int use_glob, int max_degree,
     float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_pk, int write_lo) {
     const int lane = threadIdx.x & 31;
-    const int O = H + (use_glob ? H : 0) + (use_nbr ? max_degree * H : 0);
-    const int kbs = O / TC_BK;
-    const unsigned rg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_seg = 1 + (use_glob ? 1 : 0) + (use_nbr ? max_degree : 0);
+    const int kb_per_seg = H / TC_BK, kbs = n_seg * kb_per_seg;
+    const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned rg = gw / (unsigned)n_seg;
+    const int sg = (int)(gw - rg * (unsigned)n_seg);
     const unsigned rows = (unsigned)B * (unsigned)A;
     const unsigned row = rg * 8 + (lane >> 2);
     const int part = lane & 3;
     if (row >= rows) return;
     const int b = (int)(row / (unsigned)A);
     const int v = agent_node[row];
-    const unsigned mt = row / TC_BM;
-    const int r = (int)(row - mt * TC_BM);
-    uint8_t* dst_row = out_pk ? out_pk + (size_t)mt * kbs * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16 : nullptr;
-    float* out_row = out ? out + (int64_t)row * ldo + part * 8 : nullptr;
-    const int kb_per_seg = H / TC_BK;
-    // one segment of the row = H columns from `src` (NULL = zero padding), k-blocks sg * kb_per_seg ...
-    auto emit_segment = [&](int sg, const float* src) {
-#pragma unroll 4
-        for (int k = 0; k < kb_per_seg; k++) {
-            const int kb = sg * kb_per_seg + k;
-            float x[8];
-            if (src) {
-                const float4 a = __ldg((const float4*)(src + k * TC_BK + part * 8)), c = __ldg((const float4*)(src + k * TC_BK + part * 8) + 1);
-                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; i++) x[i] = 0.f;
-            }
-            if (out_row) {
-                float4* o = (float4*)(out_row + kb * TC_BK);
-                o[0] = make_float4(x[0], x[1], x[2], x[3]);
-                o[1] = make_float4(x[4], x[5], x[6], x[7]);
-            }
-            if (dst_row) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    hi[i] = agg_pack2(x[2 * i], x[2 * i + 1]);
-                    lo[i] = agg_pack2(x[2 * i] - __uint_as_float(hi[i] << 16), x[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
-                }
-                uint8_t* dst = dst_row + (size_t)kb * TC_PK_BLOCK;
-                *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-        }
-    };
-    // row = [h_v | gmean_b | last[n_1] .. last[n_maxdeg]]
-    int sg = 0;
-    emit_segment(sg++, h + ((size_t)b * N + v) * ldh);
-    if (use_glob) emit_segment(sg++, gmean + (size_t)b * H);
-    if (use_nbr) {
+    const float* src = nullptr;
+    if (sg == 0) {
+        src = h + ((size_t)b * N + v) * ldh;
+    } else if (use_glob && sg == 1) {
+        src = gmean + (size_t)b * H;
+    } else {
+        int slot = sg - 1 - (use_glob ? 1 : 0);
         const int li = list_index ? list_index[b] : b;
         const int* lst = nbr + ((size_t)li * N + v) * DM;
         const int dg = deg[(size_t)li * N + v];
-        int slot = 0;
-        for (int q = 0; q < dg && slot < max_degree; q++) {
+        for (int q = 0; q < dg; q++) {
             const int u = lst[q];
             if (u == v) continue;
-            emit_segment(sg++, last + ((size_t)b * N + u) * ldl);
-            slot++;
+            if (slot-- == 0) { src = last + ((size_t)b * N + u) * ldl; break; }
         }
-        for (; slot < max_degree; slot++) emit_segment(sg++, nullptr);
+    }
+    const unsigned mt = row / TC_BM;
+    const int r = (int)(row - mt * TC_BM);
+    uint8_t* dst_row = out_pk ? out_pk + ((size_t)mt * kbs + (size_t)sg * kb_per_seg) * TC_PK_BLOCK + (size_t)(r >> 3) * (TC_BK * 16) + part * 128 + (r & 7) * 16 : nullptr;
+    float* out_row = out ? out + (int64_t)row * ldo + sg * H + part * 8 : nullptr;
+#pragma unroll 4
+    for (int k = 0; k < kb_per_seg; k++) {
+        float x[8];
+        if (src) {
+            const float4 a = __ldg((const float4*)(src + k * TC_BK + part * 8)), c = __ldg((const float4*)(src + k * TC_BK + part * 8) + 1);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = c.x; x[5] = c.y; x[6] = c.z; x[7] = c.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = 0.f;
+        }
+        if (out_row) {
+            float4* o = (float4*)(out_row + k * TC_BK);
+            o[0] = make_float4(x[0], x[1], x[2], x[3]);
+            o[1] = make_float4(x[4], x[5], x[6], x[7]);
+        }
+        if (dst_row) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                hi[i] = agg_pack2(x[2 * i], x[2 * i + 1]);
+                lo[i] = agg_pack2(x[2 * i] - __uint_as_float(hi[i] << 16), x[2 * i + 1] - __uint_as_float(hi[i] & 0xffff0000u));
+            }
+            uint8_t* dst = dst_row + (size_t)k * TC_PK_BLOCK;
+            *(uint4*)dst = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (write_lo) *(uint4*)(dst + TC_BM * TC_BK * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
     }
 }
 
@@ -1145,7 +1142,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                      "tile-packed agent readout needs agent_node, hidden %% 32 == 0 and 16-byte aligned rows");
         GM_CHECK_ARG((int64_t)B * A * (O / TC_BK) < (1ll << 31) && (int64_t)B * N < (1ll << 31), "batch too large for the 32-bit row arithmetic of the readout / aggregation kernels");
         int64_t rows = (int64_t)B * A;
-        const unsigned blocks = (unsigned)((((rows + 7) / 8) + 7) / 8);
+        const int n_seg = 1 + (use_glob ? 1 : 0) + (use_nbr ? max_degree : 0);
+        const unsigned blocks = (unsigned)((((rows + 7) / 8) * n_seg + 7) / 8);
         {
             ProfileScope prof(PROF_READOUT, s);
             readout_agents_pk_kernel<<<blocks, 256, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index, agent_node, A,

@@ -28,6 +28,9 @@ class NetMonWrapper:
         self.last_netmon_state = self.current_netmon_state = None
         self.frozen = False
         self.netmon_out = None
+        # batched rollouts: where the NEXT NetMon step writes its new state (a block of the replay ring's node_state
+        # field, rollout.Rollout); consumed by that step
+        self._state_sink = None
 
     def __getattr__(self, name):
         # anything the wrapper does not define is the env's (wrapper.py:25-26)
@@ -54,8 +57,10 @@ class NetMonWrapper:
         self.frozen = False
         self.last_netmon_state = self.current_netmon_state = None
         obs, adj = self.env.reset()
+        sink, self._state_sink = self._state_sink, None
         for _ in range(self.startup_iterations - 1):  # warm-up passes; the last one below builds the obs
             self._netmon_step()
+        self._state_sink = sink
         return self._with_graph_obs(obs), adj
 
     def step(self, actions):
@@ -117,6 +122,7 @@ class NetMonWrapper:
             lean = self._batched and self.split_obs
             self.netmon_out, agent_out = self.netmon.forward_lists(
                 node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=not lean,
-                want_agent_pk=lean, want_agent_fp32=self.graph_obs_fp32 or not lean)
+                want_agent_pk=lean, want_agent_fp32=self.graph_obs_fp32 or not lean, state_out=self._state_sink)
+            self._state_sink = None
             self.current_netmon_state = self.netmon.state
         return self._ret(agent_out)

@@ -482,12 +482,13 @@ class NetMon(nn.Module):
         return H + (H if self.output_global_hidden else 0) + (max_degree * H if self.output_neighbor_hidden else 0)
 
     def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
-                      want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True):
+                      want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True, state_out=None):
         """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
         nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
         Updates self.state; returns (node_out | None, agent_out | None).  want_agent_fp32=False with
         want_agent_pk (tensor-core modes): the agents' graph observation is written ONCE, tile-packed, and
-        returned as PackedRows (no fp32 rows)."""
+        returned as PackedRows (no fp32 rows).  state_out: optional f32 [B,N,S] tensor that receives the new state (e.g.
+        a block of the replay ring's node_state field, so that the state is never copied)."""
         _lib.require_device()
         if not x.is_cuda:
             raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
@@ -504,7 +505,11 @@ class NetMon(nn.Module):
             tag = getattr(self.state, "_gm_hpk", None)  # tile-packed h left by the step that produced this very tensor
             if tag is not None and tag[1] == self.math and st_in.data_ptr() == self.state.data_ptr():
                 hpk_in = tag[0]
-        st_out = torch.empty((B, N, S), dtype=torch.float32, device=dev)
+        if state_out is not None:
+            assert state_out.shape == (B, N, S) and state_out.dtype == torch.float32 and state_out.is_contiguous() and state_out.device == dev
+            st_out = state_out
+        else:
+            st_out = torch.empty((B, N, S), dtype=torch.float32, device=dev)
         # fused tensor-core cells (same condition as pack_layout() in csrc/netmon.cu) also leave h tile-packed
         H = self.hidden_features
         fused = self.math != "fp32" and self.rnn_carryover and self.iterations >= 1 and (

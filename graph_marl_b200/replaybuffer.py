@@ -252,7 +252,12 @@ class CompactReplayBuffer(_RingSampler):
 
     FIELDS = ("rec", "next_rec", "topo", "action", "reward", "done", "episode_done", "node_state")
 
-    def __init__(self, seed, buffer_size, env, device_sampler=False):
+    def __init__(self, seed, buffer_size, env, device_sampler=False, state_ring=False, ring_align=1):
+        """state_ring: the node_state field doubles as the NetMon state history of the rollout (rollout.Rollout): the
+        NetMon step that produces the observations of transition t+1 reads its state from that transition's block and
+        writes the next one, so the state is never copied into the ring.  The field then has its own modulus
+        (capacity in steps + 2 blocks: two states are always "ahead" of the newest committed transition), rounded up to a
+        multiple of `ring_align` steps so that captured CUDA-graph units of that length meet the same blocks again."""
         self.env = env
         be = env.get()
         self.device = be.device
@@ -267,12 +272,37 @@ class CompactReplayBuffer(_RingSampler):
         self.topo = z((), torch.int32)
         self.action, self.reward, self.done = z((A,), torch.int8), z((A,), torch.float32), z((A,), torch.bool)
         self.episode_done = z((), torch.bool)
-        self.node_state = z((N, S), torch.float32)
+        self.state_ring = bool(state_ring)
+        self.steps_total = 0  # batched steps committed so far (state-ring mode: transition t <-> state block t % M)
+        if self.state_ring:
+            B = be.num_envs
+            assert self.buffer_size % B == 0 and self.buffer_size // B >= 1, "a state ring needs a capacity of whole batched steps"
+            self._B, self.cap_steps = B, self.buffer_size // B
+            a = max(1, int(ring_align))
+            self.M = -(-(self.cap_steps + 2) // a) * a
+            self.node_state = torch.zeros((self.M * B, N, S), dtype=torch.float32, device=self.device)
+        else:
+            self.node_state = z((N, S), torch.float32)
         self._zero_topo = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self._flags = {v: torch.full((1,), v, dtype=torch.bool, device=self.device) for v in (False, True)}
         self._dev_index = None  # _lib.DeviceCounter in CUDA-graph mode (rollout.Rollout)
         self._staged = False
         self._init_sampler(seed, device_sampler)
+
+    def state_block(self, t):
+        """State-ring mode: the [B,N,S] block that holds the node_state of transition (batched step) t."""
+        b = (int(t) % self.M) * self._B
+        return self.node_state[b:b + self._B]
+
+    def _state_slots(self, idx):
+        """Ring slots (device int64) -> rows of the state ring: slot s was written by step t = T - 1 - age."""
+        if not self.state_ring:
+            return idx
+        B, cap = self._B, self.cap_steps
+        j_now = (self.index // B) % cap
+        age = (j_now - 1 - idx // B) % cap
+        t = self.steps_total - 1 - age
+        return (t % self.M) * B + idx % B
 
     def bytes_per_transition(self):
         return sum(getattr(self, f)[0].numel() * getattr(self, f).element_size() for f in self.FIELDS)
@@ -319,17 +349,22 @@ class CompactReplayBuffer(_RingSampler):
             ep, ep_b = episode_done.to(torch.bool).reshape(-1).contiguous(), 0 if episode_done.numel() == n else 1
         else:
             ep, ep_b = self._flags[bool(episode_done)], 1
-        if node_state is None or (isinstance(node_state, (int, float)) and node_state == 0):
-            ns, ns_b = torch.zeros_like(self.node_state[:1]), 1  # main.py:692-696 stores 0 before the first step
-        else:
-            ns, ns_b = node_state.reshape(n, *self.node_state.shape[1:]).contiguous(), 0
         items = [(self.next_rec, be._state, 0, 0), (self.action, action.contiguous(), conv, 0),
                  (self.reward, reward.reshape(n, -1).contiguous(), 0, 0), (self.done, done_b.reshape(n, -1), 0, 0),
-                 (self.episode_done, ep, 0, ep_b), (self.node_state, ns, 0, ns_b)]
+                 (self.episode_done, ep, 0, ep_b)]
+        if not self.state_ring:  # (state-ring mode: the NetMon steps wrote it in place)
+            if node_state is None or (isinstance(node_state, (int, float)) and node_state == 0):
+                if getattr(self, "_zero_state", None) is None:
+                    self._zero_state = torch.zeros_like(self.node_state[:1])  # main.py:692-696 stores 0 before the first step
+                ns, ns_b = self._zero_state, 1
+            else:
+                ns, ns_b = node_state.reshape(n, *self.node_state.shape[1:]).contiguous(), 0
+            items.append((self.node_state, ns, 0, ns_b))
         self._keep1 = self._insert(items, n)
         self._staged = False
         self.count = min(self.buffer_size, self.count + n)
         self.index = (self.index + n) % self.buffer_size
+        self.steps_total += 1
 
     # ---- sample: gather the compact fields, rebuild the reference's 17 dense fields ----------------
     def _gather(self, idx):
@@ -345,7 +380,14 @@ class CompactReplayBuffer(_RingSampler):
             fields[k].ring, fields[k].dst, fields[k].convert = ring.data_ptr(), out[name].data_ptr(), conv
             fields[k].elem_bytes = ring[0].numel() * ring.element_size()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().gm_replay_sample(fields, len(spec), idx.data_ptr(), n, _lib.current_stream()))
+            if self.state_ring:  # the state field has its own modulus: gather it with its own row indices
+                sidx = self._state_slots(idx).contiguous()
+                _lib.check(_lib.lib().gm_replay_sample(fields, len(spec) - 1, idx.data_ptr(), n, _lib.current_stream()))
+                last = (_lib.ReplayField * 1)()
+                C.memmove(last, C.byref(fields[len(spec) - 1]), C.sizeof(_lib.ReplayField))
+                _lib.check(_lib.lib().gm_replay_sample(last, 1, sidx.data_ptr(), n, _lib.current_stream()))
+            else:
+                _lib.check(_lib.lib().gm_replay_sample(fields, len(spec), idx.data_ptr(), n, _lib.current_stream()))
         return out
 
     def _get_transition_batch(self, indices, device) -> TransitionBatch:

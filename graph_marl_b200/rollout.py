@@ -62,7 +62,7 @@ def aggregate_throughput(units_per_rank, ms_local, world_size):
 class Rollout:
     def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
                  epsilon=1.0, seed=0, with_replay=True, host_draws=False, overlap_replay=True, host_draw_steps=64,
-                 graph_steps=0, replay="compact", device_sampler=False):
+                 graph_steps=0, replay="compact", device_sampler=False, state_ring=True):
         """replay: "compact" (default; replaybuffer.CompactReplayBuffer: env records + NetMon state, dense fields are
         rebuilt when sampled) or "dense" (the reference's 17 dense fields per transition, replaybuffer.ReplayBuffer)."""
         c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
@@ -81,6 +81,7 @@ class Rollout:
                              output_neighbor_hidden=True, math=math).to(device).eval()
         assert replay in ("compact", "dense")
         self.compact = bool(with_replay) and replay == "compact"
+        self.state_ring = False
         # the compact ring does not store the graph observation (it is recomputed when sampled): on the tensor-core
         # path it then exists only tile-packed, written once by the readout and pulled by the DQN's bulk copies
         lean_graph_obs = (self.compact or not with_replay) and math != "fp32" and c["H"] % 32 == 0
@@ -96,10 +97,14 @@ class Rollout:
             steps_fit = max(2, min(8, int(48e9 // (per_transition * num_envs))))
             cap = replay_capacity or steps_fit * num_envs
             if self.compact:
-                self.buff = CompactReplayBuffer(seed, cap, self.env, device_sampler=device_sampler)
+                # state ring: NetMon reads / writes its carried state directly in the ring's node_state field
+                ring = state_ring and cap % num_envs == 0 and cap // num_envs >= 1
+                self.buff = CompactReplayBuffer(seed, cap, self.env, device_sampler=device_sampler, state_ring=ring,
+                                                ring_align=max(int(graph_steps), 1))
             else:
                 self.buff = ReplayBuffer(seed, cap, A, Dj, 0, N, Dn, self.netmon.get_state_size(), N, device=device,
                                          device_sampler=device_sampler)
+        self.state_ring = self.compact and self.buff.state_ring
         self.sizes = dict(N=N, A=A, Dn=Dn, Da=Da, Dj=Dj, H=c["H"], K=c["K"])
         self.host_draws = host_draws
         if host_draws:
@@ -150,8 +155,25 @@ class Rollout:
         self._h["dt"].numpy()[...] = r.integers(0, N, (T, B, A), dtype=np.int32)
         self._h["dz"].numpy()[...] = r.random((T, B, A))
 
+    def _ring_states(self):
+        """State-ring mode: point the wrapper's carried states at their ring blocks (T = committed steps: the state that
+        produced the current observations is the node_state of transition T, the current one that of T + 1)."""
+        T, env = self.buff.steps_total, self.env
+        hpk = getattr(env.current_netmon_state, "_gm_hpk", None)
+        env.last_netmon_state = self.buff.state_block(T)
+        env.current_netmon_state = self.buff.state_block(T + 1)
+        if hpk is not None:
+            env.current_netmon_state._gm_hpk = hpk
+        env.netmon.state = env.current_netmon_state
+
     def reset(self):
+        if self.state_ring:
+            T = self.buff.steps_total
+            self.buff.state_block(T).zero_()  # the state before an episode's first NetMon step (wrapper.py:40-41)
+            self.env._state_sink = self.buff.state_block(T + 1)
         self.obs, self.adj = self.env.reset()
+        if self.state_ring:
+            self._ring_states()
         aux = self.env.get_node_aux()
         if (self.node_aux is not None and self.node_aux.shape == aux.shape and self.node_aux.is_contiguous()
                 and aux.data_ptr() != self.node_aux.data_ptr()):
@@ -197,6 +219,8 @@ class Rollout:
             self.buff.stage(self.B)  # the env records are advanced in place: snapshot them into the ring first
         next_obs_a, next_adj, reward, done, info = self.base_env.step(actions)
         self._mark("env_step")
+        if self.state_ring:
+            env._state_sink = self.buff.state_block(self.buff.steps_total + 2)
         next_obs = env._with_graph_obs(next_obs_a)
         self._mark("netmon")
         next_info = env.get_netmon_info()
@@ -204,6 +228,8 @@ class Rollout:
         episode_done = self.episode_step >= c["episode_steps"]
         if self.compact:
             self.buff.commit(actions, reward, done, episode_done, last_state, num=self.B)
+            if self.state_ring:
+                self._ring_states()
         elif self.buff is not None:
             node_state = last_state if last_state is not None else 0
             if self.overlap_replay:
@@ -232,8 +258,9 @@ class Rollout:
     def _carried(self):
         env, be = self.env, self.base_env
         obs_a, obs_g = self.obs
-        d = dict(obs_a=obs_a, adj=self.adj, cur=env.current_netmon_state, node_obs=be._out["node_obs"],
-                 node_agent=be._out["node_agent"])
+        d = dict(obs_a=obs_a, adj=self.adj, node_obs=be._out["node_obs"], node_agent=be._out["node_agent"])
+        if not self.state_ring:  # (ring mode: the carried states live in ring blocks that a captured unit addresses directly)
+            d["cur"] = env.current_netmon_state
         if isinstance(obs_g, PackedRows):  # graph observation exists only tile-packed
             d["pk"] = obs_g.buf
             self._pk_shape = obs_g.shape
@@ -243,7 +270,7 @@ class Rollout:
             pk = getattr(obs_g, "_gm_pk", None)
             if pk is not None:
                 d["pk"] = pk[0]
-        if env.last_netmon_state is not None:
+        if env.last_netmon_state is not None and not self.state_ring:
             d["last"] = env.last_netmon_state
         hpk = getattr(env.current_netmon_state, "_gm_hpk", None)  # tile-packed hidden half of the carried state
         if hpk is not None:
@@ -260,22 +287,29 @@ class Rollout:
             if "pk" in t:
                 obs_g._gm_pk = (t["pk"], math)
         self.obs, self.adj = (t["obs_a"], obs_g), t["adj"]
-        if "cur_hpk" in t:
-            t["cur"]._gm_hpk = (t["cur_hpk"], env.netmon.math)
-        env.current_netmon_state = t["cur"]
-        env.netmon.state = t["cur"]
-        if "last" in t:
-            env.last_netmon_state = t["last"]
+        if self.state_ring:
+            self._ring_states()
+            if "cur_hpk" in t:
+                env.current_netmon_state._gm_hpk = (t["cur_hpk"], env.netmon.math)
+        else:
+            if "cur_hpk" in t:
+                t["cur"]._gm_hpk = (t["cur_hpk"], env.netmon.math)
+            env.current_netmon_state = t["cur"]
+            env.netmon.state = t["cur"]
+            if "last" in t:
+                env.last_netmon_state = t["last"]
         be._out["node_obs"], be._out["node_agent"] = t["node_obs"], t["node_agent"]
 
     def _counters(self):
         return (self.episode_step, self.base_env._calls, self.policy._step,
-                (self.buff.index, self.buff.count) if self.buff is not None else None)
+                (self.buff.index, self.buff.count, getattr(self.buff, "steps_total", 0)) if self.buff is not None else None)
 
     def _set_counters(self, c):
         self.episode_step, self.base_env._calls, self.policy._step = c[0], c[1], c[2]
         if self.buff is not None:
-            self.buff.index, self.buff.count = c[3]
+            self.buff.index, self.buff.count = c[3][0], c[3][1]
+            if hasattr(self.buff, "steps_total"):
+                self.buff.steps_total = c[3][2]
 
     def _sync_device_counters(self):
         # a replay insert still pending on the side stream reads the ring-index counter (and the static
@@ -285,6 +319,11 @@ class Rollout:
         self.policy._dev_step.set(self.policy._step)
         if self.buff is not None:
             self.buff._dev_index.set(self.buff.index)
+
+    def _ring_phase(self):
+        """A captured unit addresses fixed blocks of the state ring: it can be replayed whenever the step counter sits at
+        the same position of the ring (the ring length is a multiple of the unit length)."""
+        return self.buff.steps_total % self.buff.M if self.state_ring else 0
 
     def _capture_unit(self, n, slot=None):
         """Capture n consecutive steps (from the current, static state) into a CUDA graph."""
@@ -367,7 +406,7 @@ class Rollout:
         c = self._counters()
         buf = None
         if self.buff is not None:
-            buf = ((c[3][0] + n * self.B) % self.buff.buffer_size, min(self.buff.buffer_size, c[3][1] + n * self.B))
+            buf = ((c[3][0] + n * self.B) % self.buff.buffer_size, min(self.buff.buffer_size, c[3][1] + n * self.B), c[3][2] + n)
         d = g.gm_delta
         self._set_counters((c[0] + d[0], c[1] + d[1], c[2], buf))
         # epsilon is a launch argument, i.e. constant inside a captured unit: the decay schedule (policy.py:55-62) is
@@ -375,6 +414,10 @@ class Rollout:
         for _ in range(d[2]):
             self.policy._step += 1
             self.policy._decay()
+        if self.state_ring:  # the carried states moved n blocks along the ring
+            self._ring_states()
+            if "cur_hpk" in self._static:
+                self.env.current_netmon_state._gm_hpk = (self._static["cur_hpk"], self.netmon.math)
         if self.host_draws:
             if self._h_trace is not None:
                 self._h_trace.extend((self._h_cursor + k) % self._h_steps for k in range(n))
@@ -402,7 +445,7 @@ class Rollout:
                 done += 1
                 continue
             slot = (self._h_cursor // n) % (self._h_steps // n) if self.host_draws else 0
-            key = (slot, left_in_episode == n, float(self.policy._epsilon))
+            key = (slot, left_in_episode == n, float(self.policy._epsilon), self._ring_phase())
             if key not in self._graphs:
                 self._graphs[key] = self._capture_unit(n, slot if self.host_draws else None)
                 self._graph_tables = self.base_env._pool
@@ -437,7 +480,7 @@ class Rollout:
             else:
                 advance_until(lambda: self.episode_step is not None and E - self.episode_step > n)
             for slot in slots:
-                key = (slot, tail, float(self.policy._epsilon))
+                key = (slot, tail, float(self.policy._epsilon), self._ring_phase())
                 if key not in self._graphs:
                     self._graphs[key] = self._capture_unit(n, slot if self.host_draws else None)
                     self._graph_tables = self.base_env._pool
