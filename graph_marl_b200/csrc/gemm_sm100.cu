@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[3 * NST + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
-    __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
+    __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? NCG - 1 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
     // NCG == 4 ("wide" epilogue): warps 8-15 are epilogue warps too (no fp32 operands, hence no producers), four
     // column groups per TMEM quadrant
     static_assert(NCG == 2 || NCG == 4, "2 or 4 column groups");
@@ -980,6 +980,7 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     if (wide < 0) { const char* e = getenv("GM_TC_WIDE"); wide = e ? atoi(e) : 1; }
     if (wide && !a.has_prod && passes == 3) {
         if (epi == EPI_LSTM) return launch_tc<256, 3, EPI_LSTM, 4>(a, s);
+        if (epi == EPI_QHEAD) return launch_tc<256, 3, EPI_QHEAD, 4>(a, s);  // Q head: 4 column groups of 64, partials summed through smem
         if (epi == EPI_LINEAR) return sh.BN == 128 ? launch_tc<128, 3, EPI_LINEAR, 4>(a, s) : launch_tc<256, 3, EPI_LINEAR, 4>(a, s);
     }
     if (epi == EPI_LSTM) return passes == 3 ? launch_tc<256, 3, EPI_LSTM>(a, s) : launch_tc<256, 1, EPI_LSTM>(a, s);
