@@ -82,7 +82,8 @@ class MlpGrads(C.Structure):
 
 
 class CellGrads(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("w_ih", "w_hh", "b_ih", "b_hh")]
+    _fields_ = [(n, C.c_void_p) for n in ("w_ih", "w_hh", "b_ih", "b_hh", "ln_in_w", "ln_in_b", "ln_hid_w", "ln_hid_b",
+                                          "ln_cell_w", "ln_cell_b")]
 
 
 class NetmonGrads(C.Structure):

@@ -198,6 +198,138 @@ __global__ void lstm_bwd_kernel(const float* __restrict__ gates, const float* __
     dc_prev[r * lddcp + j] = dct * f_;
 }
 
+// ---- LayerNormLSTM cell (layernormlstm.py:24-42), one warp per row -------------------------------------------
+__device__ __forceinline__ float wsum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+// training forward: gi / gh [R,4H] hold x W_ih^T and h W_hh^T and are overwritten with their NORMALISED values
+// (the LayerNorm backward needs y_hat and 1/sigma, not the raw rows); gates <- activated (i,f,g,o);
+// chat <- normalised pre-LN cell; stats[r] = (rstd_i, rstd_h, rstd_c)
+__global__ void lnlstm_train_fwd_kernel(float* __restrict__ gi, float* __restrict__ gh, gm_cell_params cp, const float* __restrict__ c_prev,
+                                        int64_t ldcp, float* __restrict__ gates, float* __restrict__ chat, float* __restrict__ stats,
+                                        float* __restrict__ h_new, float* __restrict__ c_new, int64_t R, int H) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const int G = 4 * H;
+    float* a = gi + r * G;
+    float* b = gh + r * G;
+    float sa = 0.f, sb = 0.f;
+    for (int c = lane; c < G; c += 32) { sa += a[c]; sb += b[c]; }
+    const float ma = wsum(sa) / (float)G, mb = wsum(sb) / (float)G;
+    float va = 0.f, vb = 0.f;
+    for (int c = lane; c < G; c += 32) {
+        const float da = a[c] - ma, db = b[c] - mb;
+        va += da * da; vb += db * db;
+    }
+    const float ra = 1.f / sqrtf(wsum(va) / (float)G + 1e-5f), rb = 1.f / sqrtf(wsum(vb) / (float)G + 1e-5f);
+    float* g = gates + r * G;
+    for (int c = lane; c < G; c += 32) {
+        const float ya = (a[c] - ma) * ra, yb = (b[c] - mb) * rb;
+        a[c] = ya; b[c] = yb;
+        g[c] = ya * cp.ln_in_w[c] + cp.ln_in_b[c] + (yb * cp.ln_hid_w[c] + cp.ln_hid_b[c]) + cp.b_ih[c];
+    }
+    __syncwarp();
+    float sc = 0.f;
+    for (int j = lane; j < H; j += 32) {
+        const float i_ = sigmoidf_(g[j]), f_ = sigmoidf_(g[H + j]), g_ = tanhf(g[2 * H + j]), o_ = sigmoidf_(g[3 * H + j]);
+        const float cpre = f_ * (c_prev ? c_prev[r * ldcp + j] : 0.f) + i_ * g_;
+        g[j] = i_; g[H + j] = f_; g[2 * H + j] = g_; g[3 * H + j] = o_;
+        chat[r * H + j] = cpre;
+        sc += cpre;
+    }
+    const float mc = wsum(sc) / (float)H;
+    float vc = 0.f;
+    for (int j = lane; j < H; j += 32) { const float d = chat[r * H + j] - mc; vc += d * d; }
+    const float rc = 1.f / sqrtf(wsum(vc) / (float)H + 1e-5f);
+    for (int j = lane; j < H; j += 32) {
+        const float yc = (chat[r * H + j] - mc) * rc;
+        const float c = yc * cp.ln_cell_w[j] + cp.ln_cell_b[j];
+        chat[r * H + j] = yc;
+        c_new[r * H + j] = c;
+        h_new[r * H + j] = g[3 * H + j] * tanhf(c);
+    }
+    if (lane == 0) { stats[r * 4] = ra; stats[r * 4 + 1] = rb; stats[r * 4 + 2] = rc; }
+}
+
+// backward: (dh, dc) of the cell outputs -> dZ [R,4H] (gradient of the summed gate pre-activations), dgi / dgh [R,4H]
+// (gradients of x W_ih^T / h W_hh^T through their LayerNorms), dct [R,H] (gradient of the post-LN cell, for the
+// ln_cell parameter gradients) and dc_prev
+__global__ void lnlstm_bwd_kernel(const float* __restrict__ yi, const float* __restrict__ yh, const float* __restrict__ gates,
+                                  const float* __restrict__ chat, const float* __restrict__ stats, const float* __restrict__ c_new,
+                                  gm_cell_params cp, const float* __restrict__ c_prev, int64_t ldcp, const float* __restrict__ dh,
+                                  int64_t lddh, const float* __restrict__ dc, int64_t lddc, float* __restrict__ dZ,
+                                  float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dct,
+                                  float* __restrict__ dc_prev, int64_t lddcp, int64_t R, int H) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const int G = 4 * H;
+    const float* g = gates + r * G;
+    const float ra = stats[r * 4], rb = stats[r * 4 + 1], rc = stats[r * 4 + 2];
+    float* z = dZ + r * G;
+    // LN_c backward: d c_pre = rstd (dyhat - mean(dyhat) - yhat mean(dyhat yhat)), dyhat = dc' * gamma_c
+    float s1 = 0.f, s2 = 0.f;
+    for (int j = lane; j < H; j += 32) {
+        const float tc = tanhf(c_new[r * H + j]);
+        const float dh_ = dh ? dh[r * lddh + j] : 0.f;
+        const float d = (dc ? dc[r * lddc + j] : 0.f) + dh_ * g[3 * H + j] * (1.f - tc * tc);
+        dct[r * H + j] = d;
+        const float dy = d * cp.ln_cell_w[j];
+        s1 += dy;
+        s2 += dy * chat[r * H + j];
+        z[3 * H + j] = dh_ * tc * g[3 * H + j] * (1.f - g[3 * H + j]);
+    }
+    const float m1 = wsum(s1) / (float)H, m2 = wsum(s2) / (float)H;
+    for (int j = lane; j < H; j += 32) {
+        const float dy = dct[r * H + j] * cp.ln_cell_w[j];
+        const float dcp = rc * (dy - m1 - chat[r * H + j] * m2);
+        const float i_ = g[j], f_ = g[H + j], g_ = g[2 * H + j];
+        const float cpv = c_prev ? c_prev[r * ldcp + j] : 0.f;
+        z[j] = dcp * g_ * i_ * (1.f - i_);
+        z[H + j] = dcp * cpv * f_ * (1.f - f_);
+        z[2 * H + j] = dcp * i_ * (1.f - g_ * g_);
+        dc_prev[r * lddcp + j] = dcp * f_;
+    }
+    __syncwarp();
+    // the two gate LayerNorms: dyhat = dZ * gamma
+    const float* a = yi + r * G;
+    const float* b = yh + r * G;
+    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (int c = lane; c < G; c += 32) {
+        const float da = z[c] * cp.ln_in_w[c], db = z[c] * cp.ln_hid_w[c];
+        a1 += da; a2 += da * a[c];
+        b1 += db; b2 += db * b[c];
+    }
+    a1 = wsum(a1) / (float)G; a2 = wsum(a2) / (float)G; b1 = wsum(b1) / (float)G; b2 = wsum(b2) / (float)G;
+    for (int c = lane; c < G; c += 32) {
+        dgi[r * G + c] = ra * (z[c] * cp.ln_in_w[c] - a1 - a[c] * a2);
+        dgh[r * G + c] = rb * (z[c] * cp.ln_hid_w[c] - b1 - b[c] * b2);
+    }
+}
+
+// out[n] (+)= sum_m Z[m,n] * Y[m,n]   (LayerNorm weight gradients)
+__global__ void __launch_bounds__(256) colsum_prod_kernel(const float* __restrict__ Z, const float* __restrict__ Y, int64_t ld,
+                                                          float* __restrict__ out, int64_t M, int N, int accumulate) {
+    __shared__ float part[8][33];
+    const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + c;
+    float s = 0.f;
+    if (n < N)
+        for (int64_t m = rl; m < M; m += 8) s += Z[m * ld + n] * Y[m * ld + n];
+    part[rl][c] = s;
+    __syncthreads();
+    if (rl == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; q++) t += part[q][c];
+        out[n] = accumulate ? out[n] + t : t;
+    }
+}
+
 // neighbour sum / mean (model.py:213-229), one warp per row; and its transpose as a scatter (any adjacency)
 __global__ void agg_fwd_kernel(const float* __restrict__ h, float* __restrict__ M, int B, int N, int H, const int* __restrict__ nbr,
                                const int* __restrict__ deg, int DM, const int* __restrict__ list_index, int mean) {
@@ -402,7 +534,9 @@ static int mlp_backward(const gm_mlp_desc* m, int64_t rows, const float* x, int6
 
 // ---- NetMon -------------------------------------------------------------------------------
 struct NmTape {
-    int64_t enc, gates, c, h, M, total;  // float offsets: enc tape | (K+1) x gates [R,4H] | (K+1) x c | (K+1) x h | K x M
+    // float offsets: enc tape | (K+1) x gates [R,4H] | (K+1) x c | (K+1) x h | K x M
+    // LayerNormLSTM adds per cell: yi, yh [R,4H] (normalised gate rows), chat [R,H], stats [R,4]
+    int64_t enc, gates, c, h, M, yi, yh, chat, stats, total;
 };
 
 static gm_mlp_desc enc_desc(const gm_netmon_params* p) {
@@ -429,6 +563,14 @@ static NmTape nm_tape(const gm_netmon_params* p, int64_t R) {
     t.h = t.c + (int64_t)(K + 1) * R * H;
     t.M = t.h + (int64_t)(K + 1) * R * H;
     t.total = t.M + (int64_t)K * R * H;
+    t.yi = t.yh = t.chat = t.stats = t.total;
+    if (p->rnn_type == GM_RNN_LNLSTM) {
+        t.yi = t.total;
+        t.yh = t.yi + (int64_t)(K + 1) * R * 4 * H;
+        t.chat = t.yh + (int64_t)(K + 1) * R * 4 * H;
+        t.stats = t.chat + (int64_t)(K + 1) * R * H;
+        t.total = t.stats + (int64_t)(K + 1) * R * 4;
+    }
     return t;
 }
 
@@ -436,15 +578,17 @@ static int nm_train_check(const gm_netmon_params* p) {
     GM_CHECK_ARG(p && p->hidden > 0 && p->n_enc_layers >= 1 && p->n_enc_layers <= GM_MAX_LAYERS &&
                      p->enc_units[p->n_enc_layers - 1] == p->hidden,
                  "bad NetMon descriptor");
-    GM_CHECK_ARG(p->rnn_type == GM_RNN_LSTM && p->rnn_carryover && !p->output_global_hidden && p->iterations >= 1,
-                 "the device backward is built for rnn_type lstm with carry-over, K >= 1, no global readout");
+    GM_CHECK_ARG((p->rnn_type == GM_RNN_LSTM || p->rnn_type == GM_RNN_LNLSTM) && p->rnn_carryover && !p->output_global_hidden &&
+                     p->iterations >= 1,
+                 "the device backward is built for rnn_type lstm / lnlstm with carry-over, K >= 1, no global readout");
     return GM_OK;
 }
 
 // scratch floats of forward / backward: dh, dc, dM, dlast, tmp [R,H] each, dZ [R,4H], MLP scratch
 static int64_t nm_scratch_floats(const gm_netmon_params* p, int64_t R) {
     const gm_mlp_desc m = enc_desc(p);
-    return 6 * R * (int64_t)p->hidden + R * 4ll * p->hidden + mlp_bwd_floats(&m, R);
+    return 6 * R * (int64_t)p->hidden + R * 4ll * p->hidden + mlp_bwd_floats(&m, R) +
+           (p->rnn_type == GM_RNN_LNLSTM ? R * 9ll * p->hidden : 0);  // + dgi, dgh [R,4H], dct [R,H]
 }
 
 }  // namespace gm
@@ -516,8 +660,27 @@ int gm_netmon_forward_train(const gm_netmon_params* p, int32_t B, int32_t N, con
     const int64_t lin_bytes = (char*)workspace + workspace_bytes - lin;
     if ((rc = mlp_forward(&m, R, node_obs, p->in_features, tape + T.enc, lin, lin_bytes, s))) return rc;
     const float* e = tape + T.enc + mlp_tape_off(&m, R, m.n_layers - 1);
+    const bool LN = p->rnn_type == GM_RNN_LNLSTM;
     auto cell = [&](const gm_cell_params& cp, const float* x, const float* hp, int64_t ldhp, const float* cprev, int64_t ldcp, int idx) -> int {
         float* gates = tape + T.gates + (int64_t)idx * R * 4 * H;
+        if (LN) {  // layernormlstm.py:28-40: the two gate GEMMs are normalised separately, no bias inside
+            float* yi = tape + T.yi + (int64_t)idx * R * 4 * H;
+            float* yh = tape + T.yh + (int64_t)idx * R * 4 * H;
+            LinearArgs a{x, H, cp.w_ih, H, nullptr, nullptr, yi, 4 * H, R, 4 * H, H, -1, 0};
+            int r2 = linear_dispatch(a, m.math, lin, lin_bytes, s);
+            if (r2) return r2;
+            if (hp) {
+                LinearArgs b{hp, ldhp, cp.w_hh, H, nullptr, nullptr, yh, 4 * H, R, 4 * H, H, -1, 0};
+                if ((r2 = linear_dispatch(b, m.math, lin, lin_bytes, s))) return r2;
+            } else {
+                GM_CUDA(cudaMemsetAsync(yh, 0, (size_t)R * 4 * H * 4, s));
+            }
+            lnlstm_train_fwd_kernel<<<nblk(R, 4), 128, 0, s>>>(yi, yh, cp, cprev, ldcp, gates, tape + T.chat + (int64_t)idx * R * H,
+                                                              tape + T.stats + (int64_t)idx * R * 4, tape + T.h + (int64_t)idx * R * H,
+                                                              tape + T.c + (int64_t)idx * R * H, R, H);
+            GM_LAUNCH_CHECK();
+            return GM_OK;
+        }
         LinearArgs a{x, H, cp.w_ih, H, cp.b_ih, cp.b_hh, gates, 4 * H, R, 4 * H, H, -1, 0};
         int r2 = linear_dispatch(a, m.math, lin, lin_bytes, s);
         if (r2) return r2;
@@ -584,23 +747,54 @@ int gm_netmon_backward(const gm_netmon_params* p, int32_t B, int32_t N, const fl
     } else {
         GM_CUDA(cudaMemsetAsync(dc, 0, (size_t)R * H * 4, s));
     }
+    // One cell backwards: (dh, dc) of its outputs -> gradients of its two GEMM outputs (dZx for x W_ih^T, dZh for
+    // h W_hh^T: the same dZ for nn.LSTMCell, the two LayerNorm backwards for LayerNormLSTMCell), dc_prev, and the
+    // cell's parameter gradients (acc: add to what is there -- the update cell is shared by the K iterations).
+    const bool LN = p->rnn_type == GM_RNN_LNLSTM;
+    float* dgi = mlp_scratch + mlp_bwd_floats(&m, R);
+    float* dgh = dgi + R * 4 * H;
+    float* dct = dgh + R * 4 * H;
+    const float* dZx = dZ;
+    const float* dZh = dZ;
+    auto cell_bwd = [&](const gm_cell_params& cp, const gm_cell_grads& g, int idx, const float* x, const float* hp, int64_t ldhp,
+                        const float* cprev, int64_t ldcp, float* dc_prev, int64_t lddcp, int acc) -> int {
+        const float* gates = tape + T.gates + (int64_t)idx * R * 4 * H;
+        const float* c_new = tape + T.c + (int64_t)idx * R * H;
+        int r2;
+        if (LN) {
+            const float* yi = tape + T.yi + (int64_t)idx * R * 4 * H;
+            const float* yh = tape + T.yh + (int64_t)idx * R * 4 * H;
+            const float* chat = tape + T.chat + (int64_t)idx * R * H;
+            lnlstm_bwd_kernel<<<nblk(R, 4), 128, 0, s>>>(yi, yh, gates, chat, tape + T.stats + (int64_t)idx * R * 4, c_new, cp, cprev, ldcp,
+                                                        dh, H, dc, H, dZ, dgi, dgh, dct, dc_prev, lddcp, R, H);
+            GM_LAUNCH_CHECK();
+            dZx = dgi; dZh = dgh;
+            if (g.ln_in_w) { colsum_prod_kernel<<<(4 * H + 31) / 32, 256, 0, s>>>(dZ, yi, 4 * H, g.ln_in_w, R, 4 * H, acc); GM_LAUNCH_CHECK(); }
+            if (g.ln_hid_w) { colsum_prod_kernel<<<(4 * H + 31) / 32, 256, 0, s>>>(dZ, yh, 4 * H, g.ln_hid_w, R, 4 * H, acc); GM_LAUNCH_CHECK(); }
+            if (g.ln_cell_w) { colsum_prod_kernel<<<(H + 31) / 32, 256, 0, s>>>(dct, chat, H, g.ln_cell_w, R, H, acc); GM_LAUNCH_CHECK(); }
+            if (g.ln_in_b && (r2 = colsum(dZ, 4 * H, g.ln_in_b, R, 4 * H, acc, s))) return r2;
+            if (g.ln_hid_b && (r2 = colsum(dZ, 4 * H, g.ln_hid_b, R, 4 * H, acc, s))) return r2;
+            if (g.ln_cell_b && (r2 = colsum(dct, H, g.ln_cell_b, R, H, acc, s))) return r2;
+        } else {
+            lstm_bwd_kernel<<<nblk(R * H), 256, 0, s>>>(gates, cprev, ldcp, c_new, dh, H, dc, H, dZ, dc_prev, lddcp, R, H);
+            GM_LAUNCH_CHECK();
+            if (g.b_hh && (r2 = colsum(dZ, 4 * H, g.b_hh, R, 4 * H, acc, s))) return r2;
+        }
+        if (g.b_ih && (r2 = colsum(dZ, 4 * H, g.b_ih, R, 4 * H, acc, s))) return r2;
+        if (g.w_ih && (r2 = gemm_tn(dZx, 4 * H, x, H, g.w_ih, H, R, 4 * H, H, acc, s))) return r2;
+        if (g.w_hh) {
+            if (hp) { if ((r2 = gemm_tn(dZh, 4 * H, hp, ldhp, g.w_hh, H, R, 4 * H, H, acc, s))) return r2; }
+            else if (!acc) GM_CUDA(cudaMemsetAsync(g.w_hh, 0, (size_t)4 * H * H * 4, s));
+        }
+        return GM_OK;
+    };
     // ---- K x (rnn_update cell, aggregation) backwards ---------------------------------------------------------------
     for (int it = K - 1; it >= 0; it--) {
-        const float* gates = tape + T.gates + (int64_t)(it + 1) * R * 4 * H;
-        const float* c_prev = tape + T.c + (int64_t)it * R * H;
-        const float* c_new = tape + T.c + (int64_t)(it + 1) * R * H;
         const float* h_prev = tape + T.h + (int64_t)it * R * H;
         const float* M = tape + T.M + (int64_t)it * R * H;
-        lstm_bwd_kernel<<<nblk(R * H), 256, 0, s>>>(gates, c_prev, H, c_new, dh, H, dc, H, dZ, dcn, H, R, H);
-        GM_LAUNCH_CHECK();
-        const int acc = it != K - 1;  // the update cell's parameters are shared by the K iterations
-        const gm_cell_grads& g = grads->rnn_update;
-        if (g.w_ih && (rc = gemm_tn(dZ, 4 * H, M, H, g.w_ih, H, R, 4 * H, H, acc, s))) return rc;
-        if (g.w_hh && (rc = gemm_tn(dZ, 4 * H, h_prev, H, g.w_hh, H, R, 4 * H, H, acc, s))) return rc;
-        if (g.b_ih && (rc = colsum(dZ, 4 * H, g.b_ih, R, 4 * H, acc, s))) return rc;
-        if (g.b_hh && (rc = colsum(dZ, 4 * H, g.b_hh, R, 4 * H, acc, s))) return rc;
-        if ((rc = gemm_nn(dZ, 4 * H, p->rnn_update.w_ih, H, dM, H, R, 4 * H, H, 0, s))) return rc;   // dM  = dZ W_ih
-        if ((rc = gemm_nn(dZ, 4 * H, p->rnn_update.w_hh, H, tmp, H, R, 4 * H, H, 0, s))) return rc;  // dh_prev (direct)
+        if ((rc = cell_bwd(p->rnn_update, grads->rnn_update, it + 1, M, h_prev, H, tape + T.c + (int64_t)it * R * H, H, dcn, H, it != K - 1))) return rc;
+        if ((rc = gemm_nn(dZx, 4 * H, p->rnn_update.w_ih, H, dM, H, R, 4 * H, H, 0, s))) return rc;   // dM  = dZx W_ih
+        if ((rc = gemm_nn(dZh, 4 * H, p->rnn_update.w_hh, H, tmp, H, R, 4 * H, H, 0, s))) return rc;  // dh_prev (direct)
         agg_bwd_kernel<<<nblk(R, 4), 128, 0, s>>>(dM, tmp, B, N, H, nbr_all, deg, DM, list_index, p->agg_type == GM_AGG_MEAN);
         GM_LAUNCH_CHECK();
         if (it == K - 1) {  // h_{K-1} is also the `last` of the readout
@@ -611,22 +805,13 @@ int gm_netmon_backward(const gm_netmon_params* p, int32_t B, int32_t N, const fl
     }
     // ---- rnn_obs cell backward ------------------------------------------------------------------------------------
     {
-        const float* gates = tape + T.gates;
         const float* e = tape + T.enc + mlp_tape_off(&m, R, m.n_layers - 1);
         float* dcs = d_state_in ? d_state_in + H : dcn;
-        lstm_bwd_kernel<<<nblk(R * H), 256, 0, s>>>(gates, state_in ? state_in + H : nullptr, 2 * H, tape + T.c, dh, H, dc, H, dZ, dcs,
-                                                   d_state_in ? 2 * H : H, R, H);
-        GM_LAUNCH_CHECK();
-        const gm_cell_grads& g = grads->rnn_obs;
-        if (g.w_ih && (rc = gemm_tn(dZ, 4 * H, e, H, g.w_ih, H, R, 4 * H, H, 0, s))) return rc;
-        if (g.w_hh) {
-            if (state_in) { if ((rc = gemm_tn(dZ, 4 * H, state_in, 2 * H, g.w_hh, H, R, 4 * H, H, 0, s))) return rc; }
-            else GM_CUDA(cudaMemsetAsync(g.w_hh, 0, (size_t)4 * H * H * 4, s));
-        }
-        if (g.b_ih && (rc = colsum(dZ, 4 * H, g.b_ih, R, 4 * H, 0, s))) return rc;
-        if (g.b_hh && (rc = colsum(dZ, 4 * H, g.b_hh, R, 4 * H, 0, s))) return rc;
-        if (d_state_in && (rc = gemm_nn(dZ, 4 * H, p->rnn_obs.w_hh, H, d_state_in, 2 * H, R, 4 * H, H, 0, s))) return rc;
-        if ((rc = gemm_nn(dZ, 4 * H, p->rnn_obs.w_ih, H, dM, H, R, 4 * H, H, 0, s))) return rc;  // de
+        if ((rc = cell_bwd(p->rnn_obs, grads->rnn_obs, 0, e, state_in, 2 * H, state_in ? state_in + H : nullptr, 2 * H, dcs,
+                           d_state_in ? 2 * H : H, 0)))
+            return rc;
+        if (d_state_in && (rc = gemm_nn(dZh, 4 * H, p->rnn_obs.w_hh, H, d_state_in, 2 * H, R, 4 * H, H, 0, s))) return rc;
+        if ((rc = gemm_nn(dZx, 4 * H, p->rnn_obs.w_ih, H, dM, H, R, 4 * H, H, 0, s))) return rc;  // de
     }
     // ---- encoder backward ---------------------------------------------------------------------------------------------
     gm_mlp_grads eg{};

@@ -196,9 +196,11 @@ class _NetMonStepFn(torch.autograd.Function):
         L = len(nm.encode.linear_layers)
         for l in range(L):
             g.enc_w[l], g.enc_b[l] = _lib.ptr(grads[2 * l]), _lib.ptr(grads[2 * l + 1])
+        names = nm._cell_param_names()
         for k, cell in enumerate((g.rnn_obs, g.rnn_update)):
-            base = 2 * L + 4 * k
-            cell.w_ih, cell.w_hh, cell.b_ih, cell.b_hh = (_lib.ptr(grads[base + j]) for j in range(4))
+            base = 2 * L + len(names) * k
+            for j, (_, field) in enumerate(names):
+                setattr(cell, field, _lib.ptr(grads[base + j]))
         d_state_in = torch.empty((B, N, 2 * H), dtype=torch.float32, device=dev) if (ctx.has_state and ctx.needs_input_grad[6]) else None
         dn = None if d_node_out is None else d_node_out.float().contiguous()
         ds = None if d_state_out is None else d_state_out.float().contiguous()
@@ -553,6 +555,23 @@ class NetMon(nn.Module):
             agent_out._gm_pk = (agent_pk, self.math)  # consumed by DQN.act of the same math mode
         return node_out, (agent_out if agent_node is not None else None)
 
+    _LIST_CACHE = {}
+
+    @staticmethod
+    def lists_from_mask_cached(mask):
+        """lists_from_mask + the readout's max degree (model.py:588-589), remembered for the last few mask tensors
+        (same storage, same version counter): a learner sequence that feeds one batch for several steps (sl.py:380-392)
+        pays the two host syncs once."""
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.dtype)
+        hit = NetMon._LIST_CACHE.get(key)
+        if hit is None:
+            nbr, deg, dm = NetMon.lists_from_mask(mask)
+            max_degree = int(mask.sum(dim=-1).max().long().item()) - 1
+            if len(NetMon._LIST_CACHE) >= 8:
+                NetMon._LIST_CACHE.pop(next(iter(NetMon._LIST_CACHE)))
+            hit = NetMon._LIST_CACHE[key] = (nbr, deg, dm, max_degree, mask)  # keeps the mask alive: the key stays unique
+        return hit[:4]
+
     @staticmethod
     def lists_from_mask(mask, max_entries=None):
         """Dense [B,N,N] mask -> (nbr_all, deg, max rowsum).  One host sync for the row-sum
@@ -569,12 +588,22 @@ class NetMon(nn.Module):
                                                   ovf.data_ptr(), _lib.current_stream()))
         return nbr, deg, dm
 
+    def _cell_param_names(self):
+        """(attribute path, gm_cell_grads field) of a recurrent cell's parameters, in the order they are handed to the
+        autograd node (nn.LSTMCell / layernormlstm.py:15-22)."""
+        if self.rnn_type == "lnlstm":
+            return [("weight_ih", "w_ih"), ("weight_hh", "w_hh"), ("bias_ih", "b_ih"), ("ln_input.weight", "ln_in_w"),
+                    ("ln_input.bias", "ln_in_b"), ("ln_hidden.weight", "ln_hid_w"), ("ln_hidden.bias", "ln_hid_b"),
+                    ("ln_cell.weight", "ln_cell_w"), ("ln_cell.bias", "ln_cell_b")]
+        return [("weight_ih", "w_ih"), ("weight_hh", "w_hh"), ("bias_ih", "b_ih"), ("bias_hh", "b_hh")]
+
     def _device_backward_reason(self, x):
         """None when the device-side backward (csrc/train.cu) covers this configuration, else why not."""
         if not x.is_cuda:
             return "CPU tensors"
-        if self.rnn_type != "lstm" or not self.rnn_carryover:
-            return f"rnn_type {self.rnn_type} / carryover {self.rnn_carryover}: the device backward is built for lstm with carry-over"
+        if self.rnn_type not in ("lstm", "lnlstm") or not self.rnn_carryover:
+            return (f"rnn_type {self.rnn_type} / carryover {self.rnn_carryover}: the device backward is built for lstm and lnlstm "
+                    "with carry-over")
         if self.output_global_hidden or self.iterations < 1:
             return "global readout / zero iterations"
         return None
@@ -590,9 +619,9 @@ class NetMon(nn.Module):
             GRAD_PATH_CALLS["device"] += 1
             B, N, _ = x.shape
             with torch.no_grad():
-                nbr, deg, dm = self.lists_from_mask(mask)
+                nbr, deg, dm, md_mask = self.lists_from_mask_cached(mask)
                 if max_degree is None:
-                    max_degree = int(mask.sum(dim=-1).max().long().item()) - 1  # model.py:588-589
+                    max_degree = md_mask  # model.py:588-589
             md = max(min(max_degree, dm), 0) if self.output_neighbor_hidden else 0
             st = self.state
             if st is not None:
@@ -600,7 +629,11 @@ class NetMon(nn.Module):
             layers = list(self.encode.linear_layers)
             params = [t for l in layers for t in (l.weight, l.bias)]
             for cell in (self.rnn_obs, self.rnn_update):
-                params += [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+                for path, _ in self._cell_param_names():
+                    obj = cell
+                    for part in path.split("."):
+                        obj = getattr(obj, part)
+                    params.append(obj)
             node_out, self.state = _NetMonStepFn.apply(self, x.float().contiguous(), nbr, deg, None, md, st, *params)
             if no_agent_mapping:
                 return node_out

@@ -353,14 +353,17 @@ GM_API int gm_mlp_backward(const gm_mlp_desc* m, int64_t rows, const float* x, i
                     const float* d_out, int64_t ldd, float* d_x, const gm_mlp_grads* grads, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
-typedef struct gm_cell_grads { float *w_ih, *w_hh, *b_ih, *b_hh; } gm_cell_grads;
+typedef struct gm_cell_grads {
+    float *w_ih, *w_hh, *b_ih, *b_hh;                                           /* b_hh: nn.LSTMCell only */
+    float *ln_in_w, *ln_in_b, *ln_hid_w, *ln_hid_b, *ln_cell_w, *ln_cell_b;     /* LayerNormLSTMCell only */
+} gm_cell_grads;
 typedef struct gm_netmon_grads {
     float* enc_w[GM_MAX_LAYERS];
     float* enc_b[GM_MAX_LAYERS];
     gm_cell_grads rnn_obs, rnn_update;
 } gm_netmon_grads;
-/* One NetMon step with a tape (rnn_type lstm with carry-over, agg sum | mean, K >= 1, no global readout; anything
- * else returns GM_ERR_INVALID).  Arguments as gm_netmon_forward; node_out f32[B,N,O] (O = H (1 + max_degree) with the
+/* One NetMon step with a tape (rnn_type lstm or lnlstm with carry-over, agg sum | mean, K >= 1, no global readout;
+ * anything else returns GM_ERR_INVALID).  Arguments as gm_netmon_forward; node_out f32[B,N,O] (O = H (1 + max_degree) with the
  * neighbour readout) or NULL; state_in f32[B,N,2H] or NULL (= zeros). */
 GM_API int64_t gm_netmon_tape_floats(const gm_netmon_params* p, int64_t rows);
 GM_API int64_t gm_netmon_train_workspace_bytes(const gm_netmon_params* p, int64_t rows);

@@ -47,18 +47,25 @@ def test_dqn_backward_matches_torch_autograd(rows, D, hidden, math, tol):
         assert p.grad is not None and _rel(p.grad, r.grad) < tol, n
 
 
-def _netmon_pair(Dn, H, enc, K, agg, nbr, math):
+def _netmon_pair(Dn, H, enc, K, agg, nbr, math, rnn="lstm"):
     import graph_marl_b200.model as M
 
     torch.manual_seed(2)
-    nm = M.NetMon(Dn, H, enc, K, F.leaky_relu, rnn_type="lstm", agg_type=agg, output_neighbor_hidden=nbr, math=math).cuda()
+    nm = M.NetMon(Dn, H, enc, K, F.leaky_relu, rnn_type=rnn, agg_type=agg, output_neighbor_hidden=nbr, math=math).cuda()
+    if rnn == "lnlstm":  # LayerNorm parameters away from their (1, 0) initial values
+        with torch.no_grad():
+            for cell in (nm.rnn_obs, nm.rnn_update):
+                for ln in (cell.ln_input, cell.ln_hidden, cell.ln_cell):
+                    ln.weight.add_(0.2 * torch.randn_like(ln.weight))
+                    ln.bias.add_(0.1 * torch.randn_like(ln.bias))
     return nm, copy.deepcopy(nm)
 
 
 @pytest.mark.parametrize("math,tol", [("fp32", 1e-4), ("bf16x3", 5e-3)])
-@pytest.mark.parametrize("H,enc,K,agg,nbr,steps", [(128, (512, 256), 2, "sum", True, 3), (32, (48,), 1, "mean", True, 2),
-                                                   (16, (24, 8), 3, "sum", False, 2)])
-def test_netmon_sequence_backward_matches_torch_autograd(H, enc, K, agg, nbr, steps, math, tol):
+@pytest.mark.parametrize("H,enc,K,agg,nbr,steps,rnn", [(128, (512, 256), 2, "sum", True, 3, "lstm"), (32, (48,), 1, "mean", True, 2, "lstm"),
+                                                       (16, (24, 8), 3, "sum", False, 2, "lstm"),
+                                                       (128, (512, 256), 2, "sum", True, 3, "lnlstm"), (32, (48,), 2, "mean", True, 2, "lnlstm")])
+def test_netmon_sequence_backward_matches_torch_autograd(H, enc, K, agg, nbr, steps, rnn, math, tol):
     """BASELINE config 5 inputs (sl.py: 32 evaluation graphs, identity node-agent matrix), a `steps`-long sequence with
     the NetMon state carried (and masked, main.py:861-864) from step to step: outputs, final state and every parameter
     gradient of the device path equal torch autograd of the composed reference math."""
@@ -69,7 +76,9 @@ def test_netmon_sequence_backward_matches_torch_autograd(H, enc, K, agg, nbr, st
     adj = torch.from_numpy(g["node_adj"][:12]).float().cuda()
     B, N, Dn = x.shape
     nam = (torch.rand(B, N, 7, device="cuda") < 0.2).float()  # an arbitrary (not one-hot) node-agent matrix
-    nm, ref = _netmon_pair(Dn, H, enc, K, agg, nbr, math)
+    nm, ref = _netmon_pair(Dn, H, enc, K, agg, nbr, math, rnn)
+    if rnn == "lnlstm":  # LayerNorm over the gate rows amplifies rounding: looser bars
+        tol = 2e-3 if math == "fp32" else 3e-2
     torch.manual_seed(4)
     s0 = torch.randn(B, N, 2 * H, device="cuda") * 0.3
     keep = (torch.rand(B, device="cuda") > 0.3).float().view(-1, 1, 1)
@@ -119,7 +128,7 @@ def test_first_step_without_state_and_unsupported_cells_take_the_torch_path():
     for (n, p), (_, r) in zip(nm.named_parameters(), ref.named_parameters()):
         assert _rel(p.grad, r.grad) < 1e-4, n
     assert float(nm.rnn_obs.weight_hh.grad.abs().max()) == 0.0
-    ln = M.NetMon(x.shape[-1], 32, (40,), 1, F.leaky_relu, rnn_type="lnlstm", output_neighbor_hidden=True).cuda()
+    ln = M.NetMon(x.shape[-1], 32, (40,), 1, F.leaky_relu, rnn_type="gru", output_neighbor_hidden=True).cuda()
     n_t = M.GRAD_PATH_CALLS["torch"]
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
@@ -128,12 +137,14 @@ def test_first_step_without_state_and_unsupported_cells_take_the_torch_path():
     assert M.GRAD_PATH_CALLS["torch"] == n_t + 1 and any("torch-composed" in str(i.message) for i in w)
 
 
-def test_sl_shape_training_step_timed(capsys):
-    """sl.py-shape training step (32 graphs x 20 nodes, paper dims, K = 2, sequence of 8 NetMon steps, loss on every
-    node output, forward + backward): device path vs the torch-composed path, same gradients; both times are printed."""
+@pytest.mark.parametrize("reps", [1, 16])
+def test_sl_shape_training_step_timed(capsys, reps):
+    """sl.py-shape training step (32 graphs x 20 nodes -- and the same batch tiled to 512 graphs --, paper dims, K = 2,
+    sequence of 8 NetMon steps, loss on every node output, forward + backward): device path vs the torch-composed path,
+    same gradients; both times are printed."""
     g = load_golden("sl_netmon")
-    x = torch.from_numpy(g["node_obs"]).cuda()
-    adj = torch.from_numpy(g["node_adj"]).float().cuda()
+    x = torch.from_numpy(g["node_obs"]).cuda().repeat(reps, 1, 1)
+    adj = torch.from_numpy(g["node_adj"]).float().cuda().repeat(reps, 1, 1)
     B, N, Dn = x.shape
     eye = torch.eye(N, device="cuda").repeat(B, 1, 1)
     nm, ref = _netmon_pair(Dn, 128, (512, 256), 2, "sum", True, "fp32")
@@ -159,6 +170,6 @@ def test_sl_shape_training_step_timed(capsys):
         torch.cuda.synchronize()
         times[name] = (time.perf_counter() - t0) / 10 * 1e3
     for (n, p), (_, r) in zip(nm.named_parameters(), ref.named_parameters()):
-        assert _rel(p.grad, r.grad) < 1e-4, n
+        assert _rel(p.grad, r.grad) < 2e-4, n
     with capsys.disabled():
-        print(f"\n[sl-shape training step, 5120 node rows] device backward {times['device']:.2f} ms, torch-composed {times['torch']:.2f} ms")
+        print(f"\n[sl-shape training step, {B} graphs = {B * N} node rows x 8 steps] device backward {times['device']:.2f} ms, torch-composed {times['torch']:.2f} ms")
