@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     __shared__ float ln_part[LN ? 2 : 1][LN ? BM : 1][4][2];  // per row and column quarter: partial sum / centred sum of squares
     __shared__ float ln_cpart[LN ? 2 : 1][LN ? BM : 1][8];    // per row: the quarters' partial sums of the LN_H pass
 
+    pdl_trigger();  // the next kernel's CTAs may take this SM as soon as this CTA has exited
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NST]);
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     if (p.csz > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();  // barriers and TMEM are set up: from here on the kernel reads what its predecessors wrote
 
     // Work units: (group of csz consecutive M tiles, one N tile).  The CTAs of a cluster walk the same
     // unit list in lockstep; CTA `rank` owns M tile mg*csz + rank and 1/csz of every weight stage copy.
@@ -863,13 +865,15 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
     if (csz == 3) csz = 2;
     if (csz > 4 && csz < 8) csz = 4;
     cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     cfg.blockDim = dim3(tc::THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = csz; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see pdl_trigger / pdl_wait in common.cuh
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 2;
     if (csz > 1 && max_clusters[csz] == 0) {
         cfg.gridDim = dim3((kNumSMs / csz) * csz);
         int n = 0;

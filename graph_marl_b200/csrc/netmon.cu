@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(STAGED ? 320 : 256) aggregate_pk_kernel(const 
                                                            const int* __restrict__ deg, int DM,
                                                            const int* __restrict__ list_index, int mean, int write_lo,
                                                            int rows_per_block) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ int agg_lists[];  // STAGED: lists i32[rows_per_block][DM] | degrees i32[rows_per_block]
     const int lane = threadIdx.x & 31;
     const int kbs = H / TC_BK;
@@ -224,6 +226,8 @@ __global__ void __launch_bounds__(352, 3) aggregate_pk_pipe_kernel(const float* 
                                                                    const int* __restrict__ deg, int DM_rt,
                                                                    const int* __restrict__ list_index, int mean, int write_lo,
                                                                    int rows_per_block, int n_blocks, int stage_bytes) {
+    pdl_trigger();
+    pdl_wait();
     const int H = HC ? HC : H_rt, DM = DMC ? DMC : DM_rt;
     extern __shared__ __align__(128) uint8_t agg_sm[];  // full[3], empty[3] mbarriers | 3 x (rows f32[rpb][H] | lists | degrees)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -591,6 +595,8 @@ __global__ void __launch_bounds__(256) readout_agents_pk_kernel(
     const int* __restrict__ nbr, const int* __restrict__ deg, int DM, const int* __restrict__ list_index,
     const int* __restrict__ agent_node, int A, int B, int N, int H, int use_nbr, int use_glob, int max_degree,
     float* __restrict__ out, int64_t ldo, uint8_t* __restrict__ out_pk, int write_lo) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int n_seg = 1 + (use_glob ? 1 : 0) + (use_nbr ? max_degree : 0);
     const int kb_per_seg = H / TC_BK, kbs = n_seg * kb_per_seg;
@@ -983,13 +989,13 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
                     static int pipe_generic = -1;
                     if (pipe_generic < 0) { const char* e = getenv("GM_AGG_PIPE_GENERIC"); pipe_generic = e ? atoi(e) : 0; }
                     if (H == 128 && DM == 4 && !pipe_generic)
-                        aggregate_pk_pipe_kernel<128, 4><<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
-                                                                                               p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
-                                                                                               (int)agg_blocks, pipe_stage);
+                        GM_CUDA(launch_pdl(aggregate_pk_pipe_kernel<128, 4>, dim3(grid), dim3(pipe_threads), pipe_smem, s, h, H, w.m_pk, B, N, H,
+                                           nbr_all, deg, DM, list_index, (int)(p->agg_type == GM_AGG_MEAN), (int)(math != GM_MATH_BF16), rpb,
+                                           (int)agg_blocks, pipe_stage));
                     else
-                        aggregate_pk_pipe_kernel<0, 0><<<grid, pipe_threads, pipe_smem, s>>>(h, H, w.m_pk, B, N, H, nbr_all, deg, DM, list_index,
-                                                                                             p->agg_type == GM_AGG_MEAN, math != GM_MATH_BF16, rpb,
-                                                                                             (int)agg_blocks, pipe_stage);
+                        GM_CUDA(launch_pdl(aggregate_pk_pipe_kernel<0, 0>, dim3(grid), dim3(pipe_threads), pipe_smem, s, h, H, w.m_pk, B, N, H,
+                                           nbr_all, deg, DM, list_index, (int)(p->agg_type == GM_AGG_MEAN), (int)(math != GM_MATH_BF16), rpb,
+                                           (int)agg_blocks, pipe_stage));
                 }
                 else if (agg_staged)
                     aggregate_pk_kernel<true><<<agg_blocks, agg_threads, (size_t)rpb * (DM + 1) * sizeof(int), s>>>(
@@ -1146,9 +1152,9 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         const unsigned blocks = (unsigned)((((rows + 7) / 8) * n_seg + 7) / 8);
         {
             ProfileScope prof(PROF_READOUT, s);
-            readout_agents_pk_kernel<<<blocks, 256, 0, s>>>(h, ldh_cur, last, H, w.gmean, nbr_all, deg, DM, list_index, agent_node, A,
-                                                            B, N, H, use_nbr, use_glob, max_degree, agent_out, agent_out_ld,
-                                                            (uint8_t*)agent_out_pk, math != GM_MATH_BF16);
+            GM_CUDA(launch_pdl(readout_agents_pk_kernel, dim3(blocks), dim3(256), 0, s, h, ldh_cur, last, (int64_t)H, w.gmean, nbr_all, deg, DM,
+                               list_index, agent_node, A, B, N, H, use_nbr, use_glob, max_degree, agent_out, agent_out_ld,
+                               (uint8_t*)agent_out_pk, (int)(math != GM_MATH_BF16)));
         }
         GM_LAUNCH_CHECK();
     } else if (agent_out) {

@@ -352,3 +352,25 @@ def test_unmodified_reference_main_py_runs_on_the_package(tmp_path):
     r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"reward_mean": 1.0' in r.stdout, r.stdout[-3000:]
+
+
+def test_unmodified_reference_sl_py_runs_on_the_package(tmp_path):
+    """BASELINE config 5 through the reference's own, unedited src/sl.py (tools/run_reference_driver.py): dataset generation
+    with the native topology generator behind `Network` / `Routing`, 40 training iterations of NetMonSL (8-... step
+    sequences unrolled through the device-side backward: no torch-composed fallback may be reported), validation and the
+    test evaluations on the EVAL_SEEDS graphs."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "baseline", "_ref", "src", "sl.py")):
+        pytest.skip("baseline/_ref/src is not staged (run __graft_entry__.build() where /root/reference exists)")
+    cmd = [sys.executable, os.path.join(root, "tools", "run_reference_driver.py"), "sl.py", "--iterations", "40",
+           "--num-samples-train", "200", "--validate-after", "20", "--test-sequence-lengths", "1,4", "--disable-progressbar"]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "NetMon Module (libgraphmarl_b200)" in r.stdout and "Extended test data eval (seq_len=4)" in r.stdout
+    assert "torch-composed" not in r.stderr and "torch-composed" not in r.stdout
+    losses = [float(l.split()[-1]) for l in r.stdout.splitlines() if l.startswith("Pred_all loss")]
+    assert len(losses) >= 3 and all(np.isfinite(losses))
