@@ -340,6 +340,10 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     __shared__ __align__(8) uint64_t bars[3 * NST + 2 * ACC_STAGES];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float qpart[EPI == EPI_QHEAD ? 2 : 1][EPI == EPI_QHEAD ? NCG - 1 : 1][EPI == EPI_QHEAD ? BM : 1][TC_MAX_ACT];
+    // Q-head weights [n_act, N <= 256]: every epilogue thread needs all of them for every tile; from global memory (the L1
+    // of this kernel is ~7 KiB) they made the Q-head epilogue the bound of the layer (17 K clocks per tile against 14.5 K
+    // of MMAs, tools/tc_trace.py)
+    __shared__ __align__(16) float qw_s[EPI == EPI_QHEAD ? TC_MAX_ACT : 1][EPI == EPI_QHEAD ? 256 : 4];
     // NCG == 4 ("wide" epilogue): warps 8-15 are epilogue warps too (no fp32 operands, hence no producers), four
     // column groups per TMEM quadrant
     static_assert(NCG == 2 || NCG == 4, "2 or 4 column groups");
@@ -380,6 +384,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(cols) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
+    }
+    if (EPI == EPI_QHEAD) {
+        for (int i = threadIdx.x; i < p.n_act * p.N; i += THREADS) qw_s[i / p.N][i % p.N] = __ldg(p.q_w + i);
     }
     tc_fence_before();
     __syncthreads();
@@ -895,7 +902,9 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
         if (trace_ptr < 0) { const char* e = getenv("GM_TC_TRACE_PTR"); trace_ptr = e ? strtoll(e, nullptr, 0) : 0; }
         static int trace_epi = -2;
         if (trace_epi == -2) { const char* e = getenv("GM_TC_TRACE_EPI"); trace_epi = e ? atoi(e) : -1; }
-        a.trace = (EPI == trace_epi) ? (void*)trace_ptr : nullptr;
+        static int trace_kp = -2;  // optional filter: only the layer whose packed K equals this (e.g. 96 = encoder L1 at N = 20)
+        if (trace_kp == -2) { const char* e = getenv("GM_TC_TRACE_KP"); trace_kp = e ? atoi(e) : -1; }
+        a.trace = (EPI == trace_epi && (trace_kp <= 0 || a.Kp == trace_kp)) ? (void*)trace_ptr : nullptr;
     }
 #endif
     attr[0].val.clusterDim.x = csz;
