@@ -652,6 +652,8 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     }
 }
 
+#include "gemm_sm100_encfused.inc"
+
 // -------------------------------------------------------------------------------------------------
 // weight packing: fp32 W[N,K] (nn.Linear layout) -> bf16 hi/lo tiles in the UMMA canonical layout
 //   out[nt][kb][part][g][kc][r][e]  (g = 8-row group, kc = 8-element K chunk, r = row in group)
@@ -925,6 +927,51 @@ static int launch_tc(TcArgs a, cudaStream_t s) {
 // the bytes in flight) and removed in round 2.  The plan query stays so that callers' packing code
 // keeps one code path.
 bool tc_ws_plan(int, int, int, int, int, TcWsPlan*) { return false; }
+
+// ---- fused encoder layers 1 + 2 for sparse input rows (gemm_sm100_encfused.inc) -----------------------------------
+bool enc_fused_ok(int D, int U1, int U2, int math) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("GM_ENC_FUSED"); on = e ? atoi(e) : 1; }
+    const int64_t smem = (int64_t)tc::EF_STAGES * tc::ef_stage_bytes(D) + 2 * tc::EF_SP_BYTES;
+    return on && math == GM_MATH_BF16X3 && D >= 1 && (U1 % tc::BK) == 0 && U1 >= tc::BK && U2 >= 32 && U2 <= tc::EF_BN && (U2 % tc::BK) == 0 &&
+           smem + 1024 <= 227 * 1024;
+}
+int64_t enc_fused_w1t_bytes(int U1, int D) { return (int64_t)(U1 / tc::BK) * tc::ef_chunk_bytes(D); }
+int64_t enc_fused_sp_bytes(int64_t R) { return ((R + tc::BM - 1) / tc::BM) * tc::EF_SP_BYTES; }
+
+int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, void* out, cudaStream_t s) {
+    tc::ef_pack_w1t_kernel<<<U1 / tc::BK, 256, 0, s>>>(W1, b1, U1, D, (float*)out);
+    GM_LAUNCH_CHECK();
+    return GM_OK;
+}
+
+// x fp32 [R, D] (row stride ldx) -> sparse rows in sp_ws -> Cpk = act(W2 act(W1 x + b1) + b2) tile-packed [R, U2]
+int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int D, const void* w1t, const void* W2p, int U1, int U2, int act, void* sp_ws,
+                     uint8_t* Cpk, int* overflow, cudaStream_t s) {
+    GM_CHECK_ARG(x && w1t && W2p && sp_ws && Cpk && R > 0, "bad fused-encoder arguments");
+    GM_CHECK_ARG((((uintptr_t)w1t | (uintptr_t)W2p | (uintptr_t)sp_ws) & 15) == 0 && ((uintptr_t)Cpk & 127) == 0, "fused-encoder buffers must be 16 / 128-byte aligned");
+    const int m_tiles = (int)((R + tc::BM - 1) / tc::BM);
+    const int64_t Rpad = (int64_t)m_tiles * tc::BM;
+    tc::ef_sparsify_kernel<<<(unsigned)((Rpad + 7) / 8), 256, 0, s>>>(x, ldx, R, Rpad, D, (int32_t*)sp_ws, overflow);
+    GM_LAUNCH_CHECK();
+    const int smem = tc::EF_STAGES * tc::ef_stage_bytes(D) + 2 * tc::EF_SP_BYTES;
+    static int configured = 0;
+    if (configured < smem) {
+        GM_CUDA(cudaFuncSetAttribute(tc::enc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    const TcShape sh = tc_shape(U2, U1, 0, EPI_LINEAR, 0);
+    GM_CHECK_ARG(sh.BN == tc::EF_BN || U2 <= 128, "unexpected layer-2 tile");
+    tc::EncFusedArgs a{};
+    a.sp = (const int32_t*)sp_ws; a.w1t = (const uint8_t*)w1t; a.Wp = (const uint8_t*)W2p;
+    a.bias_tile = (const float*)((const uint8_t*)W2p + sh.w_bytes);
+    a.Cpk = Cpk; a.M = R; a.D = D; a.U1 = U1; a.U2 = U2; a.act = act; a.m_tiles = m_tiles;
+    const int grid = std::min(m_tiles, kNumSMs);
+    ProfileScope prof(PROF_TC, s);
+    GM_CUDA(launch_pdl(tc::enc_fused_kernel, dim3(grid), dim3(tc::THREADS), (size_t)smem, s, a));
+    count_launch();
+    return GM_OK;
+}
 
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s) {
     if (a.M <= 0) return GM_OK;

@@ -78,6 +78,16 @@ int tc_pack_weights(const float* W, int64_t ldw, const float* W1, int64_t ldw1, 
                     int K0, int K1, int epi, int H, void* out, cudaStream_t s, int ws = 0);
 int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
 
+// Encoder layers 1 + 2 as one kernel for input rows with at most 12 non-zeros (gemm_sm100_encfused.inc): layer 1 on the
+// CUDA cores inside the producer warps, layer 2 on tcgen05.  W2 is packed by tc_pack_weights(N = U2, K0 = U1, EPI_LINEAR)
+// and must come out as ONE 256-column tile; W1 by enc_fused_pack_w1t.
+bool enc_fused_ok(int D, int U1, int U2, int math);
+int64_t enc_fused_w1t_bytes(int U1, int D);
+int64_t enc_fused_sp_bytes(int64_t R);
+int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, void* out, cudaStream_t s);
+int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int D, const void* w1t, const void* W2p, int U1, int U2, int act, void* sp_ws,
+                     uint8_t* Cpk, int* overflow, cudaStream_t s);
+
 // LayerNormLSTM cell (H == 128) -> packed weights for EPI_LNLSTM: tc_shape(4H, H, H, EPI_LNLSTM, H).packed_bytes
 // (Gram + gate tiles, LN parameters, and the staging area the packing kernels use), 256-byte aligned destination.
 int tc_pack_lnlstm(const float* w_ih, const float* w_hh, const float* b_ih, const float* ln_in_w, const float* ln_in_b,
