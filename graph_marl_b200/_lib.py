@@ -51,7 +51,7 @@ class NetmonParams(C.Structure):
                 ("enc_units", C.c_int32 * GM_MAX_LAYERS), ("iterations", C.c_int32),
                 ("rnn_type", C.c_int32), ("agg_type", C.c_int32), ("activation", C.c_int32),
                 ("rnn_carryover", C.c_int32), ("output_neighbor_hidden", C.c_int32),
-                ("output_global_hidden", C.c_int32), ("math", C.c_int32),
+                ("output_global_hidden", C.c_int32), ("math", C.c_int32), ("sparse_input_nnz", C.c_int32),
                 ("enc_w", C.c_void_p * GM_MAX_LAYERS), ("enc_b", C.c_void_p * GM_MAX_LAYERS),
                 ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p)]
 

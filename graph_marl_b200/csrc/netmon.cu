@@ -681,6 +681,8 @@ struct NetmonPack {
     int cell_epi;  // EPI_LSTM, or EPI_LNLSTM (LayerNormLSTM with hidden 128)
     bool ws_enc[GM_MAX_LAYERS];  // layer runs on the weight-stationary cluster kernel (tile-packed input)
     bool ws_cells;
+    bool enc_fused;   // encoder layers 1 + 2 can run as one kernel for sparse input rows (gemm_sm100_encfused.inc)
+    int64_t w1t;      // offset of layer 1's W^T chunks for that kernel
 };
 
 static NetmonPack pack_layout(const gm_netmon_params* p) {
@@ -707,6 +709,12 @@ static NetmonPack pack_layout(const gm_netmon_params* p) {
         L.upd = off + cell;
         off += 2 * cell;
     }
+    // fused encoder L1 + L2 (sparse input rows): layer 1 additionally as W^T chunks; layer 2's pack is the normal one
+    L.enc_fused = L.fused_cells && p->n_enc_layers >= 2 && p->activation == GM_ACT_LEAKY_RELU &&
+                  enc_fused_ok(p->in_features, p->enc_units[0], p->enc_units[1], p->math == GM_MATH_BF16 ? -1 : p->math) &&
+                  tc_shape(p->enc_units[1], p->enc_units[0], 0, EPI_LINEAR, 0).n_tiles == 1;
+    L.w1t = off;
+    if (L.enc_fused) off += round_up(enc_fused_w1t_bytes(p->enc_units[0], p->in_features), 256);
     L.total = off;
     return L;
 }
@@ -720,6 +728,7 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
             return rc;
         kin = p->enc_units[l];
     }
+    if (L.enc_fused && (rc = enc_fused_pack_w1t(p->enc_w[0], p->enc_b[0], p->enc_units[0], p->in_features, (char*)out + L.w1t, s))) return rc;
     if (L.fused_cells && L.cell_epi == EPI_LNLSTM) {
         const gm_cell_params* cells[2] = {&p->rnn_obs, &p->rnn_update};
         const int64_t offs[2] = {L.obs, L.upd};
@@ -743,6 +752,7 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
 
 struct NetmonWs {
     float *act0, *act1, *g0, *g1, *hA, *hB, *cA, *cB, *M, *gmean;
+    void* sp;  // sparse input rows of the fused encoder kernel (+ 256 bytes behind them: the overflow flag)
     uint8_t *pk0, *pk1, *e_pk, *m_pk, *h_pk0, *h_pk1;  // tile-packed activations of the tensor-core path
     int64_t bytes;
 };
@@ -769,7 +779,9 @@ static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
     w.M = take(R * H);
     w.gmean = take((int64_t)max(B, 1) * H);
     w.pk0 = w.pk1 = w.e_pk = w.m_pk = w.h_pk0 = w.h_pk1 = nullptr;
+    w.sp = nullptr;
     if (tc_math(p->math)) {
+        w.sp = (void*)take((enc_fused_sp_bytes(R) + 256) / 4);
         auto take_pk = [&](int width) { return (uint8_t*)take(tc_pk_bytes(R, (int)round_up(width, TC_BK)) / 4 + 64); };
         w.pk0 = take_pk(maxw); w.pk1 = take_pk(maxw);
         w.e_pk = take_pk(H); w.m_pk = take_pk(H); w.h_pk0 = take_pk(H); w.h_pk1 = take_pk(H);
@@ -872,7 +884,31 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     const uint8_t* xpk = nullptr;
     int64_t ldx = p->in_features;
     int kin = p->in_features;
-    for (int l = 0; l < L; l++) {
+    int l_first = 0;
+    if (fused && PL.enc_fused && p->sparse_input_nnz > 0 && p->sparse_input_nnz <= 12) {
+        // layers 1 + 2 in one launch: layer 1 on the CUDA cores inside the producer warps (the caller declared rows of at
+        // most sparse_input_nnz non-zeros, e.g. the one-hot node observations of the Routing env), layer 2 on tcgen05
+        uint8_t* ypk = (L == 2) ? w.e_pk : w.pk1;
+        int* overflow = (int*)((char*)w.sp + enc_fused_sp_bytes(R));
+        static int check = -1;
+        if (check < 0) { const char* e = getenv("GM_CHECK_SPARSE"); check = e ? atoi(e) : 0; }
+        if (check) GM_CUDA(cudaMemsetAsync(overflow, 0, 4, s));
+        int rc = enc_fused_launch(node_obs, p->in_features, R, p->in_features, packed + PL.w1t, packed + PL.enc[1], p->enc_units[0],
+                                  p->enc_units[1], p->activation, w.sp, ypk, check ? overflow : nullptr, s);
+        if (rc) return rc;
+        if (check) {  // debug runs: the declared sparsity must hold
+            int flag = 0;
+            GM_CUDA(cudaMemcpyAsync(&flag, overflow, 4, cudaMemcpyDeviceToHost, s));
+            GM_CUDA(cudaStreamSynchronize(s));
+            GM_CHECK_ARG(flag == 0, "node observation rows have more than 12 non-zeros but sparse_input_nnz was declared");
+        }
+        xpk = ypk;
+        x = nullptr;
+        kin = p->enc_units[1];
+        ldx = kin;
+        l_first = 2;
+    }
+    for (int l = l_first; l < L; l++) {
         float* y = (l & 1) ? w.act1 : w.act0;
         int rc;
         if (tc) {

@@ -79,6 +79,9 @@ class Routing(NetworkEnv):
         self.enable_action_mask = enable_action_mask
         self.action_space = Discrete(4, start=0)
         self.eval_info_enabled = False
+        # a node observation row (routing.py:193-234) has at most 12 non-zero entries: one-hot(node), #waiting, their
+        # size sum, 3 x (one-hot(neighbour), length, load); NetMon's tensor-core encoder exploits that
+        self.node_obs_nnz = 12
 
         self.num_envs = int(num_envs)
         self.batched = (self.num_envs > 1) if batched is None else bool(batched)

@@ -79,7 +79,8 @@ class NetMonWrapper:
                 keep = self.netmon.state
                 self.netmon.state = self.last_netmon_state
                 self.netmon_out, _ = self.netmon.forward_lists(env._out["node_obs"], nbr_all, deg, list_index,
-                                                               nbr_all.shape[-1] - 1, want_node_out=True)
+                                                               nbr_all.shape[-1] - 1, want_node_out=True,
+                                                               sparse_nnz=getattr(env, "node_obs_nnz", 0))
                 self.netmon.state = keep
         self.frozen = True
 
@@ -122,7 +123,8 @@ class NetMonWrapper:
             lean = self._batched and self.split_obs
             self.netmon_out, agent_out = self.netmon.forward_lists(
                 node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=not lean,
-                want_agent_pk=lean, want_agent_fp32=self.graph_obs_fp32 or not lean, state_out=self._state_sink)
+                want_agent_pk=lean, want_agent_fp32=self.graph_obs_fp32 or not lean, state_out=self._state_sink,
+                sparse_nnz=getattr(env, "node_obs_nnz", 0))
             self._state_sink = None
             self.current_netmon_state = self.netmon.state
         return self._ret(agent_out)

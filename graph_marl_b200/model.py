@@ -466,6 +466,7 @@ class NetMon(nn.Module):
         p.output_neighbor_hidden = int(self.output_neighbor_hidden)
         p.output_global_hidden = int(self.output_global_hidden)
         p.math = _lib.MATH_MODES[self.math]
+        p.sparse_input_nnz = int(getattr(self, "_sparse_nnz", 0) or 0)
         p.rnn_obs = self._cell(getattr(self, "rnn_obs", None))
         p.rnn_update = self._cell(getattr(self, "rnn_update", None))
         if packed and self.math != "fp32" and layers[0].weight.is_cuda:
@@ -484,13 +485,16 @@ class NetMon(nn.Module):
         return H + (H if self.output_global_hidden else 0) + (max_degree * H if self.output_neighbor_hidden else 0)
 
     def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
-                      want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True, state_out=None):
+                      want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True, state_out=None,
+                      sparse_nnz=0):
         """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
         nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
         Updates self.state; returns (node_out | None, agent_out | None).  want_agent_fp32=False with
         want_agent_pk (tensor-core modes): the agents' graph observation is written ONCE, tile-packed, and
         returned as PackedRows (no fp32 rows).  state_out: optional f32 [B,N,S] tensor that receives the new state (e.g.
-        a block of the replay ring's node_state field, so that the state is never copied)."""
+        a block of the replay ring's node_state field, so that the state is never copied).  sparse_nnz > 0: the caller
+        guarantees rows of x with at most that many (<= 12) non-zeros (the Routing env's one-hot node observations have 12):
+        the tensor-core path then runs encoder layers 1 + 2 as one kernel."""
         _lib.require_device()
         if not x.is_cuda:
             raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
@@ -498,7 +502,9 @@ class NetMon(nn.Module):
         dev = x.device
         x = x.float().contiguous()
         S = self.state_size
+        self._sparse_nnz = int(sparse_nnz or 0)
         p = self._params()
+        self._sparse_nnz = 0
         ws = self._ws.get(_lib.lib().gm_netmon_workspace_bytes(C.byref(p), B * N), dev)
         st_in = None
         hpk_in = None

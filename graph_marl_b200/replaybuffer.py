@@ -409,8 +409,9 @@ class CompactReplayBuffer(_RingSampler):
         with torch.no_grad():
             nm.state = g["node_state"]
             md = pool.nbr_all.shape[-1] - 1
-            _, tail = nm.forward_lists(cur["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=cur["agent_node"])
-            _, ntail = nm.forward_lists(nxt["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=nxt["agent_node"])
+            nnz = getattr(be, "node_obs_nnz", 0)  # same encoder path as the rollout that produced the transitions
+            _, tail = nm.forward_lists(cur["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=cur["agent_node"], sparse_nnz=nnz)
+            _, ntail = nm.forward_lists(nxt["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=nxt["agent_node"], sparse_nnz=nnz)
         nm.state = saved
         A = be._A
         f = dict(

@@ -192,6 +192,10 @@ typedef struct gm_netmon_params {
     int32_t rnn_carryover;                  /* model.py:281 */
     int32_t output_neighbor_hidden, output_global_hidden; /* model.py:279-280 */
     int32_t math;                           /* GM_MATH_* */
+    /* > 0: the caller guarantees that every node observation row has at most this many (<= 12) non-zero entries (the
+     * one-hot layout of routing.py:193-234 has 12): the tensor-core path then runs encoder layers 1 + 2 as one kernel
+     * (layer 1 as 12 weight-column gathers, SURVEY 8d "one-hot layer-1 gathers").  0 = dense rows. */
+    int32_t sparse_input_nnz;
     const float* enc_w[GM_MAX_LAYERS];      /* [out,in] row-major, nn.Linear layout */
     const float* enc_b[GM_MAX_LAYERS];
     gm_cell_params rnn_obs, rnn_update;

@@ -154,6 +154,69 @@ def test_netmon_layernorm_cell_single_step_from_reference_recording(math, tol):
             assert err < tol and serr < tol, (t, err, serr)
 
 
+@pytest.mark.parametrize("B", [3, 96, 700])
+def test_netmon_fused_sparse_encoder(B):
+    """Encoder layers 1 + 2 as one kernel for sparse rows (gemm_sm100_encfused.inc: layer 1 as 12 weight-column gathers
+    inside the producer warps, layer 2 on tcgen05): real Routing node observations (12 non-zeros per row), paper dims.
+    Against the dense tensor-core path (2e-5), against the reference recording (1e-4, single step from the recorded
+    state) and, at B = 700 (5.5 M tiles per ... partial last tile, several tiles per CTA), against the fp64 oracle."""
+    from graph_marl_b200.model import NetMon
+    from oracle import netmon_oracle as NO
+
+    name, cfg = netmon_case(G, [x for x in G["case_names"] if str(x).startswith("lstm_sum_k3_paper")][0])
+    X, ADJ, NAM = G["node_obs"], G["node_adj"], G["node_agent"]
+    assert int((X != 0).sum(-1).max()) <= 12
+    nm, w = _netmon(cfg, X.shape[-1], "bf16x3")
+    t = 2
+    reps = -(-B // X.shape[1])
+    x = np.concatenate([X[(t + i) % X.shape[0]] for i in range(reps)])[:B]
+    adj = np.concatenate([ADJ[(t + i) % X.shape[0]] for i in range(reps)])[:B]
+    st = np.concatenate([G[name + "_state"][(t - 1 + i) % X.shape[0]] for i in range(reps)])[:B]
+    with torch.no_grad():
+        nbr, deg, dm = NetMon.lists_from_mask(torch.from_numpy(adj).float().cuda())
+        outs = {}
+        for nnz in (0, 12):
+            nm.state = torch.from_numpy(st).cuda()
+            no, _ = nm.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, want_node_out=True, sparse_nnz=nnz)
+            outs[nnz] = (no.cpu().numpy(), nm.state.cpu().numpy())
+    assert np.abs(outs[12][0] - outs[0][0]).max() < 2e-5 and np.abs(outs[12][1] - outs[0][1]).max() < 2e-5
+    if B == 3:  # the reference's own step from its recorded state
+        nm.state = torch.from_numpy(G[name + "_state"][t - 1]).cuda()
+        agent_node = torch.from_numpy(NAM[t].argmax(axis=1).astype(np.int32)).cuda()
+        with torch.no_grad():
+            _, ao = nm.forward_lists(torch.from_numpy(X[t]).cuda(), nbr, deg, None, 3, agent_node=agent_node, sparse_nnz=12)
+        assert np.abs(ao.cpu().numpy() - G[name + "_agent_out"][t]).max() < 1e-4
+        assert np.abs(nm.state.cpu().numpy() - G[name + "_state"][t]).max() < 1e-4
+    if B == 700:
+        ref_out, ref_state, _ = NO.netmon_forward(w, cfg, x, adj.astype(np.float32), st, dtype=np.float64)
+        assert np.abs(outs[12][0] - ref_out).max() < 1e-4 and np.abs(outs[12][1] - ref_state).max() < 1e-4
+
+
+def test_fused_sparse_encoder_reports_rows_that_are_not_sparse():
+    """GM_CHECK_SPARSE=1 (debug switch, read once per process): a batch whose rows break the declared sparsity is an error."""
+    import os, subprocess, sys, textwrap
+
+    code = textwrap.dedent("""
+        import sys, torch, torch.nn.functional as F
+        sys.path.insert(0, %r)
+        from graph_marl_b200.model import NetMon
+        from graph_marl_b200._lib import GraphMarlError
+        nm = NetMon(88, 128, (512, 256), 1, F.leaky_relu, output_neighbor_hidden=True, math="bf16x3").cuda().eval()
+        x = torch.rand(4, 20, 88, device="cuda")
+        mask = torch.eye(20, device="cuda").repeat(4, 1, 1)
+        nbr, deg, dm = NetMon.lists_from_mask(mask)
+        with torch.no_grad():
+            nm.forward_lists(x, nbr, deg, None, 0, want_node_out=True)            # dense rows, dense path: fine
+            try:
+                nm.forward_lists(x, nbr, deg, None, 0, want_node_out=True, sparse_nnz=12)
+                print("no error")
+            except GraphMarlError as e:
+                print("caught", "non-zeros" in str(e))
+    """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GM_CHECK_SPARSE="1"), capture_output=True, text=True, timeout=300)
+    assert "caught True" in r.stdout, r.stdout + r.stderr
+
+
 def test_packed_weight_cache_follows_parameter_updates():
     cfg = dict(hidden=64, iterations=1, rnn_type="lstm", rnn_carryover=True, agg_type="sum", output_neighbor_hidden=True,
                output_global_hidden=False, enc=[32], wseed=3)
