@@ -35,7 +35,7 @@ class RoutingDesc(C.Structure):
 class RoutingIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("actions", "env_mask", "draw_start", "draw_target", "draw_size")] + \
                [("philox_seed", C.c_uint64), ("philox_step", C.c_uint64), ("philox_step_dev", C.c_void_p)] + \
-               [(n, C.c_void_p) for n in ("obs", "adj", "node_obs", "node_agent", "agent_node", "reward",
+               [(n, C.c_void_p) for n in ("obs", "adj", "node_obs", "node_agent", "agent_node", "node_sparse", "reward",
                                           "done", "delays", "arrived", "spr", "info", "n_resets",
                                           "action_mask_out", "eval_f64", "eval_i32", "packet_dist", "packet_sizes",
                                           "sum_packets_per_node", "sum_packets_per_edge")]
@@ -53,7 +53,7 @@ class NetmonParams(C.Structure):
                 ("rnn_carryover", C.c_int32), ("output_neighbor_hidden", C.c_int32),
                 ("output_global_hidden", C.c_int32), ("math", C.c_int32), ("sparse_input_nnz", C.c_int32),
                 ("enc_w", C.c_void_p * GM_MAX_LAYERS), ("enc_b", C.c_void_p * GM_MAX_LAYERS),
-                ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p)]
+                ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p), ("sparse_rows", C.c_void_p)]
 
 
 class DqnParams(C.Structure):

@@ -946,14 +946,19 @@ int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, void* ou
 }
 
 // x fp32 [R, D] (row stride ldx) -> sparse rows in sp_ws -> Cpk = act(W2 act(W1 x + b1) + b2) tile-packed [R, U2]
+// (or, with sp_rows != NULL, takes the caller's sparse rows [ceil(R/128)*128][24] as they are: 12 column indices then 12 values)
 int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int D, const void* w1t, const void* W2p, int U1, int U2, int act, void* sp_ws,
-                     uint8_t* Cpk, int* overflow, cudaStream_t s) {
-    GM_CHECK_ARG(x && w1t && W2p && sp_ws && Cpk && R > 0, "bad fused-encoder arguments");
-    GM_CHECK_ARG((((uintptr_t)w1t | (uintptr_t)W2p | (uintptr_t)sp_ws) & 15) == 0 && ((uintptr_t)Cpk & 127) == 0, "fused-encoder buffers must be 16 / 128-byte aligned");
+                     const int32_t* sp_rows, uint8_t* Cpk, int* overflow, cudaStream_t s) {
+    GM_CHECK_ARG((x || sp_rows) && w1t && W2p && sp_ws && Cpk && R > 0, "bad fused-encoder arguments");
+    GM_CHECK_ARG((((uintptr_t)w1t | (uintptr_t)W2p | (uintptr_t)sp_ws | (uintptr_t)sp_rows) & 15) == 0 && ((uintptr_t)Cpk & 127) == 0,
+                 "fused-encoder buffers must be 16 / 128-byte aligned");
     const int m_tiles = (int)((R + tc::BM - 1) / tc::BM);
     const int64_t Rpad = (int64_t)m_tiles * tc::BM;
-    tc::ef_sparsify_kernel<<<(unsigned)((Rpad + 7) / 8), 256, 0, s>>>(x, ldx, R, Rpad, D, (int32_t*)sp_ws, overflow);
-    GM_LAUNCH_CHECK();
+    if (sp_rows == nullptr) {
+        tc::ef_sparsify_kernel<<<(unsigned)((Rpad + 7) / 8), 256, 0, s>>>(x, ldx, R, Rpad, D, (int32_t*)sp_ws, overflow);
+        GM_LAUNCH_CHECK();
+        sp_rows = (const int32_t*)sp_ws;
+    }
     const int smem = tc::EF_STAGES * tc::ef_stage_bytes(D) + 2 * tc::EF_SP_BYTES;
     static int configured = 0;
     if (configured < smem) {
@@ -963,7 +968,7 @@ int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int D, const void* 
     const TcShape sh = tc_shape(U2, U1, 0, EPI_LINEAR, 0);
     GM_CHECK_ARG(sh.BN == tc::EF_BN || U2 <= 128, "unexpected layer-2 tile");
     tc::EncFusedArgs a{};
-    a.sp = (const int32_t*)sp_ws; a.w1t = (const uint8_t*)w1t; a.Wp = (const uint8_t*)W2p;
+    a.sp = sp_rows; a.w1t = (const uint8_t*)w1t; a.Wp = (const uint8_t*)W2p;
     a.bias_tile = (const float*)((const uint8_t*)W2p + sh.w_bytes);
     a.Cpk = Cpk; a.M = R; a.D = D; a.U1 = U1; a.U2 = U2; a.act = act; a.m_tiles = m_tiles;
     const int grid = std::min(m_tiles, kNumSMs);

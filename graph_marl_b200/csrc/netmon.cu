@@ -894,7 +894,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         if (check < 0) { const char* e = getenv("GM_CHECK_SPARSE"); check = e ? atoi(e) : 0; }
         if (check) GM_CUDA(cudaMemsetAsync(overflow, 0, 4, s));
         int rc = enc_fused_launch(node_obs, p->in_features, R, p->in_features, packed + PL.w1t, packed + PL.enc[1], p->enc_units[0],
-                                  p->enc_units[1], p->activation, w.sp, ypk, check ? overflow : nullptr, s);
+                                  p->enc_units[1], p->activation, w.sp, p->sparse_rows, ypk, check ? overflow : nullptr, s);
         if (rc) return rc;
         if (check) {  // debug runs: the declared sparsity must hold
             int flag = 0;

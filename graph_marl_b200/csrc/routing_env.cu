@@ -530,7 +530,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
 
     // waiting packets per node: count and fp64 size sum in packet-id order (routing.py:200-205); needed by
     // the node observations and by the GLOBAL agent observation
-    const bool need_wait = (io.node_obs != nullptr && do_node) || (io.obs != nullptr && env_var == 3);
+    const bool need_wait = ((io.node_obs != nullptr || io.node_sparse != nullptr) && do_node) || (io.obs != nullptr && env_var == 3);
     auto waiting_sums = [&]() {
         for (int j = lane; j < N; j += 32) { v.tl[j] = 0.0; v.cnt[j] = 0; }
         __syncwarp();
@@ -544,6 +544,31 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             });
         }
         __syncwarp();
+    };
+    // the node rows once more in sparse form (12 (column, value) slots in a fixed order) for NetMon's fused encoder
+    auto emit_node_sparse = [&]() {
+        if (!(io.node_sparse && do_node)) return;
+        for (int j = lane; j < N; j += 32) {
+            int32_t* o = io.node_sparse + ((size_t)b * N + j) * 24;
+            int cols[12];
+            float vals[12];
+            cols[0] = j; vals[0] = 1.f;
+            cols[1] = N; vals[1] = (float)v.cnt[j];
+            cols[2] = N + 1; vals[2] = (float)v.tl[j];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int k = ne[j * 3 + q], b2 = N + 2 + q * (N + 2);
+                cols[3 + 3 * q] = b2 + nb[j * 3 + q]; vals[3 + 3 * q] = 1.f;
+                cols[4 + 3 * q] = b2 + N; vals[4 + 3 * q] = (float)ed[k].z;
+                cols[5 + 3 * q] = b2 + N + 1; vals[5 + 3 * q] = (float)v.load[k];
+            }
+#pragma unroll
+            for (int t4 = 0; t4 < 3; t4++) {
+                ((int4*)o)[t4] = make_int4(cols[4 * t4], cols[4 * t4 + 1], cols[4 * t4 + 2], cols[4 * t4 + 3]);
+                ((int4*)o)[3 + t4] = make_int4(__float_as_int(vals[4 * t4]), __float_as_int(vals[4 * t4 + 1]),
+                                               __float_as_int(vals[4 * t4 + 2]), __float_as_int(vals[4 * t4 + 3]));
+            }
+        }
     };
     // the GLOBAL agent observation embeds node rows and the direct store mode emits everything in one pass: both need the
     // sums (and, to keep one code path, the record write-back) first
@@ -633,6 +658,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                 }
             }
         }
+        emit_node_sparse();
         if (io.adj) emit_adj_rows(v.now, nb, io.adj + (size_t)b * A * A, N, A, lane);
         if (io.node_agent) emit_node_agent_rows(v.now, io.node_agent + (size_t)b * N * A, N, A, lane);
         return;
@@ -706,6 +732,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         GM_PROBE(5);
         if (need_wait) waiting_sums();
     }
+    emit_node_sparse();
     if (do_node) GM_PROBE(6);
     // ---- node observations (routing.py:193-234), row width 4N+8 ------------------------
     if (io.node_obs && do_node) {

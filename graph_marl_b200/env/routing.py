@@ -170,7 +170,8 @@ class Routing(NetworkEnv):
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
         o = dict(obs=e((B, A, self.obs_width()), torch.float32), adj=e((B, A, A), torch.int8),
                  node_obs=e((B, N, 4 * N + 8), torch.float32), node_agent=e((B, N, A), torch.int8),
-                 agent_node=e((B, A), torch.int32), n_resets=e((B,), torch.int32))
+                 agent_node=e((B, A), torch.int32), n_resets=e((B,), torch.int32),
+                 node_sparse=self._sparse_rows_buffer(B))
         if step:
             o.update(reward=e((B, A), torch.float32), done=e((B, A), torch.uint8), delays=e((B, A), torch.int32),
                      arrived=e((B, A), torch.uint8), spr=e((B, A), torch.float64), info=e((B, 4), torch.int32))
@@ -184,6 +185,15 @@ class Routing(NetworkEnv):
                 self._sum_edge = torch.zeros((B, self._E), dtype=torch.int32, device=dev)
             o.update(sum_packets_per_node=self._sum_node, sum_packets_per_edge=self._sum_edge)
         return o
+
+    def _sparse_rows_buffer(self, n):
+        """[n, N, 24] int32 view for the node observation rows in sparse form (12 column indices + 12 fp32 bit patterns
+        per row, csrc/routing_env.cu) on an allocation rounded up to whole 128-row tiles: NetMon's fused encoder pulls
+        the rows tile by tile with bulk copies (rows behind n * N are never used as data)."""
+        N = self._N
+        rows = -(-(n * N) // 128) * 128
+        flat = torch.empty((rows * 24,), dtype=torch.int32, device=self.device)
+        return flat[:n * N * 24].view(n, N, 24)
 
     def _io(self, out, actions=None, env_mask=None):
         io = _lib.RoutingIO()
@@ -348,7 +358,7 @@ class Routing(NetworkEnv):
         e = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
         out = dict(obs=e((n, A, self.obs_width()), torch.float32), adj=e((n, A, A), torch.int8),
                    node_obs=e((n, N, 4 * N + 8), torch.float32), node_agent=e((n, N, A), torch.int8),
-                   agent_node=e((n, A), torch.int32))
+                   agent_node=e((n, A), torch.int32), node_sparse=self._sparse_rows_buffer(n))
         d = self._desc()
         d.B, d.state = n, records.data_ptr()
         d.topo_index = None if topo_index is None else topo_index.data_ptr()

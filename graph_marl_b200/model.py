@@ -486,7 +486,7 @@ class NetMon(nn.Module):
 
     def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
                       want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True, state_out=None,
-                      sparse_nnz=0):
+                      sparse_nnz=0, sparse_rows=None):
         """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
         nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
         Updates self.state; returns (node_out | None, agent_out | None).  want_agent_fp32=False with
@@ -494,7 +494,8 @@ class NetMon(nn.Module):
         returned as PackedRows (no fp32 rows).  state_out: optional f32 [B,N,S] tensor that receives the new state (e.g.
         a block of the replay ring's node_state field, so that the state is never copied).  sparse_nnz > 0: the caller
         guarantees rows of x with at most that many (<= 12) non-zeros (the Routing env's one-hot node observations have 12):
-        the tensor-core path then runs encoder layers 1 + 2 as one kernel."""
+        the tensor-core path then runs encoder layers 1 + 2 as one kernel.  sparse_rows: those rows already in sparse form
+        (int32 [B,N,24] on a 128-row padded allocation, Routing's `node_sparse` output); None = derived from x."""
         _lib.require_device()
         if not x.is_cuda:
             raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
@@ -505,6 +506,9 @@ class NetMon(nn.Module):
         self._sparse_nnz = int(sparse_nnz or 0)
         p = self._params()
         self._sparse_nnz = 0
+        if sparse_rows is not None and p.sparse_input_nnz > 0:
+            assert sparse_rows.dtype == torch.int32 and sparse_rows.shape == (B, N, 24) and sparse_rows.is_contiguous()
+            p.sparse_rows = sparse_rows.data_ptr()
         ws = self._ws.get(_lib.lib().gm_netmon_workspace_bytes(C.byref(p), B * N), dev)
         st_in = None
         hpk_in = None

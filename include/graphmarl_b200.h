@@ -124,6 +124,9 @@ typedef struct gm_routing_io {
     float* node_obs;             /* [B,N,4N+8]   routing.py:187-235 */
     int8_t* node_agent;          /* [B,N,A]      routing.py:256-267 */
     int32_t* agent_node;         /* [B,A] node of each agent (= argmax of node_agent column) */
+    int32_t* node_sparse;        /* [B,N,24] the node observation rows in sparse form: 12 column indices then 12 fp32
+                                    values (bit patterns) in the fixed slot order node, #waiting, size sum, 3 x (neighbour,
+                                    length, load); consumed by gm_netmon_params.sparse_rows */
     float* reward;               /* [B,A] f32    routing.py:361,398,474 */
     uint8_t* done;               /* [B,A]        routing.py:475 */
     int32_t* delays;             /* [B,A] agent_steps at done else 0 (routing.py:488) */
@@ -202,6 +205,11 @@ typedef struct gm_netmon_params {
     /* tensor-core modes only: weights packed by gm_netmon_pack_weights (device, 256-byte aligned),
      * or NULL = pack into the workspace on every forward call */
     const void* packed;
+    /* per call, optional (with sparse_input_nnz > 0): the rows already in sparse form, i32[ceil(B*N/128)*128][24] = 12
+     * column indices then 12 fp32 values per row (gm_routing_io.node_sparse writes them in a fixed slot order, which
+     * lets the kernel's shared-memory gathers of the fixed columns broadcast); NULL = the library derives them from
+     * node_obs.  Rows behind B*N are never read as data. */
+    const int32_t* sparse_rows;
 } gm_netmon_params;
 
 /* Packed tensor-core weights (GM_MATH_BF16X3 / GM_MATH_BF16): the fp32 parameters split into bf16

@@ -140,6 +140,13 @@ def test_batched_against_oracle(cfg):
         assert np.array_equal(env._out["node_obs"].cpu().numpy(), o["node_obs"]), t
         assert np.array_equal(env._out["node_agent"].cpu().numpy(), o["node_agent"]), t
         assert np.array_equal(env._out["agent_node"].cpu().numpy(), orc.now), t
+        # the sparse form of the node rows (12 fixed slots of (column, value)) scatters back to exactly the dense rows
+        sp = env._out["node_sparse"].cpu().numpy()
+        dense = np.zeros_like(o["node_obs"])
+        bi, ji = np.meshgrid(np.arange(B), np.arange(N), indexing="ij")
+        for k in range(12):
+            np.add.at(dense, (bi, ji, sp[..., k]), sp[..., 12 + k].view(np.float32))
+        assert np.array_equal(dense, o["node_obs"]), t
         s = env.get_state()
         for k, ref in (("now", orc.now), ("target", orc.target), ("edge", orc.edge), ("time", orc.time),
                        ("ttl", orc.ttl_left), ("spw", orc.spw), ("size", orc.size), ("load", orc.load),
