@@ -28,7 +28,7 @@ class GraphMarlError(RuntimeError):
 
 class RoutingDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("B", "N", "A", "E", "T", "env_var", "k", "congestion",
-                                         "action_mask", "ttl", "state_stride", "store_mode")] + \
+                                         "action_mask", "ttl", "state_stride", "node_sparse_static", "store_mode")] + \
                [(n, C.c_void_p) for n in ("node_edges", "node_nbrs", "edges", "apsp", "topo_index", "state")]
 
 
@@ -53,7 +53,8 @@ class NetmonParams(C.Structure):
                 ("rnn_carryover", C.c_int32), ("output_neighbor_hidden", C.c_int32),
                 ("output_global_hidden", C.c_int32), ("math", C.c_int32), ("sparse_input_nnz", C.c_int32),
                 ("enc_w", C.c_void_p * GM_MAX_LAYERS), ("enc_b", C.c_void_p * GM_MAX_LAYERS),
-                ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p), ("sparse_rows", C.c_void_p)]
+                ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p), ("sparse_rows", C.c_void_p),
+                ("static_rows", C.c_void_p), ("n_static_rows", C.c_int32), ("pad_", C.c_int32)]
 
 
 class DqnParams(C.Structure):

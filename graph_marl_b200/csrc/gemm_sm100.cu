@@ -939,30 +939,34 @@ bool enc_fused_ok(int D, int U1, int U2, int math) {
 int64_t enc_fused_w1t_bytes(int U1, int D) { return (int64_t)(U1 / tc::BK) * tc::ef_chunk_bytes(D); }
 int64_t enc_fused_sp_bytes(int64_t R) { return ((R + tc::BM - 1) / tc::BM) * tc::EF_SP_BYTES; }
 
-int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, void* out, cudaStream_t s) {
-    tc::ef_pack_w1t_kernel<<<U1 / tc::BK, 256, 0, s>>>(W1, b1, U1, D, (float*)out);
+// D = input width, S static rows (dense [S, D], may be 0 / NULL): the chunks hold D + S rows
+int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, const float* static_rows, int S, void* out, cudaStream_t s) {
+    tc::ef_pack_w1t_kernel<<<U1 / tc::BK, 256, 0, s>>>(W1, b1, U1, D, static_rows, static_rows ? S : 0, (float*)out);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
 
 // x fp32 [R, D] (row stride ldx) -> sparse rows in sp_ws -> Cpk = act(W2 act(W1 x + b1) + b2) tile-packed [R, U2]
 // (or, with sp_rows != NULL, takes the caller's sparse rows [ceil(R/128)*128][24] as they are: 12 column indices then 12 values)
-int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int D, const void* w1t, const void* W2p, int U1, int U2, int act, void* sp_ws,
-                     const int32_t* sp_rows, uint8_t* Cpk, int* overflow, cudaStream_t s) {
+// D: rows of the W1^T chunks (input width + static rows); nnz: 12, or 6 when the rows name a static part
+int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int Dx, int D, int nnz, const void* w1t, const void* W2p, int U1, int U2, int act,
+                     void* sp_ws, const int32_t* sp_rows, uint8_t* Cpk, int* overflow, cudaStream_t s) {
+    GM_CHECK_ARG(nnz == 12 || (nnz == 6 && sp_rows != nullptr), "6-term rows must be supplied by the caller");
     GM_CHECK_ARG((x || sp_rows) && w1t && W2p && sp_ws && Cpk && R > 0, "bad fused-encoder arguments");
     GM_CHECK_ARG((((uintptr_t)w1t | (uintptr_t)W2p | (uintptr_t)sp_ws | (uintptr_t)sp_rows) & 15) == 0 && ((uintptr_t)Cpk & 127) == 0,
                  "fused-encoder buffers must be 16 / 128-byte aligned");
     const int m_tiles = (int)((R + tc::BM - 1) / tc::BM);
     const int64_t Rpad = (int64_t)m_tiles * tc::BM;
     if (sp_rows == nullptr) {
-        tc::ef_sparsify_kernel<<<(unsigned)((Rpad + 7) / 8), 256, 0, s>>>(x, ldx, R, Rpad, D, (int32_t*)sp_ws, overflow);
+        tc::ef_sparsify_kernel<<<(unsigned)((Rpad + 7) / 8), 256, 0, s>>>(x, ldx, R, Rpad, Dx, (int32_t*)sp_ws, overflow);
         GM_LAUNCH_CHECK();
         sp_rows = (const int32_t*)sp_ws;
     }
     const int smem = tc::EF_STAGES * tc::ef_stage_bytes(D) + 2 * tc::EF_SP_BYTES;
     static int configured = 0;
     if (configured < smem) {
-        GM_CUDA(cudaFuncSetAttribute(tc::enc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GM_CUDA(cudaFuncSetAttribute(tc::enc_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        GM_CUDA(cudaFuncSetAttribute(tc::enc_fused_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
     const TcShape sh = tc_shape(U2, U1, 0, EPI_LINEAR, 0);
@@ -973,7 +977,8 @@ int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int D, const void* 
     a.Cpk = Cpk; a.M = R; a.D = D; a.U1 = U1; a.U2 = U2; a.act = act; a.m_tiles = m_tiles;
     const int grid = std::min(m_tiles, kNumSMs);
     ProfileScope prof(PROF_TC, s);
-    GM_CUDA(launch_pdl(tc::enc_fused_kernel, dim3(grid), dim3(tc::THREADS), (size_t)smem, s, a));
+    if (nnz == 6) GM_CUDA(launch_pdl(tc::enc_fused_kernel<6>, dim3(grid), dim3(tc::THREADS), (size_t)smem, s, a));
+    else GM_CUDA(launch_pdl(tc::enc_fused_kernel<12>, dim3(grid), dim3(tc::THREADS), (size_t)smem, s, a));
     count_launch();
     return GM_OK;
 }

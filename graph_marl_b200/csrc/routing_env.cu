@@ -552,15 +552,28 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             int32_t* o = io.node_sparse + ((size_t)b * N + j) * 24;
             int cols[12];
             float vals[12];
-            cols[0] = j; vals[0] = 1.f;
-            cols[1] = N; vals[1] = (float)v.cnt[j];
-            cols[2] = N + 1; vals[2] = (float)v.tl[j];
+            if (d.node_sparse_static) {
+                // the constant part of the row (one-hots, lengths) as ONE entry: column 4N+8 + topology*N + node
+                cols[0] = 4 * N + 8 + topo * N + j; vals[0] = 1.f;
+                cols[1] = N; vals[1] = (float)v.cnt[j];
+                cols[2] = N + 1; vals[2] = (float)v.tl[j];
 #pragma unroll
-            for (int q = 0; q < 3; q++) {
-                const int k = ne[j * 3 + q], b2 = N + 2 + q * (N + 2);
-                cols[3 + 3 * q] = b2 + nb[j * 3 + q]; vals[3 + 3 * q] = 1.f;
-                cols[4 + 3 * q] = b2 + N; vals[4 + 3 * q] = (float)ed[k].z;
-                cols[5 + 3 * q] = b2 + N + 1; vals[5 + 3 * q] = (float)v.load[k];
+                for (int q = 0; q < 3; q++) {
+                    cols[3 + q] = N + 2 + q * (N + 2) + N + 1; vals[3 + q] = (float)v.load[ne[j * 3 + q]];
+                }
+#pragma unroll
+                for (int t = 6; t < 12; t++) { cols[t] = 0; vals[t] = 0.f; }
+            } else {
+                cols[0] = j; vals[0] = 1.f;
+                cols[1] = N; vals[1] = (float)v.cnt[j];
+                cols[2] = N + 1; vals[2] = (float)v.tl[j];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int k = ne[j * 3 + q], b2 = N + 2 + q * (N + 2);
+                    cols[3 + 3 * q] = b2 + nb[j * 3 + q]; vals[3 + 3 * q] = 1.f;
+                    cols[4 + 3 * q] = b2 + N; vals[4 + 3 * q] = (float)ed[k].z;
+                    cols[5 + 3 * q] = b2 + N + 1; vals[5 + 3 * q] = (float)v.load[k];
+                }
             }
 #pragma unroll
             for (int t4 = 0; t4 < 3; t4++) {

@@ -55,6 +55,21 @@ class TopologyPool:
         self.deg = torch.from_numpy(np.stack([l[1] for l in lists])).to(device)
         self.seeds = [t.get("seed") for t in tables]
         self.edges_host = np.array(tables[0]["edges"], copy=True) if self.T == 1 else None
+        # The constant part of every node observation row (routing.py:193-234: one-hot of the node, of its three
+        # neighbours, the three edge lengths) as dense rows [T*N, 4N+8], for small pools: NetMon folds layer 1 applied to
+        # them into its weight pack and the env then names that part of a row as ONE sparse entry (model.NetMon).
+        self.static_rows = None
+        N = tables[0]["node_edges"].shape[0]
+        if self.T * N + 4 * N + 8 <= 130:
+            rows = np.zeros((self.T, N, 4 * N + 8), np.float32)
+            for t, tab in enumerate(tables):
+                for j in range(N):
+                    rows[t, j, j] = 1.0
+                    for q in range(3):
+                        b2 = N + 2 + q * (N + 2)
+                        rows[t, j, b2 + int(tab["node_nbrs"][j, q])] = 1.0
+                        rows[t, j, b2 + N] = float(tab["edges"][int(tab["node_edges"][j, q])][2])
+            self.static_rows = torch.from_numpy(rows.reshape(self.T * N, 4 * N + 8)).to(device)
 
 
 class Routing(NetworkEnv):
@@ -81,7 +96,7 @@ class Routing(NetworkEnv):
         self.eval_info_enabled = False
         # a node observation row (routing.py:193-234) has at most 12 non-zero entries: one-hot(node), #waiting, their
         # size sum, 3 x (one-hot(neighbour), length, load); NetMon's tensor-core encoder exploits that
-        self.node_obs_nnz = 12
+        self._node_obs_nnz = 12
 
         self.num_envs = int(num_envs)
         self.batched = (self.num_envs > 1) if batched is None else bool(batched)
@@ -106,6 +121,15 @@ class Routing(NetworkEnv):
         self.agent_steps = np.zeros(n_data)
 
     # ------------------------------------------------------------------------------------------
+    @property
+    def node_obs_nnz(self):
+        """Entries per row of the `node_sparse` output: 12, or 6 when the pool is small enough for static rows."""
+        return 6 if (self._pool is not None and self._pool.static_rows is not None) else self._node_obs_nnz
+
+    @property
+    def node_static_rows(self):
+        return None if self._pool is None else self._pool.static_rows
+
     def set_eval_info(self, val):
         """Whether step() returns the evaluation extras (routing.py:111-117, 384-386, 414-441)."""
         self.eval_info_enabled = bool(val)
@@ -159,6 +183,7 @@ class Routing(NetworkEnv):
         d.env_var, d.k = self.env_var.value, self.k
         d.congestion, d.action_mask, d.ttl = int(self.enable_congestion), int(self.enable_action_mask), int(self.ttl)
         d.state_stride, d.store_mode = self._layout["stride"], self._store_mode
+        d.node_sparse_static = int(p.static_rows is not None)
         d.node_edges, d.node_nbrs, d.edges, d.apsp = (p.node_edges.data_ptr(), p.node_nbrs.data_ptr(),
                                                       p.edges.data_ptr(), p.apsp.data_ptr())
         d.topo_index = None if self._topo_index is None else self._topo_index.data_ptr()

@@ -81,7 +81,8 @@ class NetMonWrapper:
                 self.netmon_out, _ = self.netmon.forward_lists(env._out["node_obs"], nbr_all, deg, list_index,
                                                                nbr_all.shape[-1] - 1, want_node_out=True,
                                                                sparse_nnz=getattr(env, "node_obs_nnz", 0),
-                                                               sparse_rows=env._out.get("node_sparse"))
+                                                               sparse_rows=env._out.get("node_sparse"),
+                                                               static_rows=getattr(env, "node_static_rows", None))
                 self.netmon.state = keep
         self.frozen = True
 
@@ -125,7 +126,8 @@ class NetMonWrapper:
             self.netmon_out, agent_out = self.netmon.forward_lists(
                 node_obs, nbr_all, deg, list_index, max_degree, agent_node=agent_node, want_node_out=not lean,
                 want_agent_pk=lean, want_agent_fp32=self.graph_obs_fp32 or not lean, state_out=self._state_sink,
-                sparse_nnz=getattr(env, "node_obs_nnz", 0), sparse_rows=env._out.get("node_sparse"))
+                sparse_nnz=getattr(env, "node_obs_nnz", 0), sparse_rows=env._out.get("node_sparse"),
+                static_rows=getattr(env, "node_static_rows", None))
             self._state_sink = None
             self.current_netmon_state = self.netmon.state
         return self._ret(agent_out)

@@ -411,9 +411,9 @@ class CompactReplayBuffer(_RingSampler):
             md = pool.nbr_all.shape[-1] - 1
             nnz = getattr(be, "node_obs_nnz", 0)  # same encoder path as the rollout that produced the transitions
             _, tail = nm.forward_lists(cur["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=cur["agent_node"], sparse_nnz=nnz,
-                                       sparse_rows=cur.get("node_sparse"))
+                                       sparse_rows=cur.get("node_sparse"), static_rows=getattr(be, "node_static_rows", None))
             _, ntail = nm.forward_lists(nxt["node_obs"], pool.nbr_all, pool.deg, topo, md, agent_node=nxt["agent_node"], sparse_nnz=nnz,
-                                        sparse_rows=nxt.get("node_sparse"))
+                                        sparse_rows=nxt.get("node_sparse"), static_rows=getattr(be, "node_static_rows", None))
         nm.state = saved
         A = be._A
         f = dict(
