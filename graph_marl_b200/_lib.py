@@ -54,7 +54,7 @@ class NetmonParams(C.Structure):
                 ("output_global_hidden", C.c_int32), ("math", C.c_int32), ("sparse_input_nnz", C.c_int32),
                 ("enc_w", C.c_void_p * GM_MAX_LAYERS), ("enc_b", C.c_void_p * GM_MAX_LAYERS),
                 ("rnn_obs", CellParams), ("rnn_update", CellParams), ("packed", C.c_void_p), ("sparse_rows", C.c_void_p),
-                ("static_rows", C.c_void_p), ("n_static_rows", C.c_int32), ("pad_", C.c_int32)]
+                ("static_rows", C.c_void_p), ("n_static_rows", C.c_int32), ("static_only", C.c_int32)]
 
 
 class DqnParams(C.Structure):

@@ -60,8 +60,12 @@ namespace tc {
 // [4] epilogue: done  [5] copies: last stage of the tile requested  [6] LSTM epilogue: first 8-unit step loaded  [7] ... done
 #if GM_TC_PROBES
 #define GM_TRACE(ptr, tile, slot) do { if ((ptr) && blockIdx.x == 0 && (tile) < 64) ((long long*)(ptr))[(tile) * 8 + (slot)] = clock64(); } while (0)
+#define GM_TRACE_VAL(ptr, tile, slot, val) do { if ((ptr) && blockIdx.x == 0 && (tile) < 64) ((long long*)(ptr))[(tile) * 8 + (slot)] = (val); } while (0)
+#define GM_CLOCK() clock64()
 #else
 #define GM_TRACE(ptr, tile, slot) do { } while (0)
+#define GM_TRACE_VAL(ptr, tile, slot, val) do { } while (0)
+#define GM_CLOCK() 0ll
 #endif
 
 constexpr int BM = TC_BM, BK = TC_BK, STAGES = 4, ACC_STAGES = 2;
@@ -932,16 +936,16 @@ bool tc_ws_plan(int, int, int, int, int, TcWsPlan*) { return false; }
 bool enc_fused_ok(int D, int U1, int U2, int math) {
     static int on = -1;
     if (on < 0) { const char* e = getenv("GM_ENC_FUSED"); on = e ? atoi(e) : 1; }
-    const int64_t smem = (int64_t)tc::EF_STAGES * tc::ef_stage_bytes(D) + 2 * tc::EF_SP_BYTES;
     return on && math == GM_MATH_BF16X3 && D >= 1 && (U1 % tc::BK) == 0 && U1 >= tc::BK && U2 >= 32 && U2 <= tc::EF_BN && (U2 % tc::BK) == 0 &&
-           smem + 1024 <= 227 * 1024;
+           tc::ef_plan(D).nw >= 3;
 }
 int64_t enc_fused_w1t_bytes(int U1, int D) { return (int64_t)(U1 / tc::BK) * tc::ef_chunk_bytes(D); }
 int64_t enc_fused_sp_bytes(int64_t R) { return ((R + tc::BM - 1) / tc::BM) * tc::EF_SP_BYTES; }
 
-// D = input width, S static rows (dense [S, D], may be 0 / NULL): the chunks hold D + S rows
-int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, const float* static_rows, int S, void* out, cudaStream_t s) {
-    tc::ef_pack_w1t_kernel<<<U1 / tc::BK, 256, 0, s>>>(W1, b1, U1, D, static_rows, static_rows ? S : 0, (float*)out);
+// D = input width, S static rows (dense [S, D], may be 0 / NULL): the chunks hold D + S rows, or (static_only) the S rows alone
+int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, const float* static_rows, int S, int static_only, void* out,
+                       cudaStream_t s) {
+    tc::ef_pack_w1t_kernel<<<U1 / tc::BK, 256, 0, s>>>(W1, b1, U1, D, static_only ? 0 : D, static_rows, static_rows ? S : 0, (float*)out);
     GM_LAUNCH_CHECK();
     return GM_OK;
 }
@@ -953,6 +957,7 @@ int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int Dx, int D, int 
                      void* sp_ws, const int32_t* sp_rows, uint8_t* Cpk, int* overflow, cudaStream_t s) {
     GM_CHECK_ARG(nnz == 12 || (nnz == 6 && sp_rows != nullptr), "6-term rows must be supplied by the caller");
     GM_CHECK_ARG((x || sp_rows) && w1t && W2p && sp_ws && Cpk && R > 0, "bad fused-encoder arguments");
+    GM_CHECK_ARG(act == GM_ACT_LEAKY_RELU, "the fused encoder kernel is built for leaky_relu only");
     GM_CHECK_ARG((((uintptr_t)w1t | (uintptr_t)W2p | (uintptr_t)sp_ws | (uintptr_t)sp_rows) & 15) == 0 && ((uintptr_t)Cpk & 127) == 0,
                  "fused-encoder buffers must be 16 / 128-byte aligned");
     const int m_tiles = (int)((R + tc::BM - 1) / tc::BM);
@@ -962,7 +967,9 @@ int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int Dx, int D, int 
         GM_LAUNCH_CHECK();
         sp_rows = (const int32_t*)sp_ws;
     }
-    const int smem = tc::EF_STAGES * tc::ef_stage_bytes(D) + 2 * tc::EF_SP_BYTES;
+    const tc::EfPlan plan = tc::ef_plan(D);
+    GM_CHECK_ARG(plan.nw >= 3, "fused-encoder chunk of %d rows does not fit in shared memory", D);
+    const int smem = plan.smem;
     static int configured = 0;
     if (configured < smem) {
         GM_CUDA(cudaFuncSetAttribute(tc::enc_fused_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -975,6 +982,16 @@ int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int Dx, int D, int 
     a.sp = sp_rows; a.w1t = (const uint8_t*)w1t; a.Wp = (const uint8_t*)W2p;
     a.bias_tile = (const float*)((const uint8_t*)W2p + sh.w_bytes);
     a.Cpk = Cpk; a.M = R; a.D = D; a.U1 = U1; a.U2 = U2; a.act = act; a.m_tiles = m_tiles;
+    a.nw = plan.nw; a.na = plan.na;
+#if GM_TC_PROBES
+    {
+        static long long trace_ptr = -1;
+        if (trace_ptr < 0) { const char* e = getenv("GM_TC_TRACE_PTR"); trace_ptr = e ? strtoll(e, nullptr, 0) : 0; }
+        static int trace_epi = -2;
+        if (trace_epi == -2) { const char* e = getenv("GM_TC_TRACE_EPI"); trace_epi = e ? atoi(e) : -1; }
+        a.trace = trace_epi == 9 ? (void*)trace_ptr : nullptr;
+    }
+#endif
     const int grid = std::min(m_tiles, kNumSMs);
     ProfileScope prof(PROF_TC, s);
     if (nnz == 6) GM_CUDA(launch_pdl(tc::enc_fused_kernel<6>, dim3(grid), dim3(tc::THREADS), (size_t)smem, s, a));

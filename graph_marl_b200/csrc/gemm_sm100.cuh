@@ -84,7 +84,8 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
 bool enc_fused_ok(int D, int U1, int U2, int math);
 int64_t enc_fused_w1t_bytes(int U1, int D);
 int64_t enc_fused_sp_bytes(int64_t R);
-int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, const float* static_rows, int S, void* out, cudaStream_t s);
+int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, const float* static_rows, int S, int static_only, void* out,
+                       cudaStream_t s);
 int enc_fused_launch(const float* x, int64_t ldx, int64_t R, int Dx, int D, int nnz, const void* w1t, const void* W2p, int U1, int U2, int act,
                      void* sp_ws, const int32_t* sp_rows, uint8_t* Cpk, int* overflow, cudaStream_t s);
 

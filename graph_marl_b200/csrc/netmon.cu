@@ -685,6 +685,12 @@ struct NetmonPack {
     int64_t w1t;      // offset of layer 1's W^T chunks for that kernel
 };
 
+// rows of the fused encoder's W1^T chunks: the input columns (unless the caller's rows index the static rows alone) + static rows
+static int chunk_rows(const gm_netmon_params* p) {
+    const int n_static = p->static_rows ? p->n_static_rows : 0;
+    return (p->static_only ? 0 : p->in_features) + n_static;
+}
+
 static NetmonPack pack_layout(const gm_netmon_params* p) {
     NetmonPack L{};
     int64_t off = 0;
@@ -710,17 +716,17 @@ static NetmonPack pack_layout(const gm_netmon_params* p) {
         off += 2 * cell;
     }
     // fused encoder L1 + L2 (sparse input rows): layer 1 additionally as W^T chunks; layer 2's pack is the normal one
-    const int n_static = p->static_rows ? p->n_static_rows : 0;
     L.enc_fused = L.fused_cells && p->n_enc_layers >= 2 && p->activation == GM_ACT_LEAKY_RELU &&
-                  enc_fused_ok(p->in_features + n_static, p->enc_units[0], p->enc_units[1], p->math == GM_MATH_BF16 ? -1 : p->math) &&
+                  enc_fused_ok(chunk_rows(p), p->enc_units[0], p->enc_units[1], p->math == GM_MATH_BF16 ? -1 : p->math) &&
                   tc_shape(p->enc_units[1], p->enc_units[0], 0, EPI_LINEAR, 0).n_tiles == 1;
     L.w1t = off;
-    if (L.enc_fused) off += round_up(enc_fused_w1t_bytes(p->enc_units[0], p->in_features + n_static), 256);
+    if (L.enc_fused) off += round_up(enc_fused_w1t_bytes(p->enc_units[0], chunk_rows(p)), 256);
     L.total = off;
     return L;
 }
 
 static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
+    GM_CHECK_ARG(!p->static_only || (p->static_rows && p->n_static_rows > 0), "static_only needs static_rows");
     NetmonPack L = pack_layout(p);
     int kin = p->in_features, rc;
     for (int l = 0; l < p->n_enc_layers; l++) {
@@ -730,7 +736,7 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
         kin = p->enc_units[l];
     }
     if (L.enc_fused && (rc = enc_fused_pack_w1t(p->enc_w[0], p->enc_b[0], p->enc_units[0], p->in_features, p->static_rows,
-                                                p->static_rows ? p->n_static_rows : 0, (char*)out + L.w1t, s)))
+                                                p->static_rows ? p->n_static_rows : 0, p->static_only, (char*)out + L.w1t, s)))
         return rc;
     if (L.fused_cells && L.cell_epi == EPI_LNLSTM) {
         const gm_cell_params* cells[2] = {&p->rnn_obs, &p->rnn_update};
@@ -889,8 +895,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     int kin = p->in_features;
     int l_first = 0;
     // supplied rows of at most 6 entries (e.g. a static part named as one entry + the dynamic fields) run the 6-term kernel
-    const int n_static = p->static_rows ? p->n_static_rows : 0;
     const bool six = p->sparse_input_nnz > 0 && p->sparse_input_nnz <= 6 && p->sparse_rows != nullptr;
+    GM_CHECK_ARG(!p->static_only || p->sparse_rows != nullptr, "static_only: the rows must be supplied in sparse form");
     if (fused && PL.enc_fused && p->sparse_input_nnz > 0 && p->sparse_input_nnz <= 12) {
         // layers 1 + 2 in one launch: layer 1 on the CUDA cores inside the producer warps (the caller declared rows of at
         // most sparse_input_nnz non-zeros, e.g. the one-hot node observations of the Routing env), layer 2 on tcgen05
@@ -899,7 +905,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
         static int check = -1;
         if (check < 0) { const char* e = getenv("GM_CHECK_SPARSE"); check = e ? atoi(e) : 0; }
         if (check) GM_CUDA(cudaMemsetAsync(overflow, 0, 4, s));
-        int rc = enc_fused_launch(node_obs, p->in_features, R, p->in_features, p->in_features + n_static, six ? 6 : 12, packed + PL.w1t,
+        int rc = enc_fused_launch(node_obs, p->in_features, R, p->in_features, chunk_rows(p), six ? 6 : 12, packed + PL.w1t,
                                   packed + PL.enc[1], p->enc_units[0], p->enc_units[1], p->activation, w.sp, p->sparse_rows, ypk,
                                   check ? overflow : nullptr, s);
         if (rc) return rc;

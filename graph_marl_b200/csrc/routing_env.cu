@@ -554,12 +554,15 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
             float vals[12];
             if (d.node_sparse_static) {
                 // the constant part of the row (one-hots, lengths) as ONE entry: column 4N+8 + topology*N + node
-                cols[0] = 4 * N + 8 + topo * N + j; vals[0] = 1.f;
-                cols[1] = N; vals[1] = (float)v.cnt[j];
-                cols[2] = N + 1; vals[2] = (float)v.tl[j];
+                // (mode 2: as indices into the T*N + 5 row dictionary instead of input columns)
+                const bool dict = d.node_sparse_static == 2;
+                const int dyn = d.T * N;
+                cols[0] = (dict ? 0 : 4 * N + 8) + topo * N + j; vals[0] = 1.f;
+                cols[1] = dict ? dyn : N; vals[1] = (float)v.cnt[j];
+                cols[2] = dict ? dyn + 1 : N + 1; vals[2] = (float)v.tl[j];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
-                    cols[3 + q] = N + 2 + q * (N + 2) + N + 1; vals[3 + q] = (float)v.load[ne[j * 3 + q]];
+                    cols[3 + q] = dict ? dyn + 2 + q : N + 2 + q * (N + 2) + N + 1; vals[3 + q] = (float)v.load[ne[j * 3 + q]];
                 }
 #pragma unroll
                 for (int t = 6; t < 12; t++) { cols[t] = 0; vals[t] = 0.f; }

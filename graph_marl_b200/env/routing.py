@@ -56,20 +56,28 @@ class TopologyPool:
         self.seeds = [t.get("seed") for t in tables]
         self.edges_host = np.array(tables[0]["edges"], copy=True) if self.T == 1 else None
         # The constant part of every node observation row (routing.py:193-234: one-hot of the node, of its three
-        # neighbours, the three edge lengths) as dense rows [T*N, 4N+8], for small pools: NetMon folds layer 1 applied to
-        # them into its weight pack and the env then names that part of a row as ONE sparse entry (model.NetMon).
+        # neighbours, the three edge lengths) as dense rows, for small pools: NetMon folds layer 1 applied to them into
+        # its weight pack and the env then names that part of a row as ONE sparse entry (model.NetMon).  The five
+        # dynamic fields (#waiting, size sum, three edge loads) follow as unit rows, so that a row is six indices into
+        # this [T*N + 5, 4N+8] dictionary and nothing else (gm_netmon_params.static_only).
         self.static_rows = None
         N = tables[0]["node_edges"].shape[0]
-        if self.T * N + 4 * N + 8 <= 130:
-            rows = np.zeros((self.T, N, 4 * N + 8), np.float32)
+        if self.T * N + 5 <= 73:  # four weight-ring slots in the fused encoder (gemm_sm100_encfused.inc: ef_plan)
+            rows = np.zeros((self.T * N + 5, 4 * N + 8), np.float32)
             for t, tab in enumerate(tables):
                 for j in range(N):
-                    rows[t, j, j] = 1.0
+                    r = rows[t * N + j]
+                    r[j] = 1.0
                     for q in range(3):
                         b2 = N + 2 + q * (N + 2)
-                        rows[t, j, b2 + int(tab["node_nbrs"][j, q])] = 1.0
-                        rows[t, j, b2 + N] = float(tab["edges"][int(tab["node_edges"][j, q])][2])
-            self.static_rows = torch.from_numpy(rows.reshape(self.T * N, 4 * N + 8)).to(device)
+                        r[b2 + int(tab["node_nbrs"][j, q])] = 1.0
+                        r[b2 + N] = float(tab["edges"][int(tab["node_edges"][j, q])][2])
+            dyn = self.T * N
+            rows[dyn, N] = 1.0
+            rows[dyn + 1, N + 1] = 1.0
+            for q in range(3):
+                rows[dyn + 2 + q, N + 2 + q * (N + 2) + N + 1] = 1.0
+            self.static_rows = torch.from_numpy(rows).to(device)
 
 
 class Routing(NetworkEnv):
@@ -183,7 +191,7 @@ class Routing(NetworkEnv):
         d.env_var, d.k = self.env_var.value, self.k
         d.congestion, d.action_mask, d.ttl = int(self.enable_congestion), int(self.enable_action_mask), int(self.ttl)
         d.state_stride, d.store_mode = self._layout["stride"], self._store_mode
-        d.node_sparse_static = int(p.static_rows is not None)
+        d.node_sparse_static = 2 if p.static_rows is not None else 0
         d.node_edges, d.node_nbrs, d.edges, d.apsp = (p.node_edges.data_ptr(), p.node_nbrs.data_ptr(),
                                                       p.edges.data_ptr(), p.apsp.data_ptr())
         d.topo_index = None if self._topo_index is None else self._topo_index.data_ptr()

@@ -469,7 +469,7 @@ class NetMon(nn.Module):
         p.sparse_input_nnz = int(getattr(self, "_sparse_nnz", 0) or 0)
         st = getattr(self, "_static_rows", None)
         if st is not None:
-            p.static_rows, p.n_static_rows = st.data_ptr(), st.shape[0]
+            p.static_rows, p.n_static_rows, p.static_only = st.data_ptr(), st.shape[0], int(getattr(self, "_static_only", True))
         p.rnn_obs = self._cell(getattr(self, "rnn_obs", None))
         p.rnn_update = self._cell(getattr(self, "rnn_update", None))
         if packed and self.math != "fp32" and layers[0].weight.is_cuda:
@@ -480,7 +480,7 @@ class NetMon(nn.Module):
                     _lib.check(_lib.lib().gm_netmon_pack_weights(C.byref(p), buf.data_ptr(), buf.numel(),
                                                                  _lib.current_stream()))
 
-            extra = 0 if st is None else (st.data_ptr(), st._version, st.shape[0])  # the pack folds the static rows in
+            extra = 0 if st is None else (st.data_ptr(), st._version, st.shape[0], int(p.static_only))  # the pack folds the static rows in
             p.packed = self._pack.get(self, extra, lambda: _lib.lib().gm_netmon_packed_bytes(C.byref(p)), pack).data_ptr()
         return p
 
@@ -490,7 +490,7 @@ class NetMon(nn.Module):
 
     def forward_lists(self, x, nbr_all, deg, list_index=None, max_degree=3, agent_node=None,
                       want_node_out=False, agent_out=None, want_agent_pk=False, want_agent_fp32=True, state_out=None,
-                      sparse_nnz=0, sparse_rows=None, static_rows=None):
+                      sparse_nnz=0, sparse_rows=None, static_rows=None, static_only=True):
         """One NetMon step from adjacency lists (no dense mask).  x [B,N,Dn] CUDA f32;
         nbr_all i32[L,N,DM], deg i32[L,N], list_index i32[B] | None; agent_node i32[B,A] | None.
         Updates self.state; returns (node_out | None, agent_out | None).  want_agent_fp32=False with
@@ -500,8 +500,9 @@ class NetMon(nn.Module):
         guarantees rows of x with at most that many (<= 12) non-zeros (the Routing env's one-hot node observations have 12):
         the tensor-core path then runs encoder layers 1 + 2 as one kernel.  sparse_rows: those rows already in sparse form
         (int32 [B,N,24] on a 128-row padded allocation, Routing's `node_sparse` output); None = derived from x.
-        static_rows: f32 [S, Dn] constant row parts that supplied sparse rows may name as column Dn + s (Routing's
-        `node_static_rows`; folded into the weight pack)."""
+        static_rows: f32 [S, Dn] dictionary of row parts (Routing's `node_static_rows`; layer 1 applied to them is folded
+        into the weight pack): the supplied sparse rows index it (static_only, Routing's form), or name static row s as
+        column Dn + s next to ordinary input columns (static_only=False)."""
         _lib.require_device()
         if not x.is_cuda:
             raise _lib.GraphMarlError("NetMon needs CUDA tensors (no CPU fallback)")
@@ -511,6 +512,7 @@ class NetMon(nn.Module):
         S = self.state_size
         self._sparse_nnz = int(sparse_nnz or 0)
         self._static_rows = static_rows if (static_rows is not None and sparse_rows is not None and self._sparse_nnz > 0) else None
+        self._static_only = bool(static_only)
         p = self._params()
         self._sparse_nnz, self._static_rows = 0, None
         if sparse_rows is not None and p.sparse_input_nnz > 0:

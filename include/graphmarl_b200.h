@@ -97,7 +97,9 @@ typedef struct gm_routing_desc {
     int32_t ttl;                 /* ttl, 0 = disabled (routing.py:63) */
     int32_t state_stride;        /* bytes per env in `state`, from gm_routing_state_layout */
     int32_t node_sparse_static;  /* 0: node_sparse rows list all 12 fields; 1: 6 entries -- (4N+8 + topology*N + node, 1)
-                                    for the constant part of the row, then #waiting, size sum and the three edge loads */
+                                    for the constant part of the row, then #waiting, size sum and the three edge loads;
+                                    2: the same 6 entries as indices into a dictionary of T*N + 5 rows: topology*N + node,
+                                    then T*N + 0..4 for #waiting, size sum and the three loads (static_only packs) */
     int32_t store_mode;          /* 0 auto, 1 smem staging + vector stores, 2 smem staging + cp.async.bulk,
                                     3 direct: zero-fill + per-row field stores (env_var 1, 16-byte granular blocks) */
     /* topology pool (device, int32) */
@@ -216,9 +218,11 @@ typedef struct gm_netmon_params {
      * the node and of its neighbours, edge lengths).  gm_netmon_pack_weights appends layer 1 applied to each of them to
      * its weight pack, and a supplied sparse row may then name its constant part as ONE entry (column D_n + s, value 1)
      * next to its dynamic entries: with sparse_input_nnz <= 6 the fused encoder runs 6 terms per row instead of 12.
-     * The pack depends on these rows: repack when they change. */
+     * static_only = 1: the supplied sparse rows index the static rows ALONE (entry s = static row s; dynamic fields name
+     * unit rows among them): the weight pack then holds S instead of D_n + S rows per chunk, which buys the fused kernel
+     * a deeper weight ring.  The pack depends on these rows: repack when they change. */
     const float* static_rows;
-    int32_t n_static_rows, pad_;
+    int32_t n_static_rows, static_only;
 } gm_netmon_params;
 
 /* Packed tensor-core weights (GM_MATH_BF16X3 / GM_MATH_BF16): the fp32 parameters split into bf16

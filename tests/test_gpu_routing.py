@@ -140,21 +140,21 @@ def test_batched_against_oracle(cfg):
         assert np.array_equal(env._out["node_obs"].cpu().numpy(), o["node_obs"]), t
         assert np.array_equal(env._out["node_agent"].cpu().numpy(), o["node_agent"]), t
         assert np.array_equal(env._out["agent_node"].cpu().numpy(), orc.now), t
-        # the sparse form of the node rows (12 fixed slots of (column, value)) scatters back to exactly the dense rows
-        # (small pools: the constant part of a row is ONE entry naming a row of env.node_static_rows, column >= 4N+8)
+        # the sparse form of the node rows scatters back to exactly the dense rows: 12 fixed slots of (column, value), or
+        # (small pools) six indices into the dictionary env.node_static_rows -- one row per (topology, node) for the
+        # constant part, five unit rows for the dynamic fields
         sp = env._out["node_sparse"].cpu().numpy()
-        Dn = 4 * N + 8
         dense = np.zeros_like(o["node_obs"])
         bi, ji = np.meshgrid(np.arange(B), np.arange(N), indexing="ij")
         stat = None if env.node_static_rows is None else env.node_static_rows.cpu().numpy()
         assert env.node_obs_nnz == (12 if stat is None else 6)
         for k in range(12):
             col, val = sp[..., k], sp[..., 12 + k].view(np.float32)
-            if stat is not None and k == 0:
-                assert (col >= Dn).all() and (val == 1).all()
-                dense += stat[col - Dn]
+            if stat is not None:
+                assert (col < stat.shape[0]).all() and (k < 6 or (val == 0).all())
+                assert k != 0 or ((val == 1).all() and (col < stat.shape[0] - 5).all())
+                dense += stat[col] * val[..., None]
             else:
-                assert (col < Dn).all()
                 np.add.at(dense, (bi, ji, col), val)
         assert np.array_equal(dense, o["node_obs"]), t
         s = env.get_state()

@@ -192,6 +192,57 @@ def test_netmon_fused_sparse_encoder(B):
         assert np.abs(outs[12][0] - ref_out).max() < 1e-4 and np.abs(outs[12][1] - ref_state).max() < 1e-4
 
 
+@pytest.mark.parametrize("B", [37, 512])
+def test_netmon_fused_encoder_with_static_rows_from_the_env(B):
+    """The 6-term form: the Routing env hands NetMon its node rows as sparse entries whose constant part (one-hots,
+    edge lengths) is ONE entry naming a static row that the weight pack folded into layer 1 (single-topology pool).
+    Same state and observations through the dense tensor-core path: 2e-5; the pack follows a topology change."""
+    from graph_marl_b200.env.network import Network
+    from graph_marl_b200.env.routing import Routing
+    from graph_marl_b200.model import NetMon
+
+    N = A = 20
+    env = Routing(Network(N, random_topology=False, topology_init_seed=923430603), A, 1, num_envs=B, seed=2, batched=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(5):
+        env.step(torch.randint(0, 4, (B, A), device="cuda", generator=g, dtype=torch.int32))
+    assert env.node_obs_nnz == 6 and env.node_static_rows.shape == (N + 5, 4 * N + 8)
+    torch.manual_seed(1)
+    nm = NetMon(4 * N + 8, 128, (512, 256), 2, F.leaky_relu, output_neighbor_hidden=True, math="bf16x3").cuda().eval()
+    nbr_all, deg, list_index = env.get_adjacency_lists()
+    st = torch.randn(B, N, 256, device="cuda") * 0.3
+    outs = []
+    with torch.no_grad():
+        # the same rows once more in the mixed form (static_only=False): entry 0 names static row s as column Dn + s, the
+        # dynamic entries are ordinary input columns
+        Dn = 4 * N + 8
+        dyn_cols = torch.tensor([N, N + 1] + [N + 2 + q * (N + 2) + N + 1 for q in range(3)], device="cuda", dtype=torch.int32)
+        mixed = env._out["node_sparse"].clone()
+        mixed[..., 0] += Dn
+        mixed[..., 1:6] = dyn_cols
+        for kw in (dict(), dict(sparse_nnz=12), dict(sparse_nnz=env.node_obs_nnz, sparse_rows=env._out["node_sparse"], static_rows=env.node_static_rows),
+                   dict(sparse_nnz=6, sparse_rows=mixed, static_rows=env.node_static_rows[:N].contiguous(), static_only=False)):
+            nm.state = st.clone()
+            no, _ = nm.forward_lists(env._out["node_obs"], nbr_all, deg, list_index, 3, want_node_out=True, **kw)
+            outs.append((no, nm.state))
+    for no, s2 in outs[1:]:
+        assert float((no - outs[0][0]).abs().max()) < 2e-5 and float((s2 - outs[0][1]).abs().max()) < 2e-5
+    # another topology: new static rows -> the cached pack must be rebuilt (same module, same weights)
+    env2 = Routing(Network(N, random_topology=False, topology_init_seed=476 if False else 923430603 + 0), A, 1, num_envs=B, seed=3, batched=True)
+    env2.network = Network(N, random_topology=True, n_random_seeds=1, topology_init_seed=5)
+    env2.reset()
+    assert env2.node_static_rows is not None and not torch.equal(env2.node_static_rows, env.node_static_rows)
+    nbr2, deg2, li2 = env2.get_adjacency_lists()
+    with torch.no_grad():
+        nm.state = st.clone()
+        a, _ = nm.forward_lists(env2._out["node_obs"], nbr2, deg2, li2, 3, want_node_out=True)
+        nm.state = st.clone()
+        b, _ = nm.forward_lists(env2._out["node_obs"], nbr2, deg2, li2, 3, want_node_out=True, sparse_nnz=env2.node_obs_nnz,
+                                sparse_rows=env2._out["node_sparse"], static_rows=env2.node_static_rows)
+    assert float((a - b).abs().max()) < 2e-5
+
+
 def test_fused_sparse_encoder_reports_rows_that_are_not_sparse():
     """GM_CHECK_SPARSE=1 (debug switch, read once per process): a batch whose rows break the declared sparsity is an error."""
     import os, subprocess, sys, textwrap

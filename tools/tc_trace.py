@@ -18,7 +18,8 @@ t = buf.cpu().numpy().reshape(64, 8)
 t0 = t[0, 0]
 names = ["mma:acc_free", "mma:first_full", "mma:issued", "epi:acc_full", "epi:done", "copy:issued", "epi:step0_loaded", "epi:step0_done"]
 print("tile " + " ".join(f"{n:>15s}" for n in names) + "   (SM clocks relative to tile 0 acc_free; last traced launch)")
+fused = os.environ.get("GM_TC_TRACE_EPI") == "9"  # fused encoder: slots 3, 4, 6, 7 = clocks one producer thread spent in the gathers, in activation + stores, waiting (chunk, A slot)
 for i in range(64):
     if t[i, 0] == 0:
         break
-    print(f"{i:4d} " + " ".join(f"{int(t[i, k] - t0):15d}" for k in range(8)))
+    print(f"{i:4d} " + " ".join(f"{int(t[i, k] - (0 if fused and k in (3, 4, 5, 6, 7) else t0)):15d}" for k in range(8)))
