@@ -45,11 +45,13 @@ def peaks():
     return p
 
 
-def env_step_bytes(N, A):
-    """algorithmic bytes of one env-step with dense outputs materialised."""
+def env_step_bytes(N, A, sparse_rows=False):
+    """algorithmic bytes of one env-step with dense outputs materialised.  sparse_rows: the launch also
+    writes the node rows in sparse form for NetMon's fused encoder (96 bytes per node, `gm_routing_io.node_sparse`)."""
     E = 3 * N // 2
     state = A * (40 + 4 * ((N + 31) // 32)) + 8 * E
-    return (2 * state + 4 * A + 4 * A * (6 * N + 10) + 4 * N * (4 * N + 8) + A * A + N * A + 4 * A + A + 32 + 4 * A)
+    return (2 * state + 4 * A + 4 * A * (6 * N + 10) + 4 * N * (4 * N + 8) + A * A + N * A + 4 * A + A + 32 + 4 * A
+            + (96 * N if sparse_rows else 0))
 
 
 def gemm_flops(N, A, H, K, enc, dqn, n_act=4):
@@ -368,6 +370,7 @@ def main():
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) -------------
     stage = ro.profile_stages(iters=max(5, min(a.steps, 20)))
+    sparse_out = getattr(ro.base_env, "_out", {}).get("node_sparse") is not None
     del ro
     torch.cuda.empty_cache()
 
@@ -401,11 +404,15 @@ def main():
     gemm_ms = stage["gemm_ms"]
     env_ms = stage["env_kernel_ms"] if stage.get("env_kernel_ms", 0) > 0 else stage["env_step_ms"]
     agg_ms = stage.get("aggregate_kernel_ms", 0.0) / max(stage.get("aggregate_kernel_launches_per_step", 1.0), 1.0)
-    env_bytes = env_step_bytes(N, A) * B
+    # the step launch also writes the node rows in sparse form (the fused encoder's input): real output bytes of the
+    # kernel, counted next to SURVEY 8(d)'s dense outputs (tools/env_only.py times the kernel against the same figure)
+    per_env = env_step_bytes(N, A, sparse_rows=sparse_out)
+    env_bytes = per_env * B
     roof_env = dict(bound="hbm", kernel="routing_kernel<STEP>", achieved=env_bytes / (env_ms * 1e-3) / 1e9,
                     peak=pk["hbm_gbs"], unit="GB/s", frac=env_bytes / (env_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                     traffic=traffic.get("routing_step_bytes_per_launch"), algorithmic_bytes_per_launch=env_bytes,
-                    peak_source=pk["source"], bytes_per_env_step=env_step_bytes(N, A), ms_per_launch=env_ms)
+                    peak_source=pk["source"], bytes_per_env_step=per_env, ms_per_launch=env_ms,
+                    note="SURVEY 8(d) dense outputs" + (" + 96 B per node of sparse node rows (gm_routing_io.node_sparse)" if sparse_out else ""))
     tf = flops_step / (gemm_ms * 1e-3) / 1e12
     passes = {"fp32": 1, "bf16x3": 3, "bf16": 1}[a.math]
     roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",

@@ -20,18 +20,23 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(10):
     env.step(acts[i % 8])
 torch.cuda.synchronize()
+# kernel time from the library's own CUDA events around the launch (gm_profile_*): Python's issue time stays outside
+import ctypes as C  # noqa: E402
+
+from graph_marl_b200 import _lib  # noqa: E402
+
 ts = []
 for i in range(iters):
     flush.zero_()  # outputs of the previous launch leave L2, like in the rollout where GEMMs run in between
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    _lib.lib().gm_profile_enable(1)
     env.step(acts[i % 8])
-    e1.record()
-    torch.cuda.synchronize()
-    ts.append(e0.elapsed_time(e1) * 1e3)
+    _lib.lib().gm_profile_enable(0)
+    ms, cnt = (C.c_double * 8)(), (C.c_int32 * 8)()
+    _lib.check(_lib.lib().gm_profile_collect(ms, cnt))
+    ts.append(ms[1] * 1e3)
 ts.sort()
 med = ts[len(ts) // 2]
-by = env_step_bytes(N, A) * B
+by = env_step_bytes(N, A, sparse_rows=env._out.get("node_sparse") is not None) * B
 print(f"B={B} store_mode={os.environ.get('GM_ROUTING_STORE_MODE', 'default')} median {med:.2f} us  min {ts[0]:.2f} us  "
       f"roofline frac (median) {by / (med * 1e-6) / 1e9 / peaks()['hbm_gbs']:.3f}")
 
