@@ -545,45 +545,50 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
         }
         __syncwarp();
     };
-    // the node rows once more in sparse form (12 (column, value) slots in a fixed order) for NetMon's fused encoder
+    // the node rows once more in sparse form (12 (column, value) slots in a fixed order) for NetMon's fused encoder.
+    // An env's block is N x 6 16-byte pieces (3 of columns, 3 of values per row): consecutive lanes write consecutive
+    // pieces, so every store instruction of the warp covers 512 contiguous bytes.
     auto emit_node_sparse = [&]() {
         if (!(io.node_sparse && do_node)) return;
-        for (int j = lane; j < N; j += 32) {
-            int32_t* o = io.node_sparse + ((size_t)b * N + j) * 24;
-            int cols[12];
-            float vals[12];
-            if (d.node_sparse_static) {
-                // the constant part of the row (one-hots, lengths) as ONE entry: column 4N+8 + topology*N + node
-                // (mode 2: as indices into the T*N + 5 row dictionary instead of input columns)
-                const bool dict = d.node_sparse_static == 2;
-                const int dyn = d.T * N;
-                cols[0] = (dict ? 0 : 4 * N + 8) + topo * N + j; vals[0] = 1.f;
-                cols[1] = dict ? dyn : N; vals[1] = (float)v.cnt[j];
-                cols[2] = dict ? dyn + 1 : N + 1; vals[2] = (float)v.tl[j];
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    cols[3 + q] = dict ? dyn + 2 + q : N + 2 + q * (N + 2) + N + 1; vals[3 + q] = (float)v.load[ne[j * 3 + q]];
+        int4* const out = (int4*)(io.node_sparse + (size_t)b * N * 24);
+        const int mode = d.node_sparse_static;
+        const int dyn = d.T * N;  // mode 2: first dictionary row of the five dynamic fields
+        // slot t of row j: (column, value)
+        auto slot = [&](int j, int t, int& col, float& val) {
+            col = 0;
+            val = 0.f;
+            if (mode) {
+                // the constant part of the row (one-hots, lengths) as ONE entry: column 4N+8 + topology*N + node (mode 1),
+                // or everything as indices into the T*N + 5 row dictionary (mode 2)
+                if (t == 0) { col = (mode == 2 ? 0 : 4 * N + 8) + topo * N + j; val = 1.f; }
+                else if (t == 1) { col = mode == 2 ? dyn : N; val = (float)v.cnt[j]; }
+                else if (t == 2) { col = mode == 2 ? dyn + 1 : N + 1; val = (float)v.tl[j]; }
+                else if (t < 6) {
+                    const int q = t - 3;
+                    col = mode == 2 ? dyn + 2 + q : N + 2 + q * (N + 2) + N + 1;
+                    val = (float)v.load[ne[j * 3 + q]];
                 }
-#pragma unroll
-                for (int t = 6; t < 12; t++) { cols[t] = 0; vals[t] = 0.f; }
             } else {
-                cols[0] = j; vals[0] = 1.f;
-                cols[1] = N; vals[1] = (float)v.cnt[j];
-                cols[2] = N + 1; vals[2] = (float)v.tl[j];
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
+                if (t == 0) { col = j; val = 1.f; }
+                else if (t == 1) { col = N; val = (float)v.cnt[j]; }
+                else if (t == 2) { col = N + 1; val = (float)v.tl[j]; }
+                else {
+                    const int q = (t - 3) / 3, f = (t - 3) % 3;
                     const int k = ne[j * 3 + q], b2 = N + 2 + q * (N + 2);
-                    cols[3 + 3 * q] = b2 + nb[j * 3 + q]; vals[3 + 3 * q] = 1.f;
-                    cols[4 + 3 * q] = b2 + N; vals[4 + 3 * q] = (float)ed[k].z;
-                    cols[5 + 3 * q] = b2 + N + 1; vals[5 + 3 * q] = (float)v.load[k];
+                    if (f == 0) { col = b2 + nb[j * 3 + q]; val = 1.f; }
+                    else if (f == 1) { col = b2 + N; val = (float)ed[k].z; }
+                    else { col = b2 + N + 1; val = (float)v.load[k]; }
                 }
             }
+        };
+        for (int q = lane; q < N * 6; q += 32) {
+            const int j = q / 6, part = q % 6, t0 = (part % 3) * 4;
+            int c[4];
+            float x[4];
 #pragma unroll
-            for (int t4 = 0; t4 < 3; t4++) {
-                ((int4*)o)[t4] = make_int4(cols[4 * t4], cols[4 * t4 + 1], cols[4 * t4 + 2], cols[4 * t4 + 3]);
-                ((int4*)o)[3 + t4] = make_int4(__float_as_int(vals[4 * t4]), __float_as_int(vals[4 * t4 + 1]),
-                                               __float_as_int(vals[4 * t4 + 2]), __float_as_int(vals[4 * t4 + 3]));
-            }
+            for (int i = 0; i < 4; i++) slot(j, t0 + i, c[i], x[i]);
+            out[q] = part < 3 ? make_int4(c[0], c[1], c[2], c[3])
+                              : make_int4(__float_as_int(x[0]), __float_as_int(x[1]), __float_as_int(x[2]), __float_as_int(x[3]));
         }
     };
     // the GLOBAL agent observation embeds node rows and the direct store mode emits everything in one pass: both need the
