@@ -934,10 +934,16 @@ bool tc_ws_plan(int, int, int, int, int, TcWsPlan*) { return false; }
 
 // ---- fused encoder layers 1 + 2 for sparse input rows (gemm_sm100_encfused.inc) -----------------------------------
 bool enc_fused_ok(int D, int U1, int U2, int math) {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("GM_ENC_FUSED"); on = e ? atoi(e) : 1; }
-    return on && math == GM_MATH_BF16X3 && D >= 1 && (U1 % tc::BK) == 0 && U1 >= tc::BK && U2 >= 32 && U2 <= tc::EF_BN && (U2 % tc::BK) == 0 &&
+    return math == GM_MATH_BF16X3 && D >= 1 && (U1 % tc::BK) == 0 && U1 >= tc::BK && U2 >= 32 && U2 <= tc::EF_BN && (U2 % tc::BK) == 0 &&
            tc::ef_plan(D).nw >= 3;
+}
+// GM_ENC_FUSED: 0 never, 1 (default) rows of at most 6 terms supplied by the caller, 2 also 12-term rows.  Measured at
+// configs 2 / 3: the 6-term kernel beats the two separate layers (80 vs 123 us), the 12-term kernel does not (its W1^T
+// chunk allows a 3-slot ring only and the producers issue 50 shared-memory loads per k-block: 0.382 vs 0.361 ms per step
+// at 2048 envs), so it is an option.  Read on every call: the weight pack does not depend on it.
+int enc_fused_mode() {
+    const char* e = getenv("GM_ENC_FUSED");
+    return e ? atoi(e) : 1;
 }
 int64_t enc_fused_w1t_bytes(int U1, int D) { return (int64_t)(U1 / tc::BK) * tc::ef_chunk_bytes(D); }
 int64_t enc_fused_sp_bytes(int64_t R) { return ((R + tc::BM - 1) / tc::BM) * tc::EF_SP_BYTES; }

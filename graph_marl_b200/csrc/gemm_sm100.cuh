@@ -82,6 +82,7 @@ int tc_launch(TcArgs a, int math, int epi, cudaStream_t s);
 // CUDA cores inside the producer warps, layer 2 on tcgen05.  W2 is packed by tc_pack_weights(N = U2, K0 = U1, EPI_LINEAR)
 // and must come out as ONE 256-column tile; W1 by enc_fused_pack_w1t.
 bool enc_fused_ok(int D, int U1, int U2, int math);
+int enc_fused_mode();
 int64_t enc_fused_w1t_bytes(int U1, int D);
 int64_t enc_fused_sp_bytes(int64_t R);
 int enc_fused_pack_w1t(const float* W1, const float* b1, int U1, int D, const float* static_rows, int S, int static_only, void* out,

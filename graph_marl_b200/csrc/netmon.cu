@@ -897,7 +897,8 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
     // supplied rows of at most 6 entries (e.g. a static part named as one entry + the dynamic fields) run the 6-term kernel
     const bool six = p->sparse_input_nnz > 0 && p->sparse_input_nnz <= 6 && p->sparse_rows != nullptr;
     GM_CHECK_ARG(!p->static_only || p->sparse_rows != nullptr, "static_only: the rows must be supplied in sparse form");
-    if (fused && PL.enc_fused && p->sparse_input_nnz > 0 && p->sparse_input_nnz <= 12) {
+    const int fuse_mode = enc_fused_mode();  // 1: 6-term rows only (the 12-term kernel is slower than two layers), 2: both
+    if (fused && PL.enc_fused && p->sparse_input_nnz > 0 && p->sparse_input_nnz <= 12 && (fuse_mode >= 2 || (fuse_mode == 1 && six))) {
         // layers 1 + 2 in one launch: layer 1 on the CUDA cores inside the producer warps (the caller declared rows of at
         // most sparse_input_nnz non-zeros, e.g. the one-hot node observations of the Routing env), layer 2 on tcgen05
         uint8_t* ypk = (L == 2) ? w.e_pk : w.pk1;

@@ -154,10 +154,26 @@ def test_netmon_layernorm_cell_single_step_from_reference_recording(math, tol):
             assert err < tol and serr < tol, (t, err, serr)
 
 
+def _tc_launches(fn):
+    """Tensor-core launches (library profile category 0) that fn() makes."""
+    import ctypes as C
+    from graph_marl_b200 import _lib
+    L = _lib.lib()
+    L.gm_profile_enable(1)
+    try:
+        out = fn()
+    finally:
+        L.gm_profile_enable(0)
+    ms, cnt = (C.c_double * 8)(), (C.c_int32 * 8)()
+    _lib.check(L.gm_profile_collect(ms, cnt))
+    return out, int(cnt[0])
+
+
 @pytest.mark.parametrize("B", [3, 96, 700])
-def test_netmon_fused_sparse_encoder(B):
+def test_netmon_fused_sparse_encoder(B, monkeypatch):
     """Encoder layers 1 + 2 as one kernel for sparse rows (gemm_sm100_encfused.inc: layer 1 as 12 weight-column gathers
     inside the producer warps, layer 2 on tcgen05): real Routing node observations (12 non-zeros per row), paper dims.
+    (The 12-term form is an option, GM_ENC_FUSED=2: only the 6-term form is faster than two layers.)
     Against the dense tensor-core path (2e-5), against the reference recording (1e-4, single step from the recorded
     state) and, at B = 700 (5.5 M tiles per ... partial last tile, several tiles per CTA), against the fp64 oracle."""
     from graph_marl_b200.model import NetMon
@@ -166,6 +182,7 @@ def test_netmon_fused_sparse_encoder(B):
     name, cfg = netmon_case(G, [x for x in G["case_names"] if str(x).startswith("lstm_sum_k3_paper")][0])
     X, ADJ, NAM = G["node_obs"], G["node_adj"], G["node_agent"]
     assert int((X != 0).sum(-1).max()) <= 12
+    monkeypatch.setenv("GM_ENC_FUSED", "2")
     nm, w = _netmon(cfg, X.shape[-1], "bf16x3")
     t = 2
     reps = -(-B // X.shape[1])
@@ -174,11 +191,18 @@ def test_netmon_fused_sparse_encoder(B):
     st = np.concatenate([G[name + "_state"][(t - 1 + i) % X.shape[0]] for i in range(reps)])[:B]
     with torch.no_grad():
         nbr, deg, dm = NetMon.lists_from_mask(torch.from_numpy(adj).float().cuda())
-        outs = {}
+        outs, n_tc = {}, {}
         for nnz in (0, 12):
             nm.state = torch.from_numpy(st).cuda()
-            no, _ = nm.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, want_node_out=True, sparse_nnz=nnz)
+            (no, _), n_tc[nnz] = _tc_launches(lambda: nm.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, want_node_out=True,
+                                                                     sparse_nnz=nnz))
             outs[nnz] = (no.cpu().numpy(), nm.state.cpu().numpy())
+        assert n_tc[12] == n_tc[0] - 1  # one launch for layers 1 + 2: the fused kernel did run
+        monkeypatch.setenv("GM_ENC_FUSED", "1")  # default mode: 12-term rows take the two-layer path
+        nm.state = torch.from_numpy(st).cuda()
+        _, n_default = _tc_launches(lambda: nm.forward_lists(torch.from_numpy(x).cuda(), nbr, deg, None, 3, want_node_out=True, sparse_nnz=12))
+        assert n_default == n_tc[0]
+        monkeypatch.setenv("GM_ENC_FUSED", "2")
     assert np.abs(outs[12][0] - outs[0][0]).max() < 2e-5 and np.abs(outs[12][1] - outs[0][1]).max() < 2e-5
     if B == 3:  # the reference's own step from its recorded state
         nm.state = torch.from_numpy(G[name + "_state"][t - 1]).cuda()
@@ -212,7 +236,7 @@ def test_netmon_fused_encoder_with_static_rows_from_the_env(B):
     nm = NetMon(4 * N + 8, 128, (512, 256), 2, F.leaky_relu, output_neighbor_hidden=True, math="bf16x3").cuda().eval()
     nbr_all, deg, list_index = env.get_adjacency_lists()
     st = torch.randn(B, N, 256, device="cuda") * 0.3
-    outs = []
+    outs, n_tc = [], []
     with torch.no_grad():
         # the same rows once more in the mixed form (static_only=False): entry 0 names static row s as column Dn + s, the
         # dynamic entries are ordinary input columns
@@ -224,8 +248,11 @@ def test_netmon_fused_encoder_with_static_rows_from_the_env(B):
         for kw in (dict(), dict(sparse_nnz=12), dict(sparse_nnz=env.node_obs_nnz, sparse_rows=env._out["node_sparse"], static_rows=env.node_static_rows),
                    dict(sparse_nnz=6, sparse_rows=mixed, static_rows=env.node_static_rows[:N].contiguous(), static_only=False)):
             nm.state = st.clone()
-            no, _ = nm.forward_lists(env._out["node_obs"], nbr_all, deg, list_index, 3, want_node_out=True, **kw)
+            (no, _), n = _tc_launches(lambda: nm.forward_lists(env._out["node_obs"], nbr_all, deg, list_index, 3, want_node_out=True, **kw))
             outs.append((no, nm.state))
+            n_tc.append(n)
+    # the 6-term forms run layers 1 + 2 as ONE tensor-core launch; derived 12-term rows take the two-layer path by default
+    assert n_tc[1] == n_tc[0] and n_tc[2] == n_tc[0] - 1 and n_tc[3] == n_tc[0] - 1, n_tc
     for no, s2 in outs[1:]:
         assert float((no - outs[0][0]).abs().max()) < 2e-5 and float((s2 - outs[0][1]).abs().max()) < 2e-5
     # another topology: new static rows -> the cached pack must be rebuilt (same module, same weights)
@@ -264,7 +291,7 @@ def test_fused_sparse_encoder_reports_rows_that_are_not_sparse():
             except GraphMarlError as e:
                 print("caught", "non-zeros" in str(e))
     """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GM_CHECK_SPARSE="1"), capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, GM_CHECK_SPARSE="1", GM_ENC_FUSED="2"), capture_output=True, text=True, timeout=300)
     assert "caught True" in r.stdout, r.stdout + r.stderr
 
 
