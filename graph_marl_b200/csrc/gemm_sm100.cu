@@ -417,12 +417,13 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
 
     if (NCG == 2 && warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
         // ================= producer: fp32 activations -> bf16 hi/lo core matrices ================
-        // Warp pw owns tile rows [16pw, 16pw+16) as two 8-row groups.  Lane = (r8 = lane/4, part = lane%4):
-        // one 32-byte load per lane = 8 rows x one 128-byte line per warp instruction, and lanes
-        // (r8, part) fill the 16-byte rows of core matrix `part` of their group: conflict-free stores.
+        // Warp pw owns tile rows [16pw, 16pw+16) as two 8-row groups.  Lane = (part = lane/8, r8 = lane%8):
+        // one 32-byte load per lane = 8 rows x one 128-byte line per warp instruction, and the 8 lanes of a
+        // quarter warp fill the 8 consecutive 16-byte rows of core matrix `part` of their group: conflict-free
+        // stores (with r8 = lane/4 a quarter warp hit two bank groups four times).
         if (p.has_prod) {
             const int pw = warp - EPI_WARPS;
-            const int r8 = lane >> 2, part = lane & 3;
+            const int r8 = lane & 7, part = lane >> 3;
             const int al0 = ptr_align_floats(p.A0, p.lda0), al1 = ptr_align_floats(p.A1, p.lda1);
             const bool prod0 = p.A0pk == nullptr, prod1 = p.K1 > 0 && p.A1pk == nullptr;
             const uint32_t total_it = (uint32_t)my_units * (uint32_t)kblocks;

@@ -268,6 +268,22 @@ def test_netmon_fused_encoder_with_static_rows_from_the_env(B):
         b, _ = nm.forward_lists(env2._out["node_obs"], nbr2, deg2, li2, 3, want_node_out=True, sparse_nnz=env2.node_obs_nnz,
                                 sparse_rows=env2._out["node_sparse"], static_rows=env2.node_static_rows)
     assert float((a - b).abs().max()) < 2e-5
+    # a pool of three topologies: the dictionary holds 3N + 5 rows and an env's rows index its own topology's block
+    env3 = Routing(Network(N, random_topology=True, n_random_seeds=3, topology_init_seed=11), A, 1, num_envs=B, seed=4, batched=True)
+    env3.reset()
+    for _ in range(3):
+        env3.step(torch.randint(0, 4, (B, A), device="cuda", generator=g, dtype=torch.int32))
+    assert env3.node_obs_nnz == 6 and env3.node_static_rows.shape == (3 * N + 5, 4 * N + 8)
+    nbr3, deg3, li3 = env3.get_adjacency_lists()
+    assert int(li3.max()) > 0  # more than one topology in use
+    with torch.no_grad():
+        nm.state = st.clone()
+        a, _ = nm.forward_lists(env3._out["node_obs"], nbr3, deg3, li3, 3, want_node_out=True)
+        nm.state = st.clone()
+        (b, _), n = _tc_launches(lambda: nm.forward_lists(env3._out["node_obs"], nbr3, deg3, li3, 3, want_node_out=True,
+                                                          sparse_nnz=env3.node_obs_nnz, sparse_rows=env3._out["node_sparse"],
+                                                          static_rows=env3.node_static_rows))
+    assert n == n_tc[0] - 1 and float((a - b).abs().max()) < 2e-5
 
 
 def test_fused_sparse_encoder_reports_rows_that_are_not_sparse():

@@ -1,5 +1,6 @@
 """Per-tile timeline of one tcgen05 kernel launch (CTA 0): needs a build with GM_NVCC_EXTRA=-DGM_TC_PROBES=1.
-usage: GM_TC_TRACE_EPI=<0 linear|1 lstm|2 qhead> [GM_TC_TRACE_KP=<packed K of the layer, e.g. 96 encoder L1, 512 encoder L2,
+usage: GM_TC_TRACE_EPI=<0 linear|1 lstm|2 qhead|9 fused encoder L1+L2 (columns 3-7 then hold one producer thread's clocks per tile:
+gathers, activation + stores, tile end, wait for the chunk, wait for a free A slot)> [GM_TC_TRACE_KP=<packed K of the layer, e.g. 96 encoder L1, 512 encoder L2,
 672 DQN L1>] [GM_LIB_PATH=build_variants/libtcprobe.so] python tools/tc_trace.py [cfg]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
