@@ -216,7 +216,7 @@ def test_netmon_fused_sparse_encoder(B, monkeypatch):
         assert np.abs(outs[12][0] - ref_out).max() < 1e-4 and np.abs(outs[12][1] - ref_state).max() < 1e-4
 
 
-@pytest.mark.parametrize("B", [37, 512])
+@pytest.mark.parametrize("B", [37, 512, 2048])  # 2048 envs = 320 M tiles: up to three tiles per CTA, rings wrap
 def test_netmon_fused_encoder_with_static_rows_from_the_env(B):
     """The 6-term form: the Routing env hands NetMon its node rows as sparse entries whose constant part (one-hots,
     edge lengths) is ONE entry naming a static row that the weight pack folded into layer 1 (single-topology pool).
