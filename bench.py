@@ -45,24 +45,6 @@ def peaks():
     return p
 
 
-def write_only_gbs(dev):
-    """HBM bandwidth of a pure store stream on this GPU (torch fill_ over 1 GiB, best of 5, CUDA events).  The env-step
-    kernel writes 17x what it reads; MEASURED_PEAKS.json's figure is a COPY (read + write bytes counted), which a
-    write-dominated kernel cannot reach: reported next to the contract's `peak` so that the fraction can be read."""
-    x = torch.empty(1 << 28, dtype=torch.float32, device=dev)
-    best = 1e9
-    for i in range(7):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        x.fill_(1.0)
-        e1.record()
-        torch.cuda.synchronize()
-        if i >= 2:
-            best = min(best, e0.elapsed_time(e1))
-    del x
-    return (1 << 30) / (best * 1e-3) / 1e9
-
-
 def env_step_bytes(N, A, sparse_rows=False):
     """algorithmic bytes of one env-step with dense outputs materialised.  sparse_rows: the launch also
     writes the node rows in sparse form for NetMon's fused encoder (96 bytes per node, `gm_routing_io.node_sparse`)."""
@@ -431,12 +413,6 @@ def main():
                     traffic=traffic.get("routing_step_bytes_per_launch"), algorithmic_bytes_per_launch=env_bytes,
                     peak_source=pk["source"], bytes_per_env_step=per_env, ms_per_launch=env_ms,
                     note="SURVEY 8(d) dense outputs" + (" + 96 B per node of sparse node rows (gm_routing_io.node_sparse)" if sparse_out else ""))
-    try:
-        wr = write_only_gbs(dev)
-        roof_env.update(write_only_peak=wr, frac_of_write_only_peak=roof_env["achieved"] / wr,
-                        write_only_note="measured here: torch fill_ over 1 GiB, best of 5; 94 % of this kernel's bytes are stores")
-    except Exception:
-        pass
     tf = flops_step / (gemm_ms * 1e-3) / 1e12
     passes = {"fp32": 1, "bf16x3": 3, "bf16": 1}[a.math]
     roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
