@@ -43,6 +43,10 @@ struct TcArgs {
     // epilogue gets each row's LayerNorm mean / variance; tiles 1.. carry [i|f|g|o] of 32 hidden units each.
     // Uses c_in / h_out / c_out / Hpk like EPI_LSTM (h_out, c_out double as scratch for the LN_H pass).
     const float* ln_params;   // filled by tc_launch: column sums, per-tile LN affine, ln_cell affine
+    // per-CTA scratch [gridDim][128 units x 128 rows] in the blocked layout of tc_blocked_off (row = tile row): sig(o) of the
+    // four gate tiles waits here for the LN_H pass (96 registers per thread leave no room for it); a warp instruction
+    // covers 1 KiB of contiguous memory.  NULL: parked in the h' slots of h_out instead (32 lines per warp instruction)
+    float* ln_scratch;
     // EPI_QHEAD (N <= 256): the layer's activated output never leaves the SM; the epilogue applies the
     // Q head q = y Wq^T + bq, the action mask, argmax and the epsilon mix (model.py:199-203, policy.py:42-51)
     const float* q_w; const float* q_b; int n_act;

@@ -762,6 +762,7 @@ static int netmon_pack(const gm_netmon_params* p, void* out, cudaStream_t s) {
 struct NetmonWs {
     float *act0, *act1, *g0, *g1, *hA, *hB, *cA, *cB, *M, *gmean;
     void* sp;  // sparse input rows of the fused encoder kernel (+ 256 bytes behind them: the overflow flag)
+    float* ln_scratch;  // LayerNormLSTM cell: [SMs][128 units x 128 rows] sig(o) of the M tile a CTA works on
     uint8_t *pk0, *pk1, *e_pk, *m_pk, *h_pk0, *h_pk1;  // tile-packed activations of the tensor-core path
     int64_t bytes;
 };
@@ -789,11 +790,14 @@ static NetmonWs carve(const gm_netmon_params* p, int64_t R, int B, void* base) {
     w.gmean = take((int64_t)max(B, 1) * H);
     w.pk0 = w.pk1 = w.e_pk = w.m_pk = w.h_pk0 = w.h_pk1 = nullptr;
     w.sp = nullptr;
+    w.ln_scratch = nullptr;
     if (tc_math(p->math)) {
         w.sp = (void*)take((enc_fused_sp_bytes(R) + 256) / 4);
         auto take_pk = [&](int width) { return (uint8_t*)take(tc_pk_bytes(R, (int)round_up(width, TC_BK)) / 4 + 64); };
         w.pk0 = take_pk(maxw); w.pk1 = take_pk(maxw);
         w.e_pk = take_pk(H); w.m_pk = take_pk(H); w.h_pk0 = take_pk(H); w.h_pk1 = take_pk(H);
+        // LayerNormLSTM cell: one M tile of sig(o) per CTA, parked between the gate tiles and the LN_H pass
+        if (p->rnn_type == GM_RNN_LNLSTM) w.ln_scratch = take((int64_t)kNumSMs * TC_BM * 128);
     }
     w.bytes = off + (32 << 20);  // + room for per-call packed weights of the unfused tensor-core layers
     return w;
@@ -975,6 +979,7 @@ int gm_netmon_forward(const gm_netmon_params* p, int32_t B, int32_t N, const flo
             a.c_in = cprev; a.ldc_in = ldcp < 0 ? H : ldcp; a.c_in_blocked = ldcp < 0;
             a.h_out = hn; a.ldh = ldhn; a.c_out = cn; a.ldco = ldcn < 0 ? H : ldcn; a.c_out_blocked = ldcn < 0;
             a.Hpk = hn_pk;
+            a.ln_scratch = w.ln_scratch;
             a.H = H; a.M = R; a.N = 4 * H;
             a.ws = PL.ws_cells;
             return tc_launch(a, math, PL.cell_epi, s);
