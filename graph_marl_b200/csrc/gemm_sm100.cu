@@ -499,6 +499,12 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                     const uint8_t* apk = seg1 ? p.A1pk : p.A0pk;
                     if (!tile_live) apk = nullptr;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);  // every CTA of the cluster has retired its MMAs on this stage
+#if GM_TC_PROBES
+                    if (p.a_stages & 8) {  // GM_TC_DEBUG & 8, timing probe: no copies at all (the MMAs run on stale shared memory)
+                        mbar_arrive(bar_full + 8 * s);
+                        continue;
+                    }
+#endif
                     mbar_arrive_expect_tx(bar_full + 8 * s, w_bytes + (apk ? a_bytes : 0u));
                     const uint8_t* src = p.Wp + ((size_t)nt * kblocks + kb) * (2 * W_SRC_PART_BYTES);
                     const uint32_t w_dst = smem_base + s * STAGE_BYTES + 2 * A_PART_BYTES;
