@@ -126,6 +126,7 @@ class Rollout:
         self.graph_launches = 0  # kernels of this library launched through graph replays
         self._h_trace = None     # optional list: indices of the host draw table consumed so far (tests)
         self._draw_bufs, self._copy_stream = None, None  # static per-step draw buffers of the captured units
+        self._d2h_stream, self._capture_keep = None, []  # reward read-back stream of the captured units
         if host_draws and self.graph_steps > 0:
             assert host_draw_steps % self.graph_steps == 0, "host draw table must hold whole graph units"
         self.episode_step = None
@@ -246,7 +247,18 @@ class Rollout:
         self._mark("replay_insert")
         self.obs, self.adj = next_obs, next_adj
         if self.host_draws:
-            self._h_reward.copy_(reward, non_blocking=True)
+            if draws is not None and self._d2h_stream is not None and torch.cuda.is_current_stream_capturing():
+                # captured unit: the read-back of this step's reward runs on its own stream, so the next step's kernels
+                # do not queue behind a PCIe copy; the unit joins that stream at its end.  The reward tensor stays
+                # referenced until the capture ends (its block must not be handed to a later allocation of the unit).
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self._d2h_stream.wait_event(ev)
+                with torch.cuda.stream(self._d2h_stream):
+                    self._h_reward.copy_(reward, non_blocking=True)
+                self._capture_keep.append(reward)
+            else:
+                self._h_reward.copy_(reward, non_blocking=True)
         return reward, done, info
 
     # ---- CUDA-graph execution ----------------------------------------------------------------------
@@ -349,6 +361,7 @@ class Rollout:
         if self.host_draws and (self._draw_bufs is None or len(self._draw_bufs) < n):
             self._draw_bufs = [{k: torch.empty_like(v[0], device=self.device) for k, v in self._h.items()} for _ in range(n)]
             self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._d2h_stream = torch.cuda.Stream(device=self.device)
         with torch.cuda.graph(g, pool=self._graph_pool):
             fetched = None
             if self.host_draws:
@@ -373,10 +386,12 @@ class Rollout:
                     self._step_eager()
             if fetched is not None:
                 torch.cuda.current_stream().wait_stream(self._copy_stream)
+                torch.cuda.current_stream().wait_stream(self._d2h_stream)
             self.join_streams()
             out, _ = self._carried()
             for k, v in self._static.items():
                 v.copy_(out[k])
+        self._capture_keep = []
         if self._graph_pool is None:
             self._graph_pool = g.pool()
         # capture executes nothing: remember by how much the host bookkeeping moved, then restore it and the

@@ -62,6 +62,11 @@ def test_graph_replay_equals_eager(host_draws, replay):
             continue
         assert torch.equal(getattr(a.buff, name), getattr(b.buff, name)), name
     assert (a.episode_step, a.base_env._calls, a.policy._step) == (b.episode_step, b.base_env._calls, b.policy._step)
+    if host_draws:  # the per-step reward read-back (side stream inside a captured unit) delivered the last step's rewards
+        assert torch.equal(a._h_reward, b._h_reward)
+        last = b.buff.reward[(b.buff.index - b.B) % b.buff.buffer_size:][:b.B] if b.buff.index >= b.B else None
+        if last is not None:
+            assert torch.equal(last.reshape(b._h_reward.shape).cpu(), b._h_reward)
     if replay == "compact":  # and the learner's view of both rings is the same
         for x, y in zip(a.buff.get_batch(24, "cuda", sequence_length=4), b.buff.get_batch(24, "cuda", sequence_length=4)):
             assert np.array_equal(x.idx, y.idx)
