@@ -47,9 +47,7 @@
 #ifndef GM_TC_PROBES
 #define GM_TC_PROBES 0
 #endif
-#ifndef GM_LSTM_UNROLL
-#define GM_LSTM_UNROLL 1
-#endif
+
 
 namespace gm {
 
@@ -75,7 +73,6 @@ constexpr int MMA_WARP = 16, W_WARP = 17;
 constexpr int THREADS = 32 * 18;
 constexpr int A_PART_BYTES = BM * BK * 2;  // one bf16 part (hi or lo) of an A stage: 8 KiB
 constexpr int SBO_BYTES = BK * 16;         // distance between 8-row groups: 512 B
-constexpr int kLstmUnroll = GM_LSTM_UNROLL;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
