@@ -216,6 +216,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
                  : "r"(addr)                                                                              \
                  : "memory")
+#define TMEM_LD4(addr, v)                                                                      \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"                    \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])                                 \
+                 : "r"(addr)                                                                      \
+                 : "memory")
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -350,8 +355,12 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     static_assert(NCG == 2 || NCG == 4, "2 or 4 column groups");
     static_assert(!LN || NCG == 4, "the LayerNormLSTM epilogue is written for four column quarters");
     constexpr int EPI_W = NCG == 4 ? EPI_WARPS + PROD_WARPS : EPI_WARPS;  // NCG == 4: no producers (all operands tile-packed)
-    __shared__ float ln_part[LN ? 2 : 1][LN ? BM : 1][4][2];  // per row and column quarter: partial sum / centred sum of squares
-    __shared__ float ln_cpart[LN ? 2 : 1][LN ? BM : 1][8];    // per row: the quarters' partial sums of the LN_H pass
+    __shared__ float ln_part[1][LN ? BM : 1][4][2];  // per row and column quarter: partial sum / centred sum of squares
+    __shared__ float ln_cpart[1][LN ? BM : 1][8];    // per row: the quarters' partial sums of the LN_H pass
+    // LayerNormLSTM: the cell's LayerNorm parameters (TcArgs::ln_params: column sums, per-tile affine + biases, ln_cell),
+    // 8 KiB at H = 128; every epilogue thread reads them for every tile, as broadcast LDS.128 instead of 32-byte global loads
+    __shared__ __align__(16) float ln_prm_s[LN ? 16 * BN : 4];
+    __shared__ __align__(16) float ln_cin_s[LN ? 16 * 32 : 1][8];  // per epilogue thread: previous cell state of the tile's 8 units (cp.async)
 
     pdl_trigger();  // the next kernel's CTAs may take this SM as soon as this CTA has exited
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -388,6 +397,9 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
     }
     if (EPI == EPI_QHEAD) {
         for (int i = threadIdx.x; i < p.n_act * p.N; i += THREADS) qw_s[i / p.N][i % p.N] = __ldg(p.q_w + i);
+    }
+    if (LN) {
+        for (int i = threadIdx.x; i < 16 * BN; i += THREADS) ln_prm_s[i] = __ldg(p.ln_params + i);
     }
     tc_fence_before();
     __syncthreads();
@@ -599,6 +611,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
         const int quad = warp & 3, chalf = warp >> 2;
         const int r = quad * 32 + lane;  // accumulator lane == tile row
         float ln_csum = 0.f;             // LayerNormLSTM: running sum of this thread's pre-LN cell values of the row
+        float ln_ma = 0.f, ln_ra = 0.f, ln_mb = 0.f, ln_rb = 0.f;  // ... and the row's LayerNorm statistics of the current M tile
         float* const ln_craw = (float*)(smem + STAGES * STAGE_BYTES);  // LayerNormLSTM only: [BN][BM] behind the ring
         for (uint32_t tcount = 0; tcount < (uint32_t)my_units; tcount++) {
             const int as = tcount % ACC_STAGES;
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const TcArgs p) {
                 }
             }
         }
-        (void)ln_csum; (void)ln_craw;
+        (void)ln_csum; (void)ln_craw; (void)ln_ma; (void)ln_ra; (void)ln_mb; (void)ln_rb; (void)ln_prm_s; (void)ln_cin_s;
     }
 
     tc_fence_before();
