@@ -284,7 +284,7 @@ def main():
                   replay_insert=not a.no_replay,
                   replay_format=("compact: env records before/after + actions/reward/done + NetMon state per transition, dense fields rebuilt by get_batch"
                                  if a.replay == "compact" else "dense: the reference's 17 fields per transition"),
-                  replay_overlap=("main stream (two small launches)" if a.replay == "compact" else "side stream, joined before the end event"),
+                  replay_overlap=("written by the env step kernel itself (gm_routing_io.ring_*), no insert launch" if a.replay == "compact" else "side stream, joined before the end event"),
                   cuda_graph_steps=a.graph_steps, sharding=f"env instances, {world} rank(s), no collective",
                   l2="per-step working set (obs + node_obs + NetMon activations + replay slots) exceeds the 126 MB L2")
 
@@ -371,6 +371,9 @@ def main():
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) -------------
     stage = ro.profile_stages(iters=max(5, min(a.steps, 20)))
     sparse_out = getattr(ro.base_env, "_out", {}).get("node_sparse") is not None
+    # fused insert: the step launch also writes the transition's compact replay record (records before / after, int8
+    # actions, f32 reward, done, topology index, episode_done) -- bytes of that launch, no separate insert kernel
+    ring_bytes = (2 * ro.base_env._layout["stride"] + 6 * A + 5) if getattr(ro, "fused_insert", False) else 0
     del ro
     torch.cuda.empty_cache()
 
@@ -406,13 +409,14 @@ def main():
     agg_ms = stage.get("aggregate_kernel_ms", 0.0) / max(stage.get("aggregate_kernel_launches_per_step", 1.0), 1.0)
     # the step launch also writes the node rows in sparse form (the fused encoder's input): real output bytes of the
     # kernel, counted next to SURVEY 8(d)'s dense outputs (tools/env_only.py times the kernel against the same figure)
-    per_env = env_step_bytes(N, A, sparse_rows=sparse_out)
+    per_env = env_step_bytes(N, A, sparse_rows=sparse_out) + ring_bytes
     env_bytes = per_env * B
     roof_env = dict(bound="hbm", kernel="routing_kernel<STEP>", achieved=env_bytes / (env_ms * 1e-3) / 1e9,
                     peak=pk["hbm_gbs"], unit="GB/s", frac=env_bytes / (env_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                     traffic=traffic.get("routing_step_bytes_per_launch"), algorithmic_bytes_per_launch=env_bytes,
                     peak_source=pk["source"], bytes_per_env_step=per_env, ms_per_launch=env_ms,
-                    note="SURVEY 8(d) dense outputs" + (" + 96 B per node of sparse node rows (gm_routing_io.node_sparse)" if sparse_out else ""))
+                    note="SURVEY 8(d) dense outputs" + (" + 96 B per node of sparse node rows (gm_routing_io.node_sparse)" if sparse_out else "")
+                         + (f" + {ring_bytes} B of compact replay transition (gm_routing_io.ring_*)" if ring_bytes else ""))
     tf = flops_step / (gemm_ms * 1e-3) / 1e12
     passes = {"fp32": 1, "bf16x3": 3, "bf16": 1}[a.math]
     roof_gemm = dict(bound="tensor", kernel=stage["gemm_kernel"], achieved=tf, peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",

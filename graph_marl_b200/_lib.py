@@ -38,7 +38,11 @@ class RoutingIO(C.Structure):
                [(n, C.c_void_p) for n in ("obs", "adj", "node_obs", "node_agent", "agent_node", "node_sparse", "reward",
                                           "done", "delays", "arrived", "spr", "info", "n_resets",
                                           "action_mask_out", "eval_f64", "eval_i32", "packet_dist", "packet_sizes",
-                                          "sum_packets_per_node", "sum_packets_per_edge")]
+                                          "sum_packets_per_node", "sum_packets_per_edge")] + \
+               [(n, C.c_void_p) for n in ("ring_rec", "ring_next_rec", "ring_topo", "ring_action", "ring_reward", "ring_done",
+                                          "ring_episode_done")] + \
+               [("ring_capacity", C.c_int64), ("ring_index", C.c_int64), ("ring_index_dev", C.c_void_p),
+                ("ring_episode_flag", C.c_int32), ("ring_pad", C.c_int32)]
 
 
 class CellParams(C.Structure):

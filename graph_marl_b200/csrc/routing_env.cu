@@ -287,6 +287,10 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
 
     GM_PROBE(0);
     int n_resets = 0;
+    // compact replay transition written by this launch (gm_routing_io.ring_*): the env's slot in the ring
+    size_t ring_slot = 0;
+    if (MODE == MODE_STEP && io.ring_rec)
+        ring_slot = (size_t)((io.ring_index + (io.ring_index_dev ? *io.ring_index_dev : 0) + b) % io.ring_capacity);
     if (role == 0) {  // ======== warp 0 of the env: record load, reset / step, write-back ========
     // ---- load the env record ------------------------------------------------------
     // (the first chunk of actions is requested before the record so that both DRAM round trips overlap; every record
@@ -297,6 +301,7 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     if (MODE != MODE_RESET) {
         const uint4* src = (const uint4*)gstate;
         uint4* dst = (uint4*)sm;
+        uint4* ring = (MODE == MODE_STEP && io.ring_rec) ? (uint4*)(io.ring_rec + ring_slot * (size_t)L.stride) : nullptr;
         const int n16 = L.stride / 16;
         for (int q0 = 0; q0 < n16; q0 += 128) {
             uint4 t[4];
@@ -305,7 +310,10 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                 if (q0 + 32 * k + lane < n16) t[k] = src[q0 + 32 * k + lane];
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (q0 + 32 * k + lane < n16) dst[q0 + 32 * k + lane] = t[k];
+                if (q0 + 32 * k + lane < n16) {
+                    dst[q0 + 32 * k + lane] = t[k];
+                    if (ring) ring[q0 + 32 * k + lane] = t[k];  // the transition's record before the step
+                }
         }
     } else {
         uint4* dst = (uint4*)sm;
@@ -465,6 +473,12 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
                 size_t o = (size_t)b * A + i;
                 if (io.reward) io.reward[o] = rew;
                 if (io.done) io.done[o] = dn ? 1 : 0;
+                if (io.ring_rec) {
+                    const size_t ro = ring_slot * A + i;
+                    if (io.ring_reward) io.ring_reward[ro] = rew;
+                    if (io.ring_done) io.ring_done[ro] = dn ? 1 : 0;
+                    if (io.ring_action) io.ring_action[ro] = (int8_t)act[i];
+                }
                 if (io.delays) io.delays[o] = dl;
                 if (io.arrived) io.arrived[o] = (dn && reached) ? 1 : 0;
                 if (io.spr) io.spr[o] = sp;
@@ -502,7 +516,16 @@ routing_kernel(const gm_routing_desc d, const gm_routing_io io, const RoutingLay
     if (MODE != MODE_OBSERVE) {
         uint4* dst = (uint4*)gstate;
         const uint4* src = (const uint4*)sm;
-        for (int q = lane; q < L.stride / 16; q += 32) dst[q] = src[q];
+        uint4* ring = (MODE == MODE_STEP && io.ring_rec && io.ring_next_rec) ? (uint4*)(io.ring_next_rec + ring_slot * (size_t)L.stride) : nullptr;
+        for (int q = lane; q < L.stride / 16; q += 32) {
+            const uint4 t = src[q];
+            dst[q] = t;
+            if (ring) ring[q] = t;  // the transition's record after the step
+        }
+        if (MODE == MODE_STEP && io.ring_rec && lane == 0) {
+            if (io.ring_topo) io.ring_topo[ring_slot] = topo;
+            if (io.ring_episode_done) io.ring_episode_done[ring_slot] = (uint8_t)(io.ring_episode_flag != 0);
+        }
         if (io.n_resets && lane == 0) io.n_resets[b] = n_resets;
     }
     if (MODE == MODE_RESET) {  // outputs that only step produces are cleared on reset

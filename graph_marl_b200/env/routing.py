@@ -122,6 +122,7 @@ class Routing(NetworkEnv):
         self._pool = None
         self._topo_index = None
         self._draws = None
+        self._ring = None  # set_ring(): the next step writes its compact replay transition itself
         self._out = {}
         self._sum_node = self._sum_edge = None
         self._dev_step = None
@@ -239,7 +240,15 @@ class Routing(NetworkEnv):
             io.philox_step, io.philox_step_dev = self._dev_step.offset(self._calls), self._dev_step.ptr()
         for k, v in out.items():
             setattr(io, k, v.data_ptr())
+        if self._ring is not None and actions is not None:  # this step also writes its compact replay transition
+            for k, v in self._ring.items():
+                setattr(io, k, v)
         return io
+
+    def set_ring(self, ring):
+        """One-shot: the next step() writes its transition (records before / after, actions, reward, done) straight into
+        the compact replay ring described by `ring` (gm_routing_io.ring_* fields, CompactReplayBuffer.ring_io)."""
+        self._ring = ring
 
     def _launch(self, fn, out, actions=None, env_mask=None):
         _lib.require_device()
@@ -248,6 +257,8 @@ class Routing(NetworkEnv):
             _lib.check(fn(C.byref(d), C.byref(io), _lib.current_stream()))
         self._keep = (d, io, actions, env_mask, self._draws)  # keep inputs alive until the next launch
         self._draws = None
+        if actions is not None:
+            self._ring = None
         self._calls += 1
         self._out = out
 

@@ -324,6 +324,27 @@ class CompactReplayBuffer(_RingSampler):
                                                    _lib.current_stream()))
         return keep
 
+    # ---- fused insert: the env's step kernel writes the transition (state-ring mode) -------------------------------
+    def ring_io(self, episode_done):
+        """gm_routing_io.ring_* arguments for Routing.set_ring(): the step kernel then writes this step's transition
+        (records before / after, topology index, actions, reward, done, episode_done) into the slots at the ring head --
+        what stage() + commit() do with two insert launches.  Follow the step with advance()."""
+        assert self.state_ring, "the fused insert needs the state ring (node_state is written in place by NetMon)"
+        index, index_dev = self.index, None
+        if self._dev_index is not None:
+            index, index_dev = self._dev_index.offset(self.index) % self.buffer_size, self._dev_index.ptr()
+        return dict(ring_rec=self.rec.data_ptr(), ring_next_rec=self.next_rec.data_ptr(), ring_topo=self.topo.data_ptr(),
+                    ring_action=self.action.data_ptr(), ring_reward=self.reward.data_ptr(), ring_done=self.done.data_ptr(),
+                    ring_episode_done=self.episode_done.data_ptr(), ring_capacity=self.buffer_size, ring_index=index,
+                    ring_index_dev=index_dev, ring_episode_flag=int(bool(episode_done)))
+
+    def advance(self, num):
+        """Host bookkeeping of the `num` transitions a step kernel wrote through ring_io()."""
+        n = int(num)
+        self.count = min(self.buffer_size, self.count + n)
+        self.index = (self.index + n) % self.buffer_size
+        self.steps_total += 1
+
     def stage(self, num):
         """Before env.step: the records (and topology indices) that produced the current observations."""
         _lib.require_device()

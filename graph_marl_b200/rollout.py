@@ -62,7 +62,7 @@ def aggregate_throughput(units_per_rank, ms_local, world_size):
 class Rollout:
     def __init__(self, cfg="cfg2", num_envs=4096, device="cuda", math="fp32", replay_capacity=None,
                  epsilon=1.0, seed=0, with_replay=True, host_draws=False, overlap_replay=True, host_draw_steps=64,
-                 graph_steps=0, replay="compact", device_sampler=False, state_ring=True):
+                 graph_steps=0, replay="compact", device_sampler=False, state_ring=True, fused_insert=True):
         """replay: "compact" (default; replaybuffer.CompactReplayBuffer: env records + NetMon state, dense fields are
         rebuilt when sampled) or "dense" (the reference's 17 dense fields per transition, replaybuffer.ReplayBuffer)."""
         c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
@@ -105,6 +105,8 @@ class Rollout:
                 self.buff = ReplayBuffer(seed, cap, A, Dj, 0, N, Dn, self.netmon.get_state_size(), N, device=device,
                                          device_sampler=device_sampler)
         self.state_ring = self.compact and self.buff.state_ring
+        # state-ring mode: the env's step kernel writes the transition into the ring itself (gm_routing_io.ring_*)
+        self.fused_insert = bool(fused_insert) and self.state_ring and hasattr(self.base_env, "set_ring")
         self.sizes = dict(N=N, A=A, Dn=Dn, Da=Da, Dj=Dj, H=c["H"], K=c["K"])
         self.host_draws = host_draws
         if host_draws:
@@ -216,7 +218,11 @@ class Rollout:
         else:
             actions = self.policy(obs, adj)
         self._mark("dqn_act")
-        if self.compact:
+        fused_insert = self.compact and self.fused_insert
+        if fused_insert:
+            # the step kernel writes the transition itself (records before / after, actions, reward, done): no insert launch
+            self.base_env.set_ring(self.buff.ring_io(self.episode_step + 1 >= c["episode_steps"]))
+        elif self.compact:
             self.buff.stage(self.B)  # the env records are advanced in place: snapshot them into the ring first
         next_obs_a, next_adj, reward, done, info = self.base_env.step(actions)
         self._mark("env_step")
@@ -227,7 +233,10 @@ class Rollout:
         next_info = env.get_netmon_info()
         self.episode_step += 1
         episode_done = self.episode_step >= c["episode_steps"]
-        if self.compact:
+        if fused_insert:
+            self.buff.advance(self.B)
+            self._ring_states()
+        elif self.compact:
             self.buff.commit(actions, reward, done, episode_done, last_state, num=self.B)
             if self.state_ring:
                 self._ring_states()

@@ -146,6 +146,21 @@ typedef struct gm_routing_io {
     double* packet_sizes;        /* [B,A] packet sizes before respawns */
     int32_t* sum_packets_per_node; /* [B,N] cumulative: += 1 per waiting packet per step (routing.py:384-386) */
     int32_t* sum_packets_per_edge; /* [B,E] cumulative: += 1 per in-flight packet per step (routing.py:428-429) */
+    /* Optional, step only: the step kernel itself writes this step's transition in the compact replay format
+     * (what ReplayBuffer.add stores, replaybuffer.py:243-287, restated by CompactReplayBuffer: the env record before and
+     * after the step instead of the dense observation rows) into ring slot (ring_index + *ring_index_dev + env) %
+     * ring_capacity.  Enabled by ring_rec != NULL; any other ring pointer may be NULL.  The record is in the kernel's
+     * shared memory at both moments, so the two separate insert launches of a rollout step disappear. */
+    uint8_t* ring_rec;           /* [capacity, state_stride] env record BEFORE the step */
+    uint8_t* ring_next_rec;      /* [capacity, state_stride] env record AFTER the step */
+    int32_t* ring_topo;          /* [capacity] topology index of the env (0 without a pool) */
+    int8_t* ring_action;         /* [capacity, A] the actions of this call */
+    float* ring_reward;          /* [capacity, A] */
+    uint8_t* ring_done;          /* [capacity, A] */
+    uint8_t* ring_episode_done;  /* [capacity] = ring_episode_flag */
+    int64_t ring_capacity, ring_index;
+    const int64_t* ring_index_dev; /* optional device counter added to ring_index (CUDA-graph replays), may be NULL */
+    int32_t ring_episode_flag, ring_pad;
 } gm_routing_io;
 
 /* byte offsets inside one env's state record; out[8] =

@@ -74,6 +74,30 @@ def test_graph_replay_equals_eager(host_draws, replay):
                 assert torch.equal(getattr(x, f), getattr(y, f)), f
 
 
+@pytest.mark.parametrize("graph_steps", [0, 5])
+def test_fused_insert_equals_stage_and_commit(graph_steps):
+    """The step kernel writing the compact transition itself (gm_routing_io.ring_*: records before / after, actions,
+    reward, done, topology index, episode_done) must leave the ring exactly as the two insert launches (stage + commit)
+    do, ring wrap and episode ends included."""
+    from graph_marl_b200.rollout import Rollout
+
+    cfg = dict(n_nodes=20, n_data=20, topo_seed=476, random_topology=True, n_topologies=5, congestion=True, K=1, rnn="lstm",
+               H=64, enc=(64,), dqn=(64,), episode_steps=9)
+    mk = lambda fused: Rollout(cfg, num_envs=40, math="bf16x3", seed=5, replay_capacity=40 * 10, replay="compact",
+                               graph_steps=graph_steps, fused_insert=fused)
+    a, b = mk(False), mk(True)
+    assert not a.fused_insert and b.fused_insert
+    for ro in (a, b):
+        np.random.seed(3)
+        ro.reset()
+        ro.run(27)  # wraps the 10-step ring twice and crosses three episode ends
+    torch.cuda.synchronize()
+    assert (a.buff.index, a.buff.count, a.buff.steps_total) == (b.buff.index, b.buff.count, b.buff.steps_total)
+    for name in COMPACT_FIELDS:
+        assert torch.equal(getattr(a.buff, name), getattr(b.buff, name)), name
+    assert b.buff.episode_done.any() and b.buff.reward.abs().sum() > 0 and b.buff.action.to(torch.int32).sum() > 0
+
+
 @pytest.mark.parametrize("math", ["bf16x3", "fp32"])
 def test_compact_ring_rebuilds_the_dense_transition(math):
     """the compact ring (env records + NetMon state, 23 kB instead of 141 kB per transition at config 2)
