@@ -370,6 +370,9 @@ def main():
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream) -------------
     stage = ro.profile_stages(iters=max(5, min(a.steps, 20)))
+    stage["note"] = ("dqn_act / env_step / netmon / replay_insert: CUDA events around the stages of an EAGER step (kernel-by-kernel issue; "
+                     "they include GPU idle time whenever the host issues slower than the GPU runs, so they can exceed ms_per_step, "
+                     "which is timed on captured CUDA-graph units); *_kernel_ms and gemm_ms: per-launch events inside the library")
     sparse_out = getattr(ro.base_env, "_out", {}).get("node_sparse") is not None
     # fused insert: the step launch also writes the transition's compact replay record (records before / after, int8
     # actions, f32 reward, done, topology index, episode_done) -- bytes of that launch, no separate insert kernel

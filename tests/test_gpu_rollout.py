@@ -74,8 +74,8 @@ def test_graph_replay_equals_eager(host_draws, replay):
                 assert torch.equal(getattr(x, f), getattr(y, f)), f
 
 
-@pytest.mark.parametrize("graph_steps", [0, 5])
-def test_fused_insert_equals_stage_and_commit(graph_steps):
+@pytest.mark.parametrize("graph_steps,B", [(0, 40), (5, 40), (5, 2100)])  # 2100 envs: the one-warp-per-env instance of the step kernel
+def test_fused_insert_equals_stage_and_commit(graph_steps, B):
     """The step kernel writing the compact transition itself (gm_routing_io.ring_*: records before / after, actions,
     reward, done, topology index, episode_done) must leave the ring exactly as the two insert launches (stage + commit)
     do, ring wrap and episode ends included."""
@@ -83,7 +83,7 @@ def test_fused_insert_equals_stage_and_commit(graph_steps):
 
     cfg = dict(n_nodes=20, n_data=20, topo_seed=476, random_topology=True, n_topologies=5, congestion=True, K=1, rnn="lstm",
                H=64, enc=(64,), dqn=(64,), episode_steps=9)
-    mk = lambda fused: Rollout(cfg, num_envs=40, math="bf16x3", seed=5, replay_capacity=40 * 10, replay="compact",
+    mk = lambda fused: Rollout(cfg, num_envs=B, math="bf16x3", seed=5, replay_capacity=B * 10, replay="compact",
                                graph_steps=graph_steps, fused_insert=fused)
     a, b = mk(False), mk(True)
     assert not a.fused_insert and b.fused_insert

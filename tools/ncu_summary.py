@@ -60,8 +60,13 @@ def main():
             b = sum(e.get("dram_read_bytes", 0) + e.get("dram_write_bytes", 0) for e in sel)
             return (b / len(sel) if per_launch else b), len(sel)
 
+        # whole steps only: the launches from one env-step launch up to (not including) the last one captured, so that the
+        # per-step sums do not depend on where in a step the capture window started
+        ridx = [i for i, e in enumerate(out) if "routing_kernel" in e["kernel"]]
+        if len(ridx) >= 2:
+            out = out[ridx[0]:ridx[-1]]
         steps = max(1, sum(1 for e in out if "routing_kernel" in e["kernel"]))
-        tc, n_tc = tot(lambda k: "linear_tc_kernel" in k, False)
+        tc, n_tc = tot(lambda k: "linear_tc_kernel" in k or "enc_fused_kernel" in k, False)
         tr = dict(source=f"ncu --set full --clock-control none over {steps} rollout step(s) of bench.py --graph-steps 0 (cold caches, serialised), {sys.argv[1]}",
                   linear_tc_bytes_per_step=None if tc is None else tc / steps, linear_tc_launches_per_step=n_tc / steps,
                   routing_step_bytes_per_launch=tot(lambda k: "routing_kernel" in k, True)[0],
