@@ -85,7 +85,9 @@ def _learner_worker(rank, world, port, out):
     gathered = [None] * world
     dist.all_gather_object(gathered, (w_after, local, reduced, n))
     if rank == 0:
-        out.put(gathered)
+        # by value (numpy): a torch tensor travels as a shared-memory handle that the parent must fetch from THIS
+        # process, which may have exited by then on a loaded machine
+        out.put([(w.numpy(), g.numpy(), r.numpy(), k) for w, g, r, k in gathered])
     dist.barrier()
     dist.destroy_process_group()
 
@@ -104,7 +106,7 @@ def test_learner_weight_broadcast_and_fused_gradient_allreduce():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (w0, g0, r0, n0), (w1, g1, r1, n1) = res
+    (w0, g0, r0, n0), (w1, g1, r1, n1) = [(torch.from_numpy(w), torch.from_numpy(g), torch.from_numpy(r), k) for w, g, r, k in res]
     assert torch.equal(w0, w1)                       # identical replicas after the broadcast
     assert not torch.equal(g0, g1)                   # ranks saw different data
     assert torch.allclose(r0, (g0 + g1) / 2, atol=1e-7) and torch.equal(r0, r1)
