@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_rollout.py tests/test_gpu_routing.py -m gpu -x -q 2>&1 | tail -5
-for i in 1 2; do
-timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read()); e=j['e2e']; s=j['stage_ms']; print('value', round(j['value']), 'ms', round(j['ms_per_step'],4), 'e2e', round(e['value']), 'env_ms', round(s['env_kernel_ms'],4), 'env frac', round(j['roofline_env_step']['frac'],3), 'replay', s['replay_kernel_ms'], s['replay_kernel_launches_per_step'], 'launches', j['gpu_launches'], 'mhz', j['clocks']['sm_mhz'])"
-done
+timeout 900 python -m pytest tests/test_gpu_tensorcore.py tests/test_gpu_rollout.py -m gpu -x -q 2>&1 | tail -3
+echo "== LSTM"; GM_LIB_PATH=build_variants/libtcprobe.so GM_TC_TRACE_EPI=1 python tools/tc_trace.py 2>&1 | sed -n 5,9p | cut -c1-100
+echo "== DQN L1"; GM_LIB_PATH=build_variants/libtcprobe.so GM_TC_TRACE_EPI=0 GM_TC_TRACE_KP=672 python tools/tc_trace.py 2>&1 | sed -n 5,9p | cut -c1-100
+echo "== DQN L2"; GM_LIB_PATH=build_variants/libtcprobe.so GM_TC_TRACE_EPI=2 python tools/tc_trace.py 2>&1 | sed -n 3,7p | cut -c1-100
+bash tools/_ab.sh build_variants/libprev.so graph_marl_b200/lib/libgraphmarl_b200.so 3
