@@ -1,4 +1,4 @@
-# A/B of two library builds in one call: tools/_ab.sh <libA> <libB> [rounds] [bench args]
+# A/B of two library builds in one call: tools/ab_bench.sh <libA> <libB> [rounds] [bench args]
 A=$1; B=$2; R=${3:-2}; shift 3
 for r in $(seq 1 $R); do
 for L in $A $B; do
