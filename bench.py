@@ -340,7 +340,14 @@ def main():
         # untimed warm-up: at least the requested steps and one full wrap of the replay ring (8 x B slots), so
         # first-touch effects of the ring are outside the timed region
         ro.precapture()  # CUDA-graph units are captured before anything is timed
-        ro.run(max(warmup, 10) + 2 * max(ro.graph_steps, 1))
+        g = max(ro.graph_steps, 1)
+        ro.run(-(-(max(warmup, 10) + 2 * g) // g) * g)  # whole units: the timed region starts on a unit boundary (same ring phase)
+        if g > 1 and steps % g != 0:
+            # K is not a whole number of units: its last K % g steps run kernel by kernel.  Warm that path up too (one
+            # unit's worth of eager steps keeps the unit boundary), or the caching allocator's first eager allocations
+            # would fall into the timed region
+            for _ in range(g):
+                ro.step()
         ro.join_streams()
         n0 = _lib.lib().gm_kernel_launch_count() + ro.graph_launches
         barrier()
